@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""Benchmark of the two hot paths on B200 (contract: see the task statement / DESIGN.md section 6).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--pairs P]
+
+One JSON line on stdout (rank 0). A "step" is one pass of the scan-match hot path over one batch
+of synthetic scan pairs (BASELINE cfg 5: 1081-beam scans, one 100 x 100 x 101 = 1.01 M candidate
+window per pair): reset + rasterise every pair's map grid, rotate/quantise/score every candidate,
+compact the per-bin minima. `value` is device throughput with inputs resident in HBM; `e2e` is the
+same work through the C-ABI call with host buffers (plan + H2D + kernels + D2H + result assembly).
+The GN solve numbers ride in the same line under "gn".
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "scan-match scores/sec"
+UNIT = "scores/s"
+WINDOW_LO = (-5.0, -5.0, -1.25)
+WINDOW_HI = (5.0, 5.0, 1.25)
+THETA_RES = 0.025
+MAX_SCORE = 0.15
+BINS = (0.5, 0.5, 0.2)
+LC = dict(ll=(-35.0, -35.0), ur=(35.0, 35.0), res=0.1, kernel_range=0.5)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pairs", type=int, default=10000, help="scan pairs per GPU per step")
+    ap.add_argument("--cpu-pairs", type=int, default=0, help="pairs in the CPU sample (0 = auto)")
+    ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 global, 2 tiled")
+    ap.add_argument("--no-gn", action="store_true")
+    return ap.parse_args()
+
+
+def make_pairs(n, rank):
+    from cg_mrslam_b200 import synth
+    maps, curs = [], []
+    for i in range(n):
+        p = synth.make_scan_pair(rank * 1000003 + i)
+        maps.append(p["map_pts"])
+        curs.append(p["cur_pts"])
+    return maps, curs
+
+
+def window_regions(n):
+    reg = np.array(list(WINDOW_LO) + list(WINDOW_HI), dtype=np.float32)[None, :]
+    return np.repeat(reg, n, axis=0)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(mx)) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU legs (the reference's own chargrid.cpp compiled verbatim when oracle/_ref exists, else the
+# restated oracle). One pair per host thread: the reference itself uses min(#regions, 4) OpenMP
+# threads, i.e. one thread for this one-region window (chargrid.cpp:223-227).
+# ------------------------------------------------------------------------------------------------
+def cpu_run(n_pairs, n_threads, repeat=1):
+    from oracle import bindings
+    kind = "reference" if bindings.have_reference() else "port"
+    lib = bindings.MatcherLib("reference" if kind == "reference" else "oracle")
+    orc = bindings.MatcherLib("oracle")
+    stamp = orc.make_stamp(LC["res"], LC["kernel_range"])
+    maps, curs = make_pairs(n_pairs, 0)
+    grids = []
+    for mp in maps:
+        g = lib.grid(LC["ll"], LC["ur"], LC["res"])
+        g.fill(64)
+        g.raster(mp, stamp)
+        grids.append(g)
+    reg = window_regions(1)
+    counts = [0] * n_pairs
+
+    def work(tid):
+        for i in range(tid, n_pairs, n_threads):
+            g = grids[i]
+            g.fill(64)
+            g.raster(maps[i], stamp)
+            r = g.greedy_search(curs[i], reg, (0.1, 0.1, THETA_RES), MAX_SCORE, BINS)
+            counts[i] = len(r)
+
+    times = []
+    for _ in range(repeat):
+        t0 = time.perf_counter()
+        ts = [threading.Thread(target=work, args=(t,)) for t in range(n_threads)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        times.append(time.perf_counter() - t0)
+    cand = 100 * 100 * 101 * n_pairs
+    return kind, cand, times
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_threads = min(cores, 64)
+    n_pairs = args.cpu_pairs or n_threads * 2
+    total = args.steps + args.warmup
+    kind, cand, times = cpu_run(n_pairs, n_threads, repeat=total)
+    timed = times[args.warmup:]
+    sec = sum(timed)
+    value = cand * len(timed) / sec
+    sample = "%d pairs x 1.01M candidates per step, one pair per thread" % n_pairs
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec / len(timed),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32",
+        "data": "synthetic",
+        "config": {"workload": "cfg5 scan matcher: 1081-beam pairs, 100x100x101 window, LC grid "
+                               "700x700 res 0.1 (CPU sample of the same workload)",
+                   "pairs_per_step": n_pairs},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": n_threads, "kind": kind,
+                         "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from cg_mrslam_b200 import matcher
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    n = args.pairs
+    maps, curs = make_pairs(n, rank)
+    map_counts = np.array([len(p) for p in maps], dtype=np.int32)
+    cur_counts = np.array([len(p) for p in curs], dtype=np.int32)
+    # pinned host buffers (the e2e path copies from these every step)
+    map_host = torch.from_numpy(np.concatenate(maps)).pin_memory()
+    cur_host = torch.from_numpy(np.concatenate(curs)).pin_memory()
+    regions = window_regions(n)
+    reg_counts = np.ones(n, dtype=np.int32)
+    map_np, cur_np = map_host.numpy(), cur_host.numpy()
+    step = (0.1, 0.1, THETA_RES)
+
+    stream = torch.cuda.Stream()
+    m = matcher.Matcher(LC["ll"], LC["ur"], LC["res"], LC["kernel_range"], n_slots=n,
+                        device=local, stream=stream.cuda_stream)
+    m.set_kernel(args.kernel)
+
+    # ---- device-resident arm: stage once, time launches ----------------------------------------
+    m.batch_stage(cur_np, cur_counts, regions, reg_counts, step, MAX_SCORE, BINS,
+                  map_pts=map_np, map_counts=map_counts)
+    launches0 = m.launch_count()
+    for _ in range(args.warmup):
+        m.batch_launch()
+    m.batch_collect(cap=4)  # also validates the launch (error flag) and drains the survivors
+    stats = m.batch_stats()
+    kms = []
+    ev0 = torch.cuda.Event(enable_timing=True)
+    ev1 = torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    launches1 = m.launch_count()
+    with torch.cuda.stream(stream):
+        ev0.record(stream)
+        for _ in range(args.steps):
+            m.batch_launch()
+        ev1.record(stream)
+    barrier()
+    dev_ms = ev0.elapsed_time(ev1)
+    launches2 = m.launch_count()
+    kms.append(m.kernel_ms())  # last step's per-kernel split (events on the same stream)
+    res, n_out = m.batch_collect(cap=4)
+    found = int((n_out > 0).sum())
+
+    # ---- end-to-end arm: host buffers in, host results out, every step -------------------------
+    e2e_t = []
+    h2d = (map_np.nbytes + cur_np.nbytes + regions.nbytes + 2 * map_counts.nbytes)
+    for it in range(args.warmup + args.steps):
+        barrier()
+        t0 = time.perf_counter()
+        m.batch_stage(cur_np, cur_counts, regions, reg_counts, step, MAX_SCORE, BINS,
+                      map_pts=map_np, map_counts=map_counts)
+        m.batch_launch()
+        res, n_out = m.batch_collect(cap=4)
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        if it >= args.warmup:
+            e2e_t.append(t1 - t0)
+    clocks = sampler.stop() if rank == 0 else None
+    d2h = int(n_out.sum()) * 16 + 32
+    e2e_sec = sum(e2e_t)
+
+    cand = stats["candidates"]
+    t = torch.tensor([dev_ms, e2e_sec * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms_max, e2e_ms_max = float(t[0]), float(t[1])
+    value = cand * world * args.steps / (dev_ms_max * 1e-3)
+    e2e_value = cand * world * args.steps / (e2e_ms_max * 1e-3)
+
+    if rank == 0:
+        pk, pk_kind = peaks()
+        alg_bytes = stats["cell_reads"] + 4 * cand
+        score_ms = kms[-1]["score"]
+        achieved = alg_bytes / (score_ms * 1e-3) / 1e9 if score_ms > 0 else 0.0
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8/int32", "data": "synthetic",
+            "config": {
+                "workload": "cfg5 scan matcher: %d pairs per GPU per step, 1081-beam scans, one "
+                            "100x100x101 = 1.01M-candidate window per pair, LC grid 700x700 res "
+                            "0.1, raster + score + compact" % n,
+                "pairs_per_gpu": n, "candidates_per_step_per_gpu": cand,
+                "mean_k": stats["cell_reads"] / max(cand, 1),
+                "l2": "inputs larger than L2 (%.1f GB of grids per GPU)" % (n * 700 * 704 / 1e9),
+                "pairs_with_match": found, "kernel": args.kernel},
+            "roofline": {
+                "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_kind": pk_kind,
+                "kernel": "score_tiled" if args.kernel != 1 else "score_global",
+                "kernel_ms": score_ms, "algorithmic_bytes": alg_bytes,
+                "note": "algorithmic bytes = sum over candidates of k_theta x 1 B + 4 B per score "
+                        "(SURVEY 8d); the gathers hit shared memory, not DRAM, so frac may exceed 1",
+                "step_split_ms": kms[-1]},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms_max / args.steps},
+            "gpu_launches": int(launches2 - launches1),
+            "clocks": clocks,
+        }
+        # CPU baseline on a bounded sample, rank 0 at N=1 only
+        if world == 1:
+            cores = os.cpu_count() or 1
+            n_threads = min(cores, 64)
+            kind, ccand, times = cpu_run(args.cpu_pairs or n_threads, n_threads, repeat=1)
+            line["cpu_baseline"] = {
+                "value": ccand / times[0], "unit": UNIT, "cores": n_threads, "kind": kind,
+                "sample": "%d pairs x 1.01M candidates, one pair per thread (%.1f s)" %
+                          (args.cpu_pairs or n_threads, times[0])}
+        print(json.dumps(line))
+    m.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        ours(args)
+
+
+if __name__ == "__main__":
+    main()

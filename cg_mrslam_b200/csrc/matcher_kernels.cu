@@ -1,0 +1,699 @@
+// CUDA back-end of the scan matcher (sm_100a). Implements matcher_device.h.
+//
+// Kernels
+//   raster_tiles        resetGrid (scan_matcher.cpp:68-76) + addAndConvolvePoints/applyKernel
+//                       (chargrid.h:205-216, chargrid.cpp:132-161): one CTA per 32x128-cell tile,
+//                       min-stamping in shared memory, coalesced byte rows out.
+//   score_global        greedySearch inner loops (chargrid.cpp:239-287) straight from the
+//                       L2/L1-resident grid; any stride, any point extent. Reference kernel.
+//   score_tiled         the same arithmetic for stride-1 windows with the touched part of the
+//                       grid staged in shared memory and four candidates per 32-bit load
+//                       (DESIGN.md section 4). Production kernel.
+//   compact_bins        drains the per-bin arg-min table into a dense survivor list.
+//   window_sum, cells_at  cold paths (countPoints, searchNonMatchedPoints).
+//
+// Bit-exactness rules: every float/double operation that the reference performs is
+// spelled with a round-to-nearest intrinsic so that nvcc cannot contract it into an FMA; cos/sin
+// come from the host (ThetaDesc); integer sums are exact in any order.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "matcher_device.h"
+
+namespace cgm {
+
+namespace {
+
+std::atomic<uint64_t> g_launches(0);
+
+#define CGM_CUDA(call)                                                              \
+  do {                                                                              \
+    cudaError_t e_ = (call);                                                        \
+    if (e_ != cudaSuccess) {                                                        \
+      if (err) *err = std::string(#call) + ": " + cudaGetErrorString(e_);           \
+      return CGM_ERR_CUDA;                                                          \
+    }                                                                               \
+  } while (0)
+
+// Geometry as the kernels need it.
+struct DevGeom {
+  float llx, lly, inv_res;
+  int rows, cols, pitch;
+  int fill_value;
+  float ikscale;  // 1.f / (float)kscale, chargrid.cpp:260
+};
+
+// --------------------------------------------------------------------------------------------
+// shared device helpers
+// --------------------------------------------------------------------------------------------
+
+// chargrid.cpp:249-250: rotate in double (two products, one sum, no FMA), scale by the float
+// inverse resolution widened to double, truncate toward zero.
+__device__ __forceinline__ int2 rotate_quantise(double c, double s, double x, double y,
+                                                double inv_res) {
+  const double px = __dsub_rn(__dmul_rn(c, x), __dmul_rn(s, y));
+  const double py = __dadd_rn(__dmul_rn(s, x), __dmul_rn(c, y));
+  int2 ip;
+  ip.x = __double2int_rz(__dmul_rn(px, inv_res));
+  ip.y = __double2int_rz(__dmul_rn(py, inv_res));
+  return ip;
+}
+
+// chargrid.cpp:275-276: float(idsum) * ikscale, divided by k in double, narrowed to float.
+__device__ __forceinline__ float score_of(int idsum, int k, float ikscale) {
+  const float dsum = __fmul_rn(__int2float_rn(idsum), ikscale);
+  return __double2float_rn(__ddiv_rn(static_cast<double>(dsum), static_cast<double>(k)));
+}
+
+// Smallest idsum that is NOT accepted by `score < maxScore` (chargrid.cpp:279). score_of is
+// monotone in idsum for fixed k, so candidates are accepted iff idsum < threshold.
+__device__ int accept_threshold(int k, int max_sum, float ikscale, double max_score) {
+  if (k <= 0) return 0;  // dsum = maxScore + 1 is never accepted
+  if (!(static_cast<double>(score_of(0, k, ikscale)) < max_score)) return 0;
+  int lo = 0, hi = max_sum + 1;  // accepted(lo) is true; hi is beyond every reachable sum
+  while (hi - lo > 1) {
+    const int mid = lo + (hi - lo) / 2;
+    if (static_cast<double>(score_of(mid, k, ikscale)) < max_score)
+      lo = mid;
+    else
+      hi = mid;
+  }
+  return hi;
+}
+
+__device__ __forceinline__ void report(uint64_t* bins, const RegionDesc& reg, const int* bin_tab,
+                                       int bin_th, int a, int b, uint32_t cand, float score) {
+  const uint32_t entry =
+      reg.bin_base +
+      (static_cast<uint32_t>(bin_tab[reg.binx_off + a]) * reg.nby + bin_tab[reg.biny_off + b]) *
+          reg.nbth +
+      bin_th;
+  const uint64_t key = (static_cast<uint64_t>(__float_as_uint(score)) << 32) | cand;
+  atomicMin(reinterpret_cast<unsigned long long*>(bins + entry),
+            static_cast<unsigned long long>(key));
+}
+
+// --------------------------------------------------------------------------------------------
+// raster
+// --------------------------------------------------------------------------------------------
+const int kTileR = 32, kTileC = 128, kRasterThreads = 256, kRasterBatch = 1024;
+
+__global__ void __launch_bounds__(kRasterThreads)
+raster_tiles(uint8_t* grids, size_t slot_bytes, DevGeom g, int first_slot, const double* pts,
+             const int* pts_off, const uint8_t* stamp, int dim, int reset) {
+  __shared__ int tile[kTileR][kTileC];
+  __shared__ int2 list[kRasterBatch];
+  __shared__ int n_list;
+  const int tiles_c = (g.cols + kTileC - 1) / kTileC;
+  const int r0 = (blockIdx.x / tiles_c) * kTileR, c0 = (blockIdx.x % tiles_c) * kTileC;
+  const int slot = first_slot + blockIdx.y;
+  uint8_t* grid = grids + static_cast<size_t>(slot) * slot_bytes;
+  const int center = (dim - 1) / 2;
+
+  for (int t = threadIdx.x; t < kTileR * kTileC; t += kRasterThreads) {
+    const int r = r0 + t / kTileC, c = c0 + t % kTileC;
+    int v = static_cast<uint8_t>(g.fill_value);
+    if (!reset && r < g.rows && c < g.cols) v = grid[static_cast<size_t>(r) * g.pitch + c];
+    tile[t / kTileC][t % kTileC] = v;
+  }
+  const int p_begin = pts_off[blockIdx.y], p_end = pts_off[blockIdx.y + 1];
+  for (int base = p_begin; base < p_end; base += kRasterBatch) {
+    if (threadIdx.x == 0) n_list = 0;
+    __syncthreads();
+    for (int p = base + threadIdx.x; p < min(base + kRasterBatch, p_end); p += kRasterThreads) {
+      // chargrid.h:209-212: double -> float, then world2grid (gridmap.h:24-27) in float + lrint.
+      const float fx = __double2float_rn(pts[2 * p]), fy = __double2float_rn(pts[2 * p + 1]);
+      const float gx = __fmul_rn(__fsub_rn(fx, g.llx), g.inv_res);
+      const float gy = __fmul_rn(__fsub_rn(fy, g.lly), g.inv_res);
+      if (!(fabsf(gx) < 1e9f) || !(fabsf(gy) < 1e9f)) continue;  // far outside: stamps nothing
+      const int ix = __float2int_rn(gx), iy = __float2int_rn(gy);
+      if (ix + center < r0 || ix - center >= r0 + kTileR || iy + center < c0 ||
+          iy - center >= c0 + kTileC)
+        continue;
+      list[atomicAdd(&n_list, 1)] = make_int2(ix, iy);
+    }
+    __syncthreads();
+    const int work = n_list * dim * dim;
+    for (int t = threadIdx.x; t < work; t += kRasterThreads) {
+      const int p = t / (dim * dim), cell = t % (dim * dim);
+      const int i = cell / dim, j = cell % dim;
+      const int r = list[p].x + i - center, c = list[p].y + j - center;  // chargrid.cpp:145-151
+      if (r < r0 || r >= r0 + kTileR || c < c0 || c >= c0 + kTileC) continue;
+      atomicMin(&tile[r - r0][c - c0], static_cast<int>(stamp[j * dim + i]));  // ker[j*kRows+i]
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < kTileR * kTileC; t += kRasterThreads) {
+    const int r = r0 + t / kTileC, c = c0 + t % kTileC;
+    if (r < g.rows && c < g.pitch)
+      grid[static_cast<size_t>(r) * g.pitch + c] =
+          c < g.cols ? static_cast<uint8_t>(tile[t / kTileC][t % kTileC]) : 0;
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// scoring, reference kernel: grid read through L1/L2
+// --------------------------------------------------------------------------------------------
+const int kGlobalThreads = 256, kGlobalChunk = 2048;
+
+__global__ void __launch_bounds__(kGlobalThreads)
+score_global(const uint8_t* __restrict__ grids, size_t slot_bytes, DevGeom g, int max_cell,
+             const double* __restrict__ pts, const RegionDesc* __restrict__ regions,
+             const ThetaDesc* __restrict__ units, const int* __restrict__ bin_tab, uint64_t* bins,
+             double max_score, unsigned long long* cell_reads) {
+  extern __shared__ short2 kept[];
+  __shared__ int s_k, s_thr, s_box[4];
+  const ThetaDesc unit = units[blockIdx.x];
+  const RegionDesc reg = regions[unit.region];
+  const int ncand = reg.nx * reg.ny;
+  const int c_begin = blockIdx.y * kGlobalChunk;
+  if (c_begin >= ncand) return;
+  if (threadIdx.x == 0) {
+    s_k = 0;
+    s_box[0] = s_box[1] = INT_MAX;
+    s_box[2] = s_box[3] = INT_MIN;
+  }
+  __syncthreads();
+  const double inv_res = static_cast<double>(g.inv_res);
+  const double2* P = reinterpret_cast<const double2*>(pts) + reg.pts_off;
+  for (int i = threadIdx.x; i < reg.pts_n; i += kGlobalThreads) {
+    const double2 p = P[i];
+    const int2 ip = rotate_quantise(unit.c, unit.s, p.x, p.y, inv_res);
+    int2 prev = make_int2(-10000, -10000);  // chargrid.cpp:242
+    if (i > 0) {
+      const double2 q = P[i - 1];
+      prev = rotate_quantise(unit.c, unit.s, q.x, q.y, inv_res);
+    }
+    if (ip.x != prev.x || ip.y != prev.y) {  // :251; the order of the kept points is irrelevant
+      kept[atomicAdd(&s_k, 1)] = make_short2(static_cast<short>(ip.x), static_cast<short>(ip.y));
+      atomicMin(&s_box[0], ip.x);
+      atomicMin(&s_box[1], ip.y);
+      atomicMax(&s_box[2], ip.x);
+      atomicMax(&s_box[3], ip.y);
+    }
+  }
+  __syncthreads();
+  const int k = s_k;
+  if (threadIdx.x == 0) {
+    s_thr = accept_threshold(k, max_cell * k, g.ikscale, max_score);
+    if (blockIdx.y == 0)
+      atomicAdd(cell_reads, static_cast<unsigned long long>(k) * static_cast<unsigned>(ncand));
+  }
+  __syncthreads();
+  const int thr = s_thr;
+  if (thr == 0) return;
+  const uint8_t* __restrict__ grid = grids + static_cast<size_t>(reg.slot) * slot_bytes;
+  // Whole footprint of this unit inside the grid => no per-cell bounds test.
+  const bool all_inside =
+      k > 0 && reg.llx + s_box[0] >= 0 && reg.lly + s_box[1] >= 0 &&
+      static_cast<long long>(reg.llx) + static_cast<long long>(reg.nx - 1) * reg.xs + s_box[2] <
+          g.rows &&
+      static_cast<long long>(reg.lly) + static_cast<long long>(reg.ny - 1) * reg.ys + s_box[3] <
+          g.cols;
+  const int c_end = min(ncand, c_begin + kGlobalChunk);
+  for (int c = c_begin + threadIdx.x; c < c_end; c += kGlobalThreads) {
+    const int a = c / reg.ny, b = c - a * reg.ny;
+    const int i = reg.llx + a * reg.xs, j = reg.lly + b * reg.ys;
+    int idsum = 0;
+    if (all_inside) {
+      const uint8_t* base = grid + static_cast<size_t>(i) * g.pitch + j;
+      for (int p = 0; p < k; ++p) {
+        const short2 q = kept[p];
+        idsum += base[static_cast<int>(q.x) * g.pitch + q.y];
+      }
+    } else {
+      for (int p = 0; p < k; ++p) {
+        const short2 q = kept[p];
+        const int x = q.x + i, y = q.y + j;  // chargrid.cpp:270-273
+        if (x >= 0 && y >= 0 && x < g.rows && y < g.cols)
+          idsum += grid[static_cast<size_t>(x) * g.pitch + y];
+      }
+    }
+    if (idsum < thr) {
+      const uint32_t per_theta = static_cast<uint32_t>(ncand);
+      const uint32_t cand = static_cast<uint32_t>(blockIdx.x - reg.theta_off) * per_theta + c;
+      report(bins, reg, bin_tab, unit.bin_th, a, b, cand, score_of(idsum, k, g.ikscale));
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// compaction of the bin table
+// --------------------------------------------------------------------------------------------
+__global__ void compact_bins(uint64_t* bins, uint64_t n_bins, Survivor* out, unsigned int* count) {
+  const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+  for (uint64_t e = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < n_bins;
+       e += stride) {
+    const uint64_t key = bins[e];
+    if (key != kEmptyBin) {
+      const unsigned int pos = atomicAdd(count, 1u);
+      Survivor s;
+      s.entry = static_cast<uint32_t>(e);
+      s.pad = 0;
+      s.key = key;
+      out[pos] = s;
+      bins[e] = kEmptyBin;
+    }
+  }
+}
+
+// --------------------------------------------------------------------------------------------
+// cold paths
+// --------------------------------------------------------------------------------------------
+__global__ void window_sum(const uint8_t* grid, DevGeom g, int ax, int ay, int bx, int by,
+                           unsigned long long* out) {
+  // chargrid.cpp:425-432 restricted to the cells that exist.
+  const int x0 = max(ax, 0), y0 = max(ay, 0), x1 = min(bx, g.rows), y1 = min(by, g.cols);
+  unsigned long long local = 0;
+  if (x1 > x0 && y1 > y0) {
+    const long long w = y1 - y0, n = static_cast<long long>(x1 - x0) * w;
+    for (long long t = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; t < n;
+         t += static_cast<long long>(gridDim.x) * blockDim.x)
+      local += grid[static_cast<size_t>(x0 + t / w) * g.pitch + (y0 + t % w)];
+  }
+  for (int o = 16; o; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
+  if ((threadIdx.x & 31) == 0 && local) atomicAdd(out, local);
+}
+
+__global__ void cells_at(const uint8_t* grid, DevGeom g, const int* gxy, int n, int* values) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int x = gxy[2 * i], y = gxy[2 * i + 1];
+  values[i] = (x >= 0 && y >= 0 && x < g.rows && y < g.cols)
+                  ? grid[static_cast<size_t>(x) * g.pitch + y]
+                  : -1;
+}
+
+// grow-only device buffer
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = n + n / 4 + 64;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&p), want * sizeof(T));
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+}  // namespace
+
+#include "matcher_tiled.cuh"
+
+struct DeviceMatcher {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int n_slots = 0;
+  GridGeom geom;
+  DevGeom dg;
+  size_t slot_bytes = 0;
+  uint8_t* grids = nullptr;
+  uint8_t* stamp = nullptr;
+  int stamp_dim = 0;
+  int sm_count = 148;
+  int smem_optin = 0;
+  // map stage
+  DevBuf<double> map_pts;
+  DevBuf<int> map_off;
+  int map_first = 0, map_n = 0;
+  bool map_reset = false, map_valid = false;
+  // search stage
+  DevBuf<double> pts;
+  DevBuf<RegionDesc> regions;
+  DevBuf<ThetaDesc> units;
+  DevBuf<int> bin_tab;
+  DevBuf<uint64_t> bins;
+  DevBuf<Survivor> surv;
+  DevBuf<TiledJob> jobs;
+  bool bins_dirty = false;
+  unsigned int* surv_count = nullptr;     // device
+  unsigned long long* scalars = nullptr;  // device: [0] cell_reads, [1] window sum
+  // cold-path scratch
+  DevBuf<int> scratch;
+  // host-side tiling plan of the staged search
+  TiledPlan tiled;
+  // timing events: 0/1 around the raster kernels, 2/3 around the scoring kernel, 4 after compaction
+  cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool map_timed = false, search_timed = false;
+};
+
+int dev_device_count() {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+uint64_t dev_launch_count() { return g_launches.load(); }
+
+static DevGeom make_dev_geom(const GridGeom& g) {
+  DevGeom d;
+  d.llx = g.llx;
+  d.lly = g.lly;
+  d.inv_res = g.inv_res;
+  d.rows = g.rows;
+  d.cols = g.cols;
+  d.pitch = g.pitch;
+  d.fill_value = g.fill_value;
+  d.ikscale = static_cast<float>(1. / static_cast<float>(g.kscale));  // chargrid.cpp:260
+  return d;
+}
+
+int dev_create(DeviceMatcher** out, int device, void* stream, int n_slots, const GridGeom& g,
+               const uint8_t* stamp_colmajor, int stamp_dim, std::string* err) {
+  *out = nullptr;
+  int n_dev = 0;
+  CGM_CUDA(cudaGetDeviceCount(&n_dev));
+  if (device < 0 || device >= n_dev) {
+    if (err) *err = "no such CUDA device";
+    return CGM_ERR_CUDA;
+  }
+  CGM_CUDA(cudaSetDevice(device));
+  DeviceMatcher* d = new DeviceMatcher();
+  d->device = device;
+  d->n_slots = n_slots;
+  d->geom = g;
+  d->dg = make_dev_geom(g);
+  d->slot_bytes = static_cast<size_t>(g.rows) * g.pitch;
+  d->stamp_dim = stamp_dim;
+  cudaDeviceGetAttribute(&d->sm_count, cudaDevAttrMultiProcessorCount, device);
+  cudaDeviceGetAttribute(&d->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  cudaError_t e = cudaSuccess;
+  if (stream) {
+    d->stream = static_cast<cudaStream_t>(stream);
+  } else {
+    e = cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking);
+    d->own_stream = e == cudaSuccess;
+  }
+  if (e == cudaSuccess)
+    e = cudaMalloc(reinterpret_cast<void**>(&d->grids), d->slot_bytes * n_slots);
+  if (e == cudaSuccess)
+    e = cudaMalloc(reinterpret_cast<void**>(&d->stamp), static_cast<size_t>(stamp_dim) * stamp_dim);
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&d->surv_count), 16);
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&d->scalars), 64);
+  if (e == cudaSuccess)
+    e = cudaMemcpyAsync(d->stamp, stamp_colmajor, static_cast<size_t>(stamp_dim) * stamp_dim,
+                        cudaMemcpyHostToDevice, d->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d->grids, 0, d->slot_bytes * n_slots, d->stream);
+  for (int i = 0; i < 5 && e == cudaSuccess; ++i) e = cudaEventCreate(&d->ev[i]);
+  if (e == cudaSuccess) e = tiled_configure(d->smem_optin);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(d->stream);
+  if (e != cudaSuccess) {
+    if (err) *err = std::string("dev_create: ") + cudaGetErrorString(e);
+    dev_destroy(d);
+    return e == cudaErrorMemoryAllocation ? CGM_ERR_ALLOC : CGM_ERR_CUDA;
+  }
+  *out = d;
+  return CGM_OK;
+}
+
+void dev_destroy(DeviceMatcher* d) {
+  if (!d) return;
+  cudaSetDevice(d->device);
+  if (d->stream) cudaStreamSynchronize(d->stream);
+  if (d->grids) cudaFree(d->grids);
+  if (d->stamp) cudaFree(d->stamp);
+  if (d->surv_count) cudaFree(d->surv_count);
+  if (d->scalars) cudaFree(d->scalars);
+  d->map_pts.release();
+  d->map_off.release();
+  d->pts.release();
+  d->regions.release();
+  d->units.release();
+  d->bin_tab.release();
+  d->bins.release();
+  d->surv.release();
+  d->jobs.release();
+  d->scratch.release();
+  for (int i = 0; i < 5; ++i)
+    if (d->ev[i]) cudaEventDestroy(d->ev[i]);
+  if (d->own_stream && d->stream) cudaStreamDestroy(d->stream);
+  delete d;
+}
+
+void* dev_stream(const DeviceMatcher* d) { return d->stream; }
+
+int dev_sync(DeviceMatcher* d, std::string* err) {
+  CGM_CUDA(cudaSetDevice(d->device));
+  CGM_CUDA(cudaStreamSynchronize(d->stream));
+  return CGM_OK;
+}
+
+int dev_grid_download(DeviceMatcher* d, int slot, uint8_t* dst, std::string* err) {
+  CGM_CUDA(cudaSetDevice(d->device));
+  CGM_CUDA(cudaMemcpy2DAsync(dst, d->geom.cols, d->grids + slot * d->slot_bytes, d->geom.pitch,
+                             d->geom.cols, d->geom.rows, cudaMemcpyDeviceToHost, d->stream));
+  CGM_CUDA(cudaStreamSynchronize(d->stream));
+  return CGM_OK;
+}
+
+int dev_grid_upload(DeviceMatcher* d, int slot, const uint8_t* src, std::string* err) {
+  CGM_CUDA(cudaSetDevice(d->device));
+  d->geom.max_cell = 255;  // arbitrary bytes may now be present
+  CGM_CUDA(cudaMemsetAsync(d->grids + slot * d->slot_bytes, 0, d->slot_bytes, d->stream));
+  CGM_CUDA(cudaMemcpy2DAsync(d->grids + slot * d->slot_bytes, d->geom.pitch, src, d->geom.cols,
+                             d->geom.cols, d->geom.rows, cudaMemcpyHostToDevice, d->stream));
+  CGM_CUDA(cudaStreamSynchronize(d->stream));
+  return CGM_OK;
+}
+
+int dev_stage_map(DeviceMatcher* d, int first_slot, int n, const double* map_xy, const int* counts,
+                  bool reset, std::string* err) {
+  CGM_CUDA(cudaSetDevice(d->device));
+  std::vector<int> off(n + 1, 0);
+  for (int i = 0; i < n; ++i) {
+    if (counts[i] < 0) {
+      if (err) *err = "negative point count";
+      return CGM_ERR_ARG;
+    }
+    off[i + 1] = off[i] + counts[i];
+  }
+  const int total = off[n];
+  if (total && !map_xy) {
+    if (err) *err = "null map points";
+    return CGM_ERR_ARG;
+  }
+  CGM_CUDA(d->map_off.reserve(n + 1));
+  CGM_CUDA(d->map_pts.reserve(2 * static_cast<size_t>(total) + 2));
+  // pageable host memory: cudaMemcpyAsync stages synchronously, so `off` may die afterwards
+  CGM_CUDA(cudaMemcpyAsync(d->map_off.p, off.data(), (n + 1) * sizeof(int), cudaMemcpyHostToDevice,
+                           d->stream));
+  if (total)
+    CGM_CUDA(cudaMemcpyAsync(d->map_pts.p, map_xy, 2 * static_cast<size_t>(total) * sizeof(double),
+                             cudaMemcpyHostToDevice, d->stream));
+  CGM_CUDA(cudaStreamSynchronize(d->stream));
+  d->map_first = first_slot;
+  d->map_n = n;
+  d->map_reset = reset;
+  d->map_valid = true;
+  return CGM_OK;
+}
+
+int dev_launch_map(DeviceMatcher* d, std::string* err) {
+  if (!d->map_valid) {
+    if (err) *err = "no map staged";
+    return CGM_ERR_ARG;
+  }
+  CGM_CUDA(cudaSetDevice(d->device));
+  if (d->map_n == 0) return CGM_OK;
+  const int tiles = ((d->geom.rows + kTileR - 1) / kTileR) * ((d->geom.cols + kTileC - 1) / kTileC);
+  CGM_CUDA(cudaEventRecord(d->ev[0], d->stream));
+  for (int s0 = 0; s0 < d->map_n; s0 += 65535) {
+    const int ns = std::min(65535, d->map_n - s0);
+    raster_tiles<<<dim3(tiles, ns), kRasterThreads, 0, d->stream>>>(
+        d->grids, d->slot_bytes, d->dg, d->map_first + s0, d->map_pts.p, d->map_off.p + s0,
+        d->stamp, d->stamp_dim, d->map_reset ? 1 : 0);
+    g_launches++;
+  }
+  CGM_CUDA(cudaGetLastError());
+  CGM_CUDA(cudaEventRecord(d->ev[1], d->stream));
+  d->map_timed = true;
+  return CGM_OK;
+}
+
+void dev_clear_map_stage(DeviceMatcher* d) { d->map_valid = false; }
+
+int dev_stage_search(DeviceMatcher* d, const SearchPlan& plan, const double* pts_xy,
+                     int n_pts_total, std::string* err) {
+  CGM_CUDA(cudaSetDevice(d->device));
+  CGM_CUDA(d->pts.reserve(2 * static_cast<size_t>(n_pts_total) + 2));
+  CGM_CUDA(d->regions.reserve(plan.regions.size()));
+  CGM_CUDA(d->units.reserve(plan.units.size()));
+  CGM_CUDA(d->bin_tab.reserve(plan.bin_tab.size() + 1));
+  const size_t old_bins = d->bins.cap;
+  CGM_CUDA(d->bins.reserve(plan.total_bins + 1));
+  CGM_CUDA(d->surv.reserve(plan.total_bins + 1));
+  if (d->bins.cap != old_bins || d->bins_dirty) {
+    CGM_CUDA(cudaMemsetAsync(d->bins.p, 0xFF, d->bins.cap * sizeof(uint64_t), d->stream));
+    d->bins_dirty = false;
+  }
+  if (n_pts_total)
+    CGM_CUDA(cudaMemcpyAsync(d->pts.p, pts_xy, 2 * static_cast<size_t>(n_pts_total) * sizeof(double),
+                             cudaMemcpyHostToDevice, d->stream));
+  CGM_CUDA(cudaMemcpyAsync(d->regions.p, plan.regions.data(),
+                           plan.regions.size() * sizeof(RegionDesc), cudaMemcpyHostToDevice,
+                           d->stream));
+  CGM_CUDA(cudaMemcpyAsync(d->units.p, plan.units.data(), plan.units.size() * sizeof(ThetaDesc),
+                           cudaMemcpyHostToDevice, d->stream));
+  if (!plan.bin_tab.empty())
+    CGM_CUDA(cudaMemcpyAsync(d->bin_tab.p, plan.bin_tab.data(), plan.bin_tab.size() * sizeof(int),
+                             cudaMemcpyHostToDevice, d->stream));
+  // Tiling plan for the shared-memory kernel (empty when the geometry does not qualify).
+  tiled_plan(d->geom, plan, pts_xy, d->smem_optin, &d->tiled);
+  if (!d->tiled.jobs.empty()) {
+    CGM_CUDA(d->jobs.reserve(d->tiled.jobs.size()));
+    CGM_CUDA(cudaMemcpyAsync(d->jobs.p, d->tiled.jobs.data(),
+                             d->tiled.jobs.size() * sizeof(TiledJob), cudaMemcpyHostToDevice,
+                             d->stream));
+  }
+  CGM_CUDA(cudaStreamSynchronize(d->stream));
+  return CGM_OK;
+}
+
+int dev_launch_search(DeviceMatcher* d, const SearchPlan& plan, int kernel_choice,
+                      int* score_launches, std::string* err) {
+  CGM_CUDA(cudaSetDevice(d->device));
+  *score_launches = 0;
+  CGM_CUDA(cudaMemsetAsync(d->surv_count, 0, sizeof(unsigned int), d->stream));
+  CGM_CUDA(cudaMemsetAsync(d->scalars, 0, sizeof(unsigned long long), d->stream));
+  CGM_CUDA(cudaMemsetAsync(d->scalars + 2, 0, sizeof(unsigned long long), d->stream));
+  if (plan.units.empty()) return CGM_OK;
+  bool use_tiled = !d->tiled.jobs.empty();
+  if (kernel_choice == 1) use_tiled = false;
+  if (kernel_choice == 2 && !use_tiled) {
+    if (err) *err = "tiled kernel requested but the window does not qualify: " + d->tiled.why_not;
+    return CGM_ERR_CAPACITY;
+  }
+  d->bins_dirty = true;
+  CGM_CUDA(cudaEventRecord(d->ev[2], d->stream));
+  if (use_tiled) {
+    cudaError_t e = tiled_launch(d->grids, d->slot_bytes, d->dg, d->geom.max_cell, d->pts.p,
+                                 d->regions.p, d->units.p, d->bin_tab.p, d->bins.p,
+                                 plan.params.max_score, d->scalars, d->jobs.p, d->tiled, d->stream);
+    if (e != cudaSuccess) {
+      if (err) *err = std::string("score_tiled launch: ") + cudaGetErrorString(e);
+      return CGM_ERR_CUDA;
+    }
+    g_launches++;
+    *score_launches = 1;
+  } else {
+    int max_cand = 0;
+    for (size_t r = 0; r < plan.regions.size(); ++r)
+      max_cand = std::max(max_cand, plan.regions[r].nx * plan.regions[r].ny);
+    const int chunks = (max_cand + kGlobalChunk - 1) / kGlobalChunk;
+    const size_t smem = static_cast<size_t>(plan.max_pts) * sizeof(short2);
+    if (smem > 48 * 1024)
+      CGM_CUDA(cudaFuncSetAttribute(score_global, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(smem)));
+    const size_t n_units = plan.units.size();
+    if (chunks > 65535) {
+      if (err) *err = "window too large for one launch";
+      return CGM_ERR_CAPACITY;
+    }
+    score_global<<<dim3(static_cast<unsigned>(n_units), chunks), kGlobalThreads, smem, d->stream>>>(
+        d->grids, d->slot_bytes, d->dg, d->geom.max_cell, d->pts.p, d->regions.p, d->units.p,
+        d->bin_tab.p, d->bins.p, plan.params.max_score, d->scalars);
+    g_launches++;
+    *score_launches = 1;
+  }
+  CGM_CUDA(cudaGetLastError());
+  CGM_CUDA(cudaEventRecord(d->ev[3], d->stream));
+  if (plan.total_bins) {
+    const int blocks = static_cast<int>(
+        std::min<uint64_t>((plan.total_bins + 255) / 256, static_cast<uint64_t>(d->sm_count) * 16));
+    compact_bins<<<blocks, 256, 0, d->stream>>>(d->bins.p, plan.total_bins, d->surv.p,
+                                                d->surv_count);
+    g_launches++;
+    CGM_CUDA(cudaGetLastError());
+  }
+  CGM_CUDA(cudaEventRecord(d->ev[4], d->stream));
+  d->search_timed = true;
+  return CGM_OK;
+}
+
+int dev_last_timings(DeviceMatcher* d, float ms[3], std::string* err) {
+  CGM_CUDA(cudaSetDevice(d->device));
+  CGM_CUDA(cudaStreamSynchronize(d->stream));
+  ms[0] = ms[1] = ms[2] = 0.f;
+  if (d->map_timed) CGM_CUDA(cudaEventElapsedTime(&ms[0], d->ev[0], d->ev[1]));
+  if (d->search_timed) {
+    CGM_CUDA(cudaEventElapsedTime(&ms[1], d->ev[2], d->ev[3]));
+    CGM_CUDA(cudaEventElapsedTime(&ms[2], d->ev[3], d->ev[4]));
+  }
+  return CGM_OK;
+}
+
+int dev_collect(DeviceMatcher* d, const SearchPlan& plan, std::vector<Survivor>* survivors,
+                uint64_t* cell_reads, std::string* err) {
+  (void)plan;
+  CGM_CUDA(cudaSetDevice(d->device));
+  unsigned int n = 0;
+  unsigned long long sc[3] = {0, 0, 0};
+  CGM_CUDA(cudaMemcpyAsync(&n, d->surv_count, sizeof n, cudaMemcpyDeviceToHost, d->stream));
+  CGM_CUDA(cudaMemcpyAsync(sc, d->scalars, sizeof sc, cudaMemcpyDeviceToHost, d->stream));
+  CGM_CUDA(cudaStreamSynchronize(d->stream));
+  d->bins_dirty = false;  // the compaction drained every bin it reported
+  if (sc[2]) {
+    if (err) *err = "score_tiled: a quantised point left the planned extent (internal bound)";
+    return CGM_ERR_CAPACITY;
+  }
+  const unsigned long long reads = sc[0];
+  survivors->resize(n);
+  if (n) {
+    CGM_CUDA(cudaMemcpyAsync(survivors->data(), d->surv.p, n * sizeof(Survivor),
+                             cudaMemcpyDeviceToHost, d->stream));
+    CGM_CUDA(cudaStreamSynchronize(d->stream));
+  }
+  *cell_reads = reads;
+  return CGM_OK;
+}
+
+int dev_window_sum(DeviceMatcher* d, int slot, int ax, int ay, int bx, int by, long long* sum,
+                   std::string* err) {
+  CGM_CUDA(cudaSetDevice(d->device));
+  CGM_CUDA(cudaMemsetAsync(d->scalars + 1, 0, sizeof(unsigned long long), d->stream));
+  window_sum<<<d->sm_count, 256, 0, d->stream>>>(d->grids + slot * d->slot_bytes, d->dg, ax, ay, bx,
+                                                 by, d->scalars + 1);
+  g_launches++;
+  unsigned long long v = 0;
+  CGM_CUDA(cudaMemcpyAsync(&v, d->scalars + 1, sizeof v, cudaMemcpyDeviceToHost, d->stream));
+  CGM_CUDA(cudaStreamSynchronize(d->stream));
+  *sum = static_cast<long long>(v);
+  return CGM_OK;
+}
+
+int dev_cells_at(DeviceMatcher* d, int slot, const int* gxy, int n, int* values, std::string* err) {
+  CGM_CUDA(cudaSetDevice(d->device));
+  CGM_CUDA(d->scratch.reserve(3 * static_cast<size_t>(n)));
+  CGM_CUDA(cudaMemcpyAsync(d->scratch.p, gxy, 2 * static_cast<size_t>(n) * sizeof(int),
+                           cudaMemcpyHostToDevice, d->stream));
+  cells_at<<<(n + 255) / 256, 256, 0, d->stream>>>(d->grids + slot * d->slot_bytes, d->dg,
+                                                   d->scratch.p, n, d->scratch.p + 2 * n);
+  g_launches++;
+  CGM_CUDA(cudaMemcpyAsync(values, d->scratch.p + 2 * n, n * sizeof(int), cudaMemcpyDeviceToHost,
+                           d->stream));
+  CGM_CUDA(cudaStreamSynchronize(d->stream));
+  return CGM_OK;
+}
+
+}  // namespace cgm
