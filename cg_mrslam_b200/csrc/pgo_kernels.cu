@@ -1,0 +1,964 @@
+// CUDA back-end of the SE(2) pose-graph solver (sm_100a). Implements pgo_device.h.
+//
+// One cooperative, persistent kernel (gn_iterations) runs whole Gauss-Newton iterations -- the
+// work of SparseOptimizer::optimize(n) with BlockSolver + LinearSolverCSparse +
+// OptimizationAlgorithmGaussNewton (configured by the reference at
+// src/slam/graph_slam.cpp:44-56) -- with grid-wide barriers between dependent phases:
+//   1. linearise: per free vertex, every incident EdgeSE2 is evaluated (error e, analytic
+//      Jacobians Ji, Jj, C4) and H_pp += Jp^T Om Jp, b_p += Jp^T (-Om e), H_qp += Jq^T Om Jp are
+//      accumulated by the one thread that owns the destination block: no atomics, fixed order
+//      (C5). chi2 = sum e^T Om e is reduced deterministically.
+//   2. factorise: block L D L^T of the permuted H, 3x3 pivots, in elimination-tree level order.
+//      Phase l applies the updates  M(i,j) -= M(i,k) Dinv(k) M(j,k)^T  whose source columns k
+//      became final in phase l-1, from a schedule precomputed on the host (pgo_symbolic.cpp);
+//      each target block is owned by one thread per phase.
+//   3. solve: level-scheduled forward and backward substitution, one warp per block row/column.
+//   4. update: VertexSE2::oplusImpl (C3) on every free vertex.
+// Algorithmic HBM bytes per phase are stated in DESIGN.md section 5.
+#include <cooperative_groups.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/pgo_solver.h"
+#include "pgo_device.h"
+
+namespace cg = cooperative_groups;
+
+namespace pgo {
+
+namespace {
+
+#define PGO_CUDA(call)                                                   \
+  do {                                                                   \
+    cudaError_t e_ = (call);                                             \
+    if (e_ != cudaSuccess) {                                             \
+      if (err) *err = std::string(#call) + ": " + cudaGetErrorString(e_); \
+      return PGO_ERR_CUDA;                                               \
+    }                                                                    \
+  } while (0)
+
+const double kPi = 3.14159265358979323846;
+
+struct Params {
+  // graph
+  int n_vertices, n_edges, n;  // n = free vertices
+  const int* edge_i;
+  const int* edge_j;
+  const int* vpos;
+  const int* inc_ptr;
+  const Incidence* inc;
+  const int* ff_edges;
+  int n_ff;
+  double* poses;
+  const double* meas;
+  const double* info6;
+  // factor structure
+  int n_levels;
+  long long nnzb;
+  const int* col_ptr;
+  const int* row_idx;
+  const int* col_of;
+  const int* row_ptr;
+  const int* row_pos;
+  const int* level_ptr;
+  const int* level_cols;
+  const int* phase_ptr;
+  const UpdateOp* ops;
+  const int* perm_vertex;  // permuted position -> vertex index
+  // numeric
+  double* M;      // [nnzb][9]
+  double* Dinv;   // [n][9]
+  double* rhs;    // [n][3]
+  double* u;      // [nrhs][n][3]
+  double* x;      // [nrhs][n][3]
+  double* chi2_partial;  // [gridDim.x]
+  double* chi2_out;      // [n_iters]
+  int* status;           // [0] error flag, [1] iterations done
+};
+
+// ---- small dense helpers, 3x3 row-major ----------------------------------------------------------
+__device__ __forceinline__ void load9(const double* __restrict__ p, double* m) {
+#pragma unroll
+  for (int i = 0; i < 9; ++i) m[i] = p[i];
+}
+
+// Inverse of a symmetric positive definite 3x3 via Cholesky; false if a pivot is not positive.
+__device__ bool spd_inverse(const double* a, double* inv) {
+  const double l00sq = a[0];
+  if (!(l00sq > 0.0)) return false;
+  const double l00 = sqrt(l00sq);
+  const double l10 = a[3] / l00, l20 = a[6] / l00;
+  const double l11sq = a[4] - l10 * l10;
+  if (!(l11sq > 0.0)) return false;
+  const double l11 = sqrt(l11sq);
+  const double l21 = (a[7] - l20 * l10) / l11;
+  const double l22sq = a[8] - l20 * l20 - l21 * l21;
+  if (!(l22sq > 0.0)) return false;
+  const double l22 = sqrt(l22sq);
+  // inverse of the lower-triangular factor
+  const double i00 = 1.0 / l00, i11 = 1.0 / l11, i22 = 1.0 / l22;
+  const double i10 = -l10 * i00 * i11;
+  const double i21 = -l21 * i11 * i22;
+  const double i20 = -(l20 * i00 + l21 * i10) * i22;
+  // A^-1 = Linv^T Linv
+  inv[0] = i00 * i00 + i10 * i10 + i20 * i20;
+  inv[1] = inv[3] = i10 * i11 + i20 * i21;
+  inv[2] = inv[6] = i20 * i22;
+  inv[4] = i11 * i11 + i21 * i21;
+  inv[5] = inv[7] = i21 * i22;
+  inv[8] = i22 * i22;
+  return true;
+}
+
+// g2o normalize_theta: identity inside [-pi, pi), else wrap.
+__device__ __forceinline__ double normalize_theta(double t) {
+  if (t >= -kPi && t < kPi) return t;
+  const double two_pi = 2.0 * kPi;
+  double w = t - two_pi * floor(t / two_pi);
+  if (w >= kPi) w -= two_pi;
+  return w;
+}
+
+struct SE2d {
+  double x, y, th;
+};
+
+__device__ __forceinline__ SE2d se2_inv(const SE2d& a) {  // C1
+  SE2d r;
+  r.th = normalize_theta(-a.th);
+  double s, c;
+  sincos(r.th, &s, &c);
+  r.x = c * (-a.x) - s * (-a.y);
+  r.y = s * (-a.x) + c * (-a.y);
+  return r;
+}
+
+__device__ __forceinline__ SE2d se2_mul(const SE2d& a, const SE2d& b) {  // C1
+  double s, c;
+  sincos(a.th, &s, &c);
+  SE2d r;
+  r.x = a.x + (c * b.x - s * b.y);
+  r.y = a.y + (s * b.x + c * b.y);
+  r.th = normalize_theta(a.th + b.th);
+  return r;
+}
+
+__device__ __forceinline__ SE2d load_pose(const double* p, int v) {
+  SE2d r = {p[3 * v], p[3 * v + 1], p[3 * v + 2]};
+  return r;
+}
+
+// EdgeSE2::computeError + linearizeOplus (C4) + Omega of one edge.
+struct EdgeLin {
+  double e[3];
+  double ji[9], jj[9];
+  double om[9];
+};
+
+__device__ void linearise_edge(const Params& P, int edge, EdgeLin* L) {
+  const SE2d xi = load_pose(P.poses, P.edge_i[edge]);
+  const SE2d xj = load_pose(P.poses, P.edge_j[edge]);
+  const SE2d z = {P.meas[3 * edge], P.meas[3 * edge + 1], P.meas[3 * edge + 2]};
+  const SE2d zinv = se2_inv(z);
+  const SE2d d = se2_mul(se2_inv(xi), xj);
+  const SE2d er = se2_mul(zinv, d);
+  L->e[0] = er.x;
+  L->e[1] = er.y;
+  L->e[2] = er.th;
+  double si, ci;
+  sincos(xi.th, &si, &ci);
+  const double dx = xj.x - xi.x, dy = xj.y - xi.y;
+  const double a[9] = {-ci, -si, -si * dx + ci * dy, si, -ci, -ci * dx - si * dy, 0.0, 0.0, -1.0};
+  const double b[9] = {ci, si, 0.0, -si, ci, 0.0, 0.0, 0.0, 1.0};
+  double sz, cz;
+  sincos(zinv.th, &sz, &cz);
+  // Rz = diag(R(theta(Z^-1)), 1); J <- Rz * J
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    L->ji[c] = cz * a[c] - sz * a[3 + c];
+    L->ji[3 + c] = sz * a[c] + cz * a[3 + c];
+    L->ji[6 + c] = a[6 + c];
+    L->jj[c] = cz * b[c] - sz * b[3 + c];
+    L->jj[3 + c] = sz * b[c] + cz * b[3 + c];
+    L->jj[6 + c] = b[6 + c];
+  }
+  const double* w = P.info6 + 6 * static_cast<size_t>(edge);
+  L->om[0] = w[0];
+  L->om[1] = L->om[3] = w[1];
+  L->om[2] = L->om[6] = w[2];
+  L->om[4] = w[3];
+  L->om[5] = L->om[7] = w[4];
+  L->om[8] = w[5];
+}
+
+__device__ __forceinline__ double edge_chi2(const EdgeLin& L) {
+  double c = 0.0;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    double t = 0.0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) t += L.om[3 * r + k] * L.e[k];
+    c += L.e[r] * t;
+  }
+  return c;
+}
+
+// Deterministic block reduction of one double per thread; result valid in thread 0.
+__device__ double block_sum(double v, double* scratch) {
+  for (int o = 16; o; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (threadIdx.x == 0)
+    for (int w = 0; w < (blockDim.x + 31) / 32; ++w) r += scratch[w];
+  __syncthreads();
+  return r;
+}
+
+// ---- phase 1: linearise ------------------------------------------------------------------------
+__device__ void phase_linearise(const Params& P, double* scratch, int it) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+  double chi = 0.0;
+  for (int p = tid; p < P.n; p += nthreads) {
+    double diag[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, b[3] = {0, 0, 0};
+    for (int t = P.inc_ptr[p]; t < P.inc_ptr[p + 1]; ++t) {
+      const Incidence inc = P.inc[t];
+      const int edge = inc.edge_role >> 1, role = inc.edge_role & 1;
+      EdgeLin L;
+      linearise_edge(P, edge, &L);
+      const double* jo = role ? L.jj : L.ji;  // this vertex
+      const double* jx = role ? L.ji : L.jj;  // the other one
+      double A[9];                            // Jo^T Omega
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          A[3 * r + c] = jo[r] * L.om[c] + jo[3 + r] * L.om[3 + c] + jo[6 + r] * L.om[6 + c];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          diag[3 * r + c] += A[3 * r] * jo[c] + A[3 * r + 1] * jo[3 + c] + A[3 * r + 2] * jo[6 + c];
+        b[r] -= A[3 * r] * L.e[0] + A[3 * r + 1] * L.e[1] + A[3 * r + 2] * L.e[2];
+      }
+      if (inc.pos >= 0) {
+        // block (row = other vertex, column = this vertex) += Jx^T Omega Jo = (A Jx)^T
+        double* dst = P.M + 9 * static_cast<size_t>(inc.pos);
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+            dst[3 * c + r] += A[3 * r] * jx[c] + A[3 * r + 1] * jx[3 + c] + A[3 * r + 2] * jx[6 + c];
+      }
+      // each edge's chi2 is counted by its i-side visit, or by the j-side one when i is fixed
+      if (role == 0 || P.vpos[P.edge_i[edge]] < 0) chi += edge_chi2(L);
+    }
+    double* d = P.M + 9 * static_cast<size_t>(P.col_ptr[p]);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) d[i] = diag[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) P.rhs[3 * p + i] = b[i];
+  }
+  for (int t = tid; t < P.n_ff; t += nthreads) {
+    EdgeLin L;
+    linearise_edge(P, P.ff_edges[t], &L);
+    chi += edge_chi2(L);
+  }
+  const double s = block_sum(chi, scratch);
+  if (threadIdx.x == 0) P.chi2_partial[blockIdx.x] = s;
+  (void)it;
+}
+
+// ---- phase 2: factorise ------------------------------------------------------------------------
+__device__ __forceinline__ void finalise_diag(const Params& P, int col, const double* m) {
+  double inv[9];
+  if (!spd_inverse(m, inv)) {
+    atomicExch(P.status, 1);
+    return;
+  }
+  double* d = P.Dinv + 9 * static_cast<size_t>(col);
+#pragma unroll
+  for (int i = 0; i < 9; ++i) d[i] = inv[i];
+}
+
+__device__ void phase_leaves(const Params& P) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+  for (int t = P.level_ptr[0] + tid; t < P.level_ptr[1]; t += nthreads) {
+    const int col = P.level_cols[t];
+    double m[9];
+    load9(P.M + 9 * static_cast<size_t>(P.col_ptr[col]), m);
+    finalise_diag(P, col, m);
+  }
+}
+
+__device__ void phase_updates(const Params& P, int l) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+  const int begin = P.phase_ptr[l], end = P.phase_ptr[l + 1];
+  for (int i = begin + tid; i < end; i += nthreads) {
+    const UpdateOp first = P.ops[i];
+    if (i > begin && P.ops[i - 1].target == first.target) continue;  // not the head of its run
+    const int target = first.target & ~kFinalFlag;
+    double acc[9];
+    double* dst = P.M + 9 * static_cast<size_t>(target);
+    load9(dst, acc);
+    int j = i;
+    UpdateOp op = first;
+    while (true) {
+      double a[9], b[9], d[9], t[9];
+      load9(P.M + 9 * static_cast<size_t>(op.a), a);
+      load9(P.M + 9 * static_cast<size_t>(op.b), b);
+      load9(P.Dinv + 9 * static_cast<size_t>(P.col_of[op.a]), d);
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          t[3 * r + c] = a[3 * r] * d[c] + a[3 * r + 1] * d[3 + c] + a[3 * r + 2] * d[6 + c];
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+          acc[3 * r + c] -= t[3 * r] * b[3 * c] + t[3 * r + 1] * b[3 * c + 1] + t[3 * r + 2] * b[3 * c + 2];
+      ++j;
+      if (j >= end) break;
+      op = P.ops[j];
+      if (op.target != first.target) break;
+    }
+#pragma unroll
+    for (int k = 0; k < 9; ++k) dst[k] = acc[k];
+    if (first.target & kFinalFlag) finalise_diag(P, P.col_of[target], acc);
+  }
+}
+
+// ---- phase 3: solves ---------------------------------------------------------------------------
+// forward, level l: z_j = b_j - sum_{k<j} M(j,k) u_k ; u_j = Dinv_j z_j      (one warp per row j)
+__device__ void phase_forward(const Params& P, int l, int nrhs, const double* rhs, size_t stride) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int n_cols = P.level_ptr[l + 1] - P.level_ptr[l];
+  for (int w = warp; w < n_cols * nrhs; w += nwarps) {
+    const int j = P.level_cols[P.level_ptr[l] + w % n_cols], r = w / n_cols;
+    const double* uu = P.u + r * stride;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    for (int t = P.row_ptr[j] + lane; t < P.row_ptr[j + 1]; t += 32) {
+      const int pos = P.row_pos[t];
+      const double* m = P.M + 9 * static_cast<size_t>(pos);
+      const double* v = uu + 3 * static_cast<size_t>(P.col_of[pos]);
+      const double v0 = v[0], v1 = v[1], v2 = v[2];
+      s0 += m[0] * v0 + m[1] * v1 + m[2] * v2;
+      s1 += m[3] * v0 + m[4] * v1 + m[5] * v2;
+      s2 += m[6] * v0 + m[7] * v1 + m[8] * v2;
+    }
+    for (int o = 16; o; o >>= 1) {
+      s0 += __shfl_down_sync(0xffffffffu, s0, o);
+      s1 += __shfl_down_sync(0xffffffffu, s1, o);
+      s2 += __shfl_down_sync(0xffffffffu, s2, o);
+    }
+    if (lane == 0) {
+      const double* b = rhs + r * stride + 3 * static_cast<size_t>(j);
+      const double z0 = b[0] - s0, z1 = b[1] - s1, z2 = b[2] - s2;
+      const double* d = P.Dinv + 9 * static_cast<size_t>(j);
+      double* out = P.u + r * stride + 3 * static_cast<size_t>(j);
+      out[0] = d[0] * z0 + d[1] * z1 + d[2] * z2;
+      out[1] = d[3] * z0 + d[4] * z1 + d[5] * z2;
+      out[2] = d[6] * z0 + d[7] * z1 + d[8] * z2;
+    }
+  }
+}
+
+// backward, level l: x_j = u_j - Dinv_j sum_{i>j} M(i,j)^T x_i                 (one warp per column j)
+__device__ void phase_backward(const Params& P, int l, int nrhs, size_t stride) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int n_cols = P.level_ptr[l + 1] - P.level_ptr[l];
+  for (int w = warp; w < n_cols * nrhs; w += nwarps) {
+    const int j = P.level_cols[P.level_ptr[l] + w % n_cols], r = w / n_cols;
+    const double* xx = P.x + r * stride;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+    for (int t = P.col_ptr[j] + 1 + lane; t < P.col_ptr[j + 1]; t += 32) {
+      const double* m = P.M + 9 * static_cast<size_t>(t);
+      const double* v = xx + 3 * static_cast<size_t>(P.row_idx[t]);
+      const double v0 = v[0], v1 = v[1], v2 = v[2];
+      s0 += m[0] * v0 + m[3] * v1 + m[6] * v2;
+      s1 += m[1] * v0 + m[4] * v1 + m[7] * v2;
+      s2 += m[2] * v0 + m[5] * v1 + m[8] * v2;
+    }
+    for (int o = 16; o; o >>= 1) {
+      s0 += __shfl_down_sync(0xffffffffu, s0, o);
+      s1 += __shfl_down_sync(0xffffffffu, s1, o);
+      s2 += __shfl_down_sync(0xffffffffu, s2, o);
+    }
+    if (lane == 0) {
+      const double* d = P.Dinv + 9 * static_cast<size_t>(j);
+      const double* uj = P.u + r * stride + 3 * static_cast<size_t>(j);
+      double* out = P.x + r * stride + 3 * static_cast<size_t>(j);
+      out[0] = uj[0] - (d[0] * s0 + d[1] * s1 + d[2] * s2);
+      out[1] = uj[1] - (d[3] * s0 + d[4] * s1 + d[5] * s2);
+      out[2] = uj[2] - (d[6] * s0 + d[7] * s1 + d[8] * s2);
+    }
+  }
+}
+
+// ---- the persistent kernels ----------------------------------------------------------------------
+const int kThreads = 256;
+
+__global__ void __launch_bounds__(kThreads) gn_iterations(Params P, int n_iters) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ double scratch[32];
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+  for (int it = 0; it < n_iters; ++it) {
+    // zero the factor storage (fill positions must start at 0)
+    for (long long i = tid; i < P.nnzb * 9; i += nthreads) P.M[i] = 0.0;
+    grid.sync();
+    phase_linearise(P, scratch, it);
+    grid.sync();
+    if (blockIdx.x == 0) {
+      double v = 0.0;
+      for (int b = threadIdx.x; b < static_cast<int>(gridDim.x); b += blockDim.x) v += P.chi2_partial[b];
+      const double s = block_sum(v, scratch);
+      if (threadIdx.x == 0) P.chi2_out[it] = s;
+    }
+    phase_leaves(P);
+    grid.sync();
+    for (int l = 1; l < P.n_levels; ++l) {
+      phase_updates(P, l);
+      grid.sync();
+    }
+    if (*reinterpret_cast<volatile int*>(P.status) != 0) return;  // uniform: read after a barrier
+    for (int l = 0; l < P.n_levels; ++l) {
+      phase_forward(P, l, 1, P.rhs, 0);
+      grid.sync();
+    }
+    for (int l = P.n_levels - 1; l >= 0; --l) {
+      phase_backward(P, l, 1, 0);
+      grid.sync();
+    }
+    // VertexSE2::oplusImpl (C3)
+    for (int p = tid; p < P.n; p += nthreads) {
+      const int v = P.perm_vertex[p];
+      double* q = P.poses + 3 * static_cast<size_t>(v);
+      q[0] += P.x[3 * p];
+      q[1] += P.x[3 * p + 1];
+      q[2] = normalize_theta(q[2] + P.x[3 * p + 2]);
+    }
+    if (tid == 0) P.status[1] = it + 1;
+    grid.sync();
+  }
+}
+
+// H X = E for nrhs right-hand sides already placed in P.rhs-like storage `rhs` ([nrhs][n][3]).
+__global__ void __launch_bounds__(kThreads) solve_many(Params P, const double* rhs, int nrhs) {
+  cg::grid_group grid = cg::this_grid();
+  const size_t stride = 3 * static_cast<size_t>(P.n);
+  for (int l = 0; l < P.n_levels; ++l) {
+    phase_forward(P, l, nrhs, rhs, stride);
+    grid.sync();
+  }
+  for (int l = P.n_levels - 1; l >= 0; --l) {
+    phase_backward(P, l, nrhs, stride);
+    grid.sync();
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) chi2_only(Params P) {
+  __shared__ double scratch[32];
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+  double chi = 0.0;
+  for (int e = tid; e < P.n_edges; e += nthreads) {
+    EdgeLin L;
+    linearise_edge(P, e, &L);
+    chi += edge_chi2(L);
+  }
+  const double s = block_sum(chi, scratch);
+  if (threadIdx.x == 0) P.chi2_partial[blockIdx.x] = s;
+}
+
+__global__ void sum_partials(const double* partial, int n, double* out) {
+  __shared__ double scratch[32];
+  double v = 0.0;
+  for (int b = threadIdx.x; b < n; b += blockDim.x) v += partial[b];
+  const double s = block_sum(v, scratch);
+  if (threadIdx.x == 0) *out = s;
+}
+
+__global__ void set_unit_rhs(double* rhs, size_t stride, const int* col_p, int n_cols) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 3 * n_cols) return;
+  const int k = t / 3, c = t % 3;  // right-hand side 3k + c has a one at scalar row 3 * col_p[k] + c
+  rhs[static_cast<size_t>(3 * k + c) * stride + 3 * static_cast<size_t>(col_p[k]) + c] = 1.0;
+}
+
+__global__ void gather_blocks(const double* x, size_t stride, const int* row_p, const int* rhs_of,
+                              int n_blocks, double* out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 9 * n_blocks) return;
+  const int k = t / 9, r = (t % 9) / 3, c = t % 3;
+  out[t] = x[static_cast<size_t>(3 * rhs_of[k] + c) * stride + 3 * static_cast<size_t>(row_p[k]) + r];
+}
+
+// EdgeLabeler::labelEdge for star edges with the gauge fixed.
+__global__ void label_star_edges(const double* poses, int gauge, int n, const int* v,
+                                 const double* cov, double* meas_out, double* info_out,
+                                 int* status) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n) return;
+  const SE2d xg = load_pose(poses, gauge), xv = load_pose(poses, v[t]);
+  const SE2d xg_inv = se2_inv(xg);
+  const SE2d z = se2_mul(xg_inv, xv);  // setMeasurementFromState
+  const SE2d zinv = se2_inv(z);
+  // sampleUnscented: dim 3, alpha 1e-3, beta 2, lambda = alpha^2 * dim
+  const double alpha = 1e-3, beta = 2.0, dim = 3.0;
+  const double lam = alpha * alpha * dim;
+  const double* c = cov + 9 * static_cast<size_t>(t);
+  double a[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) a[i] = c[i] * (dim + lam);
+  // lower Cholesky factor of a
+  double L[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  bool ok = a[0] > 0.0;
+  if (ok) {
+    L[0] = sqrt(a[0]);
+    L[3] = a[3] / L[0];
+    L[6] = a[6] / L[0];
+    const double d1 = a[4] - L[3] * L[3];
+    ok = d1 > 0.0;
+    if (ok) {
+      L[4] = sqrt(d1);
+      L[7] = (a[7] - L[6] * L[3]) / L[4];
+      const double d2 = a[8] - L[6] * L[6] - L[7] * L[7];
+      ok = d2 > 0.0;
+      if (ok) L[8] = sqrt(d2);
+    }
+  }
+  if (!ok) {
+    atomicExch(status, 1);
+    return;
+  }
+  const double wi = 1.0 / (2.0 * (dim + lam));
+  const double w0m = lam / (dim + lam);
+  const double w0c = w0m + (1.0 - alpha * alpha + beta);
+  double errs[7][3], wm[7], wc[7];
+  for (int k = 0; k < 7; ++k) {
+    double p[3] = {0.0, 0.0, 0.0};
+    if (k > 0) {
+      const int col = (k - 1) / 2;
+      const double sgn = (k - 1) % 2 ? -1.0 : 1.0;
+      p[0] = sgn * L[col];
+      p[1] = sgn * L[3 + col];
+      p[2] = sgn * L[6 + col];
+    }
+    SE2d pv = xv;  // oplus
+    pv.x += p[0];
+    pv.y += p[1];
+    pv.th = normalize_theta(pv.th + p[2]);
+    const SE2d e = se2_mul(zinv, se2_mul(xg_inv, pv));
+    errs[k][0] = e.x;
+    errs[k][1] = e.y;
+    errs[k][2] = e.th;
+    wm[k] = k ? wi : w0m;
+    wc[k] = k ? wi : w0c;
+  }
+  double mean[3] = {0.0, 0.0, 0.0};
+  for (int k = 0; k < 7; ++k)
+    for (int i = 0; i < 3; ++i) mean[i] += wm[k] * errs[k][i];
+  double s[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int k = 0; k < 7; ++k)
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) s[3 * i + j] += wc[k] * (errs[k][i] - mean[i]) * (errs[k][j] - mean[j]);
+  double inv[9];
+  if (!spd_inverse(s, inv)) {
+    atomicExch(status, 1);
+    return;
+  }
+  meas_out[3 * t] = z.x;
+  meas_out[3 * t + 1] = z.y;
+  meas_out[3 * t + 2] = z.th;
+  for (int i = 0; i < 9; ++i) info_out[9 * static_cast<size_t>(t) + i] = inv[i];
+}
+
+template <typename T>
+struct Buf {
+  T* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t n) {
+    if (n <= cap && p) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    const size_t want = n ? n : 1;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&p), want * sizeof(T));
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  cudaError_t upload(const std::vector<T>& v, cudaStream_t s) {
+    cudaError_t e = reserve(v.size());
+    if (e != cudaSuccess || v.empty()) return e;
+    return cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s);
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+}  // namespace
+
+struct DeviceSolver {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int sm_count = 148;
+  int grid = 0;  // co-resident CTAs of the cooperative kernels
+  uint64_t launches = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  Params P;
+  bool have_structure = false, have_values = false, have_factor = false;
+  Buf<int> edge_i, edge_j, vpos, inc_ptr, ff_edges, col_ptr, row_idx, col_of, row_ptr, row_pos,
+      level_ptr, level_cols, phase_ptr, perm_vertex, status, scratch_i;
+  Buf<Incidence> inc;
+  Buf<UpdateOp> ops;
+  Buf<double> poses, meas, info6, M, Dinv, rhs, u, x, chi2_partial, chi2_out, many_rhs, scratch_d;
+  size_t vec_cap = 0;  // right-hand sides u/x can hold
+};
+
+int dev_create(DeviceSolver** out, int device, void* stream, std::string* err) {
+  *out = nullptr;
+  int n_dev = 0;
+  PGO_CUDA(cudaGetDeviceCount(&n_dev));
+  if (device < 0 || device >= n_dev) {
+    if (err) *err = "no such CUDA device";
+    return PGO_ERR_CUDA;
+  }
+  PGO_CUDA(cudaSetDevice(device));
+  int coop = 0;
+  PGO_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
+  if (!coop) {
+    if (err) *err = "device does not support cooperative launches";
+    return PGO_ERR_CUDA;
+  }
+  DeviceSolver* d = new DeviceSolver();
+  d->device = device;
+  cudaDeviceGetAttribute(&d->sm_count, cudaDevAttrMultiProcessorCount, device);
+  int per_sm = 0, per_sm2 = 0;
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gn_iterations, kThreads, 0);
+  if (e == cudaSuccess)
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, solve_many, kThreads, 0);
+  if (e == cudaSuccess) {
+    per_sm = std::max(1, std::min(per_sm, per_sm2));
+    d->grid = d->sm_count * per_sm;
+    if (stream) {
+      d->stream = static_cast<cudaStream_t>(stream);
+    } else {
+      e = cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking);
+      d->own_stream = e == cudaSuccess;
+    }
+  }
+  if (e == cudaSuccess) e = cudaEventCreate(&d->ev0);
+  if (e == cudaSuccess) e = cudaEventCreate(&d->ev1);
+  if (e == cudaSuccess) e = d->status.reserve(4);
+  if (e == cudaSuccess) e = d->chi2_partial.reserve(d->grid);
+  if (e != cudaSuccess) {
+    if (err) *err = std::string("pgo dev_create: ") + cudaGetErrorString(e);
+    dev_destroy(d);
+    return PGO_ERR_CUDA;
+  }
+  *out = d;
+  return PGO_OK;
+}
+
+void dev_destroy(DeviceSolver* d) {
+  if (!d) return;
+  cudaSetDevice(d->device);
+  if (d->stream) cudaStreamSynchronize(d->stream);
+  Buf<int>* ib[] = {&d->edge_i, &d->edge_j, &d->vpos, &d->inc_ptr, &d->ff_edges, &d->col_ptr,
+                    &d->row_idx, &d->col_of, &d->row_ptr, &d->row_pos, &d->level_ptr,
+                    &d->level_cols, &d->phase_ptr, &d->perm_vertex, &d->status, &d->scratch_i};
+  for (size_t i = 0; i < sizeof(ib) / sizeof(ib[0]); ++i) ib[i]->release();
+  Buf<double>* db[] = {&d->poses, &d->meas, &d->info6, &d->M, &d->Dinv, &d->rhs, &d->u, &d->x,
+                       &d->chi2_partial, &d->chi2_out, &d->many_rhs, &d->scratch_d};
+  for (size_t i = 0; i < sizeof(db) / sizeof(db[0]); ++i) db[i]->release();
+  d->inc.release();
+  d->ops.release();
+  if (d->ev0) cudaEventDestroy(d->ev0);
+  if (d->ev1) cudaEventDestroy(d->ev1);
+  if (d->own_stream && d->stream) cudaStreamDestroy(d->stream);
+  delete d;
+}
+
+void* dev_stream(const DeviceSolver* d) { return d->stream; }
+uint64_t dev_launches(const DeviceSolver* d) { return d->launches; }
+
+int dev_set_structure(DeviceSolver* d, const Symbolic& S, const GraphTables& G, std::string* err) {
+  PGO_CUDA(cudaSetDevice(d->device));
+  cudaStream_t s = d->stream;
+  d->have_structure = d->have_values = d->have_factor = false;
+  PGO_CUDA(d->edge_i.upload(G.edge_i, s));
+  PGO_CUDA(d->edge_j.upload(G.edge_j, s));
+  PGO_CUDA(d->vpos.upload(G.vpos, s));
+  PGO_CUDA(d->inc_ptr.upload(G.inc_ptr, s));
+  PGO_CUDA(d->inc.upload(G.inc, s));
+  PGO_CUDA(d->ff_edges.upload(G.ff_edges, s));
+  PGO_CUDA(d->col_ptr.upload(S.col_ptr, s));
+  PGO_CUDA(d->row_idx.upload(S.row_idx, s));
+  PGO_CUDA(d->col_of.upload(S.col_of, s));
+  PGO_CUDA(d->row_ptr.upload(S.row_ptr, s));
+  PGO_CUDA(d->row_pos.upload(S.row_pos, s));
+  PGO_CUDA(d->level_ptr.upload(S.level_ptr, s));
+  PGO_CUDA(d->level_cols.upload(S.level_cols, s));
+  PGO_CUDA(d->phase_ptr.upload(S.phase_ptr, s));
+  PGO_CUDA(d->ops.upload(S.ops, s));
+  std::vector<int> perm_vertex(S.n);
+  for (int v = 0; v < G.n_vertices; ++v)
+    if (G.vpos[v] >= 0) perm_vertex[G.vpos[v]] = v;
+  PGO_CUDA(d->perm_vertex.upload(perm_vertex, s));
+  PGO_CUDA(d->poses.reserve(3 * static_cast<size_t>(G.n_vertices)));
+  PGO_CUDA(d->meas.reserve(3 * static_cast<size_t>(G.n_edges)));
+  PGO_CUDA(d->info6.reserve(6 * static_cast<size_t>(G.n_edges)));
+  PGO_CUDA(d->M.reserve(9 * static_cast<size_t>(S.nnzb)));
+  PGO_CUDA(d->Dinv.reserve(9 * static_cast<size_t>(S.n)));
+  PGO_CUDA(d->rhs.reserve(3 * static_cast<size_t>(S.n)));
+  PGO_CUDA(d->u.reserve(3 * static_cast<size_t>(S.n)));
+  PGO_CUDA(d->x.reserve(3 * static_cast<size_t>(S.n)));
+  d->vec_cap = 1;
+  PGO_CUDA(cudaStreamSynchronize(s));  // the host vectors may go away
+  Params& P = d->P;
+  P.n_vertices = G.n_vertices;
+  P.n_edges = G.n_edges;
+  P.n = S.n;
+  P.edge_i = d->edge_i.p;
+  P.edge_j = d->edge_j.p;
+  P.vpos = d->vpos.p;
+  P.inc_ptr = d->inc_ptr.p;
+  P.inc = d->inc.p;
+  P.ff_edges = d->ff_edges.p;
+  P.n_ff = static_cast<int>(G.ff_edges.size());
+  P.poses = d->poses.p;
+  P.meas = d->meas.p;
+  P.info6 = d->info6.p;
+  P.n_levels = S.n_levels;
+  P.nnzb = S.nnzb;
+  P.col_ptr = d->col_ptr.p;
+  P.row_idx = d->row_idx.p;
+  P.col_of = d->col_of.p;
+  P.row_ptr = d->row_ptr.p;
+  P.row_pos = d->row_pos.p;
+  P.level_ptr = d->level_ptr.p;
+  P.level_cols = d->level_cols.p;
+  P.phase_ptr = d->phase_ptr.p;
+  P.ops = d->ops.p;
+  P.perm_vertex = d->perm_vertex.p;
+  P.M = d->M.p;
+  P.Dinv = d->Dinv.p;
+  P.rhs = d->rhs.p;
+  P.u = d->u.p;
+  P.x = d->x.p;
+  P.chi2_partial = d->chi2_partial.p;
+  P.chi2_out = nullptr;
+  P.status = d->status.p;
+  d->have_structure = true;
+  return PGO_OK;
+}
+
+int dev_upload(DeviceSolver* d, const double* poses, const double* meas, const double* info6,
+               std::string* err) {
+  if (!d->have_structure) {
+    if (err) *err = "pgo_set_graph has not been called";
+    return PGO_ERR_ARG;
+  }
+  PGO_CUDA(cudaSetDevice(d->device));
+  const Params& P = d->P;
+  PGO_CUDA(cudaMemcpyAsync(d->poses.p, poses, 3 * sizeof(double) * P.n_vertices,
+                           cudaMemcpyHostToDevice, d->stream));
+  if (P.n_edges) {
+    PGO_CUDA(cudaMemcpyAsync(d->meas.p, meas, 3 * sizeof(double) * P.n_edges,
+                             cudaMemcpyHostToDevice, d->stream));
+    PGO_CUDA(cudaMemcpyAsync(d->info6.p, info6, 6 * sizeof(double) * P.n_edges,
+                             cudaMemcpyHostToDevice, d->stream));
+  }
+  PGO_CUDA(cudaStreamSynchronize(d->stream));
+  d->have_values = true;
+  d->have_factor = false;
+  return PGO_OK;
+}
+
+int dev_set_poses(DeviceSolver* d, const double* poses, std::string* err) {
+  if (!d->have_values) {
+    if (err) *err = "pgo_upload has not been called";
+    return PGO_ERR_ARG;
+  }
+  PGO_CUDA(cudaSetDevice(d->device));
+  PGO_CUDA(cudaMemcpyAsync(d->poses.p, poses, 3 * sizeof(double) * d->P.n_vertices,
+                           cudaMemcpyHostToDevice, d->stream));
+  PGO_CUDA(cudaStreamSynchronize(d->stream));
+  return PGO_OK;
+}
+
+int dev_get_poses(DeviceSolver* d, double* poses, std::string* err) {
+  if (!d->have_values) {
+    if (err) *err = "pgo_upload has not been called";
+    return PGO_ERR_ARG;
+  }
+  PGO_CUDA(cudaSetDevice(d->device));
+  PGO_CUDA(cudaMemcpyAsync(poses, d->poses.p, 3 * sizeof(double) * d->P.n_vertices,
+                           cudaMemcpyDeviceToHost, d->stream));
+  PGO_CUDA(cudaStreamSynchronize(d->stream));
+  return PGO_OK;
+}
+
+int dev_iterate(DeviceSolver* d, int n_iters, double* chi2_out, int* iters_done, float* ms,
+                std::string* err) {
+  if (!d->have_values) {
+    if (err) *err = "pgo_upload has not been called";
+    return PGO_ERR_ARG;
+  }
+  PGO_CUDA(cudaSetDevice(d->device));
+  *iters_done = 0;
+  *ms = 0.f;
+  if (n_iters <= 0) return PGO_OK;
+  PGO_CUDA(d->chi2_out.reserve(n_iters));
+  PGO_CUDA(cudaMemsetAsync(d->status.p, 0, 4 * sizeof(int), d->stream));
+  PGO_CUDA(cudaMemsetAsync(d->chi2_out.p, 0, n_iters * sizeof(double), d->stream));
+  Params P = d->P;
+  P.chi2_out = d->chi2_out.p;
+  void* args[] = {&P, &n_iters};
+  PGO_CUDA(cudaEventRecord(d->ev0, d->stream));
+  PGO_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(gn_iterations), dim3(d->grid),
+                                       dim3(kThreads), args, 0, d->stream));
+  PGO_CUDA(cudaEventRecord(d->ev1, d->stream));
+  d->launches++;
+  int status[4] = {0, 0, 0, 0};
+  PGO_CUDA(cudaMemcpyAsync(status, d->status.p, sizeof status, cudaMemcpyDeviceToHost, d->stream));
+  if (chi2_out)
+    PGO_CUDA(cudaMemcpyAsync(chi2_out, d->chi2_out.p, n_iters * sizeof(double),
+                             cudaMemcpyDeviceToHost, d->stream));
+  PGO_CUDA(cudaStreamSynchronize(d->stream));
+  PGO_CUDA(cudaEventElapsedTime(ms, d->ev0, d->ev1));
+  *iters_done = status[1];
+  d->have_factor = status[1] > 0;
+  if (status[0]) {
+    if (err) *err = "H is not positive definite (a 3x3 pivot failed): is a vertex fixed?";
+    return PGO_ERR_NUMERIC;
+  }
+  return PGO_OK;
+}
+
+int dev_chi2(DeviceSolver* d, double* chi2, std::string* err) {
+  if (!d->have_values) {
+    if (err) *err = "pgo_upload has not been called";
+    return PGO_ERR_ARG;
+  }
+  PGO_CUDA(cudaSetDevice(d->device));
+  PGO_CUDA(d->scratch_d.reserve(1));
+  const int blocks = std::min(d->grid, std::max(1, (d->P.n_edges + kThreads - 1) / kThreads));
+  chi2_only<<<blocks, kThreads, 0, d->stream>>>(d->P);
+  sum_partials<<<1, 256, 0, d->stream>>>(d->chi2_partial.p, blocks, d->scratch_d.p);
+  d->launches += 2;
+  PGO_CUDA(cudaGetLastError());
+  PGO_CUDA(cudaMemcpyAsync(chi2, d->scratch_d.p, sizeof(double), cudaMemcpyDeviceToHost, d->stream));
+  PGO_CUDA(cudaStreamSynchronize(d->stream));
+  return PGO_OK;
+}
+
+int dev_marginals(DeviceSolver* d, int n, const int* col_p, const int* row_p, double* cov_out,
+                  std::string* err) {
+  if (!d->have_factor) {
+    if (err) *err = "no factorisation: call pgo_iterate first (computeMarginals uses its H)";
+    return PGO_ERR_ARG;
+  }
+  if (n <= 0) return PGO_OK;
+  PGO_CUDA(cudaSetDevice(d->device));
+  // distinct columns -> right-hand sides
+  std::vector<int> cols(col_p, col_p + n);
+  std::sort(cols.begin(), cols.end());
+  cols.erase(std::unique(cols.begin(), cols.end()), cols.end());
+  std::vector<int> rhs_of(n);
+  for (int k = 0; k < n; ++k)
+    rhs_of[k] = static_cast<int>(std::lower_bound(cols.begin(), cols.end(), col_p[k]) - cols.begin());
+  const int batch_cols = 16;  // 48 right-hand sides per cooperative launch
+  const size_t stride = 3 * static_cast<size_t>(d->P.n);
+  PGO_CUDA(d->many_rhs.reserve(3 * batch_cols * stride));
+  if (d->vec_cap < static_cast<size_t>(3 * batch_cols)) {
+    PGO_CUDA(d->u.reserve(3 * batch_cols * stride));
+    PGO_CUDA(d->x.reserve(3 * batch_cols * stride));
+    d->vec_cap = 3 * batch_cols;
+    d->P.u = d->u.p;
+    d->P.x = d->x.p;
+  }
+  PGO_CUDA(d->scratch_i.reserve(3 * static_cast<size_t>(n) + batch_cols));
+  PGO_CUDA(d->scratch_d.reserve(9 * static_cast<size_t>(n) + 1));
+  std::vector<double> out_all(9 * static_cast<size_t>(n));
+  for (size_t c0 = 0; c0 < cols.size(); c0 += batch_cols) {
+    const int nc = static_cast<int>(std::min<size_t>(batch_cols, cols.size() - c0));
+    // requests served by this batch
+    std::vector<int> idx, rows, local_rhs;
+    for (int k = 0; k < n; ++k)
+      if (rhs_of[k] >= static_cast<int>(c0) && rhs_of[k] < static_cast<int>(c0) + nc) {
+        idx.push_back(k);
+        rows.push_back(row_p[k]);
+        local_rhs.push_back(rhs_of[k] - static_cast<int>(c0));
+      }
+    const int nb = static_cast<int>(idx.size());
+    int* d_cols = d->scratch_i.p;
+    int* d_rows = d_cols + batch_cols;
+    int* d_rhs_of = d_rows + n;
+    PGO_CUDA(cudaMemcpyAsync(d_cols, cols.data() + c0, nc * sizeof(int), cudaMemcpyHostToDevice, d->stream));
+    PGO_CUDA(cudaMemcpyAsync(d_rows, rows.data(), nb * sizeof(int), cudaMemcpyHostToDevice, d->stream));
+    PGO_CUDA(cudaMemcpyAsync(d_rhs_of, local_rhs.data(), nb * sizeof(int), cudaMemcpyHostToDevice, d->stream));
+    PGO_CUDA(cudaMemsetAsync(d->many_rhs.p, 0, 3 * nc * stride * sizeof(double), d->stream));
+    set_unit_rhs<<<(3 * nc + 127) / 128, 128, 0, d->stream>>>(d->many_rhs.p, stride, d_cols, nc);
+    Params P = d->P;
+    const double* rhs = d->many_rhs.p;
+    int nrhs = 3 * nc;
+    void* args[] = {&P, &rhs, &nrhs};
+    PGO_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(solve_many), dim3(d->grid),
+                                         dim3(kThreads), args, 0, d->stream));
+    gather_blocks<<<(9 * nb + 127) / 128, 128, 0, d->stream>>>(d->x.p, stride, d_rows, d_rhs_of, nb,
+                                                              d->scratch_d.p);
+    d->launches += 3;
+    PGO_CUDA(cudaGetLastError());
+    std::vector<double> part(9 * static_cast<size_t>(nb));
+    PGO_CUDA(cudaMemcpyAsync(part.data(), d->scratch_d.p, part.size() * sizeof(double),
+                             cudaMemcpyDeviceToHost, d->stream));
+    PGO_CUDA(cudaStreamSynchronize(d->stream));
+    for (int t = 0; t < nb; ++t)
+      std::copy(part.begin() + 9 * t, part.begin() + 9 * t + 9, out_all.begin() + 9 * idx[t]);
+  }
+  std::copy(out_all.begin(), out_all.end(), cov_out);
+  return PGO_OK;
+}
+
+int dev_label_star(DeviceSolver* d, int gauge_vertex, int n, const int* v, const double* cov,
+                   double* meas_out, double* info_out, std::string* err) {
+  if (n <= 0) return PGO_OK;
+  PGO_CUDA(cudaSetDevice(d->device));
+  PGO_CUDA(d->scratch_i.reserve(static_cast<size_t>(n) + 4));
+  PGO_CUDA(d->scratch_d.reserve(21 * static_cast<size_t>(n)));
+  double* d_cov = d->scratch_d.p;
+  double* d_meas = d_cov + 9 * static_cast<size_t>(n);
+  double* d_info = d_meas + 3 * static_cast<size_t>(n);
+  PGO_CUDA(cudaMemcpyAsync(d->scratch_i.p, v, n * sizeof(int), cudaMemcpyHostToDevice, d->stream));
+  PGO_CUDA(cudaMemcpyAsync(d_cov, cov, 9 * sizeof(double) * n, cudaMemcpyHostToDevice, d->stream));
+  PGO_CUDA(cudaMemsetAsync(d->status.p, 0, sizeof(int), d->stream));
+  label_star_edges<<<(n + 63) / 64, 64, 0, d->stream>>>(d->poses.p, gauge_vertex, n, d->scratch_i.p,
+                                                        d_cov, d_meas, d_info, d->status.p);
+  d->launches++;
+  PGO_CUDA(cudaGetLastError());
+  int status = 0;
+  PGO_CUDA(cudaMemcpyAsync(&status, d->status.p, sizeof status, cudaMemcpyDeviceToHost, d->stream));
+  PGO_CUDA(cudaMemcpyAsync(meas_out, d_meas, 3 * sizeof(double) * n, cudaMemcpyDeviceToHost, d->stream));
+  PGO_CUDA(cudaMemcpyAsync(info_out, d_info, 9 * sizeof(double) * n, cudaMemcpyDeviceToHost, d->stream));
+  PGO_CUDA(cudaStreamSynchronize(d->stream));
+  if (status) {
+    if (err) *err = "edge labelling: a covariance was not positive definite";
+    return PGO_ERR_NUMERIC;
+  }
+  return PGO_OK;
+}
+
+}  // namespace pgo

@@ -1,0 +1,391 @@
+// Structure analysis of the pose-graph solver. See pgo_symbolic.h.
+#include "pgo_symbolic.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cstring>
+#include <numeric>
+
+namespace pgo {
+
+namespace {
+
+struct Graph {
+  int n;
+  std::vector<int> ptr, adj;  // CSR, symmetric, no self loops, no duplicates
+};
+
+Graph build_graph(int n, const std::vector<std::pair<int, int> >& edges) {
+  Graph g;
+  g.n = n;
+  std::vector<int> deg(n + 1, 0);
+  for (size_t e = 0; e < edges.size(); ++e) {
+    const int a = edges[e].first, b = edges[e].second;
+    if (a == b) continue;
+    ++deg[a + 1];
+    ++deg[b + 1];
+  }
+  g.ptr.assign(n + 1, 0);
+  for (int i = 0; i < n; ++i) g.ptr[i + 1] = g.ptr[i] + deg[i + 1];
+  std::vector<int> tmp(g.ptr[n]);
+  std::vector<int> cur(g.ptr.begin(), g.ptr.end() - 1);
+  for (size_t e = 0; e < edges.size(); ++e) {
+    const int a = edges[e].first, b = edges[e].second;
+    if (a == b) continue;
+    tmp[cur[a]++] = b;
+    tmp[cur[b]++] = a;
+  }
+  // sort + unique per row (parallel edges between the same pair collapse)
+  g.adj.clear();
+  g.adj.reserve(tmp.size());
+  std::vector<int> new_ptr(n + 1, 0);
+  for (int i = 0; i < n; ++i) {
+    std::sort(tmp.begin() + g.ptr[i], tmp.begin() + g.ptr[i + 1]);
+    int last = -1;
+    for (int t = g.ptr[i]; t < g.ptr[i + 1]; ++t)
+      if (tmp[t] != last) {
+        g.adj.push_back(tmp[t]);
+        last = tmp[t];
+      }
+    new_ptr[i + 1] = static_cast<int>(g.adj.size());
+  }
+  g.ptr.swap(new_ptr);
+  return g;
+}
+
+// ---- nested dissection by breadth-first level structures -----------------------------------
+class Dissector {
+ public:
+  Dissector(const Graph& g, int leaf) : g_(g), leaf_(leaf), mark_(g.n, -1), dist_(g.n, -1) {}
+
+  void run(std::vector<int>* order) {
+    order_ = order;
+    order_->clear();
+    order_->reserve(g_.n);
+    std::vector<int> all(g_.n);
+    std::iota(all.begin(), all.end(), 0);
+    rec(all);
+  }
+
+ private:
+  // BFS inside the current subset (mark_ == id) from `start`; fills dist_, returns visit order.
+  void bfs(int start, int id, std::vector<int>* visit) {
+    visit->clear();
+    visit->push_back(start);
+    dist_[start] = 0;
+    for (size_t h = 0; h < visit->size(); ++h) {
+      const int v = (*visit)[h];
+      for (int t = g_.ptr[v]; t < g_.ptr[v + 1]; ++t) {
+        const int w = g_.adj[t];
+        if (mark_[w] == id && dist_[w] < 0) {
+          dist_[w] = dist_[v] + 1;
+          visit->push_back(w);
+        }
+      }
+    }
+  }
+
+  void rec(std::vector<int>& s) {
+    if (static_cast<int>(s.size()) <= leaf_) {
+      order_->insert(order_->end(), s.begin(), s.end());
+      return;
+    }
+    const int id = next_id_++;
+    for (size_t i = 0; i < s.size(); ++i) {
+      mark_[s[i]] = id;
+      dist_[s[i]] = -1;
+    }
+    // connected components first
+    std::vector<int> visit;
+    bfs(s[0], id, &visit);
+    if (visit.size() != s.size()) {
+      std::vector<std::vector<int> > comps;
+      comps.push_back(visit);
+      for (size_t i = 0; i < s.size(); ++i)
+        if (dist_[s[i]] < 0) {
+          bfs(s[i], id, &visit);
+          comps.push_back(visit);
+        }
+      for (size_t c = 0; c < comps.size(); ++c) rec(comps[c]);
+      return;
+    }
+    // pseudo-peripheral start: repeat BFS from the farthest vertex
+    int start = visit.back();
+    for (int rep = 0; rep < 2; ++rep) {
+      for (size_t i = 0; i < s.size(); ++i) dist_[s[i]] = -1;
+      bfs(start, id, &visit);
+      start = visit.back();
+    }
+    const int depth = dist_[visit.back()];
+    if (depth < 2) {  // (nearly) a clique: nothing to dissect
+      order_->insert(order_->end(), s.begin(), s.end());
+      return;
+    }
+    std::vector<int> level_size(depth + 1, 0);
+    for (size_t i = 0; i < s.size(); ++i) ++level_size[dist_[s[i]]];
+    // separator = the smallest level whose removal leaves both sides >= 30 % (else the median)
+    const double total = static_cast<double>(s.size());
+    int best = -1, below = 0, median = 1;
+    for (int m = 0; m <= depth; ++m) {
+      const int above = static_cast<int>(s.size()) - below - level_size[m];
+      if (m >= 1 && m < depth) {
+        if (below >= 0.3 * total && above >= 0.3 * total &&
+            (best < 0 || level_size[m] < level_size[best]))
+          best = m;
+      }
+      if (below + level_size[m] / 2 <= total / 2) median = std::max(1, std::min(m, depth - 1));
+      below += level_size[m];
+    }
+    const int cut = best >= 0 ? best : median;
+    std::vector<int> a, b, sep;
+    for (size_t i = 0; i < visit.size(); ++i) {
+      const int v = visit[i];
+      if (dist_[v] < cut) {
+        a.push_back(v);
+      } else if (dist_[v] > cut) {
+        b.push_back(v);
+      } else {
+        // thin the separator: a level-`cut` vertex without a neighbour beyond it joins side A
+        bool touches_b = false;
+        for (int t = g_.ptr[v]; t < g_.ptr[v + 1] && !touches_b; ++t) {
+          const int w = g_.adj[t];
+          touches_b = mark_[w] == id && dist_[w] > cut;
+        }
+        if (touches_b) sep.push_back(v);
+        else a.push_back(v);
+      }
+    }
+    if (a.empty() || b.empty()) {
+      order_->insert(order_->end(), s.begin(), s.end());
+      return;
+    }
+    { std::vector<int>().swap(s); }  // release before recursing
+    rec(a);
+    rec(b);
+    order_->insert(order_->end(), sep.begin(), sep.end());
+  }
+
+  const Graph& g_;
+  int leaf_;
+  std::vector<int> mark_, dist_;
+  std::vector<int>* order_ = nullptr;
+  int next_id_ = 0;
+};
+
+}  // namespace
+
+bool analyse(int n, const std::vector<std::pair<int, int> >& edges, int ordering, Symbolic* out,
+             std::string* err) {
+  const auto t0 = std::chrono::steady_clock::now();
+  *out = Symbolic();
+  Symbolic& S = *out;
+  S.n = n;
+  for (size_t e = 0; e < edges.size(); ++e)
+    if (edges[e].first < 0 || edges[e].first >= n || edges[e].second < 0 || edges[e].second >= n) {
+      if (err) *err = "edge endpoint outside the free-vertex range";
+      return false;
+    }
+  const Graph g = build_graph(n, edges);
+
+  // ---- ordering -------------------------------------------------------------------------------
+  if (ordering == 1) {
+    S.perm.resize(n);
+    std::iota(S.perm.begin(), S.perm.end(), 0);
+  } else {
+    Dissector d(g, 8);
+    d.run(&S.perm);
+  }
+  if (static_cast<int>(S.perm.size()) != n) {
+    if (err) *err = "internal: ordering lost vertices";
+    return false;
+  }
+  S.iperm.assign(n, -1);
+  for (int p = 0; p < n; ++p) S.iperm[S.perm[p]] = p;
+
+  // ---- elimination tree (Liu, with path compression) ------------------------------------------
+  S.parent.assign(n, -1);
+  {
+    std::vector<int> ancestor(n, -1);
+    for (int p = 0; p < n; ++p) {
+      const int v = S.perm[p];
+      for (int t = g.ptr[v]; t < g.ptr[v + 1]; ++t) {
+        int r = S.iperm[g.adj[t]];
+        if (r >= p) continue;
+        while (ancestor[r] != -1 && ancestor[r] != p) {
+          const int next = ancestor[r];
+          ancestor[r] = p;
+          r = next;
+        }
+        if (ancestor[r] == -1) {
+          ancestor[r] = p;
+          S.parent[r] = p;
+        }
+      }
+    }
+  }
+  // children lists
+  std::vector<int> child_ptr(n + 1, 0), child(n > 0 ? n : 0);
+  for (int p = 0; p < n; ++p)
+    if (S.parent[p] >= 0) ++child_ptr[S.parent[p] + 1];
+  for (int p = 0; p < n; ++p) child_ptr[p + 1] += child_ptr[p];
+  {
+    std::vector<int> cur(child_ptr.begin(), child_ptr.end() - 1);
+    for (int p = 0; p < n; ++p)
+      if (S.parent[p] >= 0) child[cur[S.parent[p]]++] = p;
+  }
+
+  // ---- factor structure -------------------------------------------------------------------------
+  std::vector<std::vector<int> > cols(n);
+  {
+    std::vector<int> flag(n, -1);
+    for (int p = 0; p < n; ++p) {
+      std::vector<int>& c = cols[p];
+      flag[p] = p;
+      const int v = S.perm[p];
+      for (int t = g.ptr[v]; t < g.ptr[v + 1]; ++t) {
+        const int q = S.iperm[g.adj[t]];
+        if (q > p && flag[q] != p) {
+          flag[q] = p;
+          c.push_back(q);
+        }
+      }
+      for (int t = child_ptr[p]; t < child_ptr[p + 1]; ++t) {
+        const std::vector<int>& cc = cols[child[t]];
+        for (size_t i = 0; i < cc.size(); ++i) {
+          const int q = cc[i];
+          if (q > p && flag[q] != p) {
+            flag[q] = p;
+            c.push_back(q);
+          }
+        }
+      }
+      std::sort(c.begin(), c.end());
+    }
+  }
+  S.col_ptr.assign(n + 1, 0);
+  for (int p = 0; p < n; ++p) S.col_ptr[p + 1] = S.col_ptr[p] + 1 + static_cast<int>(cols[p].size());
+  S.nnzb = S.col_ptr[n];
+  if (S.nnzb > 0x7FFFFFF0LL) {
+    if (err) *err = "factor too large for 32-bit block positions";
+    return false;
+  }
+  S.row_idx.resize(S.nnzb);
+  S.col_of.resize(S.nnzb);
+  for (int p = 0; p < n; ++p) {
+    int w = S.col_ptr[p];
+    S.row_idx[w] = p;
+    S.col_of[w++] = p;
+    for (size_t i = 0; i < cols[p].size(); ++i) {
+      S.row_idx[w] = cols[p][i];
+      S.col_of[w++] = p;
+    }
+    std::vector<int>().swap(cols[p]);
+  }
+  // row view of the strictly lower part
+  S.row_ptr.assign(n + 1, 0);
+  for (int p = 0; p < n; ++p)
+    for (int w = S.col_ptr[p] + 1; w < S.col_ptr[p + 1]; ++w) ++S.row_ptr[S.row_idx[w] + 1];
+  for (int p = 0; p < n; ++p) S.row_ptr[p + 1] += S.row_ptr[p];
+  S.row_pos.resize(S.row_ptr[n]);
+  {
+    std::vector<int> cur(S.row_ptr.begin(), S.row_ptr.end() - 1);
+    for (int p = 0; p < n; ++p)
+      for (int w = S.col_ptr[p] + 1; w < S.col_ptr[p + 1]; ++w) S.row_pos[cur[S.row_idx[w]]++] = w;
+  }
+
+  // ---- levels -----------------------------------------------------------------------------------
+  S.level.assign(n, 0);
+  S.n_levels = n ? 1 : 0;
+  for (int p = 0; p < n; ++p) {
+    const int par = S.parent[p];
+    if (par >= 0) S.level[par] = std::max(S.level[par], S.level[p] + 1);
+    S.n_levels = std::max(S.n_levels, S.level[p] + 1);
+  }
+  S.level_ptr.assign(S.n_levels + 1, 0);
+  for (int p = 0; p < n; ++p) ++S.level_ptr[S.level[p] + 1];
+  for (int l = 0; l < S.n_levels; ++l) S.level_ptr[l + 1] += S.level_ptr[l];
+  S.level_cols.resize(n);
+  {
+    std::vector<int> cur(S.level_ptr.begin(), S.level_ptr.end() - 1);
+    for (int p = 0; p < n; ++p) S.level_cols[cur[S.level[p]]++] = p;
+  }
+
+  // ---- update schedule --------------------------------------------------------------------------
+  // Phase l applies every update whose source column has level l - 1. Within a phase the updates
+  // are grouped by target block so that one thread group owns each target (no atomics), in a
+  // fixed order (deterministic rounding).
+  int64_t n_ops = 0;
+  for (int p = 0; p < n; ++p) {
+    const int64_t m = S.col_ptr[p + 1] - S.col_ptr[p] - 1;
+    n_ops += m * (m + 1) / 2;
+  }
+  if (n_ops > 0x3FFFFFF0LL || S.nnzb >= kFinalFlag) {
+    if (err) *err = "more than 2^30 block updates: graph too dense for this solver";
+    return false;
+  }
+  S.n_ops = n_ops;
+  S.ops.resize(n_ops);
+  S.phase_ptr.assign(S.n_levels + 1, 0);
+  std::vector<int> count(S.nnzb, 0), touched;
+  std::vector<UpdateOp> raw;
+  int64_t op_cursor = 0;
+  std::vector<char> fin(n, 0);
+  for (int l = 1; l < S.n_levels; ++l) {
+    S.phase_ptr[l] = static_cast<int>(op_cursor);
+    raw.clear();
+    touched.clear();
+    for (int t = S.level_ptr[l - 1]; t < S.level_ptr[l]; ++t) {
+      const int k = S.level_cols[t];
+      const int base = S.col_ptr[k], m = S.col_ptr[k + 1] - base;  // rows base+1 .. base+m-1
+      for (int b = 1; b < m; ++b) {
+        const int c = S.row_idx[base + b];
+        int w = S.col_ptr[c];  // diagonal of column c == row c
+        for (int a = b; a < m; ++a) {
+          const int r = S.row_idx[base + a];
+          while (S.row_idx[w] != r) ++w;  // struct(k) rows >= c are a subset of struct(c) + {c}
+          UpdateOp x = {w, base + a, base + b};
+          raw.push_back(x);
+          if (count[w]++ == 0) touched.push_back(w);
+        }
+      }
+    }
+    std::sort(touched.begin(), touched.end());
+    // counting sort of the phase's updates by target (stable: generation order within a target)
+    int64_t off = op_cursor;
+    for (size_t i = 0; i < touched.size(); ++i) {
+      const int w = touched[i];
+      const int c = count[w];
+      S.max_run = std::max(S.max_run, c);
+      count[w] = static_cast<int>(off);  // reuse as write cursor
+      off += c;
+    }
+    for (size_t i = 0; i < raw.size(); ++i) {
+      UpdateOp o = raw[i];
+      const int w = o.target;
+      const int col = S.col_of[w];
+      if (S.row_idx[w] == col && S.level[col] == l) {
+        o.target |= kFinalFlag;
+        fin[col] = 1;
+      }
+      S.ops[count[w]++] = o;
+    }
+    for (size_t i = 0; i < touched.size(); ++i) count[touched[i]] = 0;
+    op_cursor = off;
+  }
+  S.phase_ptr[S.n_levels] = static_cast<int>(op_cursor);
+  if (op_cursor != n_ops) {
+    if (err) *err = "internal: update count mismatch";
+    return false;
+  }
+  // every non-leaf column must be finalised by an update of its own phase
+  for (int p = 0; p < n; ++p)
+    if (S.level[p] > 0 && !fin[p]) {
+      if (err) *err = "internal: column without finalising update";
+      return false;
+    }
+  S.analyse_seconds =
+      std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  return true;
+}
+
+}  // namespace pgo

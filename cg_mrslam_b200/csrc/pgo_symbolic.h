@@ -1,0 +1,65 @@
+// Host-side structure analysis of the pose-graph solver (no CUDA in this header).
+//
+// g2o's BlockSolver::buildStructure + LinearSolverCSparse's symbolic step (SURVEY.md appendix C5,
+// C6, C8) decide, once per graph structure, where every 3x3 block of H lives and in which order
+// the unknowns are eliminated. This file does the same job for the GPU factorisation:
+//   * fill-reducing ordering of the free vertices (nested dissection on the block graph; g2o
+//     uses scalar AMD, SURVEY C8 -- the ordering changes rounding only, not the solution);
+//   * elimination tree, block structure of the factor, column levels;
+//   * an explicit, ordered list of every block update  M(i,j) -= M(i,k) D(k)^-1 M(j,k)^T  grouped
+//     by the phase in which its source column k becomes final ("inspector"), which the kernels in
+//     pgo_kernels.cu execute without searching and without atomics ("executor").
+#ifndef CGM_PGO_SYMBOLIC_H
+#define CGM_PGO_SYMBOLIC_H
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace pgo {
+
+// One block update  M(target) -= M(a) * Dinv(col_of(a)) * M(b)^T.  Updates of one phase are sorted
+// by target; a thread owns a maximal run of equal targets (runs are short: the sources of one
+// phase rarely share a target). kFinalFlag marks runs that complete the diagonal block of a
+// column whose level equals the phase: the owner then also inverts it.
+struct UpdateOp {
+  int target;  // position of M(i,j) | kFinalFlag
+  int a;       // position of M(i,k)
+  int b;       // position of M(j,k)
+};
+static const int kFinalFlag = 0x40000000;
+
+struct Symbolic {
+  int n = 0;                    // free (non-fixed) vertices = block rows of H
+  std::vector<int> perm;        // perm[p] = hessian index eliminated p-th
+  std::vector<int> iperm;       // iperm[hessian index] = p
+  std::vector<int> parent;      // elimination tree over permuted columns (-1 = root)
+  std::vector<int> level;       // level[p]: 0 for leaves, 1 + max(level of children) otherwise
+  int n_levels = 0;
+  // factor structure, block CSC, diagonal first, rows ascending
+  std::vector<int> col_ptr;     // n + 1
+  std::vector<int> row_idx;     // nnzb
+  std::vector<int> col_of;      // nnzb: column of each position
+  // the same structure by rows (strictly lower part), for the forward substitution
+  std::vector<int> row_ptr;     // n + 1
+  std::vector<int> row_pos;     // position of M(j,k) for each k < j in row j, k ascending
+  // columns grouped by level
+  std::vector<int> level_ptr;   // n_levels + 1
+  std::vector<int> level_cols;  // n
+  // update schedule: phase l (1 <= l < n_levels) applies ops [phase_ptr[l], phase_ptr[l+1])
+  std::vector<int> phase_ptr;   // n_levels + 1 (phase 0 is empty)
+  std::vector<UpdateOp> ops;
+  // statistics
+  int64_t nnzb = 0, n_ops = 0;
+  int max_run = 0;              // longest run of updates sharing one target within a phase
+  double analyse_seconds = 0.0;
+};
+
+// Block adjacency of the free vertices: edges given as pairs of hessian indices (both >= 0).
+// Returns false (with *err) on inconsistent input. `ordering`: 0 = nested dissection (default),
+// 1 = natural (testing).
+bool analyse(int n, const std::vector<std::pair<int, int> >& edges, int ordering, Symbolic* out,
+             std::string* err);
+
+}  // namespace pgo
+#endif

@@ -1,0 +1,198 @@
+"""Python face of the pose-graph solver C ABI (include/pgo_solver.h).
+
+Thin ctypes glue for tests/, bench.py and tools/. Method names follow the g2o calls the reference
+makes (SparseOptimizer::initializeOptimization / optimize / computeMarginals /
+computeInitialGuess, EdgeLabeler::labelEdges; call sites listed in SURVEY.md section 8b).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+_bp = C.POINTER(C.c_uint8)
+
+
+class pgo_stats(C.Structure):
+    _fields_ = [("n_vertices", C.c_int32), ("n_edges", C.c_int32), ("n_free", C.c_int32),
+                ("n_levels", C.c_int32), ("factor_blocks", C.c_int64), ("update_ops", C.c_int64),
+                ("hessian_blocks", C.c_int64), ("analyse_seconds", C.c_double),
+                ("last_iterate_ms", C.c_double), ("kernel_launches", C.c_int64)]
+
+
+class SolverError(RuntimeError):
+    def __init__(self, code, msg):
+        RuntimeError.__init__(self, "pgo error %d: %s" % (code, msg))
+        self.code = code
+
+
+_SIGS = {
+    "pgo_last_error": (C.c_char_p, []),
+    "pgo_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.c_void_p]),
+    "pgo_destroy": (None, [C.c_void_p]),
+    "pgo_set_graph": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _ip, _ip, _bp]),
+    "pgo_upload": (C.c_int, [C.c_void_p, _dp, _dp, _dp]),
+    "pgo_set_poses": (C.c_int, [C.c_void_p, _dp]),
+    "pgo_get_poses": (C.c_int, [C.c_void_p, _dp]),
+    "pgo_iterate": (C.c_int, [C.c_void_p, C.c_int, _dp, _dp, C.POINTER(C.c_int)]),
+    "pgo_chi2": (C.c_int, [C.c_void_p, _dp]),
+    "pgo_marginals": (C.c_int, [C.c_void_p, C.c_int, _ip, _ip, _dp]),
+    "pgo_initial_guess": (C.c_int, [C.c_void_p]),
+    "pgo_label_star_edges": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _ip, _dp, _dp]),
+    "pgo_get_stats": (C.c_int, [C.c_void_p, C.POINTER(pgo_stats)]),
+    "pgo_stream": (C.c_void_p, [C.c_void_p]),
+}
+
+PGO_SYMBOLS = sorted(_SIGS)
+PGO_ERR_NUMERIC = -5
+
+
+def bind(lib):
+    for name, (res, args) in _SIGS.items():
+        f = getattr(lib, name)
+        f.restype = res
+        f.argtypes = args
+    return lib
+
+
+def _d(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _p(a, t):
+    return a.ctypes.data_as(t) if a is not None and a.size else None
+
+
+class Solver:
+    """One SparseOptimizer-like solver on one GPU."""
+
+    def __init__(self, device=0, stream=None):
+        self.lib = bind(_lib.load())
+        self.h = C.c_void_p()
+        self._check(self.lib.pgo_create(C.byref(self.h), device, stream))
+        self.n_vertices = self.n_edges = 0
+
+    def _check(self, rc):
+        if rc:
+            raise SolverError(rc, self.lib.pgo_last_error().decode())
+
+    def close(self):
+        if self.h:
+            self.lib.pgo_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_graph(self, n_vertices, edge_ij, fixed):
+        """initializeOptimization: structure of the active graph. ``fixed`` = vertex indices."""
+        e = np.asarray(edge_ij).reshape(-1, 2)
+        ei, ej = _i(e[:, 0]), _i(e[:, 1])
+        mask = np.zeros(n_vertices, dtype=np.uint8)
+        mask[np.asarray(fixed, dtype=np.int64)] = 1
+        self._check(self.lib.pgo_set_graph(self.h, n_vertices, len(e), _p(ei, _ip), _p(ej, _ip),
+                                           _p(mask, _bp)))
+        self.n_vertices, self.n_edges = n_vertices, len(e)
+
+    def upload(self, poses, meas, info6):
+        poses, meas, info6 = _d(poses), _d(meas), _d(info6)
+        assert poses.shape == (self.n_vertices, 3) and meas.shape == (self.n_edges, 3) \
+            and info6.shape == (self.n_edges, 6)
+        self._check(self.lib.pgo_upload(self.h, _p(poses, _dp), _p(meas, _dp), _p(info6, _dp)))
+
+    def set_poses(self, poses):
+        poses = _d(poses)
+        assert poses.shape == (self.n_vertices, 3)
+        self._check(self.lib.pgo_set_poses(self.h, _p(poses, _dp)))
+
+    def poses(self):
+        out = np.empty((self.n_vertices, 3))
+        self._check(self.lib.pgo_get_poses(self.h, _p(out, _dp)))
+        return out
+
+    def optimize(self, n_iters, want_poses=True):
+        """SparseOptimizer::optimize(n): returns (iterations done, chi2 per iteration, poses)."""
+        chi2 = np.zeros(max(n_iters, 1))
+        out = np.empty((self.n_vertices, 3)) if want_poses else None
+        done = C.c_int()
+        rc = self.lib.pgo_iterate(self.h, n_iters, _p(out, _dp) if want_poses else None,
+                                  _p(chi2, _dp), C.byref(done))
+        if rc and rc != PGO_ERR_NUMERIC:
+            self._check(rc)
+        return done.value, chi2[:n_iters], out
+
+    def chi2(self):
+        v = C.c_double()
+        self._check(self.lib.pgo_chi2(self.h, C.byref(v)))
+        return v.value
+
+    def marginals(self, pairs):
+        """computeMarginals: blocks (r, c) of H^-1, vertex index pairs -> [n, 3, 3]."""
+        pr = np.asarray(pairs, dtype=np.int32).reshape(-1, 2)
+        r, c = _i(pr[:, 0]), _i(pr[:, 1])
+        out = np.empty((len(pr), 3, 3))
+        self._check(self.lib.pgo_marginals(self.h, len(pr), _p(r, _ip), _p(c, _ip), _p(out, _dp)))
+        return out
+
+    def initial_guess(self):
+        self._check(self.lib.pgo_initial_guess(self.h))
+
+    def label_star_edges(self, gauge, vs):
+        v = _i(vs)
+        meas = np.empty((len(v), 3))
+        info = np.empty((len(v), 3, 3))
+        self._check(self.lib.pgo_label_star_edges(self.h, int(gauge), len(v), _p(v, _ip),
+                                                  _p(meas, _dp), _p(info, _dp)))
+        return meas, info
+
+    def stats(self):
+        s = pgo_stats()
+        self._check(self.lib.pgo_get_stats(self.h, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in pgo_stats._fields_}
+
+    def stream(self):
+        return self.lib.pgo_stream(self.h)
+
+
+def condensed_star(solver_factory, poses, edge_ij, meas, info6, gauge, separators):
+    """CondensedGraphCreator::compute (condensed_graph_creator.cpp:33-66) on the GPU solver: fix
+    only the gauge, computeInitialGuess, optimize(1), label star edges gauge -> v."""
+    s = solver_factory()
+    try:
+        s.set_graph(len(poses), edge_ij, [gauge])
+        s.upload(poses, meas, info6)
+        s.initial_guess()
+        done, _, _ = s.optimize(1, want_poses=False)
+        if done != 1:
+            raise SolverError(PGO_ERR_NUMERIC, "optimize(1) failed")
+        vs = [int(v) for v in separators if int(v) != int(gauge)]
+        z, om = s.label_star_edges(gauge, vs)
+    finally:
+        s.close()
+    return z, om, vs
+
+
+def smoke():
+    """One small GN solve on cuda:0 checked against the CPU oracle (test infrastructure)."""
+    from oracle import pgo_oracle as po
+    from . import synth
+    g = synth.make_pose_graph(400, 1600, seed=3, box=22.0)
+    s = Solver()
+    s.set_graph(len(g["poses0"]), g["edge_ij"], g["fixed"])
+    s.upload(g["poses0"], g["meas"], g["info"])
+    done, chi2, poses = s.optimize(5)
+    ref = po.gauss_newton(g["poses0"], g["edge_ij"], g["meas"], g["info"], g["fixed"], 5)
+    err = float(np.abs(poses - ref.poses).max())
+    assert done == 5 and err < 1e-6, (done, err)
+    print("smoke: pgo OK (5 GN iterations, max |pose - oracle| = %.2e, chi2 %.4f -> %.4f)" %
+          (err, chi2[0], chi2[-1]))
+    s.close()

@@ -1,0 +1,107 @@
+/* pgo_solver.h -- C ABI of the B200 SE(2) pose-graph solver (libcgmrslam_b200.so).
+ *
+ * Drop-in boundary for the arithmetic the reference delegates to g2o ("Seam S", SURVEY.md section
+ * 8b): SparseOptimizer::initializeOptimization / optimize(n) with BlockSolver<-1,-1> +
+ * LinearSolverCSparse + OptimizationAlgorithmGaussNewton (configured at
+ * src/slam/graph_slam.cpp:44-56; called at graph_slam.cpp:392-393,564-565 and
+ * graph_manipulator.cpp:116-124), SparseOptimizer::computeMarginals
+ * (graph_manipulator.cpp:134-142), computeInitialGuess (graph_manipulator.cpp:122) and
+ * EdgeLabeler::labelEdges (condensed_graph_creator.cpp:62-63). A g2o-compatible C++ layer
+ * (include/g2o_compat/) marshals the active vertices and edges into the flat arrays below.
+ *
+ * Conventions
+ *   - vertices are the ACTIVE vertices in ascending id order (g2o's activeVertices order,
+ *     SURVEY appendix C6), poses are packed (x, y, theta) doubles; edges are EdgeSE2: vertex
+ *     indices (i, j) into that array, measurement (dx, dy, dtheta), information as the 6 upper-
+ *     triangle entries (I11 I12 I13 I22 I23 I33) -- the layout of the g2o text format;
+ *   - the caller owns every host buffer; the handle owns device memory and one CUDA stream;
+ *   - return 0 on success, a negative pgo_status on failure; pgo_last_error() has the message;
+ *   - there is no CPU fallback: compute entry points need a CUDA device.
+ */
+#ifndef PGO_SOLVER_H
+#define PGO_SOLVER_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum pgo_status {
+  PGO_OK = 0,
+  PGO_ERR_ARG = -1,
+  PGO_ERR_CUDA = -2,
+  PGO_ERR_CAPACITY = -3,
+  PGO_ERR_ALLOC = -4,
+  PGO_ERR_NUMERIC = -5 /* H not positive definite (g2o: linear solver failure) */
+} pgo_status;
+
+typedef struct pgo_solver pgo_solver;
+
+typedef struct pgo_stats {
+  int32_t n_vertices, n_edges, n_free;   /* as given / non-fixed vertices                        */
+  int32_t n_levels;                      /* elimination-tree height = phases per factorisation   */
+  int64_t factor_blocks;                 /* 3x3 blocks in the factor (incl. diagonal)            */
+  int64_t update_ops;                    /* block updates per factorisation                      */
+  int64_t hessian_blocks;                /* non-zero 3x3 blocks of H (lower triangle + diagonal) */
+  double analyse_seconds;                /* host time of the structure analysis                  */
+  double last_iterate_ms;                /* device time of the last pgo_iterate call             */
+  int64_t kernel_launches;               /* kernels launched by this solver so far               */
+} pgo_stats;
+
+const char* pgo_last_error(void);
+
+/* `stream`: a cudaStream_t to run on, or NULL to create one. */
+int pgo_create(pgo_solver** out, int device, void* stream);
+void pgo_destroy(pgo_solver* s);
+
+/* SparseOptimizer::initializeOptimization + BlockSolver::buildStructure + the symbolic part of
+ * LinearSolverCSparse: active set, hessian indices (fixed -> -1, the others
+ * 0..n-1 in vertex order), fill-reducing ordering, factor structure, update schedule.
+ * fixed[v] != 0 marks a fixed vertex. At least one vertex must be fixed per connected component,
+ * exactly as with g2o (otherwise H is singular and pgo_iterate reports PGO_ERR_NUMERIC). */
+int pgo_set_graph(pgo_solver* s, int n_vertices, int n_edges, const int32_t* edge_i,
+                  const int32_t* edge_j, const uint8_t* fixed);
+
+/* Estimates, measurements, information matrices of the graph set above (host -> device). */
+int pgo_upload(pgo_solver* s, const double* poses, const double* meas, const double* info6);
+/* Estimates only (VertexSE2::setEstimate on every vertex). */
+int pgo_set_poses(pgo_solver* s, const double* poses);
+int pgo_get_poses(pgo_solver* s, double* poses);
+
+/* SparseOptimizer::optimize(n_iters) with Gauss-Newton: per iteration
+ * computeActiveErrors, buildSystem, solve, update; exactly n_iters iterations, no damping, no
+ * termination test. chi2_out (may be NULL) receives chi2 at the linearisation point of every
+ * iteration; poses_out (may be NULL) the final estimates. *iters_done = iterations completed
+ * (fewer than n_iters only if the factorisation fails, in which case the result is
+ * PGO_ERR_NUMERIC and the estimates are those before the failing iteration). */
+int pgo_iterate(pgo_solver* s, int n_iters, double* poses_out, double* chi2_out, int* iters_done);
+
+/* EdgeSE2::computeError + chi2() over all edges at the current estimates (computeActiveErrors). */
+int pgo_chi2(pgo_solver* s, double* chi2);
+
+/* SparseOptimizer::computeMarginals(spinv, blockIndices): blocks (r, c) of H^-1 for
+ * the H assembled by the LAST iteration of pgo_iterate (not re-linearised). vertex_r / vertex_c
+ * are vertex indices of non-fixed vertices; cov_out[k] is the row-major 3x3 block. */
+int pgo_marginals(pgo_solver* s, int n_blocks, const int32_t* vertex_r, const int32_t* vertex_c,
+                  double* cov_out);
+
+/* SparseOptimizer::computeInitialGuess: breadth-first propagation of the edge
+ * measurements from the fixed vertices (EdgeSE2::initialEstimate); ties broken by hop count, then
+ * edge index. Overwrites the estimates of every reached non-fixed vertex. */
+int pgo_initial_guess(pgo_solver* s);
+
+/* EdgeLabeler::labelEdges for star edges gauge -> v with the gauge fixed (used by
+ * CondensedGraphCreator::compute, condensed_graph_creator.cpp:49-63): measurement = Xg^-1 * Xv
+ * at the current estimates, information = inverse of the unscented-transform covariance of the
+ * edge error under v's marginal (from the last factorisation). meas_out [n][3], info_out [n][9]. */
+int pgo_label_star_edges(pgo_solver* s, int gauge, int n, const int32_t* v, double* meas_out,
+                         double* info_out);
+
+int pgo_get_stats(const pgo_solver* s, pgo_stats* out);
+void* pgo_stream(const pgo_solver* s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
