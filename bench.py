@@ -265,7 +265,8 @@ def gn_ours(args, local, world, barrier):
         "config": {"workload": "cfg4 synthetic Manhattan graph, %d vertices / %d edges, seed 42, "
                                "truth+noise start, vertex 0 fixed" % (st["n_vertices"], st["n_edges"]),
                    "factor_blocks": st["factor_blocks"], "update_ops": st["update_ops"],
-                   "levels": st["n_levels"], "analyse_seconds": analyse_s},
+                   "levels": st["n_levels"], "analyse_seconds": analyse_s,
+                   "stage_ms_last_iter": st["stage_ms"]},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                      "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_kind": pk_kind,
                      "kernel": "gn_iterations", "algorithmic_bytes": nbytes},

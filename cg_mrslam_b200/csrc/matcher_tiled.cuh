@@ -68,7 +68,7 @@ __host__ __device__ inline TiledLayout tiled_layout(int ny, int ta, int rc, int 
 }
 
 template <int G>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(1024)
 score_tiled(const uint8_t* __restrict__ grids, size_t slot_bytes, DevGeom g, int max_cell,
             const double* __restrict__ pts, const RegionDesc* __restrict__ regions,
             const ThetaDesc* __restrict__ units, const int* __restrict__ bin_tab, uint64_t* bins,
@@ -356,7 +356,9 @@ static void tiled_plan(const GridGeom& g, const SearchPlan& plan, const double* 
     (void)n_tiles;
   }
   out->smem = max_smem;
-  out->threads = std::max(128, std::min(512, (max_tt + 31) / 32 * 32));
+  // one thread per thread tile where possible; otherwise the fewest equal passes
+  const int passes = (max_tt + 1023) / 1024;
+  out->threads = std::max(128, std::min(1024, ((max_tt + passes - 1) / passes + 31) / 32 * 32));
 }
 
 static cudaError_t tiled_launch(const uint8_t* grids, size_t slot_bytes, const DevGeom& dg,

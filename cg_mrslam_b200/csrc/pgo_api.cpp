@@ -315,6 +315,7 @@ int pgo_get_stats(const pgo_solver* s, pgo_stats* out) {
   out->analyse_seconds = s->sym.analyse_seconds;
   out->last_iterate_ms = s->last_ms;
   out->kernel_launches = static_cast<int64_t>(pgo::dev_launches(s->dev));
+  for (int k = 0; k < 5; ++k) out->stage_ms[k] = pgo::dev_stage_ms(s->dev)[k];
   return PGO_OK;
 }
 

@@ -33,6 +33,9 @@ int dev_create(DeviceSolver** out, int device, void* stream, std::string* err);
 void dev_destroy(DeviceSolver* d);
 void* dev_stream(const DeviceSolver* d);
 uint64_t dev_launches(const DeviceSolver* d);
+// Device time of the stages of the last GN iteration: linearise (incl. zero fill and leaf pivots),
+// factor updates, forward solve, backward solve, update.
+const double* dev_stage_ms(const DeviceSolver* d);
 
 int dev_set_structure(DeviceSolver* d, const Symbolic& S, const GraphTables& G, std::string* err);
 int dev_upload(DeviceSolver* d, const double* poses, const double* meas, const double* info6,

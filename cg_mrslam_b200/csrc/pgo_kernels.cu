@@ -69,6 +69,8 @@ struct Params {
   const int* level_cols;
   const int* phase_ptr;
   const UpdateOp* ops;
+  const int* fwd_ptr;
+  const SolveOp* fwd_ops;
   const int* perm_vertex;  // permuted position -> vertex index
   // numeric
   double* M;      // [nnzb][9]
@@ -79,6 +81,7 @@ struct Params {
   double* chi2_partial;  // [gridDim.x]
   double* chi2_out;      // [n_iters]
   int* status;           // [0] error flag, [1] iterations done
+  unsigned long long* stamps;  // [6] globaltimer at the stage boundaries of the last iteration
 };
 
 // ---- small dense helpers, 3x3 row-major ----------------------------------------------------------
@@ -336,51 +339,91 @@ __device__ void phase_updates(const Params& P, int l) {
 }
 
 // ---- phase 3: solves ---------------------------------------------------------------------------
-// forward, level l: z_j = b_j - sum_{k<j} M(j,k) u_k ; u_j = Dinv_j z_j      (one warp per row j)
-__device__ void phase_forward(const Params& P, int l, int nrhs, const double* rhs, size_t stride) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  const int n_cols = P.level_ptr[l + 1] - P.level_ptr[l];
-  for (int w = warp; w < n_cols * nrhs; w += nwarps) {
-    const int j = P.level_cols[P.level_ptr[l] + w % n_cols], r = w / n_cols;
-    const double* uu = P.u + r * stride;
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-    for (int t = P.row_ptr[j] + lane; t < P.row_ptr[j + 1]; t += 32) {
-      const int pos = P.row_pos[t];
-      const double* m = P.M + 9 * static_cast<size_t>(pos);
-      const double* v = uu + 3 * static_cast<size_t>(P.col_of[pos]);
-      const double v0 = v[0], v1 = v[1], v2 = v[2];
-      s0 += m[0] * v0 + m[1] * v1 + m[2] * v2;
-      s1 += m[3] * v0 + m[4] * v1 + m[5] * v2;
-      s2 += m[6] * v0 + m[7] * v1 + m[8] * v2;
-    }
-    for (int o = 16; o; o >>= 1) {
-      s0 += __shfl_down_sync(0xffffffffu, s0, o);
-      s1 += __shfl_down_sync(0xffffffffu, s1, o);
-      s2 += __shfl_down_sync(0xffffffffu, s2, o);
-    }
-    if (lane == 0) {
-      const double* b = rhs + r * stride + 3 * static_cast<size_t>(j);
-      const double z0 = b[0] - s0, z1 = b[1] - s1, z2 = b[2] - s2;
-      const double* d = P.Dinv + 9 * static_cast<size_t>(j);
-      double* out = P.u + r * stride + 3 * static_cast<size_t>(j);
-      out[0] = d[0] * z0 + d[1] * z1 + d[2] * z2;
-      out[1] = d[3] * z0 + d[4] * z1 + d[5] * z2;
-      out[2] = d[6] * z0 + d[7] * z1 + d[8] * z2;
+// Forward substitution works in place on the right-hand side z (initially b):
+//   level-0 rows:  u_j = Dinv_j z_j
+//   phase l >= 1:  z_i -= M(i,k) u_k for the blocks of the columns k of level l-1 (eager, right-
+//                  looking timing), one thread per target row (left-looking ownership); a row of
+//                  level l is complete after this phase: u_i = Dinv_i z_i.
+__device__ __forceinline__ void finish_row(const Params& P, int row, const double* z, double* u) {
+  const double* d = P.Dinv + 9 * static_cast<size_t>(row);
+  u[0] = d[0] * z[0] + d[1] * z[1] + d[2] * z[2];
+  u[1] = d[3] * z[0] + d[4] * z[1] + d[5] * z[2];
+  u[2] = d[6] * z[0] + d[7] * z[1] + d[8] * z[2];
+}
+
+__device__ void phase_forward_leaves(const Params& P, int nrhs, double* z, size_t stride) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+  const int n0 = P.level_ptr[1] - P.level_ptr[0];
+  for (int t = tid; t < n0 * nrhs; t += nthreads) {
+    const int j = P.level_cols[P.level_ptr[0] + t % n0], r = t / n0;
+    finish_row(P, j, z + r * stride + 3 * static_cast<size_t>(j),
+               P.u + r * stride + 3 * static_cast<size_t>(j));
+  }
+}
+
+__device__ void phase_forward(const Params& P, int l, int nrhs, double* z, size_t stride) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+  const int begin = P.fwd_ptr[l], end = P.fwd_ptr[l + 1];
+  for (int i = begin + tid; i < end; i += nthreads) {
+    const SolveOp first = P.fwd_ops[i];
+    if (i > begin && P.fwd_ops[i - 1].row == first.row) continue;  // not the head of its run
+    const int row = first.row & ~kFinalFlag;
+    for (int r = 0; r < nrhs; ++r) {
+      double* zz = z + r * stride + 3 * static_cast<size_t>(row);
+      const double* uu = P.u + r * stride;
+      double z0 = zz[0], z1 = zz[1], z2 = zz[2];
+      int j = i;
+      SolveOp op = first;
+      while (true) {
+        const double* m = P.M + 9 * static_cast<size_t>(op.pos);
+        const double* v = uu + 3 * static_cast<size_t>(P.col_of[op.pos]);
+        const double v0 = v[0], v1 = v[1], v2 = v[2];
+        z0 -= m[0] * v0 + m[1] * v1 + m[2] * v2;
+        z1 -= m[3] * v0 + m[4] * v1 + m[5] * v2;
+        z2 -= m[6] * v0 + m[7] * v1 + m[8] * v2;
+        ++j;
+        if (j >= end) break;
+        op = P.fwd_ops[j];
+        if (op.row != first.row) break;
+      }
+      zz[0] = z0;
+      zz[1] = z1;
+      zz[2] = z2;
+      if (first.row & kFinalFlag) {
+        const double zf[3] = {z0, z1, z2};
+        finish_row(P, row, zf, P.u + r * stride + 3 * static_cast<size_t>(row));
+      }
     }
   }
 }
 
-// backward, level l: x_j = u_j - Dinv_j sum_{i>j} M(i,j)^T x_i                 (one warp per column j)
-__device__ void phase_backward(const Params& P, int l, int nrhs, size_t stride) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+// backward, level l: x_j = u_j - Dinv_j sum_{i>j} M(i,j)^T x_i. A column's blocks are contiguous,
+// so the lanes of the group that owns column j read consecutive 72-byte blocks. Narrow levels (the
+// separator chains) give each column a whole CTA, wide levels a warp.
+__device__ __forceinline__ void backward_store(const Params& P, int j, int r, size_t stride,
+                                               double s0, double s1, double s2) {
+  const double* d = P.Dinv + 9 * static_cast<size_t>(j);
+  const double* uj = P.u + r * stride + 3 * static_cast<size_t>(j);
+  double* out = P.x + r * stride + 3 * static_cast<size_t>(j);
+  out[0] = uj[0] - (d[0] * s0 + d[1] * s1 + d[2] * s2);
+  out[1] = uj[1] - (d[3] * s0 + d[4] * s1 + d[5] * s2);
+  out[2] = uj[2] - (d[6] * s0 + d[7] * s1 + d[8] * s2);
+}
+
+__device__ void phase_backward(const Params& P, int l, int nrhs, size_t stride, double* scratch) {
+  const int lane = threadIdx.x & 31;
   const int n_cols = P.level_ptr[l + 1] - P.level_ptr[l];
-  for (int w = warp; w < n_cols * nrhs; w += nwarps) {
+  const int n_items = n_cols * nrhs;
+  const bool cta_mode = n_items <= static_cast<int>(gridDim.x);
+  const int group = cta_mode ? blockDim.x : 32;
+  const int gid = cta_mode ? blockIdx.x : ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  const int n_groups = cta_mode ? gridDim.x : ((gridDim.x * blockDim.x) >> 5);
+  const int rank = cta_mode ? threadIdx.x : lane;
+  for (int w = gid; w < n_items; w += n_groups) {
     const int j = P.level_cols[P.level_ptr[l] + w % n_cols], r = w / n_cols;
     const double* xx = P.x + r * stride;
     double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-    for (int t = P.col_ptr[j] + 1 + lane; t < P.col_ptr[j + 1]; t += 32) {
+    for (int t = P.col_ptr[j] + 1 + rank; t < P.col_ptr[j + 1]; t += group) {
       const double* m = P.M + 9 * static_cast<size_t>(t);
       const double* v = xx + 3 * static_cast<size_t>(P.row_idx[t]);
       const double v0 = v[0], v1 = v[1], v2 = v[2];
@@ -393,13 +436,26 @@ __device__ void phase_backward(const Params& P, int l, int nrhs, size_t stride) 
       s1 += __shfl_down_sync(0xffffffffu, s1, o);
       s2 += __shfl_down_sync(0xffffffffu, s2, o);
     }
-    if (lane == 0) {
-      const double* d = P.Dinv + 9 * static_cast<size_t>(j);
-      const double* uj = P.u + r * stride + 3 * static_cast<size_t>(j);
-      double* out = P.x + r * stride + 3 * static_cast<size_t>(j);
-      out[0] = uj[0] - (d[0] * s0 + d[1] * s1 + d[2] * s2);
-      out[1] = uj[1] - (d[3] * s0 + d[4] * s1 + d[5] * s2);
-      out[2] = uj[2] - (d[6] * s0 + d[7] * s1 + d[8] * s2);
+    if (!cta_mode) {
+      if (lane == 0) backward_store(P, j, r, stride, s0, s1, s2);
+    } else {
+      const int warp = threadIdx.x >> 5, n_warps = (blockDim.x + 31) >> 5;
+      if (lane == 0) {
+        scratch[3 * warp] = s0;
+        scratch[3 * warp + 1] = s1;
+        scratch[3 * warp + 2] = s2;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        double t0 = 0.0, t1 = 0.0, t2 = 0.0;
+        for (int q = 0; q < n_warps; ++q) {
+          t0 += scratch[3 * q];
+          t1 += scratch[3 * q + 1];
+          t2 += scratch[3 * q + 2];
+        }
+        backward_store(P, j, r, stride, t0, t1, t2);
+      }
+      __syncthreads();
     }
   }
 }
@@ -407,11 +463,20 @@ __device__ void phase_backward(const Params& P, int l, int nrhs, size_t stride) 
 // ---- the persistent kernels ----------------------------------------------------------------------
 const int kThreads = 256;
 
+__device__ __forceinline__ void stamp(const Params& P, int k) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    P.stamps[k] = t;
+  }
+}
+
 __global__ void __launch_bounds__(kThreads) gn_iterations(Params P, int n_iters) {
   cg::grid_group grid = cg::this_grid();
   __shared__ double scratch[32];
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
   for (int it = 0; it < n_iters; ++it) {
+    stamp(P, 0);
     // zero the factor storage (fill positions must start at 0)
     for (long long i = tid; i < P.nnzb * 9; i += nthreads) P.M[i] = 0.0;
     grid.sync();
@@ -425,19 +490,25 @@ __global__ void __launch_bounds__(kThreads) gn_iterations(Params P, int n_iters)
     }
     phase_leaves(P);
     grid.sync();
+    stamp(P, 1);
     for (int l = 1; l < P.n_levels; ++l) {
       phase_updates(P, l);
       grid.sync();
     }
     if (*reinterpret_cast<volatile int*>(P.status) != 0) return;  // uniform: read after a barrier
-    for (int l = 0; l < P.n_levels; ++l) {
+    stamp(P, 2);
+    phase_forward_leaves(P, 1, P.rhs, 0);
+    grid.sync();
+    for (int l = 1; l < P.n_levels; ++l) {
       phase_forward(P, l, 1, P.rhs, 0);
       grid.sync();
     }
+    stamp(P, 3);
     for (int l = P.n_levels - 1; l >= 0; --l) {
-      phase_backward(P, l, 1, 0);
+      phase_backward(P, l, 1, 0, scratch);
       grid.sync();
     }
+    stamp(P, 4);
     // VertexSE2::oplusImpl (C3)
     for (int p = tid; p < P.n; p += nthreads) {
       const int v = P.perm_vertex[p];
@@ -448,19 +519,23 @@ __global__ void __launch_bounds__(kThreads) gn_iterations(Params P, int n_iters)
     }
     if (tid == 0) P.status[1] = it + 1;
     grid.sync();
+    stamp(P, 5);
   }
 }
 
 // H X = E for nrhs right-hand sides already placed in P.rhs-like storage `rhs` ([nrhs][n][3]).
-__global__ void __launch_bounds__(kThreads) solve_many(Params P, const double* rhs, int nrhs) {
+__global__ void __launch_bounds__(kThreads) solve_many(Params P, double* rhs, int nrhs) {
   cg::grid_group grid = cg::this_grid();
+  __shared__ double scratch[32];
   const size_t stride = 3 * static_cast<size_t>(P.n);
-  for (int l = 0; l < P.n_levels; ++l) {
+  phase_forward_leaves(P, nrhs, rhs, stride);
+  grid.sync();
+  for (int l = 1; l < P.n_levels; ++l) {
     phase_forward(P, l, nrhs, rhs, stride);
     grid.sync();
   }
   for (int l = P.n_levels - 1; l >= 0; --l) {
-    phase_backward(P, l, nrhs, stride);
+    phase_backward(P, l, nrhs, stride, scratch);
     grid.sync();
   }
 }
@@ -623,6 +698,10 @@ struct DeviceSolver {
       level_ptr, level_cols, phase_ptr, perm_vertex, status, scratch_i;
   Buf<Incidence> inc;
   Buf<UpdateOp> ops;
+  Buf<SolveOp> fwd_ops;
+  Buf<int> fwd_ptr;
+  Buf<unsigned long long> stamps;
+  double stage_ms[5] = {0, 0, 0, 0, 0};
   Buf<double> poses, meas, info6, M, Dinv, rhs, u, x, chi2_partial, chi2_out, many_rhs, scratch_d;
   size_t vec_cap = 0;  // right-hand sides u/x can hold
 };
@@ -662,6 +741,7 @@ int dev_create(DeviceSolver** out, int device, void* stream, std::string* err) {
   if (e == cudaSuccess) e = cudaEventCreate(&d->ev0);
   if (e == cudaSuccess) e = cudaEventCreate(&d->ev1);
   if (e == cudaSuccess) e = d->status.reserve(4);
+  if (e == cudaSuccess) e = d->stamps.reserve(8);
   if (e == cudaSuccess) e = d->chi2_partial.reserve(d->grid);
   if (e != cudaSuccess) {
     if (err) *err = std::string("pgo dev_create: ") + cudaGetErrorString(e);
@@ -685,6 +765,9 @@ void dev_destroy(DeviceSolver* d) {
   for (size_t i = 0; i < sizeof(db) / sizeof(db[0]); ++i) db[i]->release();
   d->inc.release();
   d->ops.release();
+  d->fwd_ops.release();
+  d->fwd_ptr.release();
+  d->stamps.release();
   if (d->ev0) cudaEventDestroy(d->ev0);
   if (d->ev1) cudaEventDestroy(d->ev1);
   if (d->own_stream && d->stream) cudaStreamDestroy(d->stream);
@@ -693,6 +776,7 @@ void dev_destroy(DeviceSolver* d) {
 
 void* dev_stream(const DeviceSolver* d) { return d->stream; }
 uint64_t dev_launches(const DeviceSolver* d) { return d->launches; }
+const double* dev_stage_ms(const DeviceSolver* d) { return d->stage_ms; }
 
 int dev_set_structure(DeviceSolver* d, const Symbolic& S, const GraphTables& G, std::string* err) {
   PGO_CUDA(cudaSetDevice(d->device));
@@ -713,6 +797,8 @@ int dev_set_structure(DeviceSolver* d, const Symbolic& S, const GraphTables& G, 
   PGO_CUDA(d->level_cols.upload(S.level_cols, s));
   PGO_CUDA(d->phase_ptr.upload(S.phase_ptr, s));
   PGO_CUDA(d->ops.upload(S.ops, s));
+  PGO_CUDA(d->fwd_ops.upload(S.fwd_ops, s));
+  PGO_CUDA(d->fwd_ptr.upload(S.fwd_ptr, s));
   std::vector<int> perm_vertex(S.n);
   for (int v = 0; v < G.n_vertices; ++v)
     if (G.vpos[v] >= 0) perm_vertex[G.vpos[v]] = v;
@@ -752,6 +838,8 @@ int dev_set_structure(DeviceSolver* d, const Symbolic& S, const GraphTables& G, 
   P.level_cols = d->level_cols.p;
   P.phase_ptr = d->phase_ptr.p;
   P.ops = d->ops.p;
+  P.fwd_ptr = d->fwd_ptr.p;
+  P.fwd_ops = d->fwd_ops.p;
   P.perm_vertex = d->perm_vertex.p;
   P.M = d->M.p;
   P.Dinv = d->Dinv.p;
@@ -761,6 +849,7 @@ int dev_set_structure(DeviceSolver* d, const Symbolic& S, const GraphTables& G, 
   P.chi2_partial = d->chi2_partial.p;
   P.chi2_out = nullptr;
   P.status = d->status.p;
+  P.stamps = d->stamps.p;
   d->have_structure = true;
   return PGO_OK;
 }
@@ -837,7 +926,10 @@ int dev_iterate(DeviceSolver* d, int n_iters, double* chi2_out, int* iters_done,
   if (chi2_out)
     PGO_CUDA(cudaMemcpyAsync(chi2_out, d->chi2_out.p, n_iters * sizeof(double),
                              cudaMemcpyDeviceToHost, d->stream));
+  unsigned long long st[6] = {0, 0, 0, 0, 0, 0};
+  PGO_CUDA(cudaMemcpyAsync(st, d->stamps.p, sizeof st, cudaMemcpyDeviceToHost, d->stream));
   PGO_CUDA(cudaStreamSynchronize(d->stream));
+  for (int k = 0; k < 5; ++k) d->stage_ms[k] = st[k + 1] > st[k] ? (st[k + 1] - st[k]) * 1e-6 : 0.0;
   PGO_CUDA(cudaEventElapsedTime(ms, d->ev0, d->ev1));
   *iters_done = status[1];
   d->have_factor = status[1] > 0;
@@ -913,7 +1005,7 @@ int dev_marginals(DeviceSolver* d, int n, const int* col_p, const int* row_p, do
     PGO_CUDA(cudaMemsetAsync(d->many_rhs.p, 0, 3 * nc * stride * sizeof(double), d->stream));
     set_unit_rhs<<<(3 * nc + 127) / 128, 128, 0, d->stream>>>(d->many_rhs.p, stride, d_cols, nc);
     Params P = d->P;
-    const double* rhs = d->many_rhs.p;
+    double* rhs = d->many_rhs.p;
     int nrhs = 3 * nc;
     void* args[] = {&P, &rhs, &nrhs};
     PGO_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(solve_many), dim3(d->grid),

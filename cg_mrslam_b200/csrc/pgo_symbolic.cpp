@@ -383,6 +383,45 @@ bool analyse(int n, const std::vector<std::pair<int, int> >& edges, int ordering
       if (err) *err = "internal: column without finalising update";
       return false;
     }
+  // ---- forward-substitution schedule ------------------------------------------------------------
+  {
+    S.fwd_ptr.assign(S.n_levels + 1, 0);
+    S.fwd_ops.resize(S.nnzb - n);
+    std::vector<int> cnt(n, 0), rows_touched;
+    int64_t cursor = 0;
+    for (int l = 1; l < S.n_levels; ++l) {
+      S.fwd_ptr[l] = static_cast<int>(cursor);
+      rows_touched.clear();
+      for (int t = S.level_ptr[l - 1]; t < S.level_ptr[l]; ++t) {
+        const int k = S.level_cols[t];
+        for (int w = S.col_ptr[k] + 1; w < S.col_ptr[k + 1]; ++w)
+          if (cnt[S.row_idx[w]]++ == 0) rows_touched.push_back(S.row_idx[w]);
+      }
+      std::sort(rows_touched.begin(), rows_touched.end());
+      int64_t off = cursor;
+      for (size_t i = 0; i < rows_touched.size(); ++i) {
+        const int r = rows_touched[i];
+        const int c = cnt[r];
+        cnt[r] = static_cast<int>(off);
+        off += c;
+      }
+      for (int t = S.level_ptr[l - 1]; t < S.level_ptr[l]; ++t) {
+        const int k = S.level_cols[t];
+        for (int w = S.col_ptr[k] + 1; w < S.col_ptr[k + 1]; ++w) {
+          const int r = S.row_idx[w];
+          SolveOp o = {S.level[r] == l ? (r | kFinalFlag) : r, w};
+          S.fwd_ops[cnt[r]++] = o;
+        }
+      }
+      for (size_t i = 0; i < rows_touched.size(); ++i) cnt[rows_touched[i]] = 0;
+      cursor = off;
+    }
+    S.fwd_ptr[S.n_levels] = static_cast<int>(cursor);
+    if (cursor != S.nnzb - n) {
+      if (err) *err = "internal: forward schedule count mismatch";
+      return false;
+    }
+  }
   S.analyse_seconds =
       std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   return true;

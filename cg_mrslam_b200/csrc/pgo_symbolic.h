@@ -29,6 +29,11 @@ struct UpdateOp {
 };
 static const int kFinalFlag = 0x40000000;
 
+struct SolveOp {
+  int row;  // target block row | kFinalFlag
+  int pos;  // position of M(row, k)
+};
+
 struct Symbolic {
   int n = 0;                    // free (non-fixed) vertices = block rows of H
   std::vector<int> perm;        // perm[p] = hessian index eliminated p-th
@@ -49,6 +54,11 @@ struct Symbolic {
   // update schedule: phase l (1 <= l < n_levels) applies ops [phase_ptr[l], phase_ptr[l+1])
   std::vector<int> phase_ptr;   // n_levels + 1 (phase 0 is empty)
   std::vector<UpdateOp> ops;
+  // forward-substitution schedule, same idea: phase l applies  z(i) -= M(i,k) u(k)  for every
+  // off-diagonal block of the columns k of level l - 1, sorted by target row i; kFinalFlag marks
+  // the runs after which row i (of level l) is complete
+  std::vector<int> fwd_ptr;     // n_levels + 1
+  std::vector<SolveOp> fwd_ops;
   // statistics
   int64_t nnzb = 0, n_ops = 0;
   int max_run = 0;              // longest run of updates sharing one target within a phase

@@ -19,7 +19,8 @@ class pgo_stats(C.Structure):
     _fields_ = [("n_vertices", C.c_int32), ("n_edges", C.c_int32), ("n_free", C.c_int32),
                 ("n_levels", C.c_int32), ("factor_blocks", C.c_int64), ("update_ops", C.c_int64),
                 ("hessian_blocks", C.c_int64), ("analyse_seconds", C.c_double),
-                ("last_iterate_ms", C.c_double), ("kernel_launches", C.c_int64)]
+                ("last_iterate_ms", C.c_double), ("kernel_launches", C.c_int64),
+                ("stage_ms", C.c_double * 5)]
 
 
 class SolverError(RuntimeError):
@@ -157,7 +158,10 @@ class Solver:
     def stats(self):
         s = pgo_stats()
         self._check(self.lib.pgo_get_stats(self.h, C.byref(s)))
-        return {k: getattr(s, k) for k, _ in pgo_stats._fields_}
+        d = {k: getattr(s, k) for k, _ in pgo_stats._fields_}
+        d["stage_ms"] = dict(zip(("linearise", "factor", "forward", "backward", "update"),
+                                 list(s.stage_ms)))
+        return d
 
     def stream(self):
         return self.lib.pgo_stream(self.h)

@@ -47,6 +47,7 @@ typedef struct pgo_stats {
   double analyse_seconds;                /* host time of the structure analysis                  */
   double last_iterate_ms;                /* device time of the last pgo_iterate call             */
   int64_t kernel_launches;               /* kernels launched by this solver so far               */
+  double stage_ms[5];                    /* last GN iteration: linearise, factor, forward, backward, update */
 } pgo_stats;
 
 const char* pgo_last_error(void);
