@@ -1,0 +1,201 @@
+// Test driver for the C++ host mirrors (include/cgm/*.hpp, include/g2o_compat/g2o_compat.hpp).
+// Reads a scenario file, runs it through the reference-shaped API (SparseOptimizer, VertexSE2,
+// EdgeSE2, RobotLaser, ScanMatcher, EdgeLabeler) and prints results with 17 significant digits;
+// tests/test_cpp_compat.py compares them with the CPU oracles.
+//
+//   V id x y th fixed n_beams first_angle step max_range r_1 ... r_n     vertex + its scan
+//   E i j dx dy dth I11 I12 I13 I22 I23 I33                              EdgeSE2
+//   OPT n                                            initializeOptimization(); optimize(n)
+//   POSES                                            print all estimates
+//   CLOSE origin current max_score k id_1 ... id_k   closeScanMatching on the close matcher
+//   LC reference current max_score k id_1 ... id_k   scanMatchingLC on the LC matcher
+//   GLOBAL reference current max_score k id_1..id_k  globalMatching on the LC matcher
+//   MARG k id_1 ... id_k                             computeMarginals diagonal blocks
+//   STAR gauge k id_1 ... id_k                       CondensedGraphCreator::compute pattern
+//   SAVE path / LOAD path                            g2o text round trip
+#include <cstdio>
+#include <fstream>
+#include <iostream>
+#include <sstream>
+
+#include "cgm/scan_matcher.hpp"
+#include "g2o_compat/g2o_compat.hpp"
+
+using namespace g2o;
+
+int main(int argc, char** argv) {
+  if (argc < 2) return 2;
+  std::ifstream f(argv[1]);
+  if (!f) return 2;
+  SparseOptimizer opt;
+  // the reference's construction idiom (graph_slam.cpp:44-55) must keep compiling
+  typedef BlockSolver<BlockSolverTraits<-1, -1> > SlamBlockSolver;
+  typedef LinearSolverCSparse<SlamBlockSolver::PoseMatrixType> SlamLinearSolver;
+  auto linearSolver = std::unique_ptr<SlamLinearSolver>(new SlamLinearSolver());
+  linearSolver->setBlockOrdering(false);
+  auto blockSolver = std::unique_ptr<SlamBlockSolver>(new SlamBlockSolver(std::move(linearSolver)));
+  opt.setAlgorithm(new OptimizationAlgorithmGaussNewton(std::move(blockSolver)));
+  opt.setVerbose(false);
+
+  ScanMatcher closeMatcher, lcMatcher;
+  bool matchers_ready = false;
+  auto ready = [&]() {
+    if (matchers_ready) return;
+    closeMatcher.initializeKernel(0.025, 0.2);  // graph_slam.cpp:59-62
+    closeMatcher.initializeGrid(Eigen::Vector2f(-15, -15), Eigen::Vector2f(15, 15), 0.025);
+    lcMatcher.initializeKernel(0.1, 0.5);
+    lcMatcher.initializeGrid(Eigen::Vector2f(-35, -35), Eigen::Vector2f(35, 35), 0.1);
+    matchers_ready = true;
+  };
+  std::string line, tag;
+  printf("BEGIN\n");
+  while (std::getline(f, line)) {
+    std::istringstream ss(line);
+    if (!(ss >> tag)) continue;
+    if (tag == "V") {
+      int id, fixed, nb;
+      double x, y, th, first, step, maxr;
+      ss >> id >> x >> y >> th >> fixed >> nb >> first >> step >> maxr;
+      VertexSE2* v = new VertexSE2();
+      v->setId(id);
+      v->setEstimate(SE2(x, y, th));
+      v->setFixed(fixed != 0);
+      if (nb > 0) {
+        std::vector<double> r(nb);
+        for (int i = 0; i < nb; ++i) ss >> r[i];
+        RobotLaser* rl = new RobotLaser();
+        LaserParameters lp(0, nb, first, step, maxr, 0.1, 0);
+        lp.laserPose = SE2(0.05, 0.0, 0.0);
+        rl->setLaserParams(lp);
+        rl->setRanges(r);
+        v->setUserData(rl);
+      }
+      opt.addVertex(v);
+    } else if (tag == "E") {
+      int a, b;
+      double x, y, th, w[6];
+      ss >> a >> b >> x >> y >> th;
+      for (int k = 0; k < 6; ++k) ss >> w[k];
+      EdgeSE2* e = new EdgeSE2();
+      e->vertices()[0] = opt.vertex(a);
+      e->vertices()[1] = opt.vertex(b);
+      e->setMeasurement(SE2(x, y, th));
+      Eigen::Matrix3d m;
+      m(0, 0) = w[0]; m(0, 1) = m(1, 0) = w[1]; m(0, 2) = m(2, 0) = w[2];
+      m(1, 1) = w[3]; m(1, 2) = m(2, 1) = w[4]; m(2, 2) = w[5];
+      e->setInformation(m);
+      opt.addEdge(e);
+    } else if (tag == "OPT") {
+      int n;
+      ss >> n;
+      opt.initializeOptimization();
+      printf("OPT %d\n", opt.optimize(n));
+    } else if (tag == "POSES") {
+      for (auto& kv : opt.vertices()) {
+        const VertexSE2* v = static_cast<const VertexSE2*>(kv.second);
+        printf("P %d %.17g %.17g %.17g\n", v->id(), v->estimate().translation().x(),
+               v->estimate().translation().y(), v->estimate().rotation().angle());
+      }
+    } else if (tag == "CLOSE" || tag == "LC" || tag == "GLOBAL") {
+      ready();
+      int ref, cur, k;
+      double max_score;
+      ss >> ref >> cur >> max_score >> k;
+      OptimizableGraph::VertexSet vset;
+      for (int i = 0; i < k; ++i) {
+        int id;
+        ss >> id;
+        vset.insert(opt.vertex(id));
+      }
+      if (tag == "CLOSE") {
+        SE2 t;
+        const bool ok = closeMatcher.closeScanMatching(vset, opt.vertex(ref), opt.vertex(cur), &t, max_score);
+        printf("CLOSE %d %.17g %.17g %.17g\n", ok ? 1 : 0, t.translation().x(), t.translation().y(),
+               t.rotation().angle());
+      } else if (tag == "LC") {
+        std::vector<SE2> ts;
+        const bool ok = lcMatcher.scanMatchingLC(vset, opt.vertex(ref), opt.vertex(cur), ts, max_score);
+        printf("LC %d %d\n", ok ? 1 : 0, static_cast<int>(ts.size()));
+        for (auto& t : ts)
+          printf("T %.17g %.17g %.17g\n", t.translation().x(), t.translation().y(), t.rotation().angle());
+      } else {
+        SE2 t;
+        const bool ok = lcMatcher.globalMatching(vset, opt.vertex(ref), opt.vertex(cur), &t, max_score);
+        printf("GLOBAL %d %.17g %.17g %.17g\n", ok ? 1 : 0, t.translation().x(), t.translation().y(),
+               t.rotation().angle());
+      }
+    } else if (tag == "MARG") {
+      int k;
+      ss >> k;
+      std::vector<std::pair<int, int> > idx;
+      for (int i = 0; i < k; ++i) {
+        int id;
+        ss >> id;
+        const int h = opt.vertex(id)->hessianIndex();
+        idx.push_back(std::make_pair(h, h));
+      }
+      SparseBlockMatrix<Eigen::MatrixXd> spinv;
+      const bool ok = opt.computeMarginals(spinv, idx);
+      printf("MARG %d\n", ok ? 1 : 0);
+      for (auto& p : idx) {
+        Eigen::MatrixXd* b = spinv.block(p.first, p.second);
+        printf("M");
+        for (int i = 0; i < 3; ++i)
+          for (int j = 0; j < 3; ++j) printf(" %.17g", b ? (*b)(i, j) : 0.0);
+        printf("\n");
+      }
+    } else if (tag == "STAR") {
+      // GraphManipulator::pushState/fixGauge/optimize + CondensedGraphCreator::compute
+      // (graph_manipulator.cpp:62-124, condensed_graph_creator.cpp:33-66)
+      int gauge, k;
+      ss >> gauge >> k;
+      std::vector<int> ids(k);
+      for (int i = 0; i < k; ++i) ss >> ids[i];
+      std::vector<bool> was_fixed;
+      for (auto& kv : opt.vertices()) {
+        OptimizableGraph::Vertex* v = static_cast<OptimizableGraph::Vertex*>(kv.second);
+        v->push();
+        was_fixed.push_back(v->fixed());
+        v->setFixed(v->id() == gauge);
+      }
+      HyperGraph::EdgeSet es = opt.edges();
+      opt.initializeOptimization(es);
+      opt.computeInitialGuess();
+      const int done = opt.optimize(1);
+      std::set<OptimizableGraph::Edge*> star;
+      std::vector<EdgeSE2*> order;
+      for (int id : ids) {
+        if (id == gauge) continue;
+        EdgeSE2* e = new EdgeSE2();
+        e->vertices()[0] = opt.vertex(gauge);
+        e->vertices()[1] = opt.vertex(id);
+        e->setSerial(1000000 + static_cast<long long>(order.size()));
+        star.insert(e);
+        order.push_back(e);
+      }
+      EdgeLabeler labeler(&opt);
+      const int labelled = labeler.labelEdges(star);
+      printf("STAR %d %d\n", done, labelled);
+      for (EdgeSE2* e : order) {
+        printf("S %d %.17g %.17g %.17g", e->vertex(1)->id(), e->measurement().translation().x(),
+               e->measurement().translation().y(), e->measurement().rotation().angle());
+        for (int i = 0; i < 3; ++i)
+          for (int j = 0; j < 3; ++j) printf(" %.17g", e->information()(i, j));
+        printf("\n");
+        delete e;
+      }
+      size_t q = 0;
+      for (auto& kv : opt.vertices()) {
+        OptimizableGraph::Vertex* v = static_cast<OptimizableGraph::Vertex*>(kv.second);
+        v->pop();
+        v->setFixed(was_fixed[q++]);
+      }
+    } else if (tag == "SAVE") {
+      std::string path;
+      ss >> path;
+      printf("SAVE %d\n", opt.save(path.c_str()) ? 1 : 0);
+    }
+  }
+  printf("END\n");
+  return 0;
+}

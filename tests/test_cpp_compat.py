@@ -1,0 +1,184 @@
+"""The C++ host mirrors of the reference API (include/cgm/scan_matcher.hpp, chargrid.hpp,
+include/g2o_compat/g2o_compat.hpp): they compile against the C ABI, keep the reference's
+construction idiom, and -- on the GPU -- reproduce the oracles through SparseOptimizer::optimize,
+computeMarginals, EdgeLabeler::labelEdges and ScanMatcher::closeScanMatching / scanMatchingLC /
+globalMatching."""
+import math
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from cg_mrslam_b200 import synth
+from oracle import pgo_oracle as po
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIBDIR = os.path.join(ROOT, "cg_mrslam_b200", "lib")
+LASER_POSE = (0.05, 0.0, 0.0)
+
+
+@pytest.fixture(scope="module")
+def driver(tmp_path_factory):
+    import __graft_entry__ as g
+    if not os.path.exists(os.path.join(LIBDIR, "libcgmrslam_b200.so")):
+        g.build()
+    exe = str(tmp_path_factory.mktemp("cpp") / "compat_driver")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O1", "-Wall", "-Werror",
+                           "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "compat_driver.cpp"), "-o", exe,
+                           "-L" + LIBDIR, "-lcgmrslam_b200", "-Wl,-rpath," + LIBDIR])
+    return exe
+
+
+def _scenario(n=14, seed=4):
+    """Keyframes along a short path in a synthetic room, with scans and a small pose graph."""
+    rng = np.random.default_rng(seed)
+    vert, horiz, size, boxes = synth._room_segments(rng)
+    x0, y0 = synth._free_pose(rng, size, boxes, margin=1.5)
+    truth = []
+    th = rng.uniform(-math.pi, math.pi)
+    x, y = x0, y0
+    for k in range(n):
+        truth.append((x, y, th))
+        th += rng.uniform(-0.25, 0.25)
+        nx, ny = x + 0.25 * math.cos(th), y + 0.25 * math.sin(th)
+        if 1.0 < nx < size[0] - 1.0 and 1.0 < ny < size[1] - 1.0 and all(
+                not (b[0] - 0.6 < nx < b[2] + 0.6 and b[1] - 0.6 < ny < b[3] + 0.6) for b in boxes):
+            x, y = nx, ny
+        else:
+            th += math.pi / 2
+    truth = np.array(truth)
+    truth[:, 2] = po.normalize_theta(truth[:, 2])
+    first, step, max_range, nb = -math.pi / 2, math.pi / 360, 8.0, 361
+    verts = []
+    for k in range(n):
+        lp = po.se2_mul(truth[k], np.array(LASER_POSE))[0]
+        r = synth.cast_scan(vert, horiz, lp, nb, first, step, max_range, 0.01, rng)
+        pose = truth[k] + rng.normal(0, [0.03, 0.03, 0.01])
+        pose[2] = po.normalize_theta(np.array([pose[2]]))[0]
+        verts.append(dict(id=100 + 3 * k, pose=pose if k else truth[0].copy(), ranges=r,
+                          first_angle=first, step=step, max_range=max_range,
+                          laser_pose=LASER_POSE, fixed=(k == 0)))
+    edges = []
+    pairs = [(k, k + 1) for k in range(n - 1)] + [q for q in [(0, 5), (2, 9), (4, 12), (1, 13)] if q[1] < n]
+    for a, b in pairs:
+        rel = po.se2_mul(po.se2_inv(truth[a]), truth[b])[0]
+        z = po.se2_mul(rel, rng.normal(0, [0.01, 0.01, 0.003]))[0]
+        w = (1000.0, 0.0, 0.0, 1000.0, 0.0, 10000.0) if b != a + 1 else (100.0, 0, 0, 100.0, 0, 1000.0)
+        edges.append((a, b, z, w))
+    return verts, edges
+
+
+def _write(path, verts, edges, commands):
+    with open(path, "w") as f:
+        for v in verts:
+            f.write("V %d %.17g %.17g %.17g %d %d %.17g %.17g %.17g %s\n" % (
+                v["id"], v["pose"][0], v["pose"][1], v["pose"][2], 1 if v["fixed"] else 0,
+                len(v["ranges"]), v["first_angle"], v["step"], v["max_range"],
+                " ".join("%.17g" % r for r in v["ranges"])))
+        for a, b, z, w in edges:
+            f.write("E %d %d %.17g %.17g %.17g %s\n" % (
+                verts[a]["id"], verts[b]["id"], z[0], z[1], z[2], " ".join("%.17g" % x for x in w)))
+        for c in commands:
+            f.write(c + "\n")
+
+
+def _run(exe, path):
+    out = subprocess.run([exe, path], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    lines = out.stdout.splitlines()
+    assert "BEGIN" in lines and lines[-1] == "END", out.stdout[-2000:]
+    return lines[lines.index("BEGIN") + 1:-1], out.stderr
+
+
+def test_graph_bookkeeping_and_text_format(driver, tmp_path):
+    verts, edges = _scenario()
+    g2o_path = str(tmp_path / "out.g2o")
+    path = str(tmp_path / "s.txt")
+    _write(path, verts, edges, ["POSES", "SAVE " + g2o_path])
+    lines, _ = _run(driver, path)
+    poses = np.array([[float(x) for x in ln.split()[2:]] for ln in lines if ln.startswith("P ")])
+    assert np.array_equal(poses, np.array([v["pose"] for v in verts]))   # id order == input order
+    assert "SAVE 1" in lines
+    g = po.read_g2o(g2o_path)
+    assert list(g["ids"]) == [v["id"] for v in verts] and list(g["fixed"]) == [0]
+    assert np.array_equal(g["poses"], np.array([v["pose"] for v in verts]))
+    assert np.array_equal(g["meas"], np.array([e[2] for e in edges]))
+    assert np.array_equal(g["edge_ij"], np.array([[e[0], e[1]] for e in edges]))
+
+
+def test_compute_calls_fail_loudly_without_gpu(driver, tmp_path):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    verts, edges = _scenario(6)
+    path = str(tmp_path / "s.txt")
+    _write(path, verts, edges, ["OPT 3"])
+    lines, err = _run(driver, path)
+    assert "OPT 0" in lines and "SparseOptimizer" in err   # reported, not silently computed
+
+
+@pytest.mark.gpu
+def test_cpp_api_matches_oracles(driver, tmp_path, oracle_lib):
+    from oracle import bindings
+    from oracle import scan_matcher_oracle as smo
+    lib = bindings.MatcherLib("reference") if bindings.have_reference() else oracle_lib
+    verts, edges = _scenario()
+    ids = [v["id"] for v in verts]
+    cmds = ["CLOSE %d %d 0.2 6 %s" % (ids[5], ids[6], " ".join(str(i) for i in ids[0:6])),
+            "LC %d %d 0.3 5 %s" % (ids[2], ids[11], " ".join(str(i) for i in ids[0:5])),
+            "GLOBAL %d %d 0.3 4 %s" % (ids[1], ids[10], " ".join(str(i) for i in ids[0:4])),
+            "OPT 5", "POSES",
+            "MARG 3 %d %d %d" % (ids[3], ids[7], ids[13]),
+            "STAR %d 4 %d %d %d %d" % (ids[6], ids[2], ids[6], ids[9], ids[13]),
+            "POSES"]
+    path = str(tmp_path / "s.txt")
+    _write(path, verts, edges, cmds)
+    lines, _ = _run(driver, path)
+
+    # --- matcher front half + GPU search vs the CPU matcher -------------------------------------
+    ok, want = smo.close_scan_matching(lib, oracle_lib, verts[0:6], verts[5], verts[6], 0.2)
+    got = [ln for ln in lines if ln.startswith("CLOSE")][0].split()
+    assert int(got[1]) == int(ok)
+    if ok:
+        assert np.array_equal(np.array([float(x) for x in got[2:]]), want)
+    want_lc = smo.scan_matching_lc(lib, oracle_lib, verts[0:5], verts[2], verts[11], 0.3)
+    k = [i for i, ln in enumerate(lines) if ln.startswith("LC ")][0]
+    n_lc = int(lines[k].split()[2])
+    got_lc = [np.array([float(x) for x in lines[k + 1 + t].split()[1:]]) for t in range(n_lc)]
+    assert n_lc == len(want_lc)
+    for a, b in zip(got_lc, want_lc):
+        assert np.array_equal(a, b)
+    okg, want_g = smo.global_matching(lib, oracle_lib, verts[0:4], verts[1], verts[10], 0.3)
+    got = [ln for ln in lines if ln.startswith("GLOBAL")][0].split()
+    assert int(got[1]) == int(okg)
+    if okg:
+        assert np.array_equal(np.array([float(x) for x in got[2:]]), want_g)
+
+    # --- optimize(5), marginals, condensed star vs the pose-graph oracle -------------------------
+    poses0 = np.array([v["pose"] for v in verts])
+    e_ij = np.array([[a, b] for a, b, _, _ in edges], dtype=np.int64)
+    meas = np.array([z for _, _, z, _ in edges])
+    info = np.array([w for _, _, _, w in edges], dtype=np.float64)
+    ref = po.gauss_newton(poses0, e_ij, meas, info, [0], 5)
+    assert "OPT 5" in lines
+    blocks = [i for i, ln in enumerate(lines) if ln.startswith("P ")]
+    first = np.array([[float(x) for x in lines[i].split()[2:]] for i in blocks[:len(verts)]])
+    d = first - ref.poses
+    d[:, 2] = po.normalize_theta(d[:, 2])
+    assert np.abs(d).max() < 1e-6
+    hidx = po.hessian_index(len(verts), [0])
+    want_m = po.marginals(ref, hidx, [(3, 3), (7, 7), (13, 13)])
+    got_m = np.array([[float(x) for x in ln.split()[1:]] for ln in lines if ln.startswith("M ")])
+    assert np.abs(got_m.reshape(-1, 3, 3) - want_m).max() < 1e-9 * max(1.0, np.abs(want_m).max())
+    z, om, vs = po.condensed_star(ref.poses, e_ij, meas, info, 6, [2, 6, 9, 13])
+    got_s = np.array([[float(x) for x in ln.split()[1:]] for ln in lines if ln.startswith("S ")])
+    assert [int(r[0]) for r in got_s] == [ids[v] for v in vs]
+    dz = got_s[:, 1:4] - z
+    dz[:, 2] = po.normalize_theta(dz[:, 2])
+    assert np.abs(dz).max() < 1e-6
+    assert np.abs(got_s[:, 4:].reshape(-1, 3, 3) - om).max() < 1e-6 * np.abs(om).max()
+    # push/pop around the condensed-graph computation restores the estimates
+    second = np.array([[float(x) for x in lines[i].split()[2:]] for i in blocks[len(verts):]])
+    assert np.array_equal(first, second)
