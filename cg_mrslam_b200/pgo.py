@@ -183,20 +183,3 @@ def condensed_star(solver_factory, poses, edge_ij, meas, info6, gauge, separator
     finally:
         s.close()
     return z, om, vs
-
-
-def smoke():
-    """One small GN solve on cuda:0 checked against the CPU oracle (test infrastructure)."""
-    from oracle import pgo_oracle as po
-    from . import synth
-    g = synth.make_pose_graph(400, 1600, seed=3, box=22.0)
-    s = Solver()
-    s.set_graph(len(g["poses0"]), g["edge_ij"], g["fixed"])
-    s.upload(g["poses0"], g["meas"], g["info"])
-    done, chi2, poses = s.optimize(5)
-    ref = po.gauss_newton(g["poses0"], g["edge_ij"], g["meas"], g["info"], g["fixed"], 5)
-    err = float(np.abs(poses - ref.poses).max())
-    assert done == 5 and err < 1e-6, (done, err)
-    print("smoke: pgo OK (5 GN iterations, max |pose - oracle| = %.2e, chi2 %.4f -> %.4f)" %
-          (err, chi2[0], chi2[-1]))
-    s.close()
