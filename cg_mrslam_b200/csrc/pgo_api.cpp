@@ -67,6 +67,7 @@ struct pgo_solver {
   std::vector<double> meas;  // host copy for the initial guess
   bool have_graph = false, have_values = false;
   double last_ms = 0.0;
+  int rank = 0, world = 1;
 };
 
 extern "C" {
@@ -120,7 +121,7 @@ int pgo_set_graph(pgo_solver* s, int n_vertices, int n_edges, const int32_t* edg
       free_edges.push_back(std::make_pair(s->hidx[i], s->hidx[j]));
   }
   std::string err;
-  if (!pgo::analyse(n, free_edges, 0, &s->sym, &err)) return fail(PGO_ERR_CAPACITY, err);
+  if (!pgo::analyse(n, free_edges, 0, s->world, &s->sym, &err)) return fail(PGO_ERR_CAPACITY, err);
   const pgo::Symbolic& S = s->sym;
 
   pgo::GraphTables& G = s->tables;
@@ -169,6 +170,7 @@ int pgo_set_graph(pgo_solver* s, int n_vertices, int n_edges, const int32_t* edg
     }
   }
   G.hessian_blocks = n + off_blocks;
+  G.rank = s->rank;
   const int rc = pgo::dev_set_structure(s->dev, S, G, &err);
   if (rc) return fail(rc, err);
   s->have_graph = true;
@@ -300,6 +302,103 @@ int pgo_label_star_edges(pgo_solver* s, int gauge, int n, const int32_t* v, doub
   std::string err;
   rc = pgo::dev_label_star(s->dev, gauge, n, v, cov.data(), meas_out, info_out, &err);
   return rc ? fail(rc, err) : PGO_OK;
+}
+
+int pgo_set_partition(pgo_solver* s, int rank, int world) {
+  if (!s || world < 1 || (world & (world - 1)) != 0 || rank < 0 || rank >= world)
+    return fail(PGO_ERR_ARG, "world must be a power of two and 0 <= rank < world");
+  s->rank = rank;
+  s->world = world;
+  s->have_graph = s->have_values = false;  // takes effect at the next pgo_set_graph
+  return PGO_OK;
+}
+
+int pgo_dd_begin(pgo_solver* s, int n_iters) {
+  if (!s || !s->have_values || n_iters < 0) return fail(PGO_ERR_ARG, "bad argument (pgo_upload first)");
+  std::string err;
+  const int rc = pgo::dev_dd_begin(s->dev, n_iters, &err);
+  return rc ? fail(rc, err) : PGO_OK;
+}
+
+int pgo_dd_local(pgo_solver* s) {
+  if (!s || !s->have_values) return fail(PGO_ERR_ARG, "bad argument (pgo_upload first)");
+  std::string err;
+  const int rc = pgo::dev_dd_local(s->dev, &err);
+  return rc ? fail(rc, err) : PGO_OK;
+}
+
+int pgo_dd_exchange_buffer(pgo_solver* s, void** dev_ptr, int64_t* n_doubles) {
+  if (!s || !s->have_graph || !dev_ptr || !n_doubles) return fail(PGO_ERR_ARG, "bad argument");
+  long long n = 0;
+  pgo::dev_dd_exchange(s->dev, dev_ptr, &n);
+  *n_doubles = n;
+  return PGO_OK;
+}
+
+int pgo_dd_shared(pgo_solver* s) {
+  if (!s || !s->have_values) return fail(PGO_ERR_ARG, "bad argument (pgo_upload first)");
+  std::string err;
+  const int rc = pgo::dev_dd_shared(s->dev, &err);
+  return rc ? fail(rc, err) : PGO_OK;
+}
+
+int pgo_dd_end(pgo_solver* s, int n_iters, double* chi2_out, int* iters_done) {
+  if (!s || !s->have_values) return fail(PGO_ERR_ARG, "bad argument (pgo_upload first)");
+  std::string err;
+  int done = 0;
+  float ms = 0.f;
+  const int rc = pgo::dev_dd_end(s->dev, n_iters, chi2_out, &done, &ms, &err);
+  s->last_ms = ms;
+  if (iters_done) *iters_done = done;
+  return rc ? fail(rc, err) : PGO_OK;
+}
+
+int pgo_dd_pose_exchange(pgo_solver* s, void** dev_ptr, int64_t* n_doubles) {
+  if (!s || !s->have_values || !dev_ptr || !n_doubles) return fail(PGO_ERR_ARG, "bad argument");
+  std::string err;
+  long long n = 0;
+  const int rc = pgo::dev_dd_pose_exchange(s->dev, dev_ptr, &n, &err);
+  *n_doubles = n;
+  return rc ? fail(rc, err) : PGO_OK;
+}
+
+int pgo_dd_pose_commit(pgo_solver* s) {
+  if (!s || !s->have_values) return fail(PGO_ERR_ARG, "bad argument");
+  std::string err;
+  const int rc = pgo::dev_dd_pose_commit(s->dev, &err);
+  return rc ? fail(rc, err) : PGO_OK;
+}
+
+int pgo_analyse_partition(int n_vertices, int n_edges, const int32_t* edge_i, const int32_t* edge_j,
+                          const uint8_t* fixed, int world, int32_t* vertex_owner, int64_t* stats) {
+  if (n_vertices <= 0 || n_edges < 0 || (n_edges && (!edge_i || !edge_j)) || !fixed || !vertex_owner)
+    return fail(PGO_ERR_ARG, "bad argument");
+  std::vector<int> hidx(n_vertices, -1);
+  int n = 0;
+  for (int v = 0; v < n_vertices; ++v)
+    if (!fixed[v]) hidx[v] = n++;
+  std::vector<std::pair<int, int> > free_edges;
+  for (int e = 0; e < n_edges; ++e) {
+    const int i = edge_i[e], j = edge_j[e];
+    if (i < 0 || i >= n_vertices || j < 0 || j >= n_vertices || i == j)
+      return fail(PGO_ERR_ARG, "bad edge");
+    if (hidx[i] >= 0 && hidx[j] >= 0) free_edges.push_back(std::make_pair(hidx[i], hidx[j]));
+  }
+  pgo::Symbolic S;
+  std::string err;
+  if (!pgo::analyse(n, free_edges, 0, world, &S, &err)) return fail(PGO_ERR_CAPACITY, err);
+  for (int v = 0; v < n_vertices; ++v)
+    vertex_owner[v] = hidx[v] < 0 ? -2 : S.owner[S.iperm[hidx[v]]];
+  if (stats) {
+    stats[0] = S.n - S.first_shared;
+    stats[1] = S.nnzb - (S.n > S.first_shared ? S.col_ptr[S.first_shared] : S.nnzb);
+    for (int r = 0; r <= world; ++r) stats[2 + r] = 0;
+    for (int p = 0; p < S.n; ++p) {
+      const int64_t m = S.col_ptr[p + 1] - S.col_ptr[p] - 1;
+      stats[2 + (S.owner[p] < 0 ? world : S.owner[p])] += m * (m + 1) / 2;
+    }
+  }
+  return PGO_OK;
 }
 
 int pgo_get_stats(const pgo_solver* s, pgo_stats* out) {

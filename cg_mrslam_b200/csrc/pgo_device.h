@@ -27,6 +27,7 @@ struct GraphTables {
   std::vector<Incidence> inc;
   std::vector<int> ff_edges;      // edges between two fixed vertices (chi2 only)
   int64_t hessian_blocks = 0;
+  int rank = 0;  // this process' rank in the domain decomposition (Symbolic::world ranks)
 };
 
 int dev_create(DeviceSolver** out, int device, void* stream, std::string* err);
@@ -47,6 +48,17 @@ int dev_get_poses(DeviceSolver* d, double* poses, std::string* err);
 // *iters_done < n_iters iff a diagonal block was not positive definite. *ms = device time.
 int dev_iterate(DeviceSolver* d, int n_iters, double* chi2_out, int* iters_done, float* ms,
                 std::string* err);
+// Domain-decomposed iteration (Symbolic::world > 1), all asynchronous on the solver's stream:
+//   begin; per iteration { local; <all-reduce(sum) of the exchange buffer by the caller>; shared };
+//   end (synchronises); then pose_exchange + <all-reduce> + pose_commit to assemble all estimates.
+int dev_dd_begin(DeviceSolver* d, int n_iters, std::string* err);
+int dev_dd_local(DeviceSolver* d, std::string* err);
+void dev_dd_exchange(DeviceSolver* d, void** ptr, long long* n_doubles);
+int dev_dd_shared(DeviceSolver* d, std::string* err);
+int dev_dd_end(DeviceSolver* d, int n_iters, double* chi2_out, int* iters_done, float* ms,
+               std::string* err);
+int dev_dd_pose_exchange(DeviceSolver* d, void** ptr, long long* n_doubles, std::string* err);
+int dev_dd_pose_commit(DeviceSolver* d, std::string* err);
 int dev_chi2(DeviceSolver* d, double* chi2, std::string* err);
 // Solve H X = E for nrhs unit-block right-hand sides (3 columns each) located at permuted block
 // columns cols[k]; returns for each k the full solution gathered at blocks rows[k] (3x3 row-major).

@@ -540,6 +540,8 @@ __global__ void __launch_bounds__(kThreads) solve_many(Params P, double* rhs, in
   }
 }
 
+#include "pgo_dd.cuh"
+
 __global__ void __launch_bounds__(kThreads) chi2_only(Params P) {
   __shared__ double scratch[32];
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
@@ -704,6 +706,12 @@ struct DeviceSolver {
   double stage_ms[5] = {0, 0, 0, 0, 0};
   Buf<double> poses, meas, info6, M, Dinv, rhs, u, x, chi2_partial, chi2_out, many_rhs, scratch_d;
   size_t vec_cap = 0;  // right-hand sides u/x can hold
+  // domain decomposition
+  DDParams D;
+  Buf<int> owner, xfinal_ptr, xfinal_cols;
+  Buf<double> pose_x;
+  long long exch_first = 0, exch_count = 0;  // doubles, relative to M
+  int dd_iter = 0;
 };
 
 int dev_create(DeviceSolver** out, int device, void* stream, std::string* err) {
@@ -768,6 +776,10 @@ void dev_destroy(DeviceSolver* d) {
   d->fwd_ops.release();
   d->fwd_ptr.release();
   d->stamps.release();
+  d->owner.release();
+  d->xfinal_ptr.release();
+  d->xfinal_cols.release();
+  d->pose_x.release();
   if (d->ev0) cudaEventDestroy(d->ev0);
   if (d->ev1) cudaEventDestroy(d->ev1);
   if (d->own_stream && d->stream) cudaStreamDestroy(d->stream);
@@ -806,7 +818,12 @@ int dev_set_structure(DeviceSolver* d, const Symbolic& S, const GraphTables& G, 
   PGO_CUDA(d->poses.reserve(3 * static_cast<size_t>(G.n_vertices)));
   PGO_CUDA(d->meas.reserve(3 * static_cast<size_t>(G.n_edges)));
   PGO_CUDA(d->info6.reserve(6 * static_cast<size_t>(G.n_edges)));
-  PGO_CUDA(d->M.reserve(9 * static_cast<size_t>(S.nnzb)));
+  const size_t n_shared = static_cast<size_t>(S.n - S.first_shared);
+  PGO_CUDA(d->M.reserve(9 * static_cast<size_t>(S.nnzb) + 3 * n_shared + 8));
+  PGO_CUDA(d->owner.upload(S.owner, s));
+  PGO_CUDA(d->xfinal_ptr.upload(S.xfinal_ptr, s));
+  PGO_CUDA(d->xfinal_cols.upload(S.xfinal_cols, s));
+  PGO_CUDA(d->pose_x.reserve(3 * static_cast<size_t>(G.n_vertices)));
   PGO_CUDA(d->Dinv.reserve(9 * static_cast<size_t>(S.n)));
   PGO_CUDA(d->rhs.reserve(3 * static_cast<size_t>(S.n)));
   PGO_CUDA(d->u.reserve(3 * static_cast<size_t>(S.n)));
@@ -850,6 +867,20 @@ int dev_set_structure(DeviceSolver* d, const Symbolic& S, const GraphTables& G, 
   P.chi2_out = nullptr;
   P.status = d->status.p;
   P.stamps = d->stamps.p;
+  DDParams& D = d->D;
+  D.owner = d->owner.p;
+  D.rank = G.rank;
+  D.world = S.world;
+  D.first_shared = S.first_shared;
+  D.local_levels = S.local_levels;
+  D.shared_min_level = S.shared_min_level;
+  D.xfinal_ptr = d->xfinal_ptr.p;
+  D.xfinal_cols = d->xfinal_cols.p;
+  D.tail = d->M.p + 9 * static_cast<size_t>(S.nnzb);
+  D.pose_x = d->pose_x.p;
+  d->exch_first = 9LL * (S.n > S.first_shared ? S.col_ptr[S.first_shared] : S.nnzb);
+  d->exch_count = 9LL * S.nnzb + 3LL * static_cast<long long>(n_shared) + 2 - d->exch_first;
+  d->dd_iter = 0;
   d->have_structure = true;
   return PGO_OK;
 }
@@ -937,6 +968,87 @@ int dev_iterate(DeviceSolver* d, int n_iters, double* chi2_out, int* iters_done,
     if (err) *err = "H is not positive definite (a 3x3 pivot failed): is a vertex fixed?";
     return PGO_ERR_NUMERIC;
   }
+  return PGO_OK;
+}
+
+int dev_dd_begin(DeviceSolver* d, int n_iters, std::string* err) {
+  if (!d->have_values) {
+    if (err) *err = "pgo_upload has not been called";
+    return PGO_ERR_ARG;
+  }
+  PGO_CUDA(cudaSetDevice(d->device));
+  PGO_CUDA(d->chi2_out.reserve(std::max(n_iters, 1)));
+  PGO_CUDA(cudaMemsetAsync(d->status.p, 0, 4 * sizeof(int), d->stream));
+  PGO_CUDA(cudaMemsetAsync(d->chi2_out.p, 0, std::max(n_iters, 1) * sizeof(double), d->stream));
+  d->dd_iter = 0;
+  PGO_CUDA(cudaEventRecord(d->ev0, d->stream));
+  return PGO_OK;
+}
+
+int dev_dd_local(DeviceSolver* d, std::string* err) {
+  PGO_CUDA(cudaSetDevice(d->device));
+  Params P = d->P;
+  P.chi2_out = d->chi2_out.p;
+  DDParams D = d->D;
+  void* args[] = {&P, &D};
+  PGO_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(gn_dd_local), dim3(d->grid),
+                                       dim3(kThreads), args, 0, d->stream));
+  d->launches++;
+  return PGO_OK;
+}
+
+void dev_dd_exchange(DeviceSolver* d, void** ptr, long long* n_doubles) {
+  *ptr = d->M.p + d->exch_first;
+  *n_doubles = d->exch_count;
+}
+
+int dev_dd_shared(DeviceSolver* d, std::string* err) {
+  PGO_CUDA(cudaSetDevice(d->device));
+  Params P = d->P;
+  P.chi2_out = d->chi2_out.p;
+  DDParams D = d->D;
+  int it = d->dd_iter++;
+  void* args[] = {&P, &D, &it};
+  PGO_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(gn_dd_shared), dim3(d->grid),
+                                       dim3(kThreads), args, 0, d->stream));
+  d->launches++;
+  return PGO_OK;
+}
+
+int dev_dd_end(DeviceSolver* d, int n_iters, double* chi2_out, int* iters_done, float* ms,
+               std::string* err) {
+  PGO_CUDA(cudaSetDevice(d->device));
+  PGO_CUDA(cudaEventRecord(d->ev1, d->stream));
+  int status[4] = {0, 0, 0, 0};
+  PGO_CUDA(cudaMemcpyAsync(status, d->status.p, sizeof status, cudaMemcpyDeviceToHost, d->stream));
+  if (chi2_out && n_iters > 0)
+    PGO_CUDA(cudaMemcpyAsync(chi2_out, d->chi2_out.p, n_iters * sizeof(double),
+                             cudaMemcpyDeviceToHost, d->stream));
+  PGO_CUDA(cudaStreamSynchronize(d->stream));
+  PGO_CUDA(cudaEventElapsedTime(ms, d->ev0, d->ev1));
+  *iters_done = status[1];
+  d->have_factor = status[1] > 0;
+  if (status[0]) {
+    if (err) *err = "H is not positive definite (a 3x3 pivot failed): is a vertex fixed?";
+    return PGO_ERR_NUMERIC;
+  }
+  return PGO_OK;
+}
+
+int dev_dd_pose_exchange(DeviceSolver* d, void** ptr, long long* n_doubles, std::string* err) {
+  PGO_CUDA(cudaSetDevice(d->device));
+  dd_mask_poses<<<(d->P.n_vertices + 255) / 256, 256, 0, d->stream>>>(d->P, d->D);
+  d->launches++;
+  PGO_CUDA(cudaGetLastError());
+  *ptr = d->pose_x.p;
+  *n_doubles = 3LL * d->P.n_vertices;
+  return PGO_OK;
+}
+
+int dev_dd_pose_commit(DeviceSolver* d, std::string* err) {
+  PGO_CUDA(cudaSetDevice(d->device));
+  PGO_CUDA(cudaMemcpyAsync(d->poses.p, d->pose_x.p, 3 * sizeof(double) * d->P.n_vertices,
+                           cudaMemcpyDeviceToDevice, d->stream));
   return PGO_OK;
 }
 

@@ -54,9 +54,20 @@ Graph build_graph(int n, const std::vector<std::pair<int, int> >& edges) {
 }
 
 // ---- nested dissection by breadth-first level structures -----------------------------------
+// each side of a cut keeps at least this share of the vertices: tighter while ranks are being
+// carved out (load balance), looser below (smaller separators, less fill)
+const double kBalanceDeciding = 0.38, kBalanceFill = 0.30;
+
 class Dissector {
  public:
-  Dissector(const Graph& g, int leaf) : g_(g), leaf_(leaf), mark_(g.n, -1), dist_(g.n, -1) {}
+  Dissector(const Graph& g, int leaf, int world)
+      : g_(g), leaf_(leaf), mark_(g.n, -1), dist_(g.n, -1), owner_(g.n, 0), load_(world, 0) {
+    cut_depth_ = 0;
+    while ((1 << cut_depth_) < world) ++cut_depth_;
+  }
+
+  // owner (per original vertex): rank, or -1 for the shared separators of the top cut_depth levels
+  const std::vector<int>& owner() const { return owner_; }
 
   void run(std::vector<int>* order) {
     order_ = order;
@@ -64,7 +75,7 @@ class Dissector {
     order_->reserve(g_.n);
     std::vector<int> all(g_.n);
     std::iota(all.begin(), all.end(), 0);
-    rec(all);
+    rec(all, 0, 0);
   }
 
  private:
@@ -85,8 +96,22 @@ class Dissector {
     }
   }
 
-  void rec(std::vector<int>& s) {
+  // Everything in `s` goes to one rank of the range this branch still owns: the least loaded.
+  void assign(const std::vector<int>& s, int depth, int path) {
+    const int span = 1 << (cut_depth_ - depth), first = path << (cut_depth_ - depth);
+    int best = first;
+    for (int r = first; r < first + span; ++r)
+      if (load_[r] < load_[best]) best = r;
+    load_[best] += static_cast<long long>(s.size());
+    for (size_t i = 0; i < s.size(); ++i) owner_[s[i]] = best;
+  }
+
+  // depth < cut_depth_: this call still decides ownership; path = branch index at that depth.
+  // depth == cut_depth_: s already belongs to a rank. depth > cut_depth_ never occurs.
+  void rec(std::vector<int>& s, int depth, int path) {
+    const bool deciding = depth < cut_depth_;
     if (static_cast<int>(s.size()) <= leaf_) {
+      if (deciding) assign(s, depth, path);
       order_->insert(order_->end(), s.begin(), s.end());
       return;
     }
@@ -106,7 +131,22 @@ class Dissector {
           bfs(s[i], id, &visit);
           comps.push_back(visit);
         }
-      for (size_t c = 0; c < comps.size(); ++c) rec(comps[c]);
+      if (!deciding) {
+        for (size_t c = 0; c < comps.size(); ++c) rec(comps[c], depth, path);
+        return;
+      }
+      // still deciding ownership: a dominant component keeps being dissected across this
+      // branch's ranks; the others go (whole) to the least loaded rank of the branch
+      size_t big = 0;
+      for (size_t c = 1; c < comps.size(); ++c)
+        if (comps[c].size() > comps[big].size()) big = c;
+      const bool dominant = comps[big].size() * 10 >= s.size() * 6;
+      if (dominant) rec(comps[big], depth, path);
+      for (size_t c = 0; c < comps.size(); ++c) {
+        if (dominant && c == big) continue;
+        assign(comps[c], depth, path);
+        rec(comps[c], cut_depth_, 0);
+      }
       return;
     }
     // pseudo-peripheral start: repeat BFS from the farthest vertex
@@ -116,24 +156,26 @@ class Dissector {
       bfs(start, id, &visit);
       start = visit.back();
     }
-    const int depth = dist_[visit.back()];
-    if (depth < 2) {  // (nearly) a clique: nothing to dissect
+    const int depth_bfs = dist_[visit.back()];
+    if (depth_bfs < 2) {  // (nearly) a clique: nothing to dissect
+      if (deciding) assign(s, depth, path);
       order_->insert(order_->end(), s.begin(), s.end());
       return;
     }
-    std::vector<int> level_size(depth + 1, 0);
+    std::vector<int> level_size(depth_bfs + 1, 0);
     for (size_t i = 0; i < s.size(); ++i) ++level_size[dist_[s[i]]];
-    // separator = the smallest level whose removal leaves both sides >= 30 % (else the median)
+    // separator = the smallest level whose removal leaves both sides >= kBalance (else the median)
     const double total = static_cast<double>(s.size());
+    const double bal = deciding ? kBalanceDeciding : kBalanceFill;
     int best = -1, below = 0, median = 1;
-    for (int m = 0; m <= depth; ++m) {
+    for (int m = 0; m <= depth_bfs; ++m) {
       const int above = static_cast<int>(s.size()) - below - level_size[m];
-      if (m >= 1 && m < depth) {
-        if (below >= 0.3 * total && above >= 0.3 * total &&
+      if (m >= 1 && m < depth_bfs) {
+        if (below >= bal * total && above >= bal * total &&
             (best < 0 || level_size[m] < level_size[best]))
           best = m;
       }
-      if (below + level_size[m] / 2 <= total / 2) median = std::max(1, std::min(m, depth - 1));
+      if (below + level_size[m] / 2 <= total / 2) median = std::max(1, std::min(m, depth_bfs - 1));
       below += level_size[m];
     }
     const int cut = best >= 0 ? best : median;
@@ -156,26 +198,39 @@ class Dissector {
       }
     }
     if (a.empty() || b.empty()) {
+      if (deciding) assign(s, depth, path);
       order_->insert(order_->end(), s.begin(), s.end());
       return;
     }
     { std::vector<int>().swap(s); }  // release before recursing
-    rec(a);
-    rec(b);
+    if (deciding) {
+      for (size_t i = 0; i < sep.size(); ++i) owner_[sep[i]] = -1;  // shared separator
+      if (depth + 1 == cut_depth_) {  // the two halves are whole ranks' interiors
+        assign(a, depth + 1, 2 * path);
+        assign(b, depth + 1, 2 * path + 1);
+      }
+      rec(a, depth + 1, 2 * path);
+      rec(b, depth + 1, 2 * path + 1);
+    } else {
+      rec(a, depth, path);
+      rec(b, depth, path);
+    }
     order_->insert(order_->end(), sep.begin(), sep.end());
   }
 
   const Graph& g_;
   int leaf_;
-  std::vector<int> mark_, dist_;
+  std::vector<int> mark_, dist_, owner_;
+  std::vector<long long> load_;
+  int cut_depth_ = 0;
   std::vector<int>* order_ = nullptr;
   int next_id_ = 0;
 };
 
 }  // namespace
 
-bool analyse(int n, const std::vector<std::pair<int, int> >& edges, int ordering, Symbolic* out,
-             std::string* err) {
+bool analyse(int n, const std::vector<std::pair<int, int> >& edges, int ordering, int world,
+             Symbolic* out, std::string* err) {
   const auto t0 = std::chrono::steady_clock::now();
   *out = Symbolic();
   Symbolic& S = *out;
@@ -188,16 +243,37 @@ bool analyse(int n, const std::vector<std::pair<int, int> >& edges, int ordering
   const Graph g = build_graph(n, edges);
 
   // ---- ordering -------------------------------------------------------------------------------
+  if (world < 1 || (world & (world - 1)) != 0) {
+    if (err) *err = "world size must be a power of two";
+    return false;
+  }
+  S.world = world;
+  std::vector<int> vertex_owner(n, 0);
   if (ordering == 1) {
+    if (world != 1) {
+      if (err) *err = "natural ordering cannot be partitioned";
+      return false;
+    }
     S.perm.resize(n);
     std::iota(S.perm.begin(), S.perm.end(), 0);
   } else {
-    Dissector d(g, 8);
+    Dissector d(g, 8, world);
     d.run(&S.perm);
+    vertex_owner = d.owner();
   }
   if (static_cast<int>(S.perm.size()) != n) {
     if (err) *err = "internal: ordering lost vertices";
     return false;
+  }
+  // shared separators last (a topological reordering of the elimination tree: same fill)
+  {
+    std::vector<int> owned, shared;
+    for (int p = 0; p < n; ++p) (vertex_owner[S.perm[p]] < 0 ? shared : owned).push_back(S.perm[p]);
+    S.first_shared = static_cast<int>(owned.size());
+    owned.insert(owned.end(), shared.begin(), shared.end());
+    S.perm.swap(owned);
+    S.owner.resize(n);
+    for (int p = 0; p < n; ++p) S.owner[p] = vertex_owner[S.perm[p]];
   }
   S.iperm.assign(n, -1);
   for (int p = 0; p < n; ++p) S.iperm[S.perm[p]] = p;
@@ -308,6 +384,42 @@ bool analyse(int n, const std::vector<std::pair<int, int> >& edges, int ordering
   {
     std::vector<int> cur(S.level_ptr.begin(), S.level_ptr.end() - 1);
     for (int p = 0; p < n; ++p) S.level_cols[cur[S.level[p]]++] = p;
+  }
+
+  // ---- partition bookkeeping -----------------------------------------------------------------------
+  S.local_levels = 0;
+  S.shared_min_level = S.n_levels;
+  for (int p = 0; p < n; ++p) {
+    if (S.owner[p] >= 0) S.local_levels = std::max(S.local_levels, S.level[p] + 1);
+    else S.shared_min_level = std::min(S.shared_min_level, S.level[p]);
+    const int par = S.parent[p];
+    if (par >= 0 && S.owner[par] >= 0 && S.owner[par] != S.owner[p]) {
+      if (err) *err = "internal: partition does not respect the elimination tree";
+      return false;
+    }
+  }
+  for (size_t e = 0; e < edges.size(); ++e) {
+    const int oa = S.owner[S.iperm[edges[e].first]], ob = S.owner[S.iperm[edges[e].second]];
+    if (oa >= 0 && ob >= 0 && oa != ob) {
+      if (err) *err = "internal: an edge crosses two ranks' interiors";
+      return false;
+    }
+  }
+  {
+    // shared columns whose diagonal no shared-source update completes at their own level
+    std::vector<char> has_shared_child(n, 0);
+    for (int p = 0; p < n; ++p) {
+      const int par = S.parent[p];
+      if (par >= 0 && S.owner[p] < 0 && S.level[p] + 1 == S.level[par]) has_shared_child[par] = 1;
+    }
+    S.xfinal_ptr.assign(S.n_levels + 1, 0);
+    for (int p = 0; p < n; ++p)
+      if (S.owner[p] < 0 && !has_shared_child[p]) ++S.xfinal_ptr[S.level[p] + 1];
+    for (int l = 0; l < S.n_levels; ++l) S.xfinal_ptr[l + 1] += S.xfinal_ptr[l];
+    S.xfinal_cols.resize(S.xfinal_ptr[S.n_levels]);
+    std::vector<int> cur(S.xfinal_ptr.begin(), S.xfinal_ptr.end() - 1);
+    for (int p = 0; p < n; ++p)
+      if (S.owner[p] < 0 && !has_shared_child[p]) S.xfinal_cols[cur[S.level[p]]++] = p;
   }
 
   // ---- update schedule --------------------------------------------------------------------------

@@ -59,6 +59,18 @@ struct Symbolic {
   // the runs after which row i (of level l) is complete
   std::vector<int> fwd_ptr;     // n_levels + 1
   std::vector<SolveOp> fwd_ops;
+  // multi-GPU domain decomposition (world > 1): owner[p] = rank that eliminates column p, or -1
+  // for the shared top separators, which are ordered last: columns [first_shared, n) are shared.
+  // A column's elimination-tree descendants all have the same owner; no edge connects two
+  // different owners. explicit_final lists, per level, the shared columns that no shared-source
+  // update completes (their children are all owned by ranks).
+  int world = 1;
+  std::vector<int> owner;          // n
+  int first_shared = 0;            // == n when world == 1
+  int local_levels = 0;            // 1 + max level of an owned column
+  int shared_min_level = 0;        // min level of a shared column (n_levels if none)
+  std::vector<int> xfinal_ptr;     // n_levels + 1
+  std::vector<int> xfinal_cols;
   // statistics
   int64_t nnzb = 0, n_ops = 0;
   int max_run = 0;              // longest run of updates sharing one target within a phase
@@ -68,8 +80,10 @@ struct Symbolic {
 // Block adjacency of the free vertices: edges given as pairs of hessian indices (both >= 0).
 // Returns false (with *err) on inconsistent input. `ordering`: 0 = nested dissection (default),
 // 1 = natural (testing).
-bool analyse(int n, const std::vector<std::pair<int, int> >& edges, int ordering, Symbolic* out,
-             std::string* err);
+// `world` > 1 (a power of two) additionally cuts the top log2(world) dissection levels into shared
+// separators and assigns every other column to a rank.
+bool analyse(int n, const std::vector<std::pair<int, int> >& edges, int ordering, int world,
+             Symbolic* out, std::string* err);
 
 }  // namespace pgo
 #endif

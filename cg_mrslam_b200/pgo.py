@@ -42,6 +42,16 @@ _SIGS = {
     "pgo_marginals": (C.c_int, [C.c_void_p, C.c_int, _ip, _ip, _dp]),
     "pgo_initial_guess": (C.c_int, [C.c_void_p]),
     "pgo_label_star_edges": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _ip, _dp, _dp]),
+    "pgo_set_partition": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "pgo_dd_begin": (C.c_int, [C.c_void_p, C.c_int]),
+    "pgo_dd_local": (C.c_int, [C.c_void_p]),
+    "pgo_dd_exchange_buffer": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
+    "pgo_dd_shared": (C.c_int, [C.c_void_p]),
+    "pgo_dd_end": (C.c_int, [C.c_void_p, C.c_int, _dp, C.POINTER(C.c_int)]),
+    "pgo_dd_pose_exchange": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
+    "pgo_dd_pose_commit": (C.c_int, [C.c_void_p]),
+    "pgo_analyse_partition": (C.c_int, [C.c_int, C.c_int, _ip, _ip, _bp, C.c_int, _ip,
+                                        C.POINTER(C.c_int64)]),
     "pgo_get_stats": (C.c_int, [C.c_void_p, C.POINTER(pgo_stats)]),
     "pgo_stream": (C.c_void_p, [C.c_void_p]),
 }
@@ -93,6 +103,10 @@ class Solver:
             self.close()
         except Exception:
             pass
+
+    def set_partition(self, rank, world):
+        """Domain decomposition: this solver is rank `rank` of `world` (before set_graph)."""
+        self._check(self.lib.pgo_set_partition(self.h, rank, world))
 
     def set_graph(self, n_vertices, edge_ij, fixed):
         """initializeOptimization: structure of the active graph. ``fixed`` = vertex indices."""
@@ -165,6 +179,73 @@ class Solver:
 
     def stream(self):
         return self.lib.pgo_stream(self.h)
+
+
+class _DeviceArray:
+    """A float64 device buffer exposed through __cuda_array_interface__ so torch can alias it."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": "<f8", "data": (int(ptr), False),
+                                         "version": 2}
+
+
+def analyse_partition(n_vertices, edge_ij, fixed, world):
+    """The partition pgo_set_partition(rank, world) + pgo_set_graph would use (host only).
+    Returns (vertex_owner [n_vertices]: rank, -1 shared, -2 fixed; stats dict)."""
+    lib = bind(_lib.load())
+    e = np.asarray(edge_ij).reshape(-1, 2)
+    ei, ej = _i(e[:, 0]), _i(e[:, 1])
+    mask = np.zeros(n_vertices, dtype=np.uint8)
+    mask[np.asarray(fixed, dtype=np.int64)] = 1
+    owner = np.empty(n_vertices, dtype=np.int32)
+    stats = np.zeros(3 + world, dtype=np.int64)
+    rc = lib.pgo_analyse_partition(n_vertices, len(e), _p(ei, _ip), _p(ej, _ip), _p(mask, _bp), world,
+                                   _p(owner, _ip), stats.ctypes.data_as(C.POINTER(C.c_int64)))
+    if rc:
+        raise SolverError(rc, lib.pgo_last_error().decode())
+    return owner, {"shared_vertices": int(stats[0]), "shared_blocks": int(stats[1]),
+                   "rank_updates": [int(x) for x in stats[2:2 + world]],
+                   "shared_updates": int(stats[2 + world])}
+
+
+def optimize_distributed(solvers, n_iters, all_reduce):
+    """Domain-decomposed SparseOptimizer::optimize(n) over the ranks' solvers held by THIS process.
+
+    ``solvers``: this process' Solver objects, each with set_partition(rank, world) applied before
+    set_graph (one per process under torchrun; several "virtual ranks" on one GPU in the tests).
+    ``all_reduce(list_of_tensors)`` sums the given tensors (one per local solver) over ALL ranks in
+    place: with one solver per process it is ``lambda ts: dist.all_reduce(ts[0])``.
+    Returns (iterations done, chi2 per iteration)."""
+    import torch
+    for s in solvers:
+        s._check(s.lib.pgo_dd_begin(s.h, n_iters))
+
+    def views(fn):
+        out = []
+        for s in solvers:
+            ptr, n = C.c_void_p(), C.c_int64()
+            s._check(fn(s.h, C.byref(ptr), C.byref(n)))
+            out.append(torch.as_tensor(_DeviceArray(ptr.value, n.value), device="cuda"))
+        return out
+
+    for _ in range(n_iters):
+        for s in solvers:
+            s._check(s.lib.pgo_dd_local(s.h))
+        all_reduce(views(lambda h, p, n: solvers[0].lib.pgo_dd_exchange_buffer(h, p, n)))
+        for s in solvers:
+            s._check(s.lib.pgo_dd_shared(s.h))
+    chi2 = np.zeros(max(n_iters, 1))
+    done = []
+    for s in solvers:
+        d = C.c_int()
+        rc = s.lib.pgo_dd_end(s.h, n_iters, _p(chi2, _dp), C.byref(d))
+        if rc and rc != PGO_ERR_NUMERIC:
+            s._check(rc)
+        done.append(d.value)
+    all_reduce(views(lambda h, p, n: solvers[0].lib.pgo_dd_pose_exchange(h, p, n)))
+    for s in solvers:
+        s._check(s.lib.pgo_dd_pose_commit(s.h))
+    return min(done), chi2[:n_iters]
 
 
 def condensed_star(solver_factory, poses, edge_ij, meas, info6, gauge, separators):

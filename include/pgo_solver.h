@@ -99,6 +99,32 @@ int pgo_initial_guess(pgo_solver* s);
 int pgo_label_star_edges(pgo_solver* s, int gauge, int n, const int32_t* v, double* meas_out,
                          double* info_out);
 
+/* ---- one graph on several GPUs (domain decomposition) ----------------------
+ * One process per GPU, all with the same graph. pgo_set_partition(rank, world) (world a power of
+ * two) before pgo_set_graph makes the structure analysis cut the top log2(world) dissection
+ * levels into shared separators and give every other vertex to one rank. One iteration is then
+ *     pgo_dd_local                       this rank's interior: linearise, eliminate, forward-solve
+ *     all-reduce(sum) of the exchange buffer over the ranks    <- the only collective: the
+ *                                        separator Schur blocks + right-hand side + chi2
+ *     pgo_dd_shared                      separators (replicated), back-substitution, update
+ * bracketed by pgo_dd_begin / pgo_dd_end; afterwards pgo_dd_pose_exchange + all-reduce(sum) +
+ * pgo_dd_pose_commit leave the complete estimate vector on every rank. The all-reduce is the
+ * caller's (ncclAllReduce, or torch.distributed on a tensor aliasing the buffer), enqueued on the
+ * solver's stream; everything here is asynchronous on that stream except pgo_dd_end. */
+int pgo_set_partition(pgo_solver* s, int rank, int world);
+int pgo_dd_begin(pgo_solver* s, int n_iters);
+int pgo_dd_local(pgo_solver* s);
+int pgo_dd_exchange_buffer(pgo_solver* s, void** dev_ptr, int64_t* n_doubles);
+int pgo_dd_shared(pgo_solver* s);
+int pgo_dd_end(pgo_solver* s, int n_iters, double* chi2_out, int* iters_done);
+int pgo_dd_pose_exchange(pgo_solver* s, void** dev_ptr, int64_t* n_doubles);
+int pgo_dd_pose_commit(pgo_solver* s);
+/* Host-only (no device needed): the partition the analysis would choose. vertex_owner[v] = rank,
+ * -1 = shared separator, -2 = fixed. stats[0] = shared vertices, stats[1] = factor blocks in shared
+ * columns, stats[2 + r] = block updates sourced by rank r, stats[2 + world] = by the separators. */
+int pgo_analyse_partition(int n_vertices, int n_edges, const int32_t* edge_i, const int32_t* edge_j,
+                          const uint8_t* fixed, int world, int32_t* vertex_owner, int64_t* stats);
+
 int pgo_get_stats(const pgo_solver* s, pgo_stats* out);
 void* pgo_stream(const pgo_solver* s);
 

@@ -128,6 +128,45 @@ def test_initial_guess_and_condensed_star_match_oracle():
     s.close()
 
 
+def _virtual_all_reduce(ts):
+    """Sum over the virtual ranks living in this process (stands in for NCCL's all-reduce)."""
+    import torch
+    torch.cuda.synchronize()
+    total = ts[0].clone()
+    for t in ts[1:]:
+        total += t
+    for t in ts:
+        t.copy_(total)
+    torch.cuda.synchronize()
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+@pytest.mark.parametrize("n,box,seed", [(400, 22.0, 3), (3000, 61.0, 5)])
+def test_domain_decomposition_matches_oracle(world, n, box, seed):
+    """One graph cut over `world` ranks (virtual ranks on one GPU, the all-reduce done by hand):
+    same poses as the oracle, same chi2, and the same answer as the single-rank solver."""
+    g = synth.make_pose_graph(n, 4 * n, seed=seed, box=box)
+    ref = po.gauss_newton(g["poses0"], g["edge_ij"], g["meas"], g["info"], g["fixed"], 4)
+    solvers = []
+    for r in range(world):
+        s = pgo.Solver()
+        s.set_partition(r, world)
+        s.set_graph(n, g["edge_ij"], g["fixed"])
+        s.upload(g["poses0"], g["meas"], g["info"])
+        solvers.append(s)
+    done, chi2 = pgo.optimize_distributed(solvers, 4, _virtual_all_reduce)
+    assert done == 4
+    assert np.allclose(chi2, ref.chi2, rtol=1e-9)
+    for s in solvers:
+        d = s.poses() - ref.poses
+        d[:, 2] = po.normalize_theta(d[:, 2])
+        assert np.abs(d).max() < POSE_TOL
+    owner, st = pgo.analyse_partition(n, g["edge_ij"], g["fixed"], world)
+    assert st["shared_vertices"] > 0 and len(set(owner[owner >= 0])) >= 2
+    for s in solvers:
+        s.close()
+
+
 def test_full_size_properties():
     """BASELINE cfg 4 (50 k vertices, 200 k edges): properties that need no oracle. After GN
     converges b -> 0, so one more iteration moves nothing (fixed point) and chi2 is stationary and
