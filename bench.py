@@ -233,7 +233,7 @@ def gn_ours(args, local, world, barrier):
     meas = torch.from_numpy(g["meas"]).pin_memory().numpy()
     info = torch.from_numpy(g["info"]).pin_memory().numpy()
     s.upload(poses0, meas, info)
-    s.optimize(args.warmup, want_poses=False)
+    _, chi2_warm, _ = s.optimize(args.warmup, want_poses=False)
     # device-resident: K iterations in one cooperative launch
     barrier()
     done, chi2, _ = s.optimize(args.steps, want_poses=False)
@@ -279,7 +279,7 @@ def gn_ours(args, local, world, barrier):
     s.close()
     if world > 1:
         out["dd"] = gn_domain_decomposed(args, g, local, world, barrier, poses0, meas, info,
-                                         float(chi2[0]) if len(chi2) else None)
+                                         float(chi2_warm[0]) if len(chi2_warm) else None)
     return out
 
 
@@ -356,7 +356,7 @@ def ours(args):
         raise SystemExit("bench.py: no CUDA device (there is no CPU fallback)")
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout (one JSON line)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # NCCL's banner off stdout (one JSON line)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():

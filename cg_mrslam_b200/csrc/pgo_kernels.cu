@@ -305,10 +305,49 @@ __device__ void phase_updates(const Params& P, int l) {
   const int begin = P.phase_ptr[l], end = P.phase_ptr[l + 1];
   for (int i = begin + tid; i < end; i += nthreads) {
     const UpdateOp first = P.ops[i];
+    if (first.target & kTileMember) continue;  // handled by the tile's lead
     if (i > begin && P.ops[i - 1].target == first.target) continue;  // not the head of its run
-    const int target = first.target & ~kFinalFlag;
-    double acc[9];
+    const int target = first.target & kPosMask;
     double* dst = P.M + 9 * static_cast<size_t>(target);
+    if (first.target & kTileLead) {
+      // four congruent runs: targets target..target+3, sources a..a+3 per update, common b
+      double acc[4][9];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) load9(dst + 9 * r, acc[r]);
+      int j = i;
+      UpdateOp op = first;
+      while (true) {
+        double b[9], d[9], u[9];
+        load9(P.M + 9 * static_cast<size_t>(op.b), b);
+        load9(P.Dinv + 9 * static_cast<size_t>(P.col_of[op.a]), d);
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int c = 0; c < 3; ++c)  // U = Dinv * b^T
+            u[3 * r + c] = d[3 * r] * b[3 * c] + d[3 * r + 1] * b[3 * c + 1] + d[3 * r + 2] * b[3 * c + 2];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          double a[9];
+          load9(P.M + 9 * (static_cast<size_t>(op.a) + q), a);
+#pragma unroll
+          for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+              acc[q][3 * r + c] -= a[3 * r] * u[c] + a[3 * r + 1] * u[3 + c] + a[3 * r + 2] * u[6 + c];
+        }
+        ++j;
+        if (j >= end) break;
+        op = P.ops[j];
+        if (op.target != first.target) break;
+      }
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int k = 0; k < 9; ++k) dst[9 * r + k] = acc[r][k];
+      if (first.target & kFinalFlag) finalise_diag(P, P.col_of[target], acc[0]);
+      continue;
+    }
+    double acc[9];
     load9(dst, acc);
     int j = i;
     UpdateOp op = first;

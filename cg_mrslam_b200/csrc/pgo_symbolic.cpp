@@ -431,64 +431,124 @@ bool analyse(int n, const std::vector<std::pair<int, int> >& edges, int ordering
     const int64_t m = S.col_ptr[p + 1] - S.col_ptr[p] - 1;
     n_ops += m * (m + 1) / 2;
   }
-  if (n_ops > 0x3FFFFFF0LL || S.nnzb >= kFinalFlag) {
-    if (err) *err = "more than 2^30 block updates: graph too dense for this solver";
+  if (n_ops > 0x3FFFFFF0LL || S.nnzb >= kPosMask) {
+    if (err) *err = "more than 2^30 block updates / 2^28 factor blocks: graph too dense for this solver";
     return false;
   }
   S.n_ops = n_ops;
-  S.ops.resize(n_ops);
+  // Panels: up to kPanelWidth consecutive columns of a chain (each the only-path parent of the
+  // previous one, nested structure, same owner). An update from column k into a column beyond k's
+  // panel is deferred to the phase after the panel's last column: all of a panel's contributions
+  // to one target then share a phase and are applied with a single read-modify-write.
+  std::vector<int> panel_last(n);
+  for (int p = 0; p < n;) {
+    int q = p;
+    while (q + 1 < n && q + 1 - p < kPanelWidth && S.parent[q] == q + 1 &&
+           S.level[q + 1] == S.level[q] + 1 && S.owner[q] == S.owner[q + 1] &&
+           S.col_ptr[q + 1] - S.col_ptr[q] == S.col_ptr[q + 2] - S.col_ptr[q + 1] + 1)
+      ++q;
+    for (int t = p; t <= q; ++t) panel_last[t] = q;
+    p = q + 1;
+  }
+  // pass 1: updates per phase
+  std::vector<int64_t> phase_count(S.n_levels + 1, 0);
+  for (int k = 0; k < n; ++k) {
+    const int base = S.col_ptr[k], m = S.col_ptr[k + 1] - base;
+    for (int b = 1; b < m; ++b) {
+      const int c = S.row_idx[base + b];
+      const int ph = (c <= panel_last[k] ? S.level[k] : S.level[panel_last[k]]) + 1;
+      phase_count[ph] += m - b;
+    }
+  }
   S.phase_ptr.assign(S.n_levels + 1, 0);
-  std::vector<int> count(S.nnzb, 0), touched;
-  std::vector<UpdateOp> raw;
-  int64_t op_cursor = 0;
-  std::vector<char> fin(n, 0);
-  for (int l = 1; l < S.n_levels; ++l) {
-    S.phase_ptr[l] = static_cast<int>(op_cursor);
-    raw.clear();
-    touched.clear();
-    for (int t = S.level_ptr[l - 1]; t < S.level_ptr[l]; ++t) {
+  {
+    int64_t run = 0;
+    for (int l = 0; l < S.n_levels; ++l) {
+      S.phase_ptr[l] = static_cast<int>(run);
+      run += phase_count[l];
+    }
+    S.phase_ptr[S.n_levels] = static_cast<int>(run);
+    if (run != n_ops || phase_count[S.n_levels] != 0) {
+      if (err) *err = "internal: update count mismatch";
+      return false;
+    }
+  }
+  // pass 2: generate, bucketed by phase (sources in level order, then column order)
+  std::vector<UpdateOp> tmp(n_ops);
+  {
+    std::vector<int64_t> cursor(S.n_levels + 1);
+    for (int l = 0; l <= S.n_levels; ++l) cursor[l] = S.phase_ptr[l];
+    for (int t = 0; t < n; ++t) {
       const int k = S.level_cols[t];
-      const int base = S.col_ptr[k], m = S.col_ptr[k + 1] - base;  // rows base+1 .. base+m-1
+      const int base = S.col_ptr[k], m = S.col_ptr[k + 1] - base;
       for (int b = 1; b < m; ++b) {
         const int c = S.row_idx[base + b];
-        int w = S.col_ptr[c];  // diagonal of column c == row c
+        const int ph = (c <= panel_last[k] ? S.level[k] : S.level[panel_last[k]]) + 1;
+        int w = S.col_ptr[c];
         for (int a = b; a < m; ++a) {
           const int r = S.row_idx[base + a];
           while (S.row_idx[w] != r) ++w;  // struct(k) rows >= c are a subset of struct(c) + {c}
           UpdateOp x = {w, base + a, base + b};
-          raw.push_back(x);
-          if (count[w]++ == 0) touched.push_back(w);
+          tmp[cursor[ph]++] = x;
         }
       }
     }
+  }
+  // pass 3: per phase, stable counting sort by target; mark finalising runs and 4-row tiles
+  S.ops.resize(n_ops);
+  std::vector<int> count(S.nnzb, 0), touched;
+  std::vector<char> fin(n, 0);
+  for (int l = 1; l < S.n_levels; ++l) {
+    const int64_t begin = S.phase_ptr[l], end = S.phase_ptr[l + 1];
+    touched.clear();
+    for (int64_t i = begin; i < end; ++i)
+      if (count[tmp[i].target]++ == 0) touched.push_back(tmp[i].target);
     std::sort(touched.begin(), touched.end());
-    // counting sort of the phase's updates by target (stable: generation order within a target)
-    int64_t off = op_cursor;
+    int64_t off = begin;
+    std::vector<int64_t> run_begin(touched.size() + 1);
     for (size_t i = 0; i < touched.size(); ++i) {
       const int w = touched[i];
       const int c = count[w];
       S.max_run = std::max(S.max_run, c);
+      run_begin[i] = off;
       count[w] = static_cast<int>(off);  // reuse as write cursor
       off += c;
     }
-    for (size_t i = 0; i < raw.size(); ++i) {
-      UpdateOp o = raw[i];
-      const int w = o.target;
+    run_begin[touched.size()] = off;
+    for (int64_t i = begin; i < end; ++i) S.ops[count[tmp[i].target]++] = tmp[i];
+    for (size_t i = 0; i < touched.size(); ++i) count[touched[i]] = 0;
+    // flags
+    for (size_t i = 0; i < touched.size();) {
+      const int w = touched[i];
       const int col = S.col_of[w];
+      const int64_t rb = run_begin[i], len = run_begin[i + 1] - rb;
+      int flags = 0;
       if (S.row_idx[w] == col && S.level[col] == l) {
-        o.target |= kFinalFlag;
+        flags |= kFinalFlag;
         fin[col] = 1;
       }
-      S.ops[count[w]++] = o;
+      // congruent runs on the next three blocks of the same column?
+      bool tile = i + 3 < touched.size();
+      for (int d = 1; tile && d < 4; ++d) {
+        const int wd = touched[i + d];
+        tile = wd == w + d && S.col_of[wd] == col && run_begin[i + d + 1] - run_begin[i + d] == len;
+        for (int64_t q = 0; tile && q < len; ++q) {
+          const UpdateOp& x = S.ops[rb + q];
+          const UpdateOp& y = S.ops[run_begin[i + d] + q];
+          tile = y.b == x.b && y.a == x.a + d;
+        }
+      }
+      if (tile) {
+        for (int64_t q = rb; q < rb + len; ++q) S.ops[q].target |= flags | kTileLead;
+        for (int64_t q = rb + len; q < rb + 4 * len; ++q) S.ops[q].target |= kTileMember;
+        i += 4;
+      } else {
+        for (int64_t q = rb; q < rb + len; ++q) S.ops[q].target |= flags;
+        i += 1;
+      }
     }
-    for (size_t i = 0; i < touched.size(); ++i) count[touched[i]] = 0;
-    op_cursor = off;
   }
-  S.phase_ptr[S.n_levels] = static_cast<int>(op_cursor);
-  if (op_cursor != n_ops) {
-    if (err) *err = "internal: update count mismatch";
-    return false;
-  }
+  { std::vector<UpdateOp>().swap(tmp); }
   // every non-leaf column must be finalised by an update of its own phase
   for (int p = 0; p < n; ++p)
     if (S.level[p] > 0 && !fin[p]) {

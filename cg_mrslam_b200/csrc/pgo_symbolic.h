@@ -28,6 +28,13 @@ struct UpdateOp {
   int b;       // position of M(j,k)
 };
 static const int kFinalFlag = 0x40000000;
+// Four consecutive target blocks of one column whose runs are congruent (same sources, source
+// blocks in consecutive positions) are processed by one thread: the lead run carries kTileLead,
+// the three member runs kTileMember (their heads skip). Positions therefore use 28 bits.
+static const int kTileLead = 0x20000000;
+static const int kTileMember = 0x10000000;
+static const int kPosMask = 0x0FFFFFFF;
+static const int kPanelWidth = 8;  // chain columns whose trailing updates are applied together
 
 struct SolveOp {
   int row;  // target block row | kFinalFlag
