@@ -99,7 +99,7 @@ __device__ void dd_updates(const Params& P, const DDParams& D, int l, int mode) 
   for (int i = begin + tid; i < end; i += nthreads) {
     const UpdateOp first = P.ops[i];
     if (i > begin && P.ops[i - 1].target == first.target) continue;
-    const int target = first.target & kPosMask;  // tile marks are ignored here: run by run
+    const int target = first.target & ~kFinalFlag;
     const int tcol = P.col_of[target];
     const int towner = D.owner[tcol];
     // a target column owned by another rank can never receive one of our updates

@@ -26,6 +26,7 @@
 
 #include "../../include/pgo_solver.h"
 #include "pgo_device.h"
+#include "pgo_supernodal.h"
 
 namespace cg = cooperative_groups;
 
@@ -290,93 +291,6 @@ __device__ __forceinline__ void finalise_diag(const Params& P, int col, const do
   for (int i = 0; i < 9; ++i) d[i] = inv[i];
 }
 
-__device__ void phase_leaves(const Params& P) {
-  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
-  for (int t = P.level_ptr[0] + tid; t < P.level_ptr[1]; t += nthreads) {
-    const int col = P.level_cols[t];
-    double m[9];
-    load9(P.M + 9 * static_cast<size_t>(P.col_ptr[col]), m);
-    finalise_diag(P, col, m);
-  }
-}
-
-__device__ void phase_updates(const Params& P, int l) {
-  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
-  const int begin = P.phase_ptr[l], end = P.phase_ptr[l + 1];
-  for (int i = begin + tid; i < end; i += nthreads) {
-    const UpdateOp first = P.ops[i];
-    if (first.target & kTileMember) continue;  // handled by the tile's lead
-    if (i > begin && P.ops[i - 1].target == first.target) continue;  // not the head of its run
-    const int target = first.target & kPosMask;
-    double* dst = P.M + 9 * static_cast<size_t>(target);
-    if (first.target & kTileLead) {
-      // four congruent runs: targets target..target+3, sources a..a+3 per update, common b
-      double acc[4][9];
-#pragma unroll
-      for (int r = 0; r < 4; ++r) load9(dst + 9 * r, acc[r]);
-      int j = i;
-      UpdateOp op = first;
-      while (true) {
-        double b[9], d[9], u[9];
-        load9(P.M + 9 * static_cast<size_t>(op.b), b);
-        load9(P.Dinv + 9 * static_cast<size_t>(P.col_of[op.a]), d);
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
-#pragma unroll
-          for (int c = 0; c < 3; ++c)  // U = Dinv * b^T
-            u[3 * r + c] = d[3 * r] * b[3 * c] + d[3 * r + 1] * b[3 * c + 1] + d[3 * r + 2] * b[3 * c + 2];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          double a[9];
-          load9(P.M + 9 * (static_cast<size_t>(op.a) + q), a);
-#pragma unroll
-          for (int r = 0; r < 3; ++r)
-#pragma unroll
-            for (int c = 0; c < 3; ++c)
-              acc[q][3 * r + c] -= a[3 * r] * u[c] + a[3 * r + 1] * u[3 + c] + a[3 * r + 2] * u[6 + c];
-        }
-        ++j;
-        if (j >= end) break;
-        op = P.ops[j];
-        if (op.target != first.target) break;
-      }
-#pragma unroll
-      for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int k = 0; k < 9; ++k) dst[9 * r + k] = acc[r][k];
-      if (first.target & kFinalFlag) finalise_diag(P, P.col_of[target], acc[0]);
-      continue;
-    }
-    double acc[9];
-    load9(dst, acc);
-    int j = i;
-    UpdateOp op = first;
-    while (true) {
-      double a[9], b[9], d[9], t[9];
-      load9(P.M + 9 * static_cast<size_t>(op.a), a);
-      load9(P.M + 9 * static_cast<size_t>(op.b), b);
-      load9(P.Dinv + 9 * static_cast<size_t>(P.col_of[op.a]), d);
-#pragma unroll
-      for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int c = 0; c < 3; ++c)
-          t[3 * r + c] = a[3 * r] * d[c] + a[3 * r + 1] * d[3 + c] + a[3 * r + 2] * d[6 + c];
-#pragma unroll
-      for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int c = 0; c < 3; ++c)
-          acc[3 * r + c] -= t[3 * r] * b[3 * c] + t[3 * r + 1] * b[3 * c + 1] + t[3 * r + 2] * b[3 * c + 2];
-      ++j;
-      if (j >= end) break;
-      op = P.ops[j];
-      if (op.target != first.target) break;
-    }
-#pragma unroll
-    for (int k = 0; k < 9; ++k) dst[k] = acc[k];
-    if (first.target & kFinalFlag) finalise_diag(P, P.col_of[target], acc);
-  }
-}
-
 // ---- phase 3: solves ---------------------------------------------------------------------------
 // Forward substitution works in place on the right-hand side z (initially b):
 //   level-0 rows:  u_j = Dinv_j z_j
@@ -510,14 +424,119 @@ __device__ __forceinline__ void stamp(const Params& P, int k) {
   }
 }
 
-__global__ void __launch_bounds__(kThreads) gn_iterations(Params P, int n_iters) {
+// ---- supernodal single-GPU iteration (pgo_supernodal.h) ------------------------------------------
+struct CtaGroup {
+  __device__ __forceinline__ int rank() const { return threadIdx.x; }
+  __device__ __forceinline__ int size() const { return blockDim.x; }
+  __device__ __forceinline__ void sync() const { __syncthreads(); }
+};
+struct WarpGroup {
+  __device__ __forceinline__ int rank() const { return threadIdx.x & 31; }
+  __device__ __forceinline__ int size() const { return 32; }
+  __device__ __forceinline__ void sync() const { __syncwarp(); }
+};
+
+struct SNDev {
+  SNView V;
+  int n_plevels, n_slevels;
+  const int *ff_ptr, *fa_ptr, *fb_ptr, *ss_ptr, *sa_ptr, *sf_ptr, *sb_ptr;
+  const Task *ff, *fa, *fb, *ss, *sa, *sf, *sb;
+  // profiling: after every grid barrier of the last iteration, (globaltimer, kind << 16 | level)
+  unsigned long long* ticks;
+};
+
+__device__ __forceinline__ void sn_tick(const SNDev& S, int* at, int kind, int level) {
+  if (blockIdx.x == 0 && threadIdx.x == 0 && S.ticks) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    S.ticks[2 * *at] = t;
+    S.ticks[2 * *at + 1] = static_cast<unsigned long long>((kind << 16) | level);
+  }
+  ++*at;
+}
+
+const size_t kSnSmemBytes = sizeof(double) * (kCtaSmemDoubles > 8 * kWarpSmemDoubles
+                                                  ? kCtaSmemDoubles
+                                                  : 8 * kWarpSmemDoubles);
+
+// Numeric factorisation: per panel level, (A) factor the level's panels -- CTA tasks for row chunks
+// of big panels, warp tasks for small panels including their outer product -- then (B) the outer
+// products of the big panels, tile by tile, subtracted from later columns with atomics.
+__device__ void sn_factorise(const SNDev& S, cg::grid_group& grid, double* sm, double* wsm,
+                             int warp_id, int n_warps, int* at) {
+  const CtaGroup cta;
+  const WarpGroup warp;
+  for (int l = 0; l < S.n_plevels; ++l) {
+    for (int i = S.fa_ptr[l] + blockIdx.x; i < S.fa_ptr[l + 1]; i += gridDim.x)
+      sn_task_factor(cta, S.V, S.fa[i], sm);
+    for (int i = S.ff_ptr[l] + warp_id; i < S.ff_ptr[l + 1]; i += n_warps)
+      sn_task_fused(warp, S.V, S.ff[i], wsm);
+    grid.sync();
+    sn_tick(S, at, 1, l);
+    if (S.fb_ptr[l + 1] > S.fb_ptr[l]) {
+      for (int i = S.fb_ptr[l] + blockIdx.x; i < S.fb_ptr[l + 1]; i += gridDim.x)
+        sn_task_update(cta, S.V, S.fb[i], sm);
+      grid.sync();
+      sn_tick(S, at, 2, l);
+    }
+  }
+}
+
+__device__ void sn_substitute(const SNDev& S, cg::grid_group& grid, double* sm, double* wsm,
+                              int warp_id, int n_warps, int* at) {
+  const CtaGroup cta;
+  const WarpGroup warp;
+  for (int l = 0; l < S.n_slevels; ++l) {
+    for (int i = S.sa_ptr[l] + blockIdx.x; i < S.sa_ptr[l + 1]; i += gridDim.x)
+      sn_task_forward_tri(cta, S.V, S.sa[i], sm);
+    for (int i = S.ss_ptr[l] + warp_id; i < S.ss_ptr[l + 1]; i += n_warps)
+      sn_task_forward_small(warp, S.V, S.ss[i], wsm);
+    grid.sync();
+    sn_tick(S, at, 3, l);
+    if (S.sf_ptr[l + 1] > S.sf_ptr[l]) {
+      for (int i = S.sf_ptr[l] + warp_id; i < S.sf_ptr[l + 1]; i += n_warps)
+        sn_forward_rows(warp, S.V, S.sf[i].id, S.sf[i].r0, S.sf[i].r1, nullptr);
+      grid.sync();
+      sn_tick(S, at, 4, l);
+    }
+  }
+}
+
+__device__ void sn_back_substitute(const SNDev& S, cg::grid_group& grid, double* sm, double* wsm,
+                                   int warp_id, int n_warps, int* at) {
+  const CtaGroup cta;
+  const WarpGroup warp;
+  for (int l = S.n_slevels - 1; l >= 0; --l) {
+    for (int i = S.sb_ptr[l] + warp_id; i < S.sb_ptr[l + 1]; i += n_warps)
+      sn_backward_rows(warp, S.V, S.sb[i].id, S.sb[i].r0, S.sb[i].r1);
+    for (int i = S.ss_ptr[l] + warp_id; i < S.ss_ptr[l + 1]; i += n_warps)
+      sn_task_backward_small(warp, S.V, S.ss[i], wsm);
+    grid.sync();
+    sn_tick(S, at, 5, l);
+    if (S.sa_ptr[l + 1] > S.sa_ptr[l]) {
+      for (int i = S.sa_ptr[l] + blockIdx.x; i < S.sa_ptr[l + 1]; i += gridDim.x)
+        sn_task_backward_tri(cta, S.V, S.sa[i], sm);
+      grid.sync();
+      sn_tick(S, at, 6, l);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 2) gn_iterations(Params P, SNDev S, int n_iters) {
   cg::grid_group grid = cg::this_grid();
+  extern __shared__ double sm[];
   __shared__ double scratch[32];
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+  // warp tasks go to the CTAs in reverse order: CTA tasks of the same phase start at CTA 0
+  const int warps_per_cta = blockDim.x >> 5;
+  const int warp_id = (gridDim.x - 1 - blockIdx.x) * warps_per_cta + (threadIdx.x >> 5);
+  const int n_warps = gridDim.x * warps_per_cta;
+  double* wsm = sm + (threadIdx.x >> 5) * kWarpSmemDoubles;
   for (int it = 0; it < n_iters; ++it) {
     stamp(P, 0);
-    // zero the factor storage (fill positions must start at 0)
+    // zero the factor storage (fill positions must start at 0) and the backward accumulators
     for (long long i = tid; i < P.nnzb * 9; i += nthreads) P.M[i] = 0.0;
+    for (int i = tid; i < 3 * P.n; i += nthreads) P.x[i] = 0.0;
     grid.sync();
     phase_linearise(P, scratch, it);
     grid.sync();
@@ -527,34 +546,24 @@ __global__ void __launch_bounds__(kThreads) gn_iterations(Params P, int n_iters)
       const double s = block_sum(v, scratch);
       if (threadIdx.x == 0) P.chi2_out[it] = s;
     }
-    phase_leaves(P);
-    grid.sync();
     stamp(P, 1);
-    for (int l = 1; l < P.n_levels; ++l) {
-      phase_updates(P, l);
-      grid.sync();
-    }
+    int at = 0;
+    sn_tick(S, &at, 0, 0);
+    sn_factorise(S, grid, sm, wsm, warp_id, n_warps, &at);
     if (*reinterpret_cast<volatile int*>(P.status) != 0) return;  // uniform: read after a barrier
     stamp(P, 2);
-    phase_forward_leaves(P, 1, P.rhs, 0);
-    grid.sync();
-    for (int l = 1; l < P.n_levels; ++l) {
-      phase_forward(P, l, 1, P.rhs, 0);
-      grid.sync();
-    }
+    sn_substitute(S, grid, sm, wsm, warp_id, n_warps, &at);
     stamp(P, 3);
-    for (int l = P.n_levels - 1; l >= 0; --l) {
-      phase_backward(P, l, 1, 0, scratch);
-      grid.sync();
-    }
+    sn_back_substitute(S, grid, sm, wsm, warp_id, n_warps, &at);
+    if (tid == 0 && S.ticks) S.ticks[2 * at] = 0;  // terminator
     stamp(P, 4);
     // VertexSE2::oplusImpl (C3)
     for (int p = tid; p < P.n; p += nthreads) {
       const int v = P.perm_vertex[p];
       double* q = P.poses + 3 * static_cast<size_t>(v);
-      q[0] += P.x[3 * p];
-      q[1] += P.x[3 * p + 1];
-      q[2] = normalize_theta(q[2] + P.x[3 * p + 2]);
+      q[0] += __ldcg(P.x + 3 * p);
+      q[1] += __ldcg(P.x + 3 * p + 1);
+      q[2] = normalize_theta(q[2] + __ldcg(P.x + 3 * p + 2));
     }
     if (tid == 0) P.status[1] = it + 1;
     grid.sync();
@@ -745,6 +754,16 @@ struct DeviceSolver {
   double stage_ms[5] = {0, 0, 0, 0, 0};
   Buf<double> poses, meas, info6, M, Dinv, rhs, u, x, chi2_partial, chi2_out, many_rhs, scratch_d;
   size_t vec_cap = 0;  // right-hand sides u/x can hold
+  // supernodal tables (single-GPU path)
+  SNDev S;
+  int grid_sn = 0;
+  Buf<int> colbase, tbl_off, tbl, ff_ptr, fa_ptr, fb_ptr, ss_ptr, sa_ptr, sf_ptr, sb_ptr;
+  Buf<PanelDesc> pn_desc;
+  Buf<SuperDesc> sn_desc;
+  Buf<Task> ff, fa, fb, ss, sa, sf, sb;
+  Buf<double> diag_scratch;
+  Buf<unsigned long long> ticks;
+  size_t n_ticks = 0;
   // domain decomposition
   DDParams D;
   Buf<int> owner, xfinal_ptr, xfinal_cols;
@@ -772,12 +791,23 @@ int dev_create(DeviceSolver** out, int device, void* stream, std::string* err) {
   d->device = device;
   cudaDeviceGetAttribute(&d->sm_count, cudaDevAttrMultiProcessorCount, device);
   int per_sm = 0, per_sm2 = 0;
-  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gn_iterations, kThreads, 0);
+  int per_sm_sn = 0;
+  cudaError_t e = cudaFuncSetAttribute(gn_iterations, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(kSnSmemBytes));
+  if (e == cudaSuccess)
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_sn, gn_iterations, kThreads, kSnSmemBytes);
+  if (e == cudaSuccess && per_sm_sn < 1) {
+    if (err) *err = "pgo dev_create: the Gauss-Newton kernel does not fit on an SM";
+    delete d;
+    return PGO_ERR_CUDA;
+  }
+  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gn_dd_local, kThreads, 0);
   if (e == cudaSuccess)
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, solve_many, kThreads, 0);
   if (e == cudaSuccess) {
     per_sm = std::max(1, std::min(per_sm, per_sm2));
     d->grid = d->sm_count * per_sm;
+    d->grid_sn = d->sm_count * std::min(per_sm_sn, 2);
     if (stream) {
       d->stream = static_cast<cudaStream_t>(stream);
     } else {
@@ -789,7 +819,7 @@ int dev_create(DeviceSolver** out, int device, void* stream, std::string* err) {
   if (e == cudaSuccess) e = cudaEventCreate(&d->ev1);
   if (e == cudaSuccess) e = d->status.reserve(4);
   if (e == cudaSuccess) e = d->stamps.reserve(8);
-  if (e == cudaSuccess) e = d->chi2_partial.reserve(d->grid);
+  if (e == cudaSuccess) e = d->chi2_partial.reserve(std::max(d->grid, d->grid_sn));
   if (e != cudaSuccess) {
     if (err) *err = std::string("pgo dev_create: ") + cudaGetErrorString(e);
     dev_destroy(d);
@@ -810,6 +840,15 @@ void dev_destroy(DeviceSolver* d) {
   Buf<double>* db[] = {&d->poses, &d->meas, &d->info6, &d->M, &d->Dinv, &d->rhs, &d->u, &d->x,
                        &d->chi2_partial, &d->chi2_out, &d->many_rhs, &d->scratch_d};
   for (size_t i = 0; i < sizeof(db) / sizeof(db[0]); ++i) db[i]->release();
+  Buf<int>* sb[] = {&d->colbase, &d->tbl_off, &d->tbl,    &d->ff_ptr, &d->fa_ptr,
+                    &d->fb_ptr,  &d->ss_ptr,  &d->sa_ptr, &d->sf_ptr, &d->sb_ptr};
+  d->pn_desc.release();
+  d->sn_desc.release();
+  for (size_t i = 0; i < sizeof(sb) / sizeof(sb[0]); ++i) sb[i]->release();
+  Buf<Task>* tb[] = {&d->ff, &d->fa, &d->fb, &d->ss, &d->sa, &d->sf, &d->sb};
+  for (size_t i = 0; i < sizeof(tb) / sizeof(tb[0]); ++i) tb[i]->release();
+  d->diag_scratch.release();
+  d->ticks.release();
   d->inc.release();
   d->ops.release();
   d->fwd_ops.release();
@@ -823,6 +862,17 @@ void dev_destroy(DeviceSolver* d) {
   if (d->ev1) cudaEventDestroy(d->ev1);
   if (d->own_stream && d->stream) cudaStreamDestroy(d->stream);
   delete d;
+}
+
+int dev_phase_ticks(DeviceSolver* d, uint64_t* out, int cap, std::string* err) {
+  PGO_CUDA(cudaSetDevice(d->device));
+  const size_t n = std::min(static_cast<size_t>(cap < 0 ? 0 : cap) / 2, d->n_ticks);
+  if (!d->have_structure || n == 0) return 0;
+  PGO_CUDA(cudaMemcpyAsync(out, d->ticks.p, 2 * n * sizeof(uint64_t), cudaMemcpyDeviceToHost, d->stream));
+  PGO_CUDA(cudaStreamSynchronize(d->stream));
+  int k = 0;
+  while (static_cast<size_t>(k) < n && out[2 * k] != 0) ++k;
+  return k;
 }
 
 void* dev_stream(const DeviceSolver* d) { return d->stream; }
@@ -850,6 +900,30 @@ int dev_set_structure(DeviceSolver* d, const Symbolic& S, const GraphTables& G, 
   PGO_CUDA(d->ops.upload(S.ops, s));
   PGO_CUDA(d->fwd_ops.upload(S.fwd_ops, s));
   PGO_CUDA(d->fwd_ptr.upload(S.fwd_ptr, s));
+  const Supernodal& N = S.sn;
+  PGO_CUDA(d->pn_desc.upload(N.pn, s));
+  PGO_CUDA(d->sn_desc.upload(N.sn, s));
+  PGO_CUDA(d->colbase.upload(N.colbase, s));
+  PGO_CUDA(d->tbl_off.upload(N.tbl_off, s));
+  PGO_CUDA(d->tbl.upload(N.tbl, s));
+  PGO_CUDA(d->ff_ptr.upload(N.ff_ptr, s));
+  PGO_CUDA(d->fa_ptr.upload(N.fa_ptr, s));
+  PGO_CUDA(d->fb_ptr.upload(N.fb_ptr, s));
+  PGO_CUDA(d->ss_ptr.upload(N.ss_ptr, s));
+  PGO_CUDA(d->sa_ptr.upload(N.sa_ptr, s));
+  PGO_CUDA(d->sf_ptr.upload(N.sf_ptr, s));
+  PGO_CUDA(d->sb_ptr.upload(N.sb_ptr, s));
+  PGO_CUDA(d->ff.upload(N.ff, s));
+  PGO_CUDA(d->fa.upload(N.fa, s));
+  PGO_CUDA(d->fb.upload(N.fb, s));
+  PGO_CUDA(d->ss.upload(N.ss, s));
+  PGO_CUDA(d->sa.upload(N.sa, s));
+  PGO_CUDA(d->sf.upload(N.sf, s));
+  PGO_CUDA(d->sb.upload(N.sb, s));
+  PGO_CUDA(d->diag_scratch.reserve(9 * static_cast<size_t>(N.scratch_blocks) + 9));
+  d->n_ticks = 2 * static_cast<size_t>(N.n_plevels) + 4 * static_cast<size_t>(N.n_slevels) + 4;
+  PGO_CUDA(d->ticks.reserve(2 * d->n_ticks));
+  PGO_CUDA(cudaMemsetAsync(d->ticks.p, 0, 2 * d->n_ticks * sizeof(unsigned long long), s));
   std::vector<int> perm_vertex(S.n);
   for (int v = 0; v < G.n_vertices; ++v)
     if (G.vpos[v] >= 0) perm_vertex[G.vpos[v]] = v;
@@ -906,6 +980,37 @@ int dev_set_structure(DeviceSolver* d, const Symbolic& S, const GraphTables& G, 
   P.chi2_out = nullptr;
   P.status = d->status.p;
   P.stamps = d->stamps.p;
+  SNDev& SD = d->S;
+  SD.V.row_idx = d->row_idx.p;
+  SD.V.pn = d->pn_desc.p;
+  SD.V.sn = d->sn_desc.p;
+  SD.V.colbase = d->colbase.p;
+  SD.V.tbl_off = d->tbl_off.p;
+  SD.V.tbl = d->tbl.p;
+  SD.V.M = d->M.p;
+  SD.V.Dinv = d->Dinv.p;
+  SD.V.z = d->rhs.p;
+  SD.V.u = d->u.p;
+  SD.V.x = d->x.p;
+  SD.V.scratch = d->diag_scratch.p;
+  SD.V.status = d->status.p;
+  SD.n_plevels = N.n_plevels;
+  SD.n_slevels = N.n_slevels;
+  SD.ff_ptr = d->ff_ptr.p;
+  SD.fa_ptr = d->fa_ptr.p;
+  SD.fb_ptr = d->fb_ptr.p;
+  SD.ss_ptr = d->ss_ptr.p;
+  SD.sa_ptr = d->sa_ptr.p;
+  SD.sf_ptr = d->sf_ptr.p;
+  SD.sb_ptr = d->sb_ptr.p;
+  SD.ff = d->ff.p;
+  SD.fa = d->fa.p;
+  SD.fb = d->fb.p;
+  SD.ss = d->ss.p;
+  SD.sa = d->sa.p;
+  SD.sf = d->sf.p;
+  SD.sb = d->sb.p;
+  SD.ticks = d->ticks.p;
   DDParams& D = d->D;
   D.owner = d->owner.p;
   D.rank = G.rank;
@@ -985,10 +1090,18 @@ int dev_iterate(DeviceSolver* d, int n_iters, double* chi2_out, int* iters_done,
   PGO_CUDA(cudaMemsetAsync(d->chi2_out.p, 0, n_iters * sizeof(double), d->stream));
   Params P = d->P;
   P.chi2_out = d->chi2_out.p;
-  void* args[] = {&P, &n_iters};
+  if (d->D.world != 1) {
+    if (err) *err = "this solver was analysed for a domain decomposition: use the pgo_dd_* calls";
+    return PGO_ERR_ARG;
+  }
+  SNDev SD = d->S;
+  // marginals may have re-allocated the substitution vectors
+  SD.V.u = d->u.p;
+  SD.V.x = d->x.p;
+  void* args[] = {&P, &SD, &n_iters};
   PGO_CUDA(cudaEventRecord(d->ev0, d->stream));
-  PGO_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(gn_iterations), dim3(d->grid),
-                                       dim3(kThreads), args, 0, d->stream));
+  PGO_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(gn_iterations), dim3(d->grid_sn),
+                                       dim3(kThreads), args, kSnSmemBytes, d->stream));
   PGO_CUDA(cudaEventRecord(d->ev1, d->stream));
   d->launches++;
   int status[4] = {0, 0, 0, 0};

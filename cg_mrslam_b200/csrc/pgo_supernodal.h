@@ -1,0 +1,623 @@
+// Supernodal numeric factorisation and substitution of the permuted block Hessian (single-GPU
+// path of the pose-graph solver). Replaces, for one GPU, the work of g2o's
+// LinearSolverCSparse::solve (selected by the reference at
+// src/slam/graph_slam.cpp:45-53): numeric Cholesky + two triangular solves.
+//
+// Storage and arithmetic are those of the level-by-level path (pgo_kernels.cu): block CSC of 3x3
+// blocks, UNSCALED blocks  M(i,j) = A(i,j) - sum_k M(i,k) Dinv(k) M(j,k)^T,  D(j) = M(j,j),
+// Dinv(j) = D(j)^-1; forward  z_i -= M(i,k) u_k, u_k = Dinv_k z_k; backward
+// x_j = u_j - Dinv_j sum_{i>j} M(i,j)^T x_i.  What changes is the schedule: columns are grouped
+// into supernodes / panels (pgo_symbolic.h), a panel is factorised as a small dense problem in
+// shared memory and its outer product is subtracted from later columns with fp64 atomics
+// (right-looking), so the number of grid-wide barriers is the number of PANEL levels (~100 for the
+// 50k-vertex benchmark graph) instead of the elimination-tree height (~1000), and the index
+// traffic is one table entry per target block instead of one 12-byte record per block product.
+//
+// Every task function is written against a "group" (rank / size / sync) and uses neither warp
+// shuffles nor per-thread state across a sync, so the SAME source runs
+//   * on the device with a CTA group (__syncthreads) or a warp group (__syncwarp), and
+//   * on the host with a one-thread group (tests/hostsim/pgo_hostsim.cpp, TEST ONLY), which is
+//     how the tables and the task logic are checked on a GPU-less box.
+#ifndef CGM_PGO_SUPERNODAL_H
+#define CGM_PGO_SUPERNODAL_H
+
+#include <cmath>
+#include <cstddef>
+
+#include "pgo_symbolic.h"
+
+#if defined(__CUDACC__)
+#define PGO_HD __host__ __device__ __forceinline__
+#else
+#define PGO_HD inline
+#endif
+
+namespace pgo {
+
+struct SNView {
+  // structure (pgo_symbolic.h)
+  const int* row_idx;
+  const PanelDesc* pn;
+  const SuperDesc* sn;
+  const int* colbase;
+  const int* tbl_off;
+  const int* tbl;
+  // numeric
+  double* M;        // [nnzb][9]
+  double* Dinv;     // [n][9]
+  double* z;        // [n][3] right-hand side, overwritten by the forward substitution
+  double* u;        // [n][3]
+  double* x;        // [n][3] must be zero before the backward substitution
+  double* scratch;  // [scratch_blocks][9]
+  int* status;      // [0] set to 1 when a pivot block is not positive definite
+};
+
+// doubles of shared memory a group needs for any task of its kind
+static const int kCtaSmemDoubles = kPanelWidth * kPanelWidth * 9 + kPanelWidth * 9 +
+                                   3 * kPanelWidth * 3 * kRowChunk;  // factor task: 11664
+static const int kWarpSmemDoubles = kSmallWidth * kSmallWidth * 9 + kSmallWidth * 9 +
+                                    3 * kSmallWidth * 3 * kSmallRows;  // fused task: 1332
+static_assert(kTileBudget * 9 <= kCtaSmemDoubles, "update tiles must fit the CTA's shared memory");
+static_assert(6 * kMaxSuperWidth + kPanelWidth * kPanelWidth * 9 + kPanelWidth * 9 + 3 * 256 <=
+                  kCtaSmemDoubles, "a wide supernode's vectors must fit the CTA's shared memory");
+
+struct SeqGroup {  // host: one thread plays every rank in turn
+  PGO_HD int rank() const { return 0; }
+  PGO_HD int size() const { return 1; }
+  PGO_HD void sync() const {}
+};
+
+// L2-coherent load / accumulate: panels are written by other SMs in the previous phase
+PGO_HD double sn_ld(const double* p) {
+#if defined(__CUDA_ARCH__)
+  return __ldcg(p);
+#else
+  return *p;
+#endif
+}
+PGO_HD void sn_add(double* p, double v) {
+#if defined(__CUDA_ARCH__)
+  atomicAdd(p, v);
+#else
+  *p += v;
+#endif
+}
+PGO_HD void sn_fail(int* status) {
+#if defined(__CUDA_ARCH__)
+  atomicExch(status, 1);
+#else
+  *status = 1;
+#endif
+}
+
+// first position of column t of a chain whose first column starts at `base` with `len` blocks
+PGO_HD int sn_colpos(int base, int len, int t) { return base + t * len - t * (t - 1) / 2; }
+
+// Inverse of a symmetric positive definite 3x3 (lower triangle read) by cofactors: one division on
+// the dependency chain instead of three square roots and six divisions. Positive definiteness by
+// Sylvester's criterion; false if a leading minor is not positive.
+PGO_HD bool sn_spd_inverse(const double* a, double* inv) {
+  const double a00 = a[0], a10 = a[3], a20 = a[6], a11 = a[4], a21 = a[7], a22 = a[8];
+  const double c00 = a11 * a22 - a21 * a21;
+  const double c10 = a20 * a21 - a10 * a22;
+  const double c20 = a10 * a21 - a20 * a11;
+  const double c11 = a00 * a22 - a20 * a20;
+  const double c21 = a10 * a20 - a00 * a21;
+  const double c22 = a00 * a11 - a10 * a10;
+  const double det = a00 * c00 + a10 * c10 + a20 * c20;
+  if (!(a00 > 0.0) || !(c22 > 0.0) || !(det > 0.0)) return false;
+  const double r = 1.0 / det;
+  inv[0] = c00 * r;
+  inv[1] = inv[3] = c10 * r;
+  inv[2] = inv[6] = c20 * r;
+  inv[4] = c11 * r;
+  inv[5] = inv[7] = c21 * r;
+  inv[8] = c22 * r;
+  return true;
+}
+
+// ---- diagonal part of a panel: w x w blocks, Dg[(i * w + t) * 9 + k], i >= t loaded -------------
+template <class G>
+PGO_HD void sn_load_diag(const G& g, const SNView& V, int base, int len, int w, double* Dg) {
+  for (int idx = g.rank(); idx < w * w * 9; idx += g.size()) {
+    const int i = idx / (w * 9), t = (idx / 9) % w, k = idx % 9;
+    Dg[idx] = i >= t ? sn_ld(V.M + 9 * static_cast<size_t>(sn_colpos(base, len, t) + (i - t)) + k) : 0.0;
+  }
+}
+
+// In-place block LDL^T of the diagonal part. On return (after a sync):
+//   Dg[i][t], i >= t : final M(c0+i, c0+t);  Dg[s][t], s < t : G(s,t) = Dinv_s M(t,s)^T;  Di[t].
+template <class G>
+PGO_HD void sn_factor_diag(const G& g, const SNView& V, int w, double* Dg, double* Di) {
+  for (int s = 0; s < w; ++s) {
+    if (g.rank() == 0) {
+      if (!sn_spd_inverse(Dg + (s * w + s) * 9, Di + 9 * s)) {
+        sn_fail(V.status);
+        for (int k = 0; k < 9; ++k) Di[9 * s + k] = 0.0;
+      }
+    }
+    g.sync();
+    // one pass: G(s,t) into the upper part, and the trailing update with G formed on the fly
+    const int rem = w - s - 1;
+    const double* d = Di + 9 * s;
+    for (int idx = g.rank(); idx < rem * rem * 9; idx += g.size()) {
+      const int i = s + 1 + idx / (rem * 9), t = s + 1 + (idx / 9) % rem;
+      const int r = (idx % 9) / 3, c = idx % 3;
+      const double* m = Dg + (t * w + s) * 9;  // M(t,s)
+      if (i == s + 1)                           // the first row of the pass also publishes G(s,t)
+        Dg[(s * w + t) * 9 + 3 * r + c] =
+            d[3 * r] * m[3 * c] + d[3 * r + 1] * m[3 * c + 1] + d[3 * r + 2] * m[3 * c + 2];
+      if (t > i) continue;
+      const double* a = Dg + (i * w + s) * 9;
+      const double g0 = d[0] * m[3 * c] + d[1] * m[3 * c + 1] + d[2] * m[3 * c + 2];
+      const double g1 = d[3] * m[3 * c] + d[4] * m[3 * c + 1] + d[5] * m[3 * c + 2];
+      const double g2 = d[6] * m[3 * c] + d[7] * m[3 * c + 1] + d[8] * m[3 * c + 2];
+      Dg[(i * w + t) * 9 + 3 * r + c] -= a[3 * r] * g0 + a[3 * r + 1] * g1 + a[3 * r + 2] * g2;
+    }
+    g.sync();
+  }
+}
+
+// Rows below the diagonal part, staged as scalar rows: xs[(3 t + c) * ldx + 3 a + r] = M(a,t)[r][c].
+template <class G>
+PGO_HD void sn_load_rows(const G& g, const SNView& V, const PanelDesc& pd, int r0, int nrows, int ldx,
+                         double* xs) {
+  for (int t = 0; t < pd.w; ++t) {
+    const double* src =
+        V.M + 9 * static_cast<size_t>(sn_colpos(pd.base, pd.w + pd.m, t) + (pd.w - t) + r0);
+    for (int idx = g.rank(); idx < 9 * nrows; idx += g.size()) {
+      const int a = idx / 9, k = idx % 9;
+      xs[(3 * t + k % 3) * ldx + 3 * a + k / 3] = sn_ld(src + idx);
+    }
+  }
+}
+
+template <class G>
+PGO_HD void sn_store_rows(const G& g, const SNView& V, const PanelDesc& pd, int r0, int nrows, int ldx,
+                          const double* xs) {
+  for (int t = 1; t < pd.w; ++t) {  // column 0 is never modified inside the panel
+    double* dst = V.M + 9 * static_cast<size_t>(sn_colpos(pd.base, pd.w + pd.m, t) + (pd.w - t) + r0);
+    for (int idx = g.rank(); idx < 9 * nrows; idx += g.size()) {
+      const int a = idx / 9, k = idx % 9;
+      dst[idx] = xs[(3 * t + k % 3) * ldx + 3 * a + k / 3];
+    }
+  }
+}
+
+// M(a,t) -= sum_{s<t} M(a,s) G(s,t), one scalar row per rank.
+template <class G>
+PGO_HD void sn_solve_rows(const G& g, int w, const double* Dg, double* xs, int ldx, int n_scalar) {
+  for (int row = g.rank(); row < n_scalar; row += g.size()) {
+    for (int t = 1; t < w; ++t) {
+      double a0 = xs[(3 * t) * ldx + row], a1 = xs[(3 * t + 1) * ldx + row],
+             a2 = xs[(3 * t + 2) * ldx + row];
+      for (int s = 0; s < t; ++s) {
+        const double x0 = xs[(3 * s) * ldx + row], x1 = xs[(3 * s + 1) * ldx + row],
+                     x2 = xs[(3 * s + 2) * ldx + row];
+        const double* gg = Dg + (s * w + t) * 9;
+        a0 -= x0 * gg[0] + x1 * gg[3] + x2 * gg[6];
+        a1 -= x0 * gg[1] + x1 * gg[4] + x2 * gg[7];
+        a2 -= x0 * gg[2] + x1 * gg[5] + x2 * gg[8];
+      }
+      xs[(3 * t) * ldx + row] = a0;
+      xs[(3 * t + 1) * ldx + row] = a1;
+      xs[(3 * t + 2) * ldx + row] = a2;
+    }
+  }
+}
+
+template <class G>
+PGO_HD void sn_store_diag(const G& g, const SNView& V, const PanelDesc& pd, const double* Dg,
+                          const double* Di, int scratch_at) {
+  const int w = pd.w;
+  if (scratch_at >= 0) {
+    double* dst = V.scratch + 9 * static_cast<size_t>(scratch_at);
+    for (int idx = g.rank(); idx < w * w * 9; idx += g.size()) dst[idx] = Dg[idx];
+  } else {
+    for (int idx = g.rank(); idx < w * w * 9; idx += g.size()) {
+      const int i = idx / (w * 9), t = (idx / 9) % w, k = idx % 9;
+      if (i >= t) V.M[9 * static_cast<size_t>(sn_colpos(pd.base, w + pd.m, t) + (i - t)) + k] = Dg[idx];
+    }
+  }
+  for (int idx = g.rank(); idx < w * 9; idx += g.size())
+    V.Dinv[9 * static_cast<size_t>(pd.c0) + idx] = Di[idx];
+}
+
+// ---- factorisation tasks ---------------------------------------------------------------------------
+// fa: factor the diagonal part (every row-chunk task of a panel repeats it: w <= 16, cheap) and
+// finish the rows [r0, r1) below it. The r0 == 0 task publishes the diagonal part and Dinv.
+template <class G>
+PGO_HD void sn_task_factor(const G& g, const SNView& V, const Task& T, double* sm) {
+  const PanelDesc pd = V.pn[T.id];
+  const int w = pd.w, nrows = T.r1 - T.r0, ldx = 3 * nrows;
+  double* Dg = sm;
+  double* Di = Dg + w * w * 9;
+  double* xs = Di + w * 9;
+  sn_load_diag(g, V, pd.base, w + pd.m, w, Dg);
+  sn_load_rows(g, V, pd, T.r0, nrows, ldx, xs);
+  g.sync();
+  sn_factor_diag(g, V, w, Dg, Di);
+  sn_solve_rows(g, w, Dg, xs, ldx, 3 * nrows);
+  g.sync();
+  sn_store_rows(g, V, pd, T.r0, nrows, ldx, xs);
+  if (T.r0 == 0) sn_store_diag(g, V, pd, Dg, Di, pd.scratch);
+  g.sync();
+}
+
+PGO_HD int sn_target(const SNView& V, int meta, int a, int b) {
+  return V.colbase[meta + b] + V.tbl[V.tbl_off[meta + b] + a];
+}
+
+// fb: one tile of the panel's outer product
+//   M(r_a, r_b) -= sum_t M(a,t) Dinv_t M(b,t)^T   (a >= b, rows of the panel's below list)
+// T.r0 = first row a, T.r1 = first column b, T.aux = (tile rows << 16) | tile columns. The (0,0)
+// tile also moves a scratch-published diagonal part into place (nothing reads it in this phase).
+template <class G>
+PGO_HD void sn_task_update(const G& g, const SNView& V, const Task& T, double* sm) {
+  const PanelDesc pd = V.pn[T.id];
+  const int w = pd.w, m = pd.m, len = w + m;
+  const int i0 = T.r0, j0 = T.r1, ti = T.aux >> 16, tj = T.aux & 0xFFFF;
+  const int ni = m - i0 < ti ? m - i0 : ti, nj = m - j0 < tj ? m - j0 : tj;
+  double* As = sm;               // [(t * 9 + k) * ti + al]
+  double* Ws = As + w * 9 * ti;  // [(t * 9 + k) * tj + bl], W = Dinv_t M(b,t)^T
+  if (i0 == 0 && j0 == 0 && pd.scratch >= 0) {
+    const double* src = V.scratch + 9 * static_cast<size_t>(pd.scratch);
+    for (int idx = g.rank(); idx < w * w * 9; idx += g.size()) {
+      const int i = idx / (w * 9), t = (idx / 9) % w, k = idx % 9;
+      if (i >= t) V.M[9 * static_cast<size_t>(sn_colpos(pd.base, len, t) + (i - t)) + k] = sn_ld(src + idx);
+    }
+  }
+  for (int t = 0; t < w; ++t) {
+    const double* src = V.M + 9 * static_cast<size_t>(sn_colpos(pd.base, len, t) + (w - t) + i0);
+    for (int idx = g.rank(); idx < 9 * ni; idx += g.size())
+      As[(t * 9 + idx % 9) * ti + idx / 9] = sn_ld(src + idx);
+  }
+  for (int idx = g.rank(); idx < w * nj; idx += g.size()) {
+    const int t = idx / nj, bl = idx % nj;
+    const double* mp = V.M + 9 * static_cast<size_t>(sn_colpos(pd.base, len, t) + (w - t) + j0 + bl);
+    const double* dp = V.Dinv + 9 * static_cast<size_t>(pd.c0 + t);
+    double mb[9], d[9];
+    for (int k = 0; k < 9; ++k) {
+      mb[k] = sn_ld(mp + k);
+      d[k] = sn_ld(dp + k);
+    }
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c)
+        Ws[(t * 9 + 3 * r + c) * tj + bl] =
+            d[3 * r] * mb[3 * c] + d[3 * r + 1] * mb[3 * c + 1] + d[3 * r + 2] * mb[3 * c + 2];
+  }
+  g.sync();
+  // 8 x 4 patches of (row, column) pairs per warp: a warp's shared loads touch 8 / 4 consecutive
+  // doubles (ti is a multiple of 8, tj of 4)
+  const int pr = ti >> 3, n_items = (ti * tj);
+  for (int item = g.rank(); item < n_items; item += g.size()) {
+    const int lane = item & 31, q = item >> 5;
+    const int al = (q % pr) * 8 + (lane & 7), bl = (q / pr) * 4 + (lane >> 3);
+    const int a = i0 + al, b = j0 + bl;
+    if (al >= ni || bl >= nj || a < b) continue;
+    double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    for (int t = 0; t < w; ++t) {
+      double av[9], wv[9];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+      for (int k = 0; k < 9; ++k) {
+        av[k] = As[(t * 9 + k) * ti + al];
+        wv[k] = Ws[(t * 9 + k) * tj + bl];
+      }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+      for (int r = 0; r < 3; ++r)
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int c = 0; c < 3; ++c)
+          acc[3 * r + c] += av[3 * r] * wv[c] + av[3 * r + 1] * wv[3 + c] + av[3 * r + 2] * wv[6 + c];
+    }
+    double* dst = V.M + 9 * static_cast<size_t>(sn_target(V, pd.meta, a, b));
+    for (int k = 0; k < 9; ++k) sn_add(dst + k, -acc[k]);
+  }
+  g.sync();
+}
+
+// ff: a small panel (w <= kSmallWidth, at most kSmallRows rows below it) start to finish.
+template <class G>
+PGO_HD void sn_task_fused(const G& g, const SNView& V, const Task& T, double* sm) {
+  const PanelDesc pd = V.pn[T.id];
+  const int w = pd.w, m = pd.m, ldx = 3 * m;
+  double* Dg = sm;
+  double* Di = Dg + w * w * 9;
+  double* xs = Di + w * 9;
+  sn_load_diag(g, V, pd.base, w + m, w, Dg);
+  sn_load_rows(g, V, pd, 0, m, ldx, xs);
+  g.sync();
+  sn_factor_diag(g, V, w, Dg, Di);
+  sn_solve_rows(g, w, Dg, xs, ldx, 3 * m);
+  g.sync();
+  sn_store_rows(g, V, pd, 0, m, ldx, xs);
+  sn_store_diag(g, V, pd, Dg, Di, -1);
+  // outer product straight from shared memory: rank = column b, every rank walks the rows a >= b
+  for (int b = g.rank(); b < m; b += g.size()) {
+    const int cb = V.colbase[pd.meta + b], to = V.tbl_off[pd.meta + b];
+    for (int a = b; a < m; ++a) {
+      double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+      for (int t = 0; t < w; ++t) {
+        double av[9], y[9], bv[9];
+        for (int k = 0; k < 9; ++k) {
+          av[k] = xs[(3 * t + k % 3) * ldx + 3 * a + k / 3];
+          bv[k] = xs[(3 * t + k % 3) * ldx + 3 * b + k / 3];
+        }
+        const double* d = Di + 9 * t;
+        for (int r = 0; r < 3; ++r)
+          for (int c = 0; c < 3; ++c)
+            y[3 * r + c] = av[3 * r] * d[c] + av[3 * r + 1] * d[3 + c] + av[3 * r + 2] * d[6 + c];
+        for (int r = 0; r < 3; ++r)
+          for (int c = 0; c < 3; ++c)
+            acc[3 * r + c] += y[3 * r] * bv[3 * c] + y[3 * r + 1] * bv[3 * c + 1] + y[3 * r + 2] * bv[3 * c + 2];
+      }
+      double* dst = V.M + 9 * static_cast<size_t>(cb + V.tbl[to + a]);
+      for (int k = 0; k < 9; ++k) sn_add(dst + k, -acc[k]);
+    }
+  }
+  g.sync();
+}
+
+// ---- substitution tasks -----------------------------------------------------------------------------
+PGO_HD void sn_mat_vec(const double* m, const double* v, double* out) {  // out = m v
+  out[0] = m[0] * v[0] + m[1] * v[1] + m[2] * v[2];
+  out[1] = m[3] * v[0] + m[4] * v[1] + m[5] * v[2];
+  out[2] = m[6] * v[0] + m[7] * v[1] + m[8] * v[2];
+}
+PGO_HD void sn_mat_t_vec_add(const double* m, const double* v, double* acc) {  // acc += m^T v
+  acc[0] += m[0] * v[0] + m[3] * v[1] + m[6] * v[2];
+  acc[1] += m[1] * v[0] + m[4] * v[1] + m[7] * v[2];
+  acc[2] += m[2] * v[0] + m[5] * v[1] + m[8] * v[2];
+}
+
+template <class G>
+PGO_HD void sn_load_dinv(const G& g, const SNView& V, int c0, int w, double* Di) {
+  for (int idx = g.rank(); idx < 9 * w; idx += g.size())
+    Di[idx] = sn_ld(V.Dinv + 9 * static_cast<size_t>(c0) + idx);
+}
+
+// Triangular part of one panel on staged vectors (all operands in shared memory).
+template <class G>
+PGO_HD void sn_forward_panel(const G& g, int w, const double* Dg, const double* Di, double* zs,
+                             double* us) {
+  for (int t = 0; t < w; ++t) {
+    if (g.rank() == 0) sn_mat_vec(Di + 9 * t, zs + 3 * t, us + 3 * t);
+    g.sync();
+    for (int tp = t + 1 + g.rank(); tp < w; tp += g.size()) {
+      double v[3];
+      sn_mat_vec(Dg + (tp * w + t) * 9, us + 3 * t, v);
+      zs[3 * tp] -= v[0];
+      zs[3 * tp + 1] -= v[1];
+      zs[3 * tp + 2] -= v[2];
+    }
+    g.sync();
+  }
+}
+
+// rows [r0, r1) below the SUPERNODE of panel p:  z_{r_a} -= sum_t M(a,t) u_t  (atomic).
+// us: the supernode's u in shared memory, or null to read it from global memory.
+template <class G>
+PGO_HD void sn_forward_rows(const G& g, const SNView& V, int p, int r0, int r1, const double* us) {
+  const PanelDesc pd = V.pn[p];
+  const SuperDesc sd = V.sn[pd.sn];
+  const int o = pd.sn_off, len = sd.W + sd.m;
+  for (int a = r0 + g.rank(); a < r1; a += g.size()) {
+    double acc[3] = {0.0, 0.0, 0.0};
+    for (int t = 0; t < pd.w; ++t) {
+      const double* mp = V.M + 9 * static_cast<size_t>(sn_colpos(sd.base, len, o + t) + (sd.W - o - t) + a);
+      double mb[9], uv[3], v[3];
+      for (int k = 0; k < 9; ++k) mb[k] = sn_ld(mp + k);
+      for (int k = 0; k < 3; ++k)
+        uv[k] = us ? us[3 * (o + t) + k] : sn_ld(V.u + 3 * static_cast<size_t>(pd.c0 + t) + k);
+      sn_mat_vec(mb, uv, v);
+      acc[0] += v[0];
+      acc[1] += v[1];
+      acc[2] += v[2];
+    }
+    const int r = V.row_idx[sd.base + sd.W + a];
+    for (int k = 0; k < 3; ++k) sn_add(V.z + 3 * static_cast<size_t>(r) + k, -acc[k]);
+  }
+}
+
+// sa (forward): triangular part of a wide supernode, panel by panel, in one group.
+// shared: zs[3W] us[3W] Dg[w*w*9] Di[w*9]
+template <class G>
+PGO_HD void sn_task_forward_tri(const G& g, const SNView& V, const Task& T, double* sm) {
+  const SuperDesc sd = V.sn[T.id];
+  const int W = sd.W, len = sd.W + sd.m;
+  double* zs = sm;
+  double* us = zs + 3 * W;
+  double* Dg = us + 3 * W;
+  double* Di = Dg + kPanelWidth * kPanelWidth * 9;
+  for (int idx = g.rank(); idx < 3 * W; idx += g.size())
+    zs[idx] = sn_ld(V.z + 3 * static_cast<size_t>(sd.c0) + idx);
+  for (int p = sd.pn_begin; p < sd.pn_end; ++p) {
+    const PanelDesc pd = V.pn[p];
+    const int w = pd.w, o = pd.sn_off;
+    sn_load_diag(g, V, pd.base, w + pd.m, w, Dg);
+    sn_load_dinv(g, V, pd.c0, w, Di);
+    g.sync();
+    sn_forward_panel(g, w, Dg, Di, zs + 3 * o, us + 3 * o);
+    // the supernode's remaining columns are rows of this panel
+    for (int tp = o + w + g.rank(); tp < W; tp += g.size()) {
+      double acc[3] = {0.0, 0.0, 0.0};
+      for (int t = 0; t < w; ++t) {
+        const double* mp =
+            V.M + 9 * static_cast<size_t>(sn_colpos(sd.base, len, o + t) + (w - t) + (tp - o - w));
+        double mb[9], v[3];
+        for (int k = 0; k < 9; ++k) mb[k] = sn_ld(mp + k);
+        sn_mat_vec(mb, us + 3 * (o + t), v);
+        acc[0] += v[0];
+        acc[1] += v[1];
+        acc[2] += v[2];
+      }
+      zs[3 * tp] -= acc[0];
+      zs[3 * tp + 1] -= acc[1];
+      zs[3 * tp + 2] -= acc[2];
+    }
+    g.sync();
+  }
+  for (int idx = g.rank(); idx < 3 * W; idx += g.size()) V.u[3 * static_cast<size_t>(sd.c0) + idx] = us[idx];
+  g.sync();
+}
+
+// ss (forward): a narrow supernode (one panel) including the rows below it.
+// shared: zs[3W] us[3W] Dg[W*W*9] Di[W*9]
+template <class G>
+PGO_HD void sn_task_forward_small(const G& g, const SNView& V, const Task& T, double* sm) {
+  const SuperDesc sd = V.sn[T.id];
+  const int W = sd.W;
+  double* zs = sm;
+  double* us = zs + 3 * W;
+  double* Dg = us + 3 * W;
+  double* Di = Dg + W * W * 9;
+  for (int idx = g.rank(); idx < 3 * W; idx += g.size())
+    zs[idx] = sn_ld(V.z + 3 * static_cast<size_t>(sd.c0) + idx);
+  sn_load_diag(g, V, sd.base, W + sd.m, W, Dg);
+  sn_load_dinv(g, V, sd.c0, W, Di);
+  g.sync();
+  sn_forward_panel(g, W, Dg, Di, zs, us);
+  for (int idx = g.rank(); idx < 3 * W; idx += g.size()) V.u[3 * static_cast<size_t>(sd.c0) + idx] = us[idx];
+  sn_forward_rows(g, V, sd.pn_begin, 0, sd.m, us);
+  g.sync();
+}
+
+// Backward, rows [r0, r1) below the supernode of panel p:  x_{c0+t} += sum_a M(a,t)^T x_{r_a}
+// (x doubles as the accumulator of a wide supernode's columns; atomic).
+template <class G>
+PGO_HD void sn_backward_rows(const G& g, const SNView& V, int p, int r0, int r1) {
+  const PanelDesc pd = V.pn[p];
+  const SuperDesc sd = V.sn[pd.sn];
+  const int w = pd.w, o = pd.sn_off, len = sd.W + sd.m;
+  const int split = g.size() / w > 0 ? g.size() / w : 1;
+  for (int item = g.rank(); item < w * split; item += g.size()) {
+    const int t = item % w, h = item / w;
+    const size_t col = static_cast<size_t>(sn_colpos(sd.base, len, o + t) + (sd.W - o - t));
+    double acc[3] = {0.0, 0.0, 0.0};
+    for (int a = r0 + h; a < r1; a += split) {
+      const double* mp = V.M + 9 * (col + a);
+      const int r = V.row_idx[sd.base + sd.W + a];
+      double mb[9], xv[3];
+      for (int k = 0; k < 9; ++k) mb[k] = sn_ld(mp + k);
+      for (int k = 0; k < 3; ++k) xv[k] = sn_ld(V.x + 3 * static_cast<size_t>(r) + k);
+      sn_mat_t_vec_add(mb, xv, acc);
+    }
+    for (int k = 0; k < 3; ++k) sn_add(V.x + 3 * static_cast<size_t>(pd.c0 + t) + k, acc[k]);
+  }
+}
+
+// Triangular part of one panel, backward: xs holds the accumulators on entry, x on return.
+template <class G>
+PGO_HD void sn_backward_panel(const G& g, int w, const double* Dg, const double* Di, const double* us,
+                              double* xs) {
+  for (int t = w - 1; t >= 0; --t) {
+    if (g.rank() == 0) {
+      double v[3];
+      sn_mat_vec(Di + 9 * t, xs + 3 * t, v);
+      for (int k = 0; k < 3; ++k) xs[3 * t + k] = us[3 * t + k] - v[k];
+    }
+    g.sync();
+    for (int sidx = g.rank(); sidx < t; sidx += g.size())
+      sn_mat_t_vec_add(Dg + (t * w + sidx) * 9, xs + 3 * t, xs + 3 * sidx);  // M(t,s)^T x_t
+    g.sync();
+  }
+}
+
+// sa (backward): triangular part of a wide supernode, last panel first.
+// shared: xs[3W] us[3W] Dg[w*w*9] Di[w*9] red[3 * max(size, w)]
+template <class G>
+PGO_HD void sn_task_backward_tri(const G& g, const SNView& V, const Task& T, double* sm) {
+  const SuperDesc sd = V.sn[T.id];
+  const int W = sd.W, len = sd.W + sd.m;
+  double* xs = sm;
+  double* us = xs + 3 * W;
+  double* Dg = us + 3 * W;
+  double* Di = Dg + kPanelWidth * kPanelWidth * 9;
+  double* red = Di + kPanelWidth * 9;
+  for (int idx = g.rank(); idx < 3 * W; idx += g.size()) {
+    xs[idx] = sn_ld(V.x + 3 * static_cast<size_t>(sd.c0) + idx);
+    us[idx] = sn_ld(V.u + 3 * static_cast<size_t>(sd.c0) + idx);
+  }
+  for (int p = sd.pn_end - 1; p >= sd.pn_begin; --p) {
+    const PanelDesc pd = V.pn[p];
+    const int w = pd.w, o = pd.sn_off;
+    sn_load_diag(g, V, pd.base, w + pd.m, w, Dg);
+    sn_load_dinv(g, V, pd.c0, w, Di);
+    // contributions of the supernode's later columns (already final) to this panel's columns
+    const int split = g.size() / w > 0 ? g.size() / w : 1;
+    for (int item = g.rank(); item < w * split; item += g.size()) {
+      const int t = item % w, h = item / w;
+      const size_t col = static_cast<size_t>(sn_colpos(sd.base, len, o + t) + (w - t));
+      double acc[3] = {0.0, 0.0, 0.0};
+      for (int tp = o + w + h; tp < W; tp += split) {
+        const double* mp = V.M + 9 * (col + (tp - o - w));
+        double mb[9];
+        for (int k = 0; k < 9; ++k) mb[k] = sn_ld(mp + k);
+        sn_mat_t_vec_add(mb, xs + 3 * tp, acc);
+      }
+      for (int k = 0; k < 3; ++k) red[3 * item + k] = acc[k];
+    }
+    g.sync();
+    for (int idx = g.rank(); idx < 3 * w; idx += g.size()) {
+      const int t = idx / 3, k = idx % 3;
+      double sum = 0.0;
+      for (int h = 0; h < split; ++h) sum += red[3 * (h * w + t) + k];
+      xs[3 * (o + t) + k] += sum;
+    }
+    g.sync();
+    sn_backward_panel(g, w, Dg, Di, us + 3 * o, xs + 3 * o);
+  }
+  for (int idx = g.rank(); idx < 3 * W; idx += g.size()) V.x[3 * static_cast<size_t>(sd.c0) + idx] = xs[idx];
+  g.sync();
+}
+
+// ss (backward): a narrow supernode including the gather over the rows below it.
+// shared: xs[3W] us[3W] Dg[W*W*9] Di[W*9] red[3 * max(size, W)]
+template <class G>
+PGO_HD void sn_task_backward_small(const G& g, const SNView& V, const Task& T, double* sm) {
+  const SuperDesc sd = V.sn[T.id];
+  const int W = sd.W, m = sd.m, len = W + m;
+  double* xs = sm;
+  double* us = xs + 3 * W;
+  double* Dg = us + 3 * W;
+  double* Di = Dg + W * W * 9;
+  double* red = Di + W * 9;
+  sn_load_diag(g, V, sd.base, len, W, Dg);
+  sn_load_dinv(g, V, sd.c0, W, Di);
+  for (int idx = g.rank(); idx < 3 * W; idx += g.size())
+    us[idx] = sn_ld(V.u + 3 * static_cast<size_t>(sd.c0) + idx);
+  const int split = g.size() / W > 0 ? g.size() / W : 1;
+  for (int item = g.rank(); item < W * split; item += g.size()) {
+    const int t = item % W, h = item / W;
+    const size_t col = static_cast<size_t>(sn_colpos(sd.base, len, t) + (W - t));
+    double acc[3] = {0.0, 0.0, 0.0};
+    for (int a = h; a < m; a += split) {
+      const double* mp = V.M + 9 * (col + a);
+      const int r = V.row_idx[sd.base + W + a];
+      double mb[9], xv[3];
+      for (int k = 0; k < 9; ++k) mb[k] = sn_ld(mp + k);
+      for (int k = 0; k < 3; ++k) xv[k] = sn_ld(V.x + 3 * static_cast<size_t>(r) + k);
+      sn_mat_t_vec_add(mb, xv, acc);
+    }
+    for (int k = 0; k < 3; ++k) red[3 * item + k] = acc[k];
+  }
+  g.sync();
+  for (int idx = g.rank(); idx < 3 * W; idx += g.size()) {
+    const int t = idx / 3, k = idx % 3;
+    double sum = 0.0;
+    for (int h = 0; h < split; ++h) sum += red[3 * (h * W + t) + k];
+    xs[idx] = sum;
+  }
+  g.sync();
+  sn_backward_panel(g, W, Dg, Di, us, xs);
+  for (int idx = g.rank(); idx < 3 * W; idx += g.size()) V.x[3 * static_cast<size_t>(sd.c0) + idx] = xs[idx];
+  g.sync();
+}
+
+}  // namespace pgo
+#endif

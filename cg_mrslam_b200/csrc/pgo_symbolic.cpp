@@ -227,6 +227,248 @@ class Dissector {
   int next_id_ = 0;
 };
 
+// Explicit per-block update schedule of the level-by-level factorisation (domain-decomposed path).
+bool build_update_schedule(Symbolic& S, std::string* err) {
+  const int n = S.n;
+  // ---- update schedule --------------------------------------------------------------------------
+  // Phase l applies every update whose source column has level l - 1. Within a phase the updates
+  // are grouped by target block so that one thread group owns each target (no atomics), in a
+  // fixed order (deterministic rounding).
+  int64_t n_ops = 0;
+  for (int p = 0; p < n; ++p) {
+    const int64_t m = S.col_ptr[p + 1] - S.col_ptr[p] - 1;
+    n_ops += m * (m + 1) / 2;
+  }
+  if (n_ops > 0x3FFFFFF0LL || S.nnzb >= kFinalFlag) {
+    if (err) *err = "more than 2^30 block updates: graph too dense for this solver";
+    return false;
+  }
+  S.n_ops = n_ops;
+  S.ops.resize(n_ops);
+  S.phase_ptr.assign(S.n_levels + 1, 0);
+  std::vector<int> count(S.nnzb, 0), touched;
+  std::vector<UpdateOp> raw;
+  int64_t op_cursor = 0;
+  std::vector<char> fin(n, 0);
+  for (int l = 1; l < S.n_levels; ++l) {
+    S.phase_ptr[l] = static_cast<int>(op_cursor);
+    raw.clear();
+    touched.clear();
+    for (int t = S.level_ptr[l - 1]; t < S.level_ptr[l]; ++t) {
+      const int k = S.level_cols[t];
+      const int base = S.col_ptr[k], m = S.col_ptr[k + 1] - base;  // rows base+1 .. base+m-1
+      for (int b = 1; b < m; ++b) {
+        const int c = S.row_idx[base + b];
+        int w = S.col_ptr[c];  // diagonal of column c == row c
+        for (int a = b; a < m; ++a) {
+          const int r = S.row_idx[base + a];
+          while (S.row_idx[w] != r) ++w;  // struct(k) rows >= c are a subset of struct(c) + {c}
+          UpdateOp x = {w, base + a, base + b};
+          raw.push_back(x);
+          if (count[w]++ == 0) touched.push_back(w);
+        }
+      }
+    }
+    std::sort(touched.begin(), touched.end());
+    // counting sort of the phase's updates by target (stable: generation order within a target)
+    int64_t off = op_cursor;
+    for (size_t i = 0; i < touched.size(); ++i) {
+      const int w = touched[i];
+      const int c = count[w];
+      S.max_run = std::max(S.max_run, c);
+      count[w] = static_cast<int>(off);  // reuse as write cursor
+      off += c;
+    }
+    for (size_t i = 0; i < raw.size(); ++i) {
+      UpdateOp o = raw[i];
+      const int w = o.target;
+      const int col = S.col_of[w];
+      if (S.row_idx[w] == col && S.level[col] == l) {
+        o.target |= kFinalFlag;
+        fin[col] = 1;
+      }
+      S.ops[count[w]++] = o;
+    }
+    for (size_t i = 0; i < touched.size(); ++i) count[touched[i]] = 0;
+    op_cursor = off;
+  }
+  S.phase_ptr[S.n_levels] = static_cast<int>(op_cursor);
+  if (op_cursor != n_ops) {
+    if (err) *err = "internal: update count mismatch";
+    return false;
+  }
+  // every non-leaf column must be finalised by an update of its own phase
+  for (int p = 0; p < n; ++p)
+    if (S.level[p] > 0 && !fin[p]) {
+      if (err) *err = "internal: column without finalising update";
+      return false;
+    }
+  return true;
+}
+
+// Supernodes, panels, scatter tables and task lists of the single-GPU path (pgo_symbolic.h).
+template <typename Key>
+void bucket_tasks(std::vector<std::pair<Key, Task> >& in, int n_levels, std::vector<int>* ptr,
+                  std::vector<Task>* out) {
+  ptr->assign(n_levels + 1, 0);
+  for (size_t i = 0; i < in.size(); ++i) ++(*ptr)[in[i].first + 1];
+  for (int l = 0; l < n_levels; ++l) (*ptr)[l + 1] += (*ptr)[l];
+  out->resize(in.size());
+  std::vector<int> cur(ptr->begin(), ptr->end() - 1);
+  for (size_t i = 0; i < in.size(); ++i) (*out)[cur[in[i].first]++] = in[i].second;
+  std::vector<std::pair<Key, Task> >().swap(in);
+}
+
+bool build_supernodal(Symbolic& S, std::string* err) {
+  Supernodal& N = S.sn;
+  N = Supernodal();
+  const int n = S.n;
+  const std::vector<int>& cp = S.col_ptr;
+  const std::vector<int>& ri = S.row_idx;
+  // supernodes: maximal chains with nested structure and one owner
+  for (int p = 0; p < n;) {
+    int q = p;
+    while (q + 1 < n && q + 1 - p < kMaxSuperWidth && S.parent[q] == q + 1 &&
+           S.owner[q] == S.owner[q + 1] && cp[q + 1] - cp[q] == cp[q + 2] - cp[q + 1] + 1)
+      ++q;
+    N.sn_first.push_back(p);
+    p = q + 1;
+  }
+  N.sn_first.push_back(n);
+  N.n_super = static_cast<int>(N.sn_first.size()) - 1;
+  // panels: balanced pieces of at most kPanelWidth columns
+  std::vector<int> pn_of(n), sn_of(n);
+  N.sn_pn_ptr.assign(1, 0);
+  for (int s = 0; s < N.n_super; ++s) {
+    const int c0 = N.sn_first[s], W = N.sn_first[s + 1] - c0;
+    const int pieces = (W + kPanelWidth - 1) / kPanelWidth;
+    for (int k = 0; k < pieces; ++k) {
+      const int a = c0 + static_cast<int>(static_cast<int64_t>(W) * k / pieces);
+      const int b = c0 + static_cast<int>(static_cast<int64_t>(W) * (k + 1) / pieces);
+      for (int c = a; c < b; ++c) {
+        pn_of[c] = static_cast<int>(N.pn_first.size());
+        sn_of[c] = s;
+      }
+      N.pn_first.push_back(a);
+      N.pn_sn.push_back(s);
+    }
+    N.sn_pn_ptr.push_back(static_cast<int>(N.pn_first.size()));
+  }
+  N.pn_first.push_back(n);
+  N.n_panels = static_cast<int>(N.pn_first.size()) - 1;
+
+  // scatter tables + panel levels (a source panel always precedes its targets)
+  std::vector<int> plevel(N.n_panels, 0);
+  N.pn_meta.assign(N.n_panels + 1, 0);
+  N.pn_scratch.assign(N.n_panels, -1);
+  std::vector<std::pair<int, Task> > ff, fa, fb;
+  for (int K = 0; K < N.n_panels; ++K) {
+    const int c0 = N.pn_first[K], w = N.pn_first[K + 1] - c0;
+    const int base = cp[c0] + w, m = cp[c0 + 1] - base;  // below rows: ri[base .. base + m)
+    N.pn_meta[K] = static_cast<int>(N.colbase.size());
+    for (int b = 0; b < m;) {
+      const int q = pn_of[ri[base + b]];
+      const int q0 = N.pn_first[q], q1 = N.pn_first[q + 1];
+      const int b_begin = b;
+      while (b < m && ri[base + b] < q1) ++b;
+      const int64_t off = static_cast<int64_t>(N.tbl.size());
+      if (off + m > 0x7FFFFFF0LL) {
+        if (err) *err = "scatter tables exceed 2^31 entries: graph too dense for this solver";
+        return false;
+      }
+      const int* rows_q = ri.data() + cp[q0];
+      const int len_q = cp[q0 + 1] - cp[q0];
+      int at = 0;
+      for (int a = b_begin; a < m; ++a) {
+        const int r = ri[base + a];
+        while (at < len_q && rows_q[at] != r) ++at;
+        if (at == len_q) {
+          if (err) *err = "internal: a source row is missing from its target panel";
+          return false;
+        }
+        N.tbl.push_back(at);
+      }
+      for (int t = b_begin; t < b; ++t) {
+        const int rb = ri[base + t];
+        N.colbase.push_back(cp[rb] - (rb - q0));
+        N.tbl_off.push_back(static_cast<int>(off) - b_begin);
+      }
+      plevel[q] = std::max(plevel[q], plevel[K] + 1);
+    }
+    N.update_blocks += static_cast<int64_t>(m) * (m + 1) / 2;
+    const double Ws = 3.0 * w, Ms = 3.0 * m;
+    N.flops += Ws * Ws * Ws / 3.0 + Ms * Ws * Ws + Ms * Ms * Ws;
+    N.n_plevels = std::max(N.n_plevels, plevel[K] + 1);
+    if (w <= kSmallWidth && m <= kSmallRows) {
+      const Task t = {K, 0, m, 0};
+      ff.push_back(std::make_pair(plevel[K], t));
+    } else {
+      int chunks = 0;
+      for (int r0 = 0; r0 == 0 || r0 < m; r0 += kRowChunk, ++chunks) {
+        const Task t = {K, r0, std::min(m, r0 + kRowChunk), 0};
+        fa.push_back(std::make_pair(plevel[K], t));
+      }
+      if (chunks > 1) {
+        N.pn_scratch[K] = static_cast<int>(N.scratch_blocks);
+        N.scratch_blocks += static_cast<int64_t>(w) * w;
+      }
+      // tile shape: (rows + columns) * w blocks are staged in shared memory
+      const int cap = kTileBudget / w;
+      const int tj = std::min((m + 3) / 4 * 4, std::max(8, std::min(64, (cap / 5 + 3) / 4 * 4)));
+      const int ti = std::max(8, std::min(std::min((m + 7) / 8 * 8, (cap - tj) / 8 * 8), 256));
+      for (int i0 = 0; i0 < m; i0 += ti)
+        for (int j0 = 0; j0 < std::min(m, i0 + ti); j0 += tj) {
+          const Task t = {K, i0, j0, (ti << 16) | tj};
+          fb.push_back(std::make_pair(plevel[K], t));
+        }
+    }
+    const int sn_id = N.pn_sn[K];
+    PanelDesc pd = {c0, w, m, cp[c0], N.pn_meta[K], N.pn_scratch[K], c0 - N.sn_first[sn_id], sn_id};
+    N.pn.push_back(pd);
+  }
+  N.pn_meta[N.n_panels] = static_cast<int>(N.colbase.size());
+  bucket_tasks(ff, N.n_plevels, &N.ff_ptr, &N.ff);
+  bucket_tasks(fa, N.n_plevels, &N.fa_ptr, &N.fa);
+  bucket_tasks(fb, N.n_plevels, &N.fb_ptr, &N.fb);
+
+  // substitution: supernode levels and tasks
+  std::vector<int> slevel(N.n_super, 0);
+  std::vector<std::pair<int, Task> > ss, sa, sf, sb;
+  for (int s = 0; s < N.n_super; ++s) {
+    const int c0 = N.sn_first[s], W = N.sn_first[s + 1] - c0;
+    const int base = cp[c0] + W, m = cp[c0 + 1] - base;
+    for (int b = 0; b < m; ++b) {
+      const int q = sn_of[ri[base + b]];
+      slevel[q] = std::max(slevel[q], slevel[s] + 1);
+    }
+    N.n_slevels = std::max(N.n_slevels, slevel[s] + 1);
+    SuperDesc sd = {c0, W, m, cp[c0], N.sn_pn_ptr[s], N.sn_pn_ptr[s + 1], 0, 0};
+    N.sn.push_back(sd);
+    if (W <= kSmallWidth) {
+      const Task t = {s, 0, m, 0};
+      ss.push_back(std::make_pair(slevel[s], t));
+      continue;
+    }
+    const Task t = {s, 0, m, 0};
+    sa.push_back(std::make_pair(slevel[s], t));
+    for (int p = N.sn_pn_ptr[s]; p < N.sn_pn_ptr[s + 1]; ++p) {
+      for (int r0 = 0; r0 < m; r0 += 32) {
+        const Task x = {p, r0, std::min(m, r0 + 32), 0};
+        sf.push_back(std::make_pair(slevel[s], x));
+      }
+      for (int r0 = 0; r0 < m; r0 += 64) {
+        const Task x = {p, r0, std::min(m, r0 + 64), 0};
+        sb.push_back(std::make_pair(slevel[s], x));
+      }
+    }
+  }
+  bucket_tasks(ss, N.n_slevels, &N.ss_ptr, &N.ss);
+  bucket_tasks(sa, N.n_slevels, &N.sa_ptr, &N.sa);
+  bucket_tasks(sf, N.n_slevels, &N.sf_ptr, &N.sf);
+  bucket_tasks(sb, N.n_slevels, &N.sb_ptr, &N.sb);
+  return true;
+}
+
 }  // namespace
 
 bool analyse(int n, const std::vector<std::pair<int, int> >& edges, int ordering, int world,
@@ -422,139 +664,9 @@ bool analyse(int n, const std::vector<std::pair<int, int> >& edges, int ordering
       if (S.owner[p] < 0 && !has_shared_child[p]) S.xfinal_cols[cur[S.level[p]]++] = p;
   }
 
-  // ---- update schedule --------------------------------------------------------------------------
-  // Phase l applies every update whose source column has level l - 1. Within a phase the updates
-  // are grouped by target block so that one thread group owns each target (no atomics), in a
-  // fixed order (deterministic rounding).
-  int64_t n_ops = 0;
-  for (int p = 0; p < n; ++p) {
-    const int64_t m = S.col_ptr[p + 1] - S.col_ptr[p] - 1;
-    n_ops += m * (m + 1) / 2;
-  }
-  if (n_ops > 0x3FFFFFF0LL || S.nnzb >= kPosMask) {
-    if (err) *err = "more than 2^30 block updates / 2^28 factor blocks: graph too dense for this solver";
-    return false;
-  }
-  S.n_ops = n_ops;
-  // Panels: up to kPanelWidth consecutive columns of a chain (each the only-path parent of the
-  // previous one, nested structure, same owner). An update from column k into a column beyond k's
-  // panel is deferred to the phase after the panel's last column: all of a panel's contributions
-  // to one target then share a phase and are applied with a single read-modify-write.
-  std::vector<int> panel_last(n);
-  for (int p = 0; p < n;) {
-    int q = p;
-    while (q + 1 < n && q + 1 - p < kPanelWidth && S.parent[q] == q + 1 &&
-           S.level[q + 1] == S.level[q] + 1 && S.owner[q] == S.owner[q + 1] &&
-           S.col_ptr[q + 1] - S.col_ptr[q] == S.col_ptr[q + 2] - S.col_ptr[q + 1] + 1)
-      ++q;
-    for (int t = p; t <= q; ++t) panel_last[t] = q;
-    p = q + 1;
-  }
-  // pass 1: updates per phase
-  std::vector<int64_t> phase_count(S.n_levels + 1, 0);
-  for (int k = 0; k < n; ++k) {
-    const int base = S.col_ptr[k], m = S.col_ptr[k + 1] - base;
-    for (int b = 1; b < m; ++b) {
-      const int c = S.row_idx[base + b];
-      const int ph = (c <= panel_last[k] ? S.level[k] : S.level[panel_last[k]]) + 1;
-      phase_count[ph] += m - b;
-    }
-  }
-  S.phase_ptr.assign(S.n_levels + 1, 0);
-  {
-    int64_t run = 0;
-    for (int l = 0; l < S.n_levels; ++l) {
-      S.phase_ptr[l] = static_cast<int>(run);
-      run += phase_count[l];
-    }
-    S.phase_ptr[S.n_levels] = static_cast<int>(run);
-    if (run != n_ops || phase_count[S.n_levels] != 0) {
-      if (err) *err = "internal: update count mismatch";
-      return false;
-    }
-  }
-  // pass 2: generate, bucketed by phase (sources in level order, then column order)
-  std::vector<UpdateOp> tmp(n_ops);
-  {
-    std::vector<int64_t> cursor(S.n_levels + 1);
-    for (int l = 0; l <= S.n_levels; ++l) cursor[l] = S.phase_ptr[l];
-    for (int t = 0; t < n; ++t) {
-      const int k = S.level_cols[t];
-      const int base = S.col_ptr[k], m = S.col_ptr[k + 1] - base;
-      for (int b = 1; b < m; ++b) {
-        const int c = S.row_idx[base + b];
-        const int ph = (c <= panel_last[k] ? S.level[k] : S.level[panel_last[k]]) + 1;
-        int w = S.col_ptr[c];
-        for (int a = b; a < m; ++a) {
-          const int r = S.row_idx[base + a];
-          while (S.row_idx[w] != r) ++w;  // struct(k) rows >= c are a subset of struct(c) + {c}
-          UpdateOp x = {w, base + a, base + b};
-          tmp[cursor[ph]++] = x;
-        }
-      }
-    }
-  }
-  // pass 3: per phase, stable counting sort by target; mark finalising runs and 4-row tiles
-  S.ops.resize(n_ops);
-  std::vector<int> count(S.nnzb, 0), touched;
-  std::vector<char> fin(n, 0);
-  for (int l = 1; l < S.n_levels; ++l) {
-    const int64_t begin = S.phase_ptr[l], end = S.phase_ptr[l + 1];
-    touched.clear();
-    for (int64_t i = begin; i < end; ++i)
-      if (count[tmp[i].target]++ == 0) touched.push_back(tmp[i].target);
-    std::sort(touched.begin(), touched.end());
-    int64_t off = begin;
-    std::vector<int64_t> run_begin(touched.size() + 1);
-    for (size_t i = 0; i < touched.size(); ++i) {
-      const int w = touched[i];
-      const int c = count[w];
-      S.max_run = std::max(S.max_run, c);
-      run_begin[i] = off;
-      count[w] = static_cast<int>(off);  // reuse as write cursor
-      off += c;
-    }
-    run_begin[touched.size()] = off;
-    for (int64_t i = begin; i < end; ++i) S.ops[count[tmp[i].target]++] = tmp[i];
-    for (size_t i = 0; i < touched.size(); ++i) count[touched[i]] = 0;
-    // flags
-    for (size_t i = 0; i < touched.size();) {
-      const int w = touched[i];
-      const int col = S.col_of[w];
-      const int64_t rb = run_begin[i], len = run_begin[i + 1] - rb;
-      int flags = 0;
-      if (S.row_idx[w] == col && S.level[col] == l) {
-        flags |= kFinalFlag;
-        fin[col] = 1;
-      }
-      // congruent runs on the next three blocks of the same column?
-      bool tile = i + 3 < touched.size();
-      for (int d = 1; tile && d < 4; ++d) {
-        const int wd = touched[i + d];
-        tile = wd == w + d && S.col_of[wd] == col && run_begin[i + d + 1] - run_begin[i + d] == len;
-        for (int64_t q = 0; tile && q < len; ++q) {
-          const UpdateOp& x = S.ops[rb + q];
-          const UpdateOp& y = S.ops[run_begin[i + d] + q];
-          tile = y.b == x.b && y.a == x.a + d;
-        }
-      }
-      if (tile) {
-        for (int64_t q = rb; q < rb + len; ++q) S.ops[q].target |= flags | kTileLead;
-        for (int64_t q = rb + len; q < rb + 4 * len; ++q) S.ops[q].target |= kTileMember;
-        i += 4;
-      } else {
-        for (int64_t q = rb; q < rb + len; ++q) S.ops[q].target |= flags;
-        i += 1;
-      }
-    }
-  }
-  { std::vector<UpdateOp>().swap(tmp); }
-  // every non-leaf column must be finalised by an update of its own phase
-  for (int p = 0; p < n; ++p)
-    if (S.level[p] > 0 && !fin[p]) {
-      if (err) *err = "internal: column without finalising update";
-      return false;
-    }
+  if (world > 1 && !build_update_schedule(S, err)) return false;
+  if (world == 1) S.phase_ptr.assign(S.n_levels + 1, 0);
+  if (!build_supernodal(S, err)) return false;
   // ---- forward-substitution schedule ------------------------------------------------------------
   {
     S.fwd_ptr.assign(S.n_levels + 1, 0);

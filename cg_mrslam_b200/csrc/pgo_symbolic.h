@@ -28,13 +28,73 @@ struct UpdateOp {
   int b;       // position of M(j,k)
 };
 static const int kFinalFlag = 0x40000000;
-// Four consecutive target blocks of one column whose runs are congruent (same sources, source
-// blocks in consecutive positions) are processed by one thread: the lead run carries kTileLead,
-// the three member runs kTileMember (their heads skip). Positions therefore use 28 bits.
-static const int kTileLead = 0x20000000;
-static const int kTileMember = 0x10000000;
-static const int kPosMask = 0x0FFFFFFF;
-static const int kPanelWidth = 8;  // chain columns whose trailing updates are applied together
+
+// ---- supernodal view (single-GPU factorisation and solves) -------------------------------------
+// A SUPERNODE is a maximal chain of columns with nested structure (column q+1 is q's parent and
+// struct(q+1) = struct(q) \ {q+1}); its blocks form a dense trapezoid in the block-CSC storage:
+// block (i, t) of the chain's row list lives at col_ptr[c0 + t] + (i - t). A PANEL is a piece of
+// at most kPanelWidth columns of a supernode: the unit of the right-looking factorisation
+// (factor the panel, then subtract its outer product from every later column with atomics).
+static const int kPanelWidth = 16;
+static const int kSmallWidth = 4;    // panels / supernodes this narrow are handled by one warp
+static const int kSmallRows = 32;    // ... if the panel also has at most this many rows below it
+static const int kRowChunk = 64;     // rows below a panel per CTA task of the panel factorisation
+// outer-product tile of one CTA task: (rows + columns) * panel width <= kTileBudget blocks staged
+static const int kTileBudget = 1296;
+static const int kMaxSuperWidth = 1024;
+
+struct Task {
+  int id;      // panel or supernode
+  int r0, r1;  // row range of the below-row list (tile tasks: first row / first column)
+  int aux;     // tile tasks: (tile rows << 16) | tile columns
+};
+
+// Geometry of a panel / supernode in the block-CSC storage. Because the structure is nested,
+// column t of the chain starts at  base + t * (w + m) - t (t - 1) / 2  and holds the chain rows
+// t .. w-1 followed by the m rows below: no col_ptr look-ups on the device.
+struct PanelDesc {
+  int c0, w, m;   // first column, width, rows below the panel (later chain columns included)
+  int base;       // col_ptr[c0]
+  int meta;       // offset of the panel's rows in colbase / tbl_off
+  int scratch;    // block offset in the diagonal scratch area, or -1
+  int sn_off;     // offset of c0 inside its supernode
+  int sn;         // supernode
+};
+struct SuperDesc {
+  int c0, W, m;   // first column, width, rows below the supernode
+  int base;       // col_ptr[c0]
+  int pn_begin, pn_end;
+  int pad0, pad1;
+};
+
+struct Supernodal {
+  int n_super = 0, n_panels = 0, n_plevels = 0, n_slevels = 0;
+  std::vector<int> sn_first;   // n_super + 1: first column of each supernode
+  std::vector<int> sn_pn_ptr;  // n_super + 1: its panels (consecutive)
+  std::vector<int> pn_first;   // n_panels + 1
+  std::vector<int> pn_sn;      // n_panels
+  std::vector<PanelDesc> pn;   // n_panels
+  std::vector<SuperDesc> sn;   // n_super
+  // scatter tables of the outer-product update. For below-row b of panel K (a block column r_b of
+  // some later panel q) and below-row a >= b:  position of M(r_a, r_b) =
+  // colbase[pn_meta[K] + b] + tbl[tbl_off[pn_meta[K] + b] + a].
+  std::vector<int> pn_meta;    // n_panels + 1
+  std::vector<int> colbase, tbl_off, tbl;
+  // panels whose factorisation is split over several CTA tasks write their diagonal part to a
+  // scratch area first (the other tasks still read the unfactored blocks): offset in blocks or -1
+  std::vector<int> pn_scratch;
+  int64_t scratch_blocks = 0;
+  // factorisation tasks by panel level: fused (factor + update) warp tasks for small panels,
+  // CTA tasks for the rest (fa: factor a row chunk; fb: one tile of the outer product)
+  std::vector<int> ff_ptr, fa_ptr, fb_ptr;  // n_plevels + 1
+  std::vector<Task> ff, fa, fb;
+  // substitution tasks by supernode level: ss = whole small supernode (warp), sa = triangular
+  // part of a wide supernode (CTA), sf / sb = rows below it, forward (chunks of 32) / backward
+  std::vector<int> ss_ptr, sa_ptr, sf_ptr, sb_ptr;  // n_slevels + 1
+  std::vector<Task> ss, sa, sf, sb;
+  int64_t update_blocks = 0;   // target blocks touched by all outer products (atomic 3x3 adds)
+  double flops = 0.0;          // of one numeric factorisation
+};
 
 struct SolveOp {
   int row;  // target block row | kFinalFlag
@@ -78,6 +138,7 @@ struct Symbolic {
   int shared_min_level = 0;        // min level of a shared column (n_levels if none)
   std::vector<int> xfinal_ptr;     // n_levels + 1
   std::vector<int> xfinal_cols;
+  Supernodal sn;
   // statistics
   int64_t nnzb = 0, n_ops = 0;
   int max_run = 0;              // longest run of updates sharing one target within a phase
@@ -87,6 +148,8 @@ struct Symbolic {
 // Block adjacency of the free vertices: edges given as pairs of hessian indices (both >= 0).
 // Returns false (with *err) on inconsistent input. `ordering`: 0 = nested dissection (default),
 // 1 = natural (testing).
+// The explicit block-update schedule (ops) is only built for world > 1; the single-GPU path uses
+// the supernodal tables (sn).
 // `world` > 1 (a power of two) additionally cuts the top log2(world) dissection levels into shared
 // separators and assigns every other column to a rank.
 bool analyse(int n, const std::vector<std::pair<int, int> >& edges, int ordering, int world,

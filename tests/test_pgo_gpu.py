@@ -54,7 +54,10 @@ def test_iteration_counts_and_restart():
     assert np.abs(d).max() < POSE_TOL
     s.set_poses(g["poses0"])
     done, chi2, poses2 = s.optimize(7)
-    assert np.array_equal(poses2, poses)  # deterministic: same bits on a re-run
+    # the outer products are accumulated with fp64 atomics: a re-run agrees to rounding, not bits
+    d2 = poses2 - poses
+    d2[:, 2] = po.normalize_theta(d2[:, 2])
+    assert np.abs(d2).max() < 1e-9
     assert np.allclose(chi2, ref.chi2, rtol=1e-9)
     s.close()
 
