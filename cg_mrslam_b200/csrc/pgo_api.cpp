@@ -418,13 +418,6 @@ int pgo_get_stats(const pgo_solver* s, pgo_stats* out) {
   return PGO_OK;
 }
 
-int pgo_phase_ticks(pgo_solver* s, uint64_t* out, int cap) {
-  if (!s || !out) return fail(PGO_ERR_ARG, "null argument");
-  std::string err;
-  const int rc = pgo::dev_phase_ticks(s->dev, out, cap, &err);
-  return rc < 0 ? fail(rc, err) : rc;
-}
-
 void* pgo_stream(const pgo_solver* s) { return s ? pgo::dev_stream(s->dev) : nullptr; }
 
 }  // extern "C"

@@ -38,12 +38,6 @@ uint64_t dev_launches(const DeviceSolver* d);
 // factor updates, forward solve, backward solve, update.
 const double* dev_stage_ms(const DeviceSolver* d);
 
-// Profiling: (globaltimer ns, kind << 16 | level) after every grid barrier of the last iteration's
-// factorisation (kind 1 = panel factor, 2 = outer products), forward (3 = triangular, 4 = rows) and
-// backward substitution (5 = rows + narrow supernodes, 6 = triangular); kind 0 = start. Returns the
-// number of pairs written (<= cap / 2), or a negative pgo_status.
-int dev_phase_ticks(DeviceSolver* d, uint64_t* out, int cap, std::string* err);
-
 int dev_set_structure(DeviceSolver* d, const Symbolic& S, const GraphTables& G, std::string* err);
 int dev_upload(DeviceSolver* d, const double* poses, const double* meas, const double* info6,
                std::string* err);

@@ -416,15 +416,11 @@ __device__ void phase_backward(const Params& P, int l, int nrhs, size_t stride, 
 // ---- the persistent kernels ----------------------------------------------------------------------
 const int kThreads = 256;
 
-__device__ __forceinline__ void stamp(const Params& P, int k) {
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    P.stamps[k] = t;
-  }
-}
-
 // ---- supernodal single-GPU iteration (pgo_supernodal.h) ------------------------------------------
+// One Gauss-Newton iteration is a CUDA graph of small kernels, one per phase and panel / supernode
+// level: a kernel boundary is the barrier between dependent phases, every task is one CTA (or one
+// warp of a 4-warp CTA) so the hardware block scheduler balances the load, each kernel gets its
+// own register and shared-memory budget, and ncu sees every phase as a launch of its own.
 struct CtaGroup {
   __device__ __forceinline__ int rank() const { return threadIdx.x; }
   __device__ __forceinline__ int size() const { return blockDim.x; }
@@ -436,139 +432,100 @@ struct WarpGroup {
   __device__ __forceinline__ void sync() const { __syncwarp(); }
 };
 
-struct SNDev {
-  SNView V;
-  int n_plevels, n_slevels;
-  const int *ff_ptr, *fa_ptr, *fb_ptr, *ss_ptr, *sa_ptr, *sf_ptr, *sb_ptr;
-  const Task *ff, *fa, *fb, *ss, *sa, *sf, *sb;
-  // profiling: after every grid barrier of the last iteration, (globaltimer, kind << 16 | level)
-  unsigned long long* ticks;
-};
+const int kCtaThreads = 256;   // CTA tasks
+const int kWarpsPerCta = 4;    // warp tasks: 4 per CTA
 
-__device__ __forceinline__ void sn_tick(const SNDev& S, int* at, int kind, int level) {
-  if (blockIdx.x == 0 && threadIdx.x == 0 && S.ticks) {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    S.ticks[2 * *at] = t;
-    S.ticks[2 * *at + 1] = static_cast<unsigned long long>((kind << 16) | level);
-  }
-  ++*at;
+__device__ __forceinline__ bool sn_failed(const SNView& V) {
+  return *reinterpret_cast<volatile int*>(V.status) != 0;
 }
 
-const size_t kSnSmemBytes = sizeof(double) * (kCtaSmemDoubles > 8 * kWarpSmemDoubles
-                                                  ? kCtaSmemDoubles
-                                                  : 8 * kWarpSmemDoubles);
-
-// Numeric factorisation: per panel level, (A) factor the level's panels -- CTA tasks for row chunks
-// of big panels, warp tasks for small panels including their outer product -- then (B) the outer
-// products of the big panels, tile by tile, subtracted from later columns with atomics.
-__device__ void sn_factorise(const SNDev& S, cg::grid_group& grid, double* sm, double* wsm,
-                             int warp_id, int n_warps, int* at) {
-  const CtaGroup cta;
-  const WarpGroup warp;
-  for (int l = 0; l < S.n_plevels; ++l) {
-    for (int i = S.fa_ptr[l] + blockIdx.x; i < S.fa_ptr[l + 1]; i += gridDim.x)
-      sn_task_factor(cta, S.V, S.fa[i], sm);
-    for (int i = S.ff_ptr[l] + warp_id; i < S.ff_ptr[l + 1]; i += n_warps)
-      sn_task_fused(warp, S.V, S.ff[i], wsm);
-    grid.sync();
-    sn_tick(S, at, 1, l);
-    if (S.fb_ptr[l + 1] > S.fb_ptr[l]) {
-      for (int i = S.fb_ptr[l] + blockIdx.x; i < S.fb_ptr[l + 1]; i += gridDim.x)
-        sn_task_update(cta, S.V, S.fb[i], sm);
-      grid.sync();
-      sn_tick(S, at, 2, l);
-    }
-  }
-}
-
-__device__ void sn_substitute(const SNDev& S, cg::grid_group& grid, double* sm, double* wsm,
-                              int warp_id, int n_warps, int* at) {
-  const CtaGroup cta;
-  const WarpGroup warp;
-  for (int l = 0; l < S.n_slevels; ++l) {
-    for (int i = S.sa_ptr[l] + blockIdx.x; i < S.sa_ptr[l + 1]; i += gridDim.x)
-      sn_task_forward_tri(cta, S.V, S.sa[i], sm);
-    for (int i = S.ss_ptr[l] + warp_id; i < S.ss_ptr[l + 1]; i += n_warps)
-      sn_task_forward_small(warp, S.V, S.ss[i], wsm);
-    grid.sync();
-    sn_tick(S, at, 3, l);
-    if (S.sf_ptr[l + 1] > S.sf_ptr[l]) {
-      for (int i = S.sf_ptr[l] + warp_id; i < S.sf_ptr[l + 1]; i += n_warps)
-        sn_forward_rows(warp, S.V, S.sf[i].id, S.sf[i].r0, S.sf[i].r1, nullptr);
-      grid.sync();
-      sn_tick(S, at, 4, l);
-    }
-  }
-}
-
-__device__ void sn_back_substitute(const SNDev& S, cg::grid_group& grid, double* sm, double* wsm,
-                                   int warp_id, int n_warps, int* at) {
-  const CtaGroup cta;
-  const WarpGroup warp;
-  for (int l = S.n_slevels - 1; l >= 0; --l) {
-    for (int i = S.sb_ptr[l] + warp_id; i < S.sb_ptr[l + 1]; i += n_warps)
-      sn_backward_rows(warp, S.V, S.sb[i].id, S.sb[i].r0, S.sb[i].r1);
-    for (int i = S.ss_ptr[l] + warp_id; i < S.ss_ptr[l + 1]; i += n_warps)
-      sn_task_backward_small(warp, S.V, S.ss[i], wsm);
-    grid.sync();
-    sn_tick(S, at, 5, l);
-    if (S.sa_ptr[l + 1] > S.sa_ptr[l]) {
-      for (int i = S.sa_ptr[l] + blockIdx.x; i < S.sa_ptr[l + 1]; i += gridDim.x)
-        sn_task_backward_tri(cta, S.V, S.sa[i], sm);
-      grid.sync();
-      sn_tick(S, at, 6, l);
-    }
-  }
-}
-
-__global__ void __launch_bounds__(kThreads, 2) gn_iterations(Params P, SNDev S, int n_iters) {
-  cg::grid_group grid = cg::this_grid();
+// fa: panel factorisation, one CTA per (panel, row chunk)
+__global__ void __launch_bounds__(kCtaThreads) sn_k_factor(SNView V, const Task* tasks) {
   extern __shared__ double sm[];
+  if (sn_failed(V)) return;
+  sn_task_factor(CtaGroup(), V, tasks[blockIdx.x], sm);
+}
+// fb: outer-product tiles, one CTA per tile
+__global__ void __launch_bounds__(kCtaThreads) sn_k_update(SNView V, const Task* tasks) {
+  extern __shared__ double sm[];
+  if (sn_failed(V)) return;
+  sn_task_update(CtaGroup(), V, tasks[blockIdx.x], sm);
+}
+// ff: small panels start to finish, one warp each
+__global__ void __launch_bounds__(32 * kWarpsPerCta) sn_k_fused(SNView V, const Task* tasks, int n) {
+  extern __shared__ double sm[];
+  const int i = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  if (i >= n || sn_failed(V)) return;
+  sn_task_fused(WarpGroup(), V, tasks[i], sm + (threadIdx.x >> 5) * kWarpSmemDoubles);
+}
+// forward substitution
+__global__ void __launch_bounds__(kCtaThreads) sn_k_fwd_tri(SNView V, const Task* tasks) {
+  extern __shared__ double sm[];
+  if (sn_failed(V)) return;
+  sn_task_forward_tri(CtaGroup(), V, tasks[blockIdx.x], sm);
+}
+__global__ void __launch_bounds__(32 * kWarpsPerCta) sn_k_fwd_small(SNView V, const Task* tasks, int n) {
+  extern __shared__ double sm[];
+  const int i = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  if (i >= n || sn_failed(V)) return;
+  sn_task_forward_small(WarpGroup(), V, tasks[i], sm + (threadIdx.x >> 5) * kWarpSmemDoubles);
+}
+__global__ void __launch_bounds__(32 * kWarpsPerCta) sn_k_fwd_rows(SNView V, const Task* tasks, int n) {
+  const int i = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  if (i >= n || sn_failed(V)) return;
+  sn_forward_rows(WarpGroup(), V, tasks[i].id, tasks[i].r0, tasks[i].r1, nullptr);
+}
+// backward substitution
+__global__ void __launch_bounds__(32 * kWarpsPerCta) sn_k_bwd_rows(SNView V, const Task* tasks, int n) {
+  const int i = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  if (i >= n || sn_failed(V)) return;
+  sn_backward_rows(WarpGroup(), V, tasks[i].id, tasks[i].r0, tasks[i].r1);
+}
+__global__ void __launch_bounds__(32 * kWarpsPerCta) sn_k_bwd_small(SNView V, const Task* tasks, int n) {
+  extern __shared__ double sm[];
+  const int i = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  if (i >= n || sn_failed(V)) return;
+  sn_task_backward_small(WarpGroup(), V, tasks[i], sm + (threadIdx.x >> 5) * kWarpSmemDoubles);
+}
+__global__ void __launch_bounds__(kCtaThreads) sn_k_bwd_tri(SNView V, const Task* tasks) {
+  extern __shared__ double sm[];
+  if (sn_failed(V)) return;
+  sn_task_backward_tri(CtaGroup(), V, tasks[blockIdx.x], sm);
+}
+
+// linearise + chi2 (phase 1) as plain kernels
+__global__ void __launch_bounds__(kThreads) gn_linearise(Params P) {
   __shared__ double scratch[32];
-  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
-  // warp tasks go to the CTAs in reverse order: CTA tasks of the same phase start at CTA 0
-  const int warps_per_cta = blockDim.x >> 5;
-  const int warp_id = (gridDim.x - 1 - blockIdx.x) * warps_per_cta + (threadIdx.x >> 5);
-  const int n_warps = gridDim.x * warps_per_cta;
-  double* wsm = sm + (threadIdx.x >> 5) * kWarpSmemDoubles;
-  for (int it = 0; it < n_iters; ++it) {
-    stamp(P, 0);
-    // zero the factor storage (fill positions must start at 0) and the backward accumulators
-    for (long long i = tid; i < P.nnzb * 9; i += nthreads) P.M[i] = 0.0;
-    for (int i = tid; i < 3 * P.n; i += nthreads) P.x[i] = 0.0;
-    grid.sync();
-    phase_linearise(P, scratch, it);
-    grid.sync();
-    if (blockIdx.x == 0) {
-      double v = 0.0;
-      for (int b = threadIdx.x; b < static_cast<int>(gridDim.x); b += blockDim.x) v += P.chi2_partial[b];
-      const double s = block_sum(v, scratch);
-      if (threadIdx.x == 0) P.chi2_out[it] = s;
-    }
-    stamp(P, 1);
-    int at = 0;
-    sn_tick(S, &at, 0, 0);
-    sn_factorise(S, grid, sm, wsm, warp_id, n_warps, &at);
-    if (*reinterpret_cast<volatile int*>(P.status) != 0) return;  // uniform: read after a barrier
-    stamp(P, 2);
-    sn_substitute(S, grid, sm, wsm, warp_id, n_warps, &at);
-    stamp(P, 3);
-    sn_back_substitute(S, grid, sm, wsm, warp_id, n_warps, &at);
-    if (tid == 0 && S.ticks) S.ticks[2 * at] = 0;  // terminator
-    stamp(P, 4);
-    // VertexSE2::oplusImpl (C3)
-    for (int p = tid; p < P.n; p += nthreads) {
-      const int v = P.perm_vertex[p];
-      double* q = P.poses + 3 * static_cast<size_t>(v);
-      q[0] += __ldcg(P.x + 3 * p);
-      q[1] += __ldcg(P.x + 3 * p + 1);
-      q[2] = normalize_theta(q[2] + __ldcg(P.x + 3 * p + 2));
-    }
-    if (tid == 0) P.status[1] = it + 1;
-    grid.sync();
-    stamp(P, 5);
+  if (*reinterpret_cast<volatile int*>(P.status) != 0) return;
+  phase_linearise(P, scratch, 0);
+}
+__global__ void gn_chi2(Params P, int n_partials) {
+  __shared__ double scratch[32];
+  if (*reinterpret_cast<volatile int*>(P.status) != 0) return;
+  double v = 0.0;
+  for (int b = threadIdx.x; b < n_partials; b += blockDim.x) v += P.chi2_partial[b];
+  const double s = block_sum(v, scratch);
+  if (threadIdx.x == 0) P.chi2_out[P.status[1]] = s;  // status[1] = iterations done so far
+}
+// VertexSE2::oplusImpl (C3); the last kernel of an iteration
+__global__ void gn_update(Params P) {
+  if (*reinterpret_cast<volatile int*>(P.status) != 0) return;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < P.n) {
+    const int v = P.perm_vertex[p];
+    double* q = P.poses + 3 * static_cast<size_t>(v);
+    q[0] += P.x[3 * p];
+    q[1] += P.x[3 * p + 1];
+    q[2] = normalize_theta(q[2] + P.x[3 * p + 2]);
   }
+}
+__global__ void gn_count_iteration(Params P) {
+  if (*reinterpret_cast<volatile int*>(P.status) == 0) P.status[1] += 1;
+}
+__global__ void gn_stamp(unsigned long long* stamps, int k) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  stamps[k] = t;
 }
 
 // H X = E for nrhs right-hand sides already placed in P.rhs-like storage `rhs` ([nrhs][n][3]).
@@ -734,6 +691,8 @@ struct Buf {
 
 }  // namespace
 
+const int kMaxItersPerCall = 1024;  // capacity of the device-side chi2 record
+
 struct DeviceSolver {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -753,17 +712,19 @@ struct DeviceSolver {
   Buf<unsigned long long> stamps;
   double stage_ms[5] = {0, 0, 0, 0, 0};
   Buf<double> poses, meas, info6, M, Dinv, rhs, u, x, chi2_partial, chi2_out, many_rhs, scratch_d;
-  size_t vec_cap = 0;  // right-hand sides u/x can hold
   // supernodal tables (single-GPU path)
-  SNDev S;
-  int grid_sn = 0;
-  Buf<int> colbase, tbl_off, tbl, ff_ptr, fa_ptr, fb_ptr, ss_ptr, sa_ptr, sf_ptr, sb_ptr;
+  SNView V;
+  Supernodal::Lists L;   // host copies of the level pointers (launch geometry)
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t graph_exec = nullptr;
+  int graph_nodes = 0;
+  int lin_blocks = 0;
+  Buf<int> colbase, tbl_off, tbl;
   Buf<PanelDesc> pn_desc;
   Buf<SuperDesc> sn_desc;
   Buf<Task> ff, fa, fb, ss, sa, sf, sb;
   Buf<double> diag_scratch;
-  Buf<unsigned long long> ticks;
-  size_t n_ticks = 0;
+  Buf<double> many_u, many_x;  // substitution vectors of the marginals (u / x never move)
   // domain decomposition
   DDParams D;
   Buf<int> owner, xfinal_ptr, xfinal_cols;
@@ -791,15 +752,18 @@ int dev_create(DeviceSolver** out, int device, void* stream, std::string* err) {
   d->device = device;
   cudaDeviceGetAttribute(&d->sm_count, cudaDevAttrMultiProcessorCount, device);
   int per_sm = 0, per_sm2 = 0;
-  int per_sm_sn = 0;
-  cudaError_t e = cudaFuncSetAttribute(gn_iterations, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(kSnSmemBytes));
-  if (e == cudaSuccess)
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_sn, gn_iterations, kThreads, kSnSmemBytes);
-  if (e == cudaSuccess && per_sm_sn < 1) {
-    if (err) *err = "pgo dev_create: the Gauss-Newton kernel does not fit on an SM";
-    delete d;
-    return PGO_ERR_CUDA;
+  cudaError_t e = cudaSuccess;
+  {
+    const int cta_bytes = static_cast<int>(sizeof(double) * kCtaSmemDoubles);
+    const int warp_bytes = static_cast<int>(sizeof(double) * kWarpSmemDoubles * kWarpsPerCta);
+    const void* cta_kernels[] = {reinterpret_cast<const void*>(sn_k_factor), reinterpret_cast<const void*>(sn_k_update),
+                                 reinterpret_cast<const void*>(sn_k_fwd_tri), reinterpret_cast<const void*>(sn_k_bwd_tri)};
+    for (size_t i = 0; i < 4 && e == cudaSuccess; ++i)
+      e = cudaFuncSetAttribute(cta_kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, cta_bytes);
+    const void* warp_kernels[] = {reinterpret_cast<const void*>(sn_k_fused), reinterpret_cast<const void*>(sn_k_fwd_small),
+                                  reinterpret_cast<const void*>(sn_k_bwd_small)};
+    for (size_t i = 0; i < 3 && e == cudaSuccess; ++i)
+      e = cudaFuncSetAttribute(warp_kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, warp_bytes);
   }
   if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gn_dd_local, kThreads, 0);
   if (e == cudaSuccess)
@@ -807,7 +771,6 @@ int dev_create(DeviceSolver** out, int device, void* stream, std::string* err) {
   if (e == cudaSuccess) {
     per_sm = std::max(1, std::min(per_sm, per_sm2));
     d->grid = d->sm_count * per_sm;
-    d->grid_sn = d->sm_count * std::min(per_sm_sn, 2);
     if (stream) {
       d->stream = static_cast<cudaStream_t>(stream);
     } else {
@@ -819,7 +782,7 @@ int dev_create(DeviceSolver** out, int device, void* stream, std::string* err) {
   if (e == cudaSuccess) e = cudaEventCreate(&d->ev1);
   if (e == cudaSuccess) e = d->status.reserve(4);
   if (e == cudaSuccess) e = d->stamps.reserve(8);
-  if (e == cudaSuccess) e = d->chi2_partial.reserve(std::max(d->grid, d->grid_sn));
+  if (e == cudaSuccess) e = d->chi2_partial.reserve(std::max(d->grid, 4 * d->sm_count));
   if (e != cudaSuccess) {
     if (err) *err = std::string("pgo dev_create: ") + cudaGetErrorString(e);
     dev_destroy(d);
@@ -840,15 +803,17 @@ void dev_destroy(DeviceSolver* d) {
   Buf<double>* db[] = {&d->poses, &d->meas, &d->info6, &d->M, &d->Dinv, &d->rhs, &d->u, &d->x,
                        &d->chi2_partial, &d->chi2_out, &d->many_rhs, &d->scratch_d};
   for (size_t i = 0; i < sizeof(db) / sizeof(db[0]); ++i) db[i]->release();
-  Buf<int>* sb[] = {&d->colbase, &d->tbl_off, &d->tbl,    &d->ff_ptr, &d->fa_ptr,
-                    &d->fb_ptr,  &d->ss_ptr,  &d->sa_ptr, &d->sf_ptr, &d->sb_ptr};
+  Buf<int>* sb[] = {&d->colbase, &d->tbl_off, &d->tbl};
   d->pn_desc.release();
   d->sn_desc.release();
   for (size_t i = 0; i < sizeof(sb) / sizeof(sb[0]); ++i) sb[i]->release();
   Buf<Task>* tb[] = {&d->ff, &d->fa, &d->fb, &d->ss, &d->sa, &d->sf, &d->sb};
   for (size_t i = 0; i < sizeof(tb) / sizeof(tb[0]); ++i) tb[i]->release();
   d->diag_scratch.release();
-  d->ticks.release();
+  d->many_u.release();
+  d->many_x.release();
+  if (d->graph_exec) cudaGraphExecDestroy(d->graph_exec);
+  if (d->graph) cudaGraphDestroy(d->graph);
   d->inc.release();
   d->ops.release();
   d->fwd_ops.release();
@@ -862,17 +827,6 @@ void dev_destroy(DeviceSolver* d) {
   if (d->ev1) cudaEventDestroy(d->ev1);
   if (d->own_stream && d->stream) cudaStreamDestroy(d->stream);
   delete d;
-}
-
-int dev_phase_ticks(DeviceSolver* d, uint64_t* out, int cap, std::string* err) {
-  PGO_CUDA(cudaSetDevice(d->device));
-  const size_t n = std::min(static_cast<size_t>(cap < 0 ? 0 : cap) / 2, d->n_ticks);
-  if (!d->have_structure || n == 0) return 0;
-  PGO_CUDA(cudaMemcpyAsync(out, d->ticks.p, 2 * n * sizeof(uint64_t), cudaMemcpyDeviceToHost, d->stream));
-  PGO_CUDA(cudaStreamSynchronize(d->stream));
-  int k = 0;
-  while (static_cast<size_t>(k) < n && out[2 * k] != 0) ++k;
-  return k;
 }
 
 void* dev_stream(const DeviceSolver* d) { return d->stream; }
@@ -906,13 +860,6 @@ int dev_set_structure(DeviceSolver* d, const Symbolic& S, const GraphTables& G, 
   PGO_CUDA(d->colbase.upload(N.colbase, s));
   PGO_CUDA(d->tbl_off.upload(N.tbl_off, s));
   PGO_CUDA(d->tbl.upload(N.tbl, s));
-  PGO_CUDA(d->ff_ptr.upload(N.ff_ptr, s));
-  PGO_CUDA(d->fa_ptr.upload(N.fa_ptr, s));
-  PGO_CUDA(d->fb_ptr.upload(N.fb_ptr, s));
-  PGO_CUDA(d->ss_ptr.upload(N.ss_ptr, s));
-  PGO_CUDA(d->sa_ptr.upload(N.sa_ptr, s));
-  PGO_CUDA(d->sf_ptr.upload(N.sf_ptr, s));
-  PGO_CUDA(d->sb_ptr.upload(N.sb_ptr, s));
   PGO_CUDA(d->ff.upload(N.ff, s));
   PGO_CUDA(d->fa.upload(N.fa, s));
   PGO_CUDA(d->fb.upload(N.fb, s));
@@ -921,9 +868,6 @@ int dev_set_structure(DeviceSolver* d, const Symbolic& S, const GraphTables& G, 
   PGO_CUDA(d->sf.upload(N.sf, s));
   PGO_CUDA(d->sb.upload(N.sb, s));
   PGO_CUDA(d->diag_scratch.reserve(9 * static_cast<size_t>(N.scratch_blocks) + 9));
-  d->n_ticks = 2 * static_cast<size_t>(N.n_plevels) + 4 * static_cast<size_t>(N.n_slevels) + 4;
-  PGO_CUDA(d->ticks.reserve(2 * d->n_ticks));
-  PGO_CUDA(cudaMemsetAsync(d->ticks.p, 0, 2 * d->n_ticks * sizeof(unsigned long long), s));
   std::vector<int> perm_vertex(S.n);
   for (int v = 0; v < G.n_vertices; ++v)
     if (G.vpos[v] >= 0) perm_vertex[G.vpos[v]] = v;
@@ -941,7 +885,6 @@ int dev_set_structure(DeviceSolver* d, const Symbolic& S, const GraphTables& G, 
   PGO_CUDA(d->rhs.reserve(3 * static_cast<size_t>(S.n)));
   PGO_CUDA(d->u.reserve(3 * static_cast<size_t>(S.n)));
   PGO_CUDA(d->x.reserve(3 * static_cast<size_t>(S.n)));
-  d->vec_cap = 1;
   PGO_CUDA(cudaStreamSynchronize(s));  // the host vectors may go away
   Params& P = d->P;
   P.n_vertices = G.n_vertices;
@@ -980,37 +923,27 @@ int dev_set_structure(DeviceSolver* d, const Symbolic& S, const GraphTables& G, 
   P.chi2_out = nullptr;
   P.status = d->status.p;
   P.stamps = d->stamps.p;
-  SNDev& SD = d->S;
-  SD.V.row_idx = d->row_idx.p;
-  SD.V.pn = d->pn_desc.p;
-  SD.V.sn = d->sn_desc.p;
-  SD.V.colbase = d->colbase.p;
-  SD.V.tbl_off = d->tbl_off.p;
-  SD.V.tbl = d->tbl.p;
-  SD.V.M = d->M.p;
-  SD.V.Dinv = d->Dinv.p;
-  SD.V.z = d->rhs.p;
-  SD.V.u = d->u.p;
-  SD.V.x = d->x.p;
-  SD.V.scratch = d->diag_scratch.p;
-  SD.V.status = d->status.p;
-  SD.n_plevels = N.n_plevels;
-  SD.n_slevels = N.n_slevels;
-  SD.ff_ptr = d->ff_ptr.p;
-  SD.fa_ptr = d->fa_ptr.p;
-  SD.fb_ptr = d->fb_ptr.p;
-  SD.ss_ptr = d->ss_ptr.p;
-  SD.sa_ptr = d->sa_ptr.p;
-  SD.sf_ptr = d->sf_ptr.p;
-  SD.sb_ptr = d->sb_ptr.p;
-  SD.ff = d->ff.p;
-  SD.fa = d->fa.p;
-  SD.fb = d->fb.p;
-  SD.ss = d->ss.p;
-  SD.sa = d->sa.p;
-  SD.sf = d->sf.p;
-  SD.sb = d->sb.p;
-  SD.ticks = d->ticks.p;
+  SNView& V = d->V;
+  V.row_idx = d->row_idx.p;
+  V.pn = d->pn_desc.p;
+  V.sn = d->sn_desc.p;
+  V.colbase = d->colbase.p;
+  V.tbl_off = d->tbl_off.p;
+  V.tbl = d->tbl.p;
+  V.M = d->M.p;
+  V.Dinv = d->Dinv.p;
+  V.z = d->rhs.p;
+  V.u = d->u.p;
+  V.x = d->x.p;
+  V.scratch = d->diag_scratch.p;
+  V.status = d->status.p;
+  d->L = N.lists();
+  PGO_CUDA(d->chi2_out.reserve(kMaxItersPerCall));
+  d->lin_blocks = std::max(1, std::min(4 * d->sm_count, (S.n + kThreads - 1) / kThreads));
+  if (d->graph_exec) cudaGraphExecDestroy(d->graph_exec);
+  if (d->graph) cudaGraphDestroy(d->graph);
+  d->graph_exec = nullptr;
+  d->graph = nullptr;
   DDParams& D = d->D;
   D.owner = d->owner.p;
   D.rank = G.rank;
@@ -1075,6 +1008,114 @@ int dev_get_poses(DeviceSolver* d, double* poses, std::string* err) {
   return PGO_OK;
 }
 
+// Records one Gauss-Newton iteration on the solver's stream (captured into a graph by the caller).
+static int enqueue_iteration(DeviceSolver* d, std::string* err) {
+  cudaStream_t st = d->stream;
+  Params P = d->P;
+  P.chi2_out = d->chi2_out.p;
+  const SNView V = d->V;
+  const Supernodal::Lists& L = d->L;
+  int nodes = 0;
+  gn_stamp<<<1, 1, 0, st>>>(d->stamps.p, 0);
+  // zero the factor storage (fill positions must start at 0) and the backward accumulators
+  PGO_CUDA(cudaMemsetAsync(P.M, 0, sizeof(double) * 9 * static_cast<size_t>(P.nnzb), st));
+  PGO_CUDA(cudaMemsetAsync(P.x, 0, sizeof(double) * 3 * static_cast<size_t>(P.n), st));
+  gn_linearise<<<d->lin_blocks, kThreads, 0, st>>>(P);
+  gn_chi2<<<1, 256, 0, st>>>(P, d->lin_blocks);
+  gn_stamp<<<1, 1, 0, st>>>(d->stamps.p, 1);
+  nodes += 6;
+  const Task* fa = d->fa.p;
+  const Task* ff = d->ff.p;
+  const Task* fb = d->fb.p;
+  for (int l = 0; l < L.n_plevels; ++l) {
+    const int n_fa = L.fa_ptr[l + 1] - L.fa_ptr[l], n_ff = L.ff_ptr[l + 1] - L.ff_ptr[l],
+              n_fb = L.fb_ptr[l + 1] - L.fb_ptr[l];
+    if (n_fa) {
+      sn_k_factor<<<n_fa, kCtaThreads, sizeof(double) * L.fa_smem[l], st>>>(V, fa + L.fa_ptr[l]);
+      ++nodes;
+    }
+    if (n_ff) {
+      sn_k_fused<<<(n_ff + kWarpsPerCta - 1) / kWarpsPerCta, 32 * kWarpsPerCta,
+                   sizeof(double) * kWarpSmemDoubles * kWarpsPerCta, st>>>(V, ff + L.ff_ptr[l], n_ff);
+      ++nodes;
+    }
+    if (n_fb) {
+      sn_k_update<<<n_fb, kCtaThreads, sizeof(double) * L.fb_smem[l], st>>>(V, fb + L.fb_ptr[l]);
+      ++nodes;
+    }
+  }
+  gn_stamp<<<1, 1, 0, st>>>(d->stamps.p, 2);
+  const Task* ss = d->ss.p;
+  const Task* sa = d->sa.p;
+  const Task* sf = d->sf.p;
+  const Task* sb = d->sb.p;
+  const size_t warp_bytes = sizeof(double) * kWarpSmemDoubles * kWarpsPerCta;
+  for (int l = 0; l < L.n_slevels; ++l) {
+    const int n_sa = L.sa_ptr[l + 1] - L.sa_ptr[l], n_ss = L.ss_ptr[l + 1] - L.ss_ptr[l],
+              n_sf = L.sf_ptr[l + 1] - L.sf_ptr[l];
+    if (n_sa) {
+      sn_k_fwd_tri<<<n_sa, kCtaThreads, sizeof(double) * L.sa_smem[l], st>>>(V, sa + L.sa_ptr[l]);
+      ++nodes;
+    }
+    if (n_ss) {
+      sn_k_fwd_small<<<(n_ss + kWarpsPerCta - 1) / kWarpsPerCta, 32 * kWarpsPerCta, warp_bytes, st>>>(
+          V, ss + L.ss_ptr[l], n_ss);
+      ++nodes;
+    }
+    if (n_sf) {
+      sn_k_fwd_rows<<<(n_sf + kWarpsPerCta - 1) / kWarpsPerCta, 32 * kWarpsPerCta, 0, st>>>(
+          V, sf + L.sf_ptr[l], n_sf);
+      ++nodes;
+    }
+  }
+  gn_stamp<<<1, 1, 0, st>>>(d->stamps.p, 3);
+  for (int l = L.n_slevels - 1; l >= 0; --l) {
+    const int n_sa = L.sa_ptr[l + 1] - L.sa_ptr[l], n_ss = L.ss_ptr[l + 1] - L.ss_ptr[l],
+              n_sb = L.sb_ptr[l + 1] - L.sb_ptr[l];
+    if (n_sb) {
+      sn_k_bwd_rows<<<(n_sb + kWarpsPerCta - 1) / kWarpsPerCta, 32 * kWarpsPerCta, 0, st>>>(
+          V, sb + L.sb_ptr[l], n_sb);
+      ++nodes;
+    }
+    if (n_ss) {
+      sn_k_bwd_small<<<(n_ss + kWarpsPerCta - 1) / kWarpsPerCta, 32 * kWarpsPerCta, warp_bytes, st>>>(
+          V, ss + L.ss_ptr[l], n_ss);
+      ++nodes;
+    }
+    if (n_sa) {
+      sn_k_bwd_tri<<<n_sa, kCtaThreads, sizeof(double) * L.sa_smem[l], st>>>(V, sa + L.sa_ptr[l]);
+      ++nodes;
+    }
+  }
+  gn_stamp<<<1, 1, 0, st>>>(d->stamps.p, 4);
+  gn_update<<<(P.n + 255) / 256, 256, 0, st>>>(P);
+  gn_count_iteration<<<1, 1, 0, st>>>(P);
+  gn_stamp<<<1, 1, 0, st>>>(d->stamps.p, 5);
+  nodes += 6;
+  d->graph_nodes = nodes;
+  PGO_CUDA(cudaGetLastError());
+  return PGO_OK;
+}
+
+static int build_iteration_graph(DeviceSolver* d, std::string* err) {
+  if (d->graph_exec) cudaGraphExecDestroy(d->graph_exec);
+  if (d->graph) cudaGraphDestroy(d->graph);
+  d->graph_exec = nullptr;
+  d->graph = nullptr;
+  PGO_CUDA(cudaStreamBeginCapture(d->stream, cudaStreamCaptureModeThreadLocal));
+  const int rc = enqueue_iteration(d, err);
+  cudaGraph_t g = nullptr;
+  const cudaError_t e = cudaStreamEndCapture(d->stream, &g);
+  if (rc != PGO_OK) {
+    if (g) cudaGraphDestroy(g);
+    return rc;
+  }
+  PGO_CUDA(e);
+  d->graph = g;
+  PGO_CUDA(cudaGraphInstantiate(&d->graph_exec, d->graph, 0));
+  return PGO_OK;
+}
+
 int dev_iterate(DeviceSolver* d, int n_iters, double* chi2_out, int* iters_done, float* ms,
                 std::string* err) {
   if (!d->have_values) {
@@ -1085,37 +1126,37 @@ int dev_iterate(DeviceSolver* d, int n_iters, double* chi2_out, int* iters_done,
   *iters_done = 0;
   *ms = 0.f;
   if (n_iters <= 0) return PGO_OK;
-  PGO_CUDA(d->chi2_out.reserve(n_iters));
-  PGO_CUDA(cudaMemsetAsync(d->status.p, 0, 4 * sizeof(int), d->stream));
-  PGO_CUDA(cudaMemsetAsync(d->chi2_out.p, 0, n_iters * sizeof(double), d->stream));
-  Params P = d->P;
-  P.chi2_out = d->chi2_out.p;
   if (d->D.world != 1) {
     if (err) *err = "this solver was analysed for a domain decomposition: use the pgo_dd_* calls";
     return PGO_ERR_ARG;
   }
-  SNDev SD = d->S;
-  // marginals may have re-allocated the substitution vectors
-  SD.V.u = d->u.p;
-  SD.V.x = d->x.p;
-  void* args[] = {&P, &SD, &n_iters};
-  PGO_CUDA(cudaEventRecord(d->ev0, d->stream));
-  PGO_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(gn_iterations), dim3(d->grid_sn),
-                                       dim3(kThreads), args, kSnSmemBytes, d->stream));
-  PGO_CUDA(cudaEventRecord(d->ev1, d->stream));
-  d->launches++;
+  if (!d->graph_exec) {
+    const int rc = build_iteration_graph(d, err);
+    if (rc != PGO_OK) return rc;
+  }
   int status[4] = {0, 0, 0, 0};
-  PGO_CUDA(cudaMemcpyAsync(status, d->status.p, sizeof status, cudaMemcpyDeviceToHost, d->stream));
-  if (chi2_out)
-    PGO_CUDA(cudaMemcpyAsync(chi2_out, d->chi2_out.p, n_iters * sizeof(double),
-                             cudaMemcpyDeviceToHost, d->stream));
+  PGO_CUDA(cudaEventRecord(d->ev0, d->stream));
+  for (int first = 0; first < n_iters && !status[0]; first += kMaxItersPerCall) {
+    const int chunk = std::min(kMaxItersPerCall, n_iters - first);
+    PGO_CUDA(cudaMemsetAsync(d->status.p, 0, 4 * sizeof(int), d->stream));
+    PGO_CUDA(cudaMemsetAsync(d->chi2_out.p, 0, chunk * sizeof(double), d->stream));
+    for (int it = 0; it < chunk; ++it) PGO_CUDA(cudaGraphLaunch(d->graph_exec, d->stream));
+    d->launches += static_cast<uint64_t>(chunk) * d->graph_nodes;
+    PGO_CUDA(cudaMemcpyAsync(status, d->status.p, sizeof status, cudaMemcpyDeviceToHost, d->stream));
+    if (chi2_out)
+      PGO_CUDA(cudaMemcpyAsync(chi2_out + first, d->chi2_out.p, chunk * sizeof(double),
+                               cudaMemcpyDeviceToHost, d->stream));
+    if (first + chunk < n_iters) PGO_CUDA(cudaStreamSynchronize(d->stream));
+    *iters_done += status[1];
+  }
+  PGO_CUDA(cudaEventRecord(d->ev1, d->stream));
   unsigned long long st[6] = {0, 0, 0, 0, 0, 0};
   PGO_CUDA(cudaMemcpyAsync(st, d->stamps.p, sizeof st, cudaMemcpyDeviceToHost, d->stream));
   PGO_CUDA(cudaStreamSynchronize(d->stream));
+  if (n_iters <= kMaxItersPerCall) *iters_done = status[1];
   for (int k = 0; k < 5; ++k) d->stage_ms[k] = st[k + 1] > st[k] ? (st[k + 1] - st[k]) * 1e-6 : 0.0;
   PGO_CUDA(cudaEventElapsedTime(ms, d->ev0, d->ev1));
-  *iters_done = status[1];
-  d->have_factor = status[1] > 0;
+  d->have_factor = *iters_done > 0;
   if (status[0]) {
     if (err) *err = "H is not positive definite (a 3x3 pivot failed): is a vertex fixed?";
     return PGO_ERR_NUMERIC;
@@ -1129,7 +1170,7 @@ int dev_dd_begin(DeviceSolver* d, int n_iters, std::string* err) {
     return PGO_ERR_ARG;
   }
   PGO_CUDA(cudaSetDevice(d->device));
-  PGO_CUDA(d->chi2_out.reserve(std::max(n_iters, 1)));
+  PGO_CUDA(d->chi2_out.reserve(std::max(n_iters, kMaxItersPerCall)));
   PGO_CUDA(cudaMemsetAsync(d->status.p, 0, 4 * sizeof(int), d->stream));
   PGO_CUDA(cudaMemsetAsync(d->chi2_out.p, 0, std::max(n_iters, 1) * sizeof(double), d->stream));
   d->dd_iter = 0;
@@ -1239,13 +1280,9 @@ int dev_marginals(DeviceSolver* d, int n, const int* col_p, const int* row_p, do
   const int batch_cols = 16;  // 48 right-hand sides per cooperative launch
   const size_t stride = 3 * static_cast<size_t>(d->P.n);
   PGO_CUDA(d->many_rhs.reserve(3 * batch_cols * stride));
-  if (d->vec_cap < static_cast<size_t>(3 * batch_cols)) {
-    PGO_CUDA(d->u.reserve(3 * batch_cols * stride));
-    PGO_CUDA(d->x.reserve(3 * batch_cols * stride));
-    d->vec_cap = 3 * batch_cols;
-    d->P.u = d->u.p;
-    d->P.x = d->x.p;
-  }
+  // the marginals' substitution vectors are separate: the iteration graph holds u / x by address
+  PGO_CUDA(d->many_u.reserve(3 * batch_cols * stride));
+  PGO_CUDA(d->many_x.reserve(3 * batch_cols * stride));
   PGO_CUDA(d->scratch_i.reserve(3 * static_cast<size_t>(n) + batch_cols));
   PGO_CUDA(d->scratch_d.reserve(9 * static_cast<size_t>(n) + 1));
   std::vector<double> out_all(9 * static_cast<size_t>(n));
@@ -1269,12 +1306,14 @@ int dev_marginals(DeviceSolver* d, int n, const int* col_p, const int* row_p, do
     PGO_CUDA(cudaMemsetAsync(d->many_rhs.p, 0, 3 * nc * stride * sizeof(double), d->stream));
     set_unit_rhs<<<(3 * nc + 127) / 128, 128, 0, d->stream>>>(d->many_rhs.p, stride, d_cols, nc);
     Params P = d->P;
+    P.u = d->many_u.p;
+    P.x = d->many_x.p;
     double* rhs = d->many_rhs.p;
     int nrhs = 3 * nc;
     void* args[] = {&P, &rhs, &nrhs};
     PGO_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(solve_many), dim3(d->grid),
                                          dim3(kThreads), args, 0, d->stream));
-    gather_blocks<<<(9 * nb + 127) / 128, 128, 0, d->stream>>>(d->x.p, stride, d_rows, d_rhs_of, nb,
+    gather_blocks<<<(9 * nb + 127) / 128, 128, 0, d->stream>>>(d->many_x.p, stride, d_rows, d_rhs_of, nb,
                                                               d->scratch_d.p);
     d->launches += 3;
     PGO_CUDA(cudaGetLastError());

@@ -53,10 +53,12 @@ struct SNView {
 };
 
 // doubles of shared memory a group needs for any task of its kind
-static const int kCtaSmemDoubles = kPanelWidth * kPanelWidth * 9 + kPanelWidth * 9 +
-                                   3 * kPanelWidth * 3 * kRowChunk;  // factor task: 11664
+static const int kPairDoubles = (kPanelWidth * (kPanelWidth + 1) / 2 + 1) / 2;  // int table
+static const int kCtaSmemDoubles = kPanelWidth * kPanelWidth * 9 + kPanelWidth * 9 + kPairDoubles +
+                                   3 * kPanelWidth * 3 * kRowChunk;  // factor task
+static const int kSmallPairDoubles = (kSmallWidth * (kSmallWidth + 1) / 2 + 1) / 2;
 static const int kWarpSmemDoubles = kSmallWidth * kSmallWidth * 9 + kSmallWidth * 9 +
-                                    3 * kSmallWidth * 3 * kSmallRows;  // fused task: 1332
+                                    kSmallPairDoubles + 3 * kSmallWidth * 3 * kSmallRows;  // fused
 static_assert(kTileBudget * 9 <= kCtaSmemDoubles, "update tiles must fit the CTA's shared memory");
 static_assert(6 * kMaxSuperWidth + kPanelWidth * kPanelWidth * 9 + kPanelWidth * 9 + 3 * 256 <=
                   kCtaSmemDoubles, "a wide supernode's vectors must fit the CTA's shared memory");
@@ -93,6 +95,41 @@ PGO_HD void sn_fail(int* status) {
 // first position of column t of a chain whose first column starts at `base` with `len` blocks
 PGO_HD int sn_colpos(int base, int len, int t) { return base + t * len - t * (t - 1) / 2; }
 
+// Memory-level parallelism: every rank issues eight independent loads before it consumes any of
+// them (a plain copy loop stalls on each load's L2 latency in turn). loc(i, &src, &dst).
+template <class G, class F>
+PGO_HD void sn_gather(const G& g, int n, F loc) {
+  const int step = g.size();
+  for (int i0 = g.rank(); i0 < n; i0 += 8 * step) {
+    double v[8];
+    double* dp[8];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int j = 0; j < 8; ++j) {
+      const int i = i0 + j * step;
+      dp[j] = nullptr;
+      if (i < n) {
+        const double* sp;
+        loc(i, &sp, &dp[j]);
+        v[j] = sn_ld(sp);
+      }
+    }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int j = 0; j < 8; ++j)
+      if (dp[j]) *dp[j] = v[j];
+  }
+}
+
+PGO_HD void sn_ld9(const double* p, double* m) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int k = 0; k < 9; ++k) m[k] = sn_ld(p + k);
+}
+
 // Inverse of a symmetric positive definite 3x3 (lower triangle read) by cofactors: one division on
 // the dependency chain instead of three square roots and six divisions. Positive definiteness by
 // Sylvester's criterion; false if a leading minor is not positive.
@@ -119,16 +156,29 @@ PGO_HD bool sn_spd_inverse(const double* a, double* inv) {
 // ---- diagonal part of a panel: w x w blocks, Dg[(i * w + t) * 9 + k], i >= t loaded -------------
 template <class G>
 PGO_HD void sn_load_diag(const G& g, const SNView& V, int base, int len, int w, double* Dg) {
-  for (int idx = g.rank(); idx < w * w * 9; idx += g.size()) {
-    const int i = idx / (w * 9), t = (idx / 9) % w, k = idx % 9;
-    Dg[idx] = i >= t ? sn_ld(V.M + 9 * static_cast<size_t>(sn_colpos(base, len, t) + (i - t)) + k) : 0.0;
-  }
+  // lower triangle incl. diagonal, pair p = i (i + 1) / 2 + t; the upper part is written later
+  const int n_pairs = w * (w + 1) / 2;
+  sn_gather(g, n_pairs * 9, [&](int idx, const double** sp, double** dp) {
+    const int p = idx / 9, k = idx % 9;
+    int i = 0;
+    while ((i + 1) * (i + 2) / 2 <= p) ++i;
+    const int t = p - i * (i + 1) / 2;
+    *sp = V.M + 9 * static_cast<size_t>(sn_colpos(base, len, t) + (i - t)) + k;
+    *dp = Dg + (i * w + t) * 9 + k;
+  });
 }
 
 // In-place block LDL^T of the diagonal part. On return (after a sync):
 //   Dg[i][t], i >= t : final M(c0+i, c0+t);  Dg[s][t], s < t : G(s,t) = Dinv_s M(t,s)^T;  Di[t].
+// pairs: scratch table of w (w + 1) / 2 ints, (i << 8) | t per lower-triangular block.
 template <class G>
-PGO_HD void sn_factor_diag(const G& g, const SNView& V, int w, double* Dg, double* Di) {
+PGO_HD void sn_factor_diag(const G& g, const SNView& V, int w, double* Dg, double* Di, int* pairs) {
+  const int n_pairs = w * (w + 1) / 2;
+  for (int p = g.rank(); p < n_pairs; p += g.size()) {
+    int i = 0;
+    while ((i + 1) * (i + 2) / 2 <= p) ++i;
+    pairs[p] = (i << 8) | (p - i * (i + 1) / 2);
+  }
   for (int s = 0; s < w; ++s) {
     if (g.rank() == 0) {
       if (!sn_spd_inverse(Dg + (s * w + s) * 9, Di + 9 * s)) {
@@ -137,22 +187,22 @@ PGO_HD void sn_factor_diag(const G& g, const SNView& V, int w, double* Dg, doubl
       }
     }
     g.sync();
-    // one pass: G(s,t) into the upper part, and the trailing update with G formed on the fly
-    const int rem = w - s - 1;
+    // one pass over the blocks (i, t), i >= t > s: the diagonal ones also publish G(s,t) into the
+    // upper part; everybody forms the column of G it needs on the fly
     const double* d = Di + 9 * s;
-    for (int idx = g.rank(); idx < rem * rem * 9; idx += g.size()) {
-      const int i = s + 1 + idx / (rem * 9), t = s + 1 + (idx / 9) % rem;
-      const int r = (idx % 9) / 3, c = idx % 3;
+    for (int idx = g.rank(); idx < n_pairs * 9; idx += g.size()) {
+      const int pr = pairs[idx / 9], i = pr >> 8, t = pr & 255;
+      if (t <= s) continue;
+      const int k = idx % 9, r = k / 3, c = k % 3;
       const double* m = Dg + (t * w + s) * 9;  // M(t,s)
-      if (i == s + 1)                           // the first row of the pass also publishes G(s,t)
-        Dg[(s * w + t) * 9 + 3 * r + c] =
+      if (i == t)
+        Dg[(s * w + t) * 9 + k] =
             d[3 * r] * m[3 * c] + d[3 * r + 1] * m[3 * c + 1] + d[3 * r + 2] * m[3 * c + 2];
-      if (t > i) continue;
       const double* a = Dg + (i * w + s) * 9;
       const double g0 = d[0] * m[3 * c] + d[1] * m[3 * c + 1] + d[2] * m[3 * c + 2];
       const double g1 = d[3] * m[3 * c] + d[4] * m[3 * c + 1] + d[5] * m[3 * c + 2];
       const double g2 = d[6] * m[3 * c] + d[7] * m[3 * c + 1] + d[8] * m[3 * c + 2];
-      Dg[(i * w + t) * 9 + 3 * r + c] -= a[3 * r] * g0 + a[3 * r + 1] * g1 + a[3 * r + 2] * g2;
+      Dg[(i * w + t) * 9 + k] -= a[3 * r] * g0 + a[3 * r + 1] * g1 + a[3 * r + 2] * g2;
     }
     g.sync();
   }
@@ -162,14 +212,12 @@ PGO_HD void sn_factor_diag(const G& g, const SNView& V, int w, double* Dg, doubl
 template <class G>
 PGO_HD void sn_load_rows(const G& g, const SNView& V, const PanelDesc& pd, int r0, int nrows, int ldx,
                          double* xs) {
-  for (int t = 0; t < pd.w; ++t) {
-    const double* src =
-        V.M + 9 * static_cast<size_t>(sn_colpos(pd.base, pd.w + pd.m, t) + (pd.w - t) + r0);
-    for (int idx = g.rank(); idx < 9 * nrows; idx += g.size()) {
-      const int a = idx / 9, k = idx % 9;
-      xs[(3 * t + k % 3) * ldx + 3 * a + k / 3] = sn_ld(src + idx);
-    }
-  }
+  const int per_col = 9 * nrows;
+  sn_gather(g, pd.w * per_col, [&](int idx, const double** sp, double** dp) {
+    const int t = idx / per_col, q = idx % per_col, a = q / 9, k = q % 9;
+    *sp = V.M + 9 * static_cast<size_t>(sn_colpos(pd.base, pd.w + pd.m, t) + (pd.w - t) + r0) + q;
+    *dp = xs + (3 * t + k % 3) * ldx + 3 * a + k / 3;
+  });
 }
 
 template <class G>
@@ -232,11 +280,12 @@ PGO_HD void sn_task_factor(const G& g, const SNView& V, const Task& T, double* s
   const int w = pd.w, nrows = T.r1 - T.r0, ldx = 3 * nrows;
   double* Dg = sm;
   double* Di = Dg + w * w * 9;
-  double* xs = Di + w * 9;
+  int* pairs = reinterpret_cast<int*>(Di + w * 9);
+  double* xs = Di + w * 9 + kPairDoubles;
   sn_load_diag(g, V, pd.base, w + pd.m, w, Dg);
   sn_load_rows(g, V, pd, T.r0, nrows, ldx, xs);
   g.sync();
-  sn_factor_diag(g, V, w, Dg, Di);
+  sn_factor_diag(g, V, w, Dg, Di, pairs);
   sn_solve_rows(g, w, Dg, xs, ldx, 3 * nrows);
   g.sync();
   sn_store_rows(g, V, pd, T.r0, nrows, ldx, xs);
@@ -267,20 +316,21 @@ PGO_HD void sn_task_update(const G& g, const SNView& V, const Task& T, double* s
       if (i >= t) V.M[9 * static_cast<size_t>(sn_colpos(pd.base, len, t) + (i - t)) + k] = sn_ld(src + idx);
     }
   }
-  for (int t = 0; t < w; ++t) {
-    const double* src = V.M + 9 * static_cast<size_t>(sn_colpos(pd.base, len, t) + (w - t) + i0);
-    for (int idx = g.rank(); idx < 9 * ni; idx += g.size())
-      As[(t * 9 + idx % 9) * ti + idx / 9] = sn_ld(src + idx);
+  {
+    const int per_col = 9 * ni;
+    sn_gather(g, w * per_col, [&](int idx, const double** sp, double** dp) {
+      const int t = idx / per_col, q = idx % per_col;
+      *sp = V.M + 9 * static_cast<size_t>(sn_colpos(pd.base, len, t) + (w - t) + i0) + q;
+      *dp = As + (t * 9 + q % 9) * ti + q / 9;
+    });
   }
   for (int idx = g.rank(); idx < w * nj; idx += g.size()) {
     const int t = idx / nj, bl = idx % nj;
     const double* mp = V.M + 9 * static_cast<size_t>(sn_colpos(pd.base, len, t) + (w - t) + j0 + bl);
     const double* dp = V.Dinv + 9 * static_cast<size_t>(pd.c0 + t);
     double mb[9], d[9];
-    for (int k = 0; k < 9; ++k) {
-      mb[k] = sn_ld(mp + k);
-      d[k] = sn_ld(dp + k);
-    }
+    sn_ld9(mp, mb);
+    sn_ld9(dp, d);
     for (int r = 0; r < 3; ++r)
       for (int c = 0; c < 3; ++c)
         Ws[(t * 9 + 3 * r + c) * tj + bl] =
@@ -295,6 +345,8 @@ PGO_HD void sn_task_update(const G& g, const SNView& V, const Task& T, double* s
     const int al = (q % pr) * 8 + (lane & 7), bl = (q / pr) * 4 + (lane >> 3);
     const int a = i0 + al, b = j0 + bl;
     if (al >= ni || bl >= nj || a < b) continue;
+    // the scatter position's two dependent look-ups overlap with the products below
+    const int tpos = V.colbase[pd.meta + b] + V.tbl[V.tbl_off[pd.meta + b] + a];
     double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     for (int t = 0; t < w; ++t) {
       double av[9], wv[9];
@@ -315,7 +367,7 @@ PGO_HD void sn_task_update(const G& g, const SNView& V, const Task& T, double* s
         for (int c = 0; c < 3; ++c)
           acc[3 * r + c] += av[3 * r] * wv[c] + av[3 * r + 1] * wv[3 + c] + av[3 * r + 2] * wv[6 + c];
     }
-    double* dst = V.M + 9 * static_cast<size_t>(sn_target(V, pd.meta, a, b));
+    double* dst = V.M + 9 * static_cast<size_t>(tpos);
     for (int k = 0; k < 9; ++k) sn_add(dst + k, -acc[k]);
   }
   g.sync();
@@ -328,11 +380,12 @@ PGO_HD void sn_task_fused(const G& g, const SNView& V, const Task& T, double* sm
   const int w = pd.w, m = pd.m, ldx = 3 * m;
   double* Dg = sm;
   double* Di = Dg + w * w * 9;
-  double* xs = Di + w * 9;
+  int* pairs = reinterpret_cast<int*>(Di + w * 9);
+  double* xs = Di + w * 9 + kSmallPairDoubles;
   sn_load_diag(g, V, pd.base, w + m, w, Dg);
   sn_load_rows(g, V, pd, 0, m, ldx, xs);
   g.sync();
-  sn_factor_diag(g, V, w, Dg, Di);
+  sn_factor_diag(g, V, w, Dg, Di, pairs);
   sn_solve_rows(g, w, Dg, xs, ldx, 3 * m);
   g.sync();
   sn_store_rows(g, V, pd, 0, m, ldx, xs);
@@ -341,6 +394,7 @@ PGO_HD void sn_task_fused(const G& g, const SNView& V, const Task& T, double* sm
   for (int b = g.rank(); b < m; b += g.size()) {
     const int cb = V.colbase[pd.meta + b], to = V.tbl_off[pd.meta + b];
     for (int a = b; a < m; ++a) {
+      const int tpos = cb + V.tbl[to + a];
       double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
       for (int t = 0; t < w; ++t) {
         double av[9], y[9], bv[9];
@@ -356,7 +410,7 @@ PGO_HD void sn_task_fused(const G& g, const SNView& V, const Task& T, double* sm
           for (int c = 0; c < 3; ++c)
             acc[3 * r + c] += y[3 * r] * bv[3 * c] + y[3 * r + 1] * bv[3 * c + 1] + y[3 * r + 2] * bv[3 * c + 2];
       }
-      double* dst = V.M + 9 * static_cast<size_t>(cb + V.tbl[to + a]);
+      double* dst = V.M + 9 * static_cast<size_t>(tpos);
       for (int k = 0; k < 9; ++k) sn_add(dst + k, -acc[k]);
     }
   }
@@ -401,25 +455,40 @@ PGO_HD void sn_forward_panel(const G& g, int w, const double* Dg, const double* 
 
 // rows [r0, r1) below the SUPERNODE of panel p:  z_{r_a} -= sum_t M(a,t) u_t  (atomic).
 // us: the supernode's u in shared memory, or null to read it from global memory.
+// Loads are issued four blocks at a time (memory-level parallelism, see sn_gather).
 template <class G>
 PGO_HD void sn_forward_rows(const G& g, const SNView& V, int p, int r0, int r1, const double* us) {
   const PanelDesc pd = V.pn[p];
   const SuperDesc sd = V.sn[pd.sn];
-  const int o = pd.sn_off, len = sd.W + sd.m;
+  const int w = pd.w, o = pd.sn_off, len = sd.W + sd.m;
   for (int a = r0 + g.rank(); a < r1; a += g.size()) {
-    double acc[3] = {0.0, 0.0, 0.0};
-    for (int t = 0; t < pd.w; ++t) {
-      const double* mp = V.M + 9 * static_cast<size_t>(sn_colpos(sd.base, len, o + t) + (sd.W - o - t) + a);
-      double mb[9], uv[3], v[3];
-      for (int k = 0; k < 9; ++k) mb[k] = sn_ld(mp + k);
-      for (int k = 0; k < 3; ++k)
-        uv[k] = us ? us[3 * (o + t) + k] : sn_ld(V.u + 3 * static_cast<size_t>(pd.c0 + t) + k);
-      sn_mat_vec(mb, uv, v);
-      acc[0] += v[0];
-      acc[1] += v[1];
-      acc[2] += v[2];
-    }
     const int r = V.row_idx[sd.base + sd.W + a];
+    double acc[3] = {0.0, 0.0, 0.0};
+    for (int t0 = 0; t0 < w; t0 += 4) {
+      double mb[4][9], uv[4][3];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+      for (int q = 0; q < 4; ++q) {
+        const int t = t0 + q;
+        if (t < w) {
+          sn_ld9(V.M + 9 * static_cast<size_t>(sn_colpos(sd.base, len, o + t) + (sd.W - o - t) + a), mb[q]);
+          for (int k = 0; k < 3; ++k)
+            uv[q][k] = us ? us[3 * (o + t) + k] : sn_ld(V.u + 3 * static_cast<size_t>(pd.c0 + t) + k);
+        }
+      }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+      for (int q = 0; q < 4; ++q)
+        if (t0 + q < w) {
+          double v[3];
+          sn_mat_vec(mb[q], uv[q], v);
+          acc[0] += v[0];
+          acc[1] += v[1];
+          acc[2] += v[2];
+        }
+    }
     for (int k = 0; k < 3; ++k) sn_add(V.z + 3 * static_cast<size_t>(r) + k, -acc[k]);
   }
 }
@@ -434,8 +503,10 @@ PGO_HD void sn_task_forward_tri(const G& g, const SNView& V, const Task& T, doub
   double* us = zs + 3 * W;
   double* Dg = us + 3 * W;
   double* Di = Dg + kPanelWidth * kPanelWidth * 9;
-  for (int idx = g.rank(); idx < 3 * W; idx += g.size())
-    zs[idx] = sn_ld(V.z + 3 * static_cast<size_t>(sd.c0) + idx);
+  sn_gather(g, 3 * W, [&](int idx, const double** sp, double** dp) {
+    *sp = V.z + 3 * static_cast<size_t>(sd.c0) + idx;
+    *dp = zs + idx;
+  });
   for (int p = sd.pn_begin; p < sd.pn_end; ++p) {
     const PanelDesc pd = V.pn[p];
     const int w = pd.w, o = pd.sn_off;
@@ -446,15 +517,26 @@ PGO_HD void sn_task_forward_tri(const G& g, const SNView& V, const Task& T, doub
     // the supernode's remaining columns are rows of this panel
     for (int tp = o + w + g.rank(); tp < W; tp += g.size()) {
       double acc[3] = {0.0, 0.0, 0.0};
-      for (int t = 0; t < w; ++t) {
-        const double* mp =
-            V.M + 9 * static_cast<size_t>(sn_colpos(sd.base, len, o + t) + (w - t) + (tp - o - w));
-        double mb[9], v[3];
-        for (int k = 0; k < 9; ++k) mb[k] = sn_ld(mp + k);
-        sn_mat_vec(mb, us + 3 * (o + t), v);
-        acc[0] += v[0];
-        acc[1] += v[1];
-        acc[2] += v[2];
+      for (int t0 = 0; t0 < w; t0 += 4) {
+        double mb[4][9];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int q = 0; q < 4; ++q)
+          if (t0 + q < w)
+            sn_ld9(V.M + 9 * static_cast<size_t>(sn_colpos(sd.base, len, o + t0 + q) + (tp - o - t0 - q)),
+                   mb[q]);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int q = 0; q < 4; ++q)
+          if (t0 + q < w) {
+            double v[3];
+            sn_mat_vec(mb[q], us + 3 * (o + t0 + q), v);
+            acc[0] += v[0];
+            acc[1] += v[1];
+            acc[2] += v[2];
+          }
       }
       zs[3 * tp] -= acc[0];
       zs[3 * tp + 1] -= acc[1];
@@ -487,6 +569,31 @@ PGO_HD void sn_task_forward_small(const G& g, const SNView& V, const Task& T, do
   g.sync();
 }
 
+// acc += sum over the rows a = first, first + step, ... < end of  M(a, col)^T x_{row(a)}, where the
+// blocks of the column are consecutive from `col` and xv(a, out) fetches x of row a. Four rows in
+// flight at a time.
+template <class XF>
+PGO_HD void sn_col_dot(const SNView& V, size_t col, int first, int step, int end, XF xv, double* acc) {
+  for (int a0 = first; a0 < end; a0 += 4 * step) {
+    double mb[4][9], x[4][3];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int q = 0; q < 4; ++q) {
+      const int a = a0 + q * step;
+      if (a < end) {
+        xv(a, x[q]);
+        sn_ld9(V.M + 9 * (col + a), mb[q]);
+      }
+    }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int q = 0; q < 4; ++q)
+      if (a0 + q * step < end) sn_mat_t_vec_add(mb[q], x[q], acc);
+  }
+}
+
 // Backward, rows [r0, r1) below the supernode of panel p:  x_{c0+t} += sum_a M(a,t)^T x_{r_a}
 // (x doubles as the accumulator of a wide supernode's columns; atomic).
 template <class G>
@@ -495,18 +602,15 @@ PGO_HD void sn_backward_rows(const G& g, const SNView& V, int p, int r0, int r1)
   const SuperDesc sd = V.sn[pd.sn];
   const int w = pd.w, o = pd.sn_off, len = sd.W + sd.m;
   const int split = g.size() / w > 0 ? g.size() / w : 1;
+  const int* rows = V.row_idx + sd.base + sd.W;
   for (int item = g.rank(); item < w * split; item += g.size()) {
     const int t = item % w, h = item / w;
     const size_t col = static_cast<size_t>(sn_colpos(sd.base, len, o + t) + (sd.W - o - t));
     double acc[3] = {0.0, 0.0, 0.0};
-    for (int a = r0 + h; a < r1; a += split) {
-      const double* mp = V.M + 9 * (col + a);
-      const int r = V.row_idx[sd.base + sd.W + a];
-      double mb[9], xv[3];
-      for (int k = 0; k < 9; ++k) mb[k] = sn_ld(mp + k);
-      for (int k = 0; k < 3; ++k) xv[k] = sn_ld(V.x + 3 * static_cast<size_t>(r) + k);
-      sn_mat_t_vec_add(mb, xv, acc);
-    }
+    sn_col_dot(V, col, r0 + h, split, r1, [&](int a, double* out) {
+      const int r = rows[a];
+      for (int k = 0; k < 3; ++k) out[k] = sn_ld(V.x + 3 * static_cast<size_t>(r) + k);
+    }, acc);
     for (int k = 0; k < 3; ++k) sn_add(V.x + 3 * static_cast<size_t>(pd.c0 + t) + k, acc[k]);
   }
 }
@@ -539,27 +643,27 @@ PGO_HD void sn_task_backward_tri(const G& g, const SNView& V, const Task& T, dou
   double* Dg = us + 3 * W;
   double* Di = Dg + kPanelWidth * kPanelWidth * 9;
   double* red = Di + kPanelWidth * 9;
-  for (int idx = g.rank(); idx < 3 * W; idx += g.size()) {
-    xs[idx] = sn_ld(V.x + 3 * static_cast<size_t>(sd.c0) + idx);
-    us[idx] = sn_ld(V.u + 3 * static_cast<size_t>(sd.c0) + idx);
-  }
+  sn_gather(g, 6 * W, [&](int idx, const double** sp, double** dp) {
+    const int j = idx < 3 * W ? idx : idx - 3 * W;
+    *sp = (idx < 3 * W ? V.x : V.u) + 3 * static_cast<size_t>(sd.c0) + j;
+    *dp = (idx < 3 * W ? xs : us) + j;
+  });
   for (int p = sd.pn_end - 1; p >= sd.pn_begin; --p) {
     const PanelDesc pd = V.pn[p];
     const int w = pd.w, o = pd.sn_off;
     sn_load_diag(g, V, pd.base, w + pd.m, w, Dg);
     sn_load_dinv(g, V, pd.c0, w, Di);
-    // contributions of the supernode's later columns (already final) to this panel's columns
+    g.sync();  // xs of the later panels is final
+    // contributions of the supernode's later columns to this panel's columns
     const int split = g.size() / w > 0 ? g.size() / w : 1;
     for (int item = g.rank(); item < w * split; item += g.size()) {
       const int t = item % w, h = item / w;
-      const size_t col = static_cast<size_t>(sn_colpos(sd.base, len, o + t) + (w - t));
+      // block (tp, o + t) sits at colpos(o + t) + (tp - o - t): index the column by tp directly
+      const size_t col = static_cast<size_t>(sn_colpos(sd.base, len, o + t)) - (o + t);
       double acc[3] = {0.0, 0.0, 0.0};
-      for (int tp = o + w + h; tp < W; tp += split) {
-        const double* mp = V.M + 9 * (col + (tp - o - w));
-        double mb[9];
-        for (int k = 0; k < 9; ++k) mb[k] = sn_ld(mp + k);
-        sn_mat_t_vec_add(mb, xs + 3 * tp, acc);
-      }
+      sn_col_dot(V, col, o + w + h, split, W, [&](int tp, double* out) {
+        for (int k = 0; k < 3; ++k) out[k] = xs[3 * tp + k];
+      }, acc);
       for (int k = 0; k < 3; ++k) red[3 * item + k] = acc[k];
     }
     g.sync();
@@ -592,18 +696,15 @@ PGO_HD void sn_task_backward_small(const G& g, const SNView& V, const Task& T, d
   for (int idx = g.rank(); idx < 3 * W; idx += g.size())
     us[idx] = sn_ld(V.u + 3 * static_cast<size_t>(sd.c0) + idx);
   const int split = g.size() / W > 0 ? g.size() / W : 1;
+  const int* rows = V.row_idx + sd.base + W;
   for (int item = g.rank(); item < W * split; item += g.size()) {
     const int t = item % W, h = item / W;
     const size_t col = static_cast<size_t>(sn_colpos(sd.base, len, t) + (W - t));
     double acc[3] = {0.0, 0.0, 0.0};
-    for (int a = h; a < m; a += split) {
-      const double* mp = V.M + 9 * (col + a);
-      const int r = V.row_idx[sd.base + W + a];
-      double mb[9], xv[3];
-      for (int k = 0; k < 9; ++k) mb[k] = sn_ld(mp + k);
-      for (int k = 0; k < 3; ++k) xv[k] = sn_ld(V.x + 3 * static_cast<size_t>(r) + k);
-      sn_mat_t_vec_add(mb, xv, acc);
-    }
+    sn_col_dot(V, col, h, split, m, [&](int a, double* out) {
+      const int r = rows[a];
+      for (int k = 0; k < 3; ++k) out[k] = sn_ld(V.x + 3 * static_cast<size_t>(r) + k);
+    }, acc);
     for (int k = 0; k < 3; ++k) red[3 * item + k] = acc[k];
   }
   g.sync();

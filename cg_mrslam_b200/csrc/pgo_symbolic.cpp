@@ -471,6 +471,38 @@ bool build_supernodal(Symbolic& S, std::string* err) {
 
 }  // namespace
 
+Supernodal::Lists Supernodal::lists() const {
+  Lists L;
+  L.n_plevels = n_plevels;
+  L.n_slevels = n_slevels;
+  L.ff_ptr = ff_ptr;
+  L.fa_ptr = fa_ptr;
+  L.fb_ptr = fb_ptr;
+  L.ss_ptr = ss_ptr;
+  L.sa_ptr = sa_ptr;
+  L.sf_ptr = sf_ptr;
+  L.sb_ptr = sb_ptr;
+  const int pair_doubles = (kPanelWidth * (kPanelWidth + 1) / 2 + 1) / 2;
+  L.fa_smem.assign(n_plevels, 0);
+  L.fb_smem.assign(n_plevels, 0);
+  for (int l = 0; l < n_plevels; ++l) {
+    for (int i = fa_ptr[l]; i < fa_ptr[l + 1]; ++i) {
+      const int w = pn[fa[i].id].w;
+      L.fa_smem[l] = std::max(L.fa_smem[l], w * w * 9 + w * 9 + pair_doubles + 9 * w * (fa[i].r1 - fa[i].r0));
+    }
+    for (int i = fb_ptr[l]; i < fb_ptr[l + 1]; ++i) {
+      const int w = pn[fb[i].id].w;
+      L.fb_smem[l] = std::max(L.fb_smem[l], w * 9 * ((fb[i].aux >> 16) + (fb[i].aux & 0xFFFF)));
+    }
+  }
+  L.sa_smem.assign(n_slevels, 0);
+  for (int l = 0; l < n_slevels; ++l)
+    for (int i = sa_ptr[l]; i < sa_ptr[l + 1]; ++i)
+      L.sa_smem[l] = std::max(L.sa_smem[l], 6 * sn[sa[i].id].W + kPanelWidth * kPanelWidth * 9 +
+                                                kPanelWidth * 9 + 3 * 256);
+  return L;
+}
+
 bool analyse(int n, const std::vector<std::pair<int, int> >& edges, int ordering, int world,
              Symbolic* out, std::string* err) {
   const auto t0 = std::chrono::steady_clock::now();

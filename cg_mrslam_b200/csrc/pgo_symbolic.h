@@ -92,6 +92,14 @@ struct Supernodal {
   // part of a wide supernode (CTA), sf / sb = rows below it, forward (chunks of 32) / backward
   std::vector<int> ss_ptr, sa_ptr, sf_ptr, sb_ptr;  // n_slevels + 1
   std::vector<Task> ss, sa, sf, sb;
+  // what the host needs to launch the phases: level pointers and per-level shared-memory needs
+  struct Lists {
+    int n_plevels = 0, n_slevels = 0;
+    std::vector<int> ff_ptr, fa_ptr, fb_ptr, ss_ptr, sa_ptr, sf_ptr, sb_ptr;
+    std::vector<int> fa_smem, fb_smem;  // doubles of shared memory of the largest task per level
+    std::vector<int> sa_smem;
+  };
+  Lists lists() const;
   int64_t update_blocks = 0;   // target blocks touched by all outer products (atomic 3x3 adds)
   double flops = 0.0;          // of one numeric factorisation
 };

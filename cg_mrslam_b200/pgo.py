@@ -53,7 +53,6 @@ _SIGS = {
     "pgo_analyse_partition": (C.c_int, [C.c_int, C.c_int, _ip, _ip, _bp, C.c_int, _ip,
                                         C.POINTER(C.c_int64)]),
     "pgo_get_stats": (C.c_int, [C.c_void_p, C.POINTER(pgo_stats)]),
-    "pgo_phase_ticks": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.c_int]),
     "pgo_stream": (C.c_void_p, [C.c_void_p]),
 }
 
@@ -177,16 +176,6 @@ class Solver:
         d["stage_ms"] = dict(zip(("linearise", "factor", "forward", "backward", "update"),
                                  list(s.stage_ms)))
         return d
-
-    def phase_ticks(self):
-        """Profiling: [(kind, level, microseconds since the previous barrier)] of the last iteration."""
-        buf = np.zeros(2 * 8192, dtype=np.uint64)
-        n = self.lib.pgo_phase_ticks(self.h, buf.ctypes.data_as(C.POINTER(C.c_uint64)), len(buf))
-        if n < 0:
-            self._check(n)
-        t = buf[0:2 * n:2].astype(np.int64)
-        code = buf[1:2 * n:2].astype(np.int64)
-        return [(int(code[i] >> 16), int(code[i] & 0xFFFF), (t[i] - t[i - 1]) * 1e-3) for i in range(1, n)]
 
     def stream(self):
         return self.lib.pgo_stream(self.h)

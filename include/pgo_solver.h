@@ -126,11 +126,6 @@ int pgo_analyse_partition(int n_vertices, int n_edges, const int32_t* edge_i, co
                           const uint8_t* fixed, int world, int32_t* vertex_owner, int64_t* stats);
 
 int pgo_get_stats(const pgo_solver* s, pgo_stats* out);
-/* Profiling aid: device timestamps after every grid-wide barrier of the last Gauss-Newton
- * iteration, as pairs (nanoseconds, kind << 16 | level); kind 0 start, 1 panel factorisation,
- * 2 outer products, 3 / 4 forward substitution (triangular / rows), 5 / 6 backward substitution
- * (rows / triangular). Returns the number of pairs written (<= cap / 2) or a negative status. */
-int pgo_phase_ticks(pgo_solver* s, uint64_t* out, int cap);
 void* pgo_stream(const pgo_solver* s);
 
 #ifdef __cplusplus
