@@ -177,43 +177,80 @@ int pgo_set_graph(pgo_solver* s, int n_vertices, int n_edges, const int32_t* edg
   return PGO_OK;
 }
 
-int pgo_upload(pgo_solver* s, const double* poses, const double* meas, const double* info6) {
+int pgo_set_batch(pgo_solver* s, int batch) {
+  if (!s) return fail(PGO_ERR_ARG, "null solver");
+  std::string err;
+  const int rc = pgo::dev_set_batch(s->dev, batch, &err);
+  if (rc) return fail(rc, err);
+  s->have_graph = s->have_values = false;
+  return PGO_OK;
+}
+
+static int upload_impl(pgo_solver* s, int inst, const double* poses, const double* meas,
+                       const double* info6) {
   if (!s || !s->have_graph || !poses || (s->n_edges && (!meas || !info6)))
     return fail(PGO_ERR_ARG, "bad argument (pgo_set_graph first)");
   std::string err;
-  const int rc = pgo::dev_upload(s->dev, poses, meas, info6, &err);
+  const int rc = pgo::dev_upload(s->dev, inst, poses, meas, info6, &err);
   if (rc) return fail(rc, err);
-  s->meas.assign(meas, meas + 3 * static_cast<size_t>(s->n_edges));
-  s->have_values = true;
+  if (inst <= 0) {  // the host copy of the measurements (initial guess) follows instance 0
+    s->meas.assign(meas, meas + 3 * static_cast<size_t>(s->n_edges));
+    s->have_values = true;
+  }
   return PGO_OK;
+}
+
+int pgo_upload(pgo_solver* s, const double* poses, const double* meas, const double* info6) {
+  return upload_impl(s, -1, poses, meas, info6);
+}
+
+int pgo_upload_instance(pgo_solver* s, int inst, const double* poses, const double* meas,
+                        const double* info6) {
+  if (inst < 0) return fail(PGO_ERR_ARG, "no such instance");
+  return upload_impl(s, inst, poses, meas, info6);
 }
 
 int pgo_set_poses(pgo_solver* s, const double* poses) {
   if (!s || !s->have_values || !poses) return fail(PGO_ERR_ARG, "bad argument (pgo_upload first)");
   std::string err;
-  const int rc = pgo::dev_set_poses(s->dev, poses, &err);
+  const int rc = pgo::dev_set_poses(s->dev, -1, poses, &err);
   return rc ? fail(rc, err) : PGO_OK;
 }
 
-int pgo_get_poses(pgo_solver* s, double* poses) {
+int pgo_get_poses(pgo_solver* s, double* poses) { return pgo_get_poses_instance(s, 0, poses); }
+
+int pgo_get_poses_instance(pgo_solver* s, int inst, double* poses) {
   if (!s || !s->have_values || !poses) return fail(PGO_ERR_ARG, "bad argument (pgo_upload first)");
   std::string err;
-  const int rc = pgo::dev_get_poses(s->dev, poses, &err);
+  const int rc = pgo::dev_get_poses(s->dev, inst, poses, &err);
+  return rc ? fail(rc, err) : PGO_OK;
+}
+
+int pgo_iterate_batch(pgo_solver* s, int n_iters, double* chi2_out, int* iters_done) {
+  if (!s || !s->have_values || n_iters < 0 || !iters_done)
+    return fail(PGO_ERR_ARG, "bad argument (pgo_upload first)");
+  std::string err;
+  float ms = 0.f;
+  const int rc = pgo::dev_iterate(s->dev, n_iters, chi2_out, iters_done, &ms, &err);
+  s->last_ms = ms;
   return rc ? fail(rc, err) : PGO_OK;
 }
 
 int pgo_iterate(pgo_solver* s, int n_iters, double* poses_out, double* chi2_out, int* iters_done) {
   if (!s || !s->have_values || n_iters < 0) return fail(PGO_ERR_ARG, "bad argument (pgo_upload first)");
   std::string err;
-  int done = 0;
+  const int batch = pgo::dev_batch(s->dev);
+  std::vector<int> done(batch, 0);
+  std::vector<double> chi2(chi2_out ? static_cast<size_t>(batch) * std::max(n_iters, 1) : 0);
   float ms = 0.f;
-  int rc = pgo::dev_iterate(s->dev, n_iters, chi2_out, &done, &ms, &err);
+  int rc = pgo::dev_iterate(s->dev, n_iters, chi2_out ? chi2.data() : nullptr, done.data(), &ms, &err);
   s->last_ms = ms;
-  if (iters_done) *iters_done = done;
+  if (iters_done) *iters_done = done[0];
+  if (chi2_out) std::copy(chi2.begin(), chi2.begin() + n_iters, chi2_out);  // instance 0
   if (rc && rc != PGO_ERR_NUMERIC) return fail(rc, err);
   if (poses_out) {
     std::string err2;
-    const int rc2 = pgo::dev_get_poses(s->dev, poses_out, &err2);
+    const int rc2 = pgo::dev_get_poses(s->dev, 0, poses_out, &err2);
     if (rc2) return fail(rc2, err2);
   }
   return rc ? fail(rc, err) : PGO_OK;
@@ -248,7 +285,7 @@ int pgo_initial_guess(pgo_solver* s) {
   const int nv = s->n_vertices, ne = s->n_edges;
   std::vector<double> poses(3 * static_cast<size_t>(nv));
   std::string err;
-  int rc = pgo::dev_get_poses(s->dev, poses.data(), &err);
+  int rc = pgo::dev_get_poses(s->dev, 0, poses.data(), &err);
   if (rc) return fail(rc, err);
   // adjacency in ascending edge index (C10 tie rule: hop count, then edge index)
   std::vector<int> ptr(nv + 1, 0);
@@ -286,7 +323,7 @@ int pgo_initial_guess(pgo_solver* s) {
       q.push_back(w);
     }
   }
-  rc = pgo::dev_set_poses(s->dev, poses.data(), &err);
+  rc = pgo::dev_set_poses(s->dev, 0, poses.data(), &err);
   return rc ? fail(rc, err) : PGO_OK;
 }
 

@@ -39,13 +39,19 @@ uint64_t dev_launches(const DeviceSolver* d);
 const double* dev_stage_ms(const DeviceSolver* d);
 
 int dev_set_structure(DeviceSolver* d, const Symbolic& S, const GraphTables& G, std::string* err);
-int dev_upload(DeviceSolver* d, const double* poses, const double* meas, const double* info6,
-               std::string* err);
-int dev_set_poses(DeviceSolver* d, const double* poses, std::string* err);
-int dev_get_poses(DeviceSolver* d, double* poses, std::string* err);
+// A solver can hold a batch of problem instances with the same structure (different estimates,
+// measurements, information matrices); every kernel of the iteration graph then runs all of them
+// (blockIdx.y = instance). Set before dev_set_structure. inst = -1 addresses every instance.
+int dev_set_batch(DeviceSolver* d, int batch, std::string* err);
+int dev_batch(const DeviceSolver* d);
+int dev_upload(DeviceSolver* d, int inst, const double* poses, const double* meas,
+               const double* info6, std::string* err);
+int dev_set_poses(DeviceSolver* d, int inst, const double* poses, std::string* err);
+int dev_get_poses(DeviceSolver* d, int inst, double* poses, std::string* err);
 
-// n_iters Gauss-Newton iterations in one cooperative launch. chi2_out[n_iters] (host).
-// *iters_done < n_iters iff a diagonal block was not positive definite. *ms = device time.
+// n_iters Gauss-Newton iterations of every instance (one CUDA graph launch per iteration).
+// chi2_out[batch][n_iters] (host, may be null), iters_done[batch]: < n_iters iff a diagonal block
+// of that instance was not positive definite. *ms = device time.
 int dev_iterate(DeviceSolver* d, int n_iters, double* chi2_out, int* iters_done, float* ms,
                 std::string* err);
 // Domain-decomposed iteration (Symbolic::world > 1), all asynchronous on the solver's stream:

@@ -83,7 +83,25 @@ struct Params {
   double* chi2_out;      // [n_iters]
   int* status;           // [0] error flag, [1] iterations done
   unsigned long long* stamps;  // [6] globaltimer at the stage boundaries of the last iteration
+  // batch of problem instances with this structure: element strides between instances
+  long long s_poses, s_meas, s_info, s_M, s_Dinv, s_vec, s_partial, s_chi2;
 };
+
+// Instance b of a batch (blockIdx.y in the kernels of the iteration graph).
+__device__ __forceinline__ Params params_at(Params P, int b) {
+  P.poses += b * P.s_poses;
+  P.meas += b * P.s_meas;
+  P.info6 += b * P.s_info;
+  P.M += b * P.s_M;
+  P.Dinv += b * P.s_Dinv;
+  P.rhs += b * P.s_vec;
+  P.u += b * P.s_vec;
+  P.x += b * P.s_vec;
+  P.chi2_partial += b * P.s_partial;
+  P.chi2_out += b * P.s_chi2;
+  P.status += 4 * b;
+  return P;
+}
 
 // ---- small dense helpers, 3x3 row-major ----------------------------------------------------------
 __device__ __forceinline__ void load9(const double* __restrict__ p, double* m) {
@@ -442,12 +460,14 @@ __device__ __forceinline__ bool sn_failed(const SNView& V) {
 // fa: panel factorisation, one CTA per (panel, row chunk)
 __global__ void __launch_bounds__(kCtaThreads) sn_k_factor(SNView V, const Task* tasks) {
   extern __shared__ double sm[];
+  V = sn_at_instance(V, blockIdx.y);
   if (sn_failed(V)) return;
   sn_task_factor(CtaGroup(), V, tasks[blockIdx.x], sm);
 }
 // fb: outer-product tiles, one CTA per tile
 __global__ void __launch_bounds__(kCtaThreads) sn_k_update(SNView V, const Task* tasks) {
   extern __shared__ double sm[];
+  V = sn_at_instance(V, blockIdx.y);
   if (sn_failed(V)) return;
   sn_task_update(CtaGroup(), V, tasks[blockIdx.x], sm);
 }
@@ -455,40 +475,27 @@ __global__ void __launch_bounds__(kCtaThreads) sn_k_update(SNView V, const Task*
 __global__ void __launch_bounds__(32 * kWarpsPerCta) sn_k_fused(SNView V, const Task* tasks, int n) {
   extern __shared__ double sm[];
   const int i = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  V = sn_at_instance(V, blockIdx.y);
   if (i >= n || sn_failed(V)) return;
   sn_task_fused(WarpGroup(), V, tasks[i], sm + (threadIdx.x >> 5) * kWarpSmemDoubles);
-}
-// forward substitution
-__global__ void __launch_bounds__(kCtaThreads) sn_k_fwd_tri(SNView V, const Task* tasks) {
-  extern __shared__ double sm[];
-  if (sn_failed(V)) return;
-  sn_task_forward_tri(CtaGroup(), V, tasks[blockIdx.x], sm);
-}
-__global__ void __launch_bounds__(32 * kWarpsPerCta) sn_k_fwd_small(SNView V, const Task* tasks, int n) {
-  extern __shared__ double sm[];
-  const int i = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
-  if (i >= n || sn_failed(V)) return;
-  sn_task_forward_small(WarpGroup(), V, tasks[i], sm + (threadIdx.x >> 5) * kWarpSmemDoubles);
-}
-__global__ void __launch_bounds__(32 * kWarpsPerCta) sn_k_fwd_rows(SNView V, const Task* tasks, int n) {
-  const int i = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
-  if (i >= n || sn_failed(V)) return;
-  sn_forward_rows(WarpGroup(), V, tasks[i].id, tasks[i].r0, tasks[i].r1, nullptr);
 }
 // backward substitution
 __global__ void __launch_bounds__(32 * kWarpsPerCta) sn_k_bwd_rows(SNView V, const Task* tasks, int n) {
   const int i = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  V = sn_at_instance(V, blockIdx.y);
   if (i >= n || sn_failed(V)) return;
   sn_backward_rows(WarpGroup(), V, tasks[i].id, tasks[i].r0, tasks[i].r1);
 }
 __global__ void __launch_bounds__(32 * kWarpsPerCta) sn_k_bwd_small(SNView V, const Task* tasks, int n) {
   extern __shared__ double sm[];
   const int i = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  V = sn_at_instance(V, blockIdx.y);
   if (i >= n || sn_failed(V)) return;
   sn_task_backward_small(WarpGroup(), V, tasks[i], sm + (threadIdx.x >> 5) * kWarpSmemDoubles);
 }
 __global__ void __launch_bounds__(kCtaThreads) sn_k_bwd_tri(SNView V, const Task* tasks) {
   extern __shared__ double sm[];
+  V = sn_at_instance(V, blockIdx.y);
   if (sn_failed(V)) return;
   sn_task_backward_tri(CtaGroup(), V, tasks[blockIdx.x], sm);
 }
@@ -496,11 +503,13 @@ __global__ void __launch_bounds__(kCtaThreads) sn_k_bwd_tri(SNView V, const Task
 // linearise + chi2 (phase 1) as plain kernels
 __global__ void __launch_bounds__(kThreads) gn_linearise(Params P) {
   __shared__ double scratch[32];
+  P = params_at(P, blockIdx.y);
   if (*reinterpret_cast<volatile int*>(P.status) != 0) return;
   phase_linearise(P, scratch, 0);
 }
 __global__ void gn_chi2(Params P, int n_partials) {
   __shared__ double scratch[32];
+  P = params_at(P, blockIdx.y);
   if (*reinterpret_cast<volatile int*>(P.status) != 0) return;
   double v = 0.0;
   for (int b = threadIdx.x; b < n_partials; b += blockDim.x) v += P.chi2_partial[b];
@@ -509,6 +518,7 @@ __global__ void gn_chi2(Params P, int n_partials) {
 }
 // VertexSE2::oplusImpl (C3); the last kernel of an iteration
 __global__ void gn_update(Params P) {
+  P = params_at(P, blockIdx.y);
   if (*reinterpret_cast<volatile int*>(P.status) != 0) return;
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p < P.n) {
@@ -519,7 +529,8 @@ __global__ void gn_update(Params P) {
     q[2] = normalize_theta(q[2] + P.x[3 * p + 2]);
   }
 }
-__global__ void gn_count_iteration(Params P) {
+__global__ void gn_count_iteration(Params P) {  // one thread per instance
+  P = params_at(P, threadIdx.x);
   if (*reinterpret_cast<volatile int*>(P.status) == 0) P.status[1] += 1;
 }
 __global__ void gn_stamp(unsigned long long* stamps, int k) {
@@ -701,6 +712,8 @@ struct DeviceSolver {
   int grid = 0;  // co-resident CTAs of the cooperative kernels
   uint64_t launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaStream_t aux = nullptr;  // second branch while capturing the iteration graph
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   Params P;
   bool have_structure = false, have_values = false, have_factor = false;
   Buf<int> edge_i, edge_j, vpos, inc_ptr, ff_edges, col_ptr, row_idx, col_of, row_ptr, row_pos,
@@ -719,10 +732,11 @@ struct DeviceSolver {
   cudaGraphExec_t graph_exec = nullptr;
   int graph_nodes = 0;
   int lin_blocks = 0;
+  int batch = 1;  // problem instances sharing this structure
   Buf<int> colbase, tbl_off, tbl;
   Buf<PanelDesc> pn_desc;
   Buf<SuperDesc> sn_desc;
-  Buf<Task> ff, fa, fb, ss, sa, sf, sb;
+  Buf<Task> ff, fa, fb, ss, sa, sb;
   Buf<double> diag_scratch;
   Buf<double> many_u, many_x;  // substitution vectors of the marginals (u / x never move)
   // domain decomposition
@@ -757,12 +771,11 @@ int dev_create(DeviceSolver** out, int device, void* stream, std::string* err) {
     const int cta_bytes = static_cast<int>(sizeof(double) * kCtaSmemDoubles);
     const int warp_bytes = static_cast<int>(sizeof(double) * kWarpSmemDoubles * kWarpsPerCta);
     const void* cta_kernels[] = {reinterpret_cast<const void*>(sn_k_factor), reinterpret_cast<const void*>(sn_k_update),
-                                 reinterpret_cast<const void*>(sn_k_fwd_tri), reinterpret_cast<const void*>(sn_k_bwd_tri)};
-    for (size_t i = 0; i < 4 && e == cudaSuccess; ++i)
+                                 reinterpret_cast<const void*>(sn_k_bwd_tri)};
+    for (size_t i = 0; i < sizeof(cta_kernels) / sizeof(cta_kernels[0]) && e == cudaSuccess; ++i)
       e = cudaFuncSetAttribute(cta_kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, cta_bytes);
-    const void* warp_kernels[] = {reinterpret_cast<const void*>(sn_k_fused), reinterpret_cast<const void*>(sn_k_fwd_small),
-                                  reinterpret_cast<const void*>(sn_k_bwd_small)};
-    for (size_t i = 0; i < 3 && e == cudaSuccess; ++i)
+    const void* warp_kernels[] = {reinterpret_cast<const void*>(sn_k_fused),                                   reinterpret_cast<const void*>(sn_k_bwd_small)};
+    for (size_t i = 0; i < sizeof(warp_kernels) / sizeof(warp_kernels[0]) && e == cudaSuccess; ++i)
       e = cudaFuncSetAttribute(warp_kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, warp_bytes);
   }
   if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gn_dd_local, kThreads, 0);
@@ -778,6 +791,9 @@ int dev_create(DeviceSolver** out, int device, void* stream, std::string* err) {
       d->own_stream = e == cudaSuccess;
     }
   }
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d->aux, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->ev_fork, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->ev_join, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreate(&d->ev0);
   if (e == cudaSuccess) e = cudaEventCreate(&d->ev1);
   if (e == cudaSuccess) e = d->status.reserve(4);
@@ -807,7 +823,7 @@ void dev_destroy(DeviceSolver* d) {
   d->pn_desc.release();
   d->sn_desc.release();
   for (size_t i = 0; i < sizeof(sb) / sizeof(sb[0]); ++i) sb[i]->release();
-  Buf<Task>* tb[] = {&d->ff, &d->fa, &d->fb, &d->ss, &d->sa, &d->sf, &d->sb};
+  Buf<Task>* tb[] = {&d->ff, &d->fa, &d->fb, &d->ss, &d->sa, &d->sb};
   for (size_t i = 0; i < sizeof(tb) / sizeof(tb[0]); ++i) tb[i]->release();
   d->diag_scratch.release();
   d->many_u.release();
@@ -823,6 +839,9 @@ void dev_destroy(DeviceSolver* d) {
   d->xfinal_ptr.release();
   d->xfinal_cols.release();
   d->pose_x.release();
+  if (d->ev_fork) cudaEventDestroy(d->ev_fork);
+  if (d->ev_join) cudaEventDestroy(d->ev_join);
+  if (d->aux) cudaStreamDestroy(d->aux);
   if (d->ev0) cudaEventDestroy(d->ev0);
   if (d->ev1) cudaEventDestroy(d->ev1);
   if (d->own_stream && d->stream) cudaStreamDestroy(d->stream);
@@ -865,26 +884,29 @@ int dev_set_structure(DeviceSolver* d, const Symbolic& S, const GraphTables& G, 
   PGO_CUDA(d->fb.upload(N.fb, s));
   PGO_CUDA(d->ss.upload(N.ss, s));
   PGO_CUDA(d->sa.upload(N.sa, s));
-  PGO_CUDA(d->sf.upload(N.sf, s));
   PGO_CUDA(d->sb.upload(N.sb, s));
-  PGO_CUDA(d->diag_scratch.reserve(9 * static_cast<size_t>(N.scratch_blocks) + 9));
+  const size_t scratch_stride = 9 * static_cast<size_t>(N.scratch_blocks) + 9;
+  PGO_CUDA(d->diag_scratch.reserve(static_cast<size_t>(d->batch) * scratch_stride));
   std::vector<int> perm_vertex(S.n);
   for (int v = 0; v < G.n_vertices; ++v)
     if (G.vpos[v] >= 0) perm_vertex[G.vpos[v]] = v;
   PGO_CUDA(d->perm_vertex.upload(perm_vertex, s));
-  PGO_CUDA(d->poses.reserve(3 * static_cast<size_t>(G.n_vertices)));
-  PGO_CUDA(d->meas.reserve(3 * static_cast<size_t>(G.n_edges)));
-  PGO_CUDA(d->info6.reserve(6 * static_cast<size_t>(G.n_edges)));
+  const size_t B = static_cast<size_t>(d->batch);
+  PGO_CUDA(d->poses.reserve(B * 3 * static_cast<size_t>(G.n_vertices)));
+  PGO_CUDA(d->meas.reserve(B * 3 * static_cast<size_t>(G.n_edges) + 1));
+  PGO_CUDA(d->info6.reserve(B * 6 * static_cast<size_t>(G.n_edges) + 1));
   const size_t n_shared = static_cast<size_t>(S.n - S.first_shared);
-  PGO_CUDA(d->M.reserve(9 * static_cast<size_t>(S.nnzb) + 3 * n_shared + 8));
+  // per-instance stride of the factor storage: a multiple of 32 doubles
+  const size_t m_stride = (9 * static_cast<size_t>(S.nnzb) + 3 * n_shared + 8 + 31) / 32 * 32;
+  PGO_CUDA(d->M.reserve(B * m_stride));
   PGO_CUDA(d->owner.upload(S.owner, s));
   PGO_CUDA(d->xfinal_ptr.upload(S.xfinal_ptr, s));
   PGO_CUDA(d->xfinal_cols.upload(S.xfinal_cols, s));
   PGO_CUDA(d->pose_x.reserve(3 * static_cast<size_t>(G.n_vertices)));
-  PGO_CUDA(d->Dinv.reserve(9 * static_cast<size_t>(S.n)));
-  PGO_CUDA(d->rhs.reserve(3 * static_cast<size_t>(S.n)));
-  PGO_CUDA(d->u.reserve(3 * static_cast<size_t>(S.n)));
-  PGO_CUDA(d->x.reserve(3 * static_cast<size_t>(S.n)));
+  PGO_CUDA(d->Dinv.reserve(B * 9 * static_cast<size_t>(S.n)));
+  PGO_CUDA(d->rhs.reserve(B * 3 * static_cast<size_t>(S.n)));
+  PGO_CUDA(d->u.reserve(B * 3 * static_cast<size_t>(S.n)));
+  PGO_CUDA(d->x.reserve(B * 3 * static_cast<size_t>(S.n)));
   PGO_CUDA(cudaStreamSynchronize(s));  // the host vectors may go away
   Params& P = d->P;
   P.n_vertices = G.n_vertices;
@@ -937,9 +959,26 @@ int dev_set_structure(DeviceSolver* d, const Symbolic& S, const GraphTables& G, 
   V.x = d->x.p;
   V.scratch = d->diag_scratch.p;
   V.status = d->status.p;
+  V.s_M = static_cast<long long>(m_stride);
+  V.s_Dinv = 9LL * S.n;
+  V.s_vec = 3LL * S.n;
+  V.s_scratch = static_cast<long long>(scratch_stride);
   d->L = N.lists();
-  PGO_CUDA(d->chi2_out.reserve(kMaxItersPerCall));
   d->lin_blocks = std::max(1, std::min(4 * d->sm_count, (S.n + kThreads - 1) / kThreads));
+  PGO_CUDA(d->chi2_out.reserve(B * kMaxItersPerCall));
+  PGO_CUDA(d->chi2_partial.reserve(std::max(B * d->lin_blocks, static_cast<size_t>(d->grid))));
+  PGO_CUDA(d->status.reserve(4 * B));
+  P.chi2_partial = d->chi2_partial.p;
+  P.status = d->status.p;
+  V.status = d->status.p;
+  P.s_poses = 3LL * G.n_vertices;
+  P.s_meas = 3LL * G.n_edges;
+  P.s_info = 6LL * G.n_edges;
+  P.s_M = V.s_M;
+  P.s_Dinv = V.s_Dinv;
+  P.s_vec = V.s_vec;
+  P.s_partial = d->lin_blocks;
+  P.s_chi2 = kMaxItersPerCall;
   if (d->graph_exec) cudaGraphExecDestroy(d->graph_exec);
   if (d->graph) cudaGraphDestroy(d->graph);
   d->graph_exec = nullptr;
@@ -962,47 +1001,74 @@ int dev_set_structure(DeviceSolver* d, const Symbolic& S, const GraphTables& G, 
   return PGO_OK;
 }
 
-int dev_upload(DeviceSolver* d, const double* poses, const double* meas, const double* info6,
-               std::string* err) {
+int dev_set_batch(DeviceSolver* d, int batch, std::string* err) {
+  if (batch < 1 || batch > 1024) {
+    if (err) *err = "batch must be in [1, 1024]";
+    return PGO_ERR_ARG;
+  }
+  if (batch != d->batch) d->have_structure = d->have_values = d->have_factor = false;
+  d->batch = batch;
+  return PGO_OK;
+}
+int dev_batch(const DeviceSolver* d) { return d->batch; }
+
+// inst = -1: every instance of the batch gets the same values
+int dev_upload(DeviceSolver* d, int inst, const double* poses, const double* meas,
+               const double* info6, std::string* err) {
   if (!d->have_structure) {
     if (err) *err = "pgo_set_graph has not been called";
     return PGO_ERR_ARG;
   }
+  if (inst < -1 || inst >= d->batch) {
+    if (err) *err = "no such instance";
+    return PGO_ERR_ARG;
+  }
   PGO_CUDA(cudaSetDevice(d->device));
   const Params& P = d->P;
-  PGO_CUDA(cudaMemcpyAsync(d->poses.p, poses, 3 * sizeof(double) * P.n_vertices,
-                           cudaMemcpyHostToDevice, d->stream));
-  if (P.n_edges) {
-    PGO_CUDA(cudaMemcpyAsync(d->meas.p, meas, 3 * sizeof(double) * P.n_edges,
+  for (int b = (inst < 0 ? 0 : inst); b < (inst < 0 ? d->batch : inst + 1); ++b) {
+    PGO_CUDA(cudaMemcpyAsync(d->poses.p + b * P.s_poses, poses, 3 * sizeof(double) * P.n_vertices,
                              cudaMemcpyHostToDevice, d->stream));
-    PGO_CUDA(cudaMemcpyAsync(d->info6.p, info6, 6 * sizeof(double) * P.n_edges,
-                             cudaMemcpyHostToDevice, d->stream));
+    if (P.n_edges) {
+      PGO_CUDA(cudaMemcpyAsync(d->meas.p + b * P.s_meas, meas, 3 * sizeof(double) * P.n_edges,
+                               cudaMemcpyHostToDevice, d->stream));
+      PGO_CUDA(cudaMemcpyAsync(d->info6.p + b * P.s_info, info6, 6 * sizeof(double) * P.n_edges,
+                               cudaMemcpyHostToDevice, d->stream));
+    }
   }
   PGO_CUDA(cudaStreamSynchronize(d->stream));
-  d->have_values = true;
+  if (inst <= 0) d->have_values = true;  // instance 0 (or all) given: the solver is usable
   d->have_factor = false;
   return PGO_OK;
 }
 
-int dev_set_poses(DeviceSolver* d, const double* poses, std::string* err) {
+int dev_set_poses(DeviceSolver* d, int inst, const double* poses, std::string* err) {
   if (!d->have_values) {
     if (err) *err = "pgo_upload has not been called";
     return PGO_ERR_ARG;
   }
+  if (inst < -1 || inst >= d->batch) {
+    if (err) *err = "no such instance";
+    return PGO_ERR_ARG;
+  }
   PGO_CUDA(cudaSetDevice(d->device));
-  PGO_CUDA(cudaMemcpyAsync(d->poses.p, poses, 3 * sizeof(double) * d->P.n_vertices,
-                           cudaMemcpyHostToDevice, d->stream));
+  for (int b = (inst < 0 ? 0 : inst); b < (inst < 0 ? d->batch : inst + 1); ++b)
+    PGO_CUDA(cudaMemcpyAsync(d->poses.p + b * d->P.s_poses, poses, 3 * sizeof(double) * d->P.n_vertices,
+                             cudaMemcpyHostToDevice, d->stream));
   PGO_CUDA(cudaStreamSynchronize(d->stream));
   return PGO_OK;
 }
 
-int dev_get_poses(DeviceSolver* d, double* poses, std::string* err) {
+int dev_get_poses(DeviceSolver* d, int inst, double* poses, std::string* err) {
   if (!d->have_values) {
     if (err) *err = "pgo_upload has not been called";
     return PGO_ERR_ARG;
   }
+  if (inst < 0 || inst >= d->batch) {
+    if (err) *err = "no such instance";
+    return PGO_ERR_ARG;
+  }
   PGO_CUDA(cudaSetDevice(d->device));
-  PGO_CUDA(cudaMemcpyAsync(poses, d->poses.p, 3 * sizeof(double) * d->P.n_vertices,
+  PGO_CUDA(cudaMemcpyAsync(poses, d->poses.p + inst * d->P.s_poses, 3 * sizeof(double) * d->P.n_vertices,
                            cudaMemcpyDeviceToHost, d->stream));
   PGO_CUDA(cudaStreamSynchronize(d->stream));
   return PGO_OK;
@@ -1018,10 +1084,11 @@ static int enqueue_iteration(DeviceSolver* d, std::string* err) {
   int nodes = 0;
   gn_stamp<<<1, 1, 0, st>>>(d->stamps.p, 0);
   // zero the factor storage (fill positions must start at 0) and the backward accumulators
-  PGO_CUDA(cudaMemsetAsync(P.M, 0, sizeof(double) * 9 * static_cast<size_t>(P.nnzb), st));
-  PGO_CUDA(cudaMemsetAsync(P.x, 0, sizeof(double) * 3 * static_cast<size_t>(P.n), st));
-  gn_linearise<<<d->lin_blocks, kThreads, 0, st>>>(P);
-  gn_chi2<<<1, 256, 0, st>>>(P, d->lin_blocks);
+  const int B = d->batch;
+  PGO_CUDA(cudaMemsetAsync(P.M, 0, sizeof(double) * static_cast<size_t>(P.s_M) * B, st));
+  PGO_CUDA(cudaMemsetAsync(P.x, 0, sizeof(double) * static_cast<size_t>(P.s_vec) * B, st));
+  gn_linearise<<<dim3(d->lin_blocks, B), kThreads, 0, st>>>(P);
+  gn_chi2<<<dim3(1, B), 256, 0, st>>>(P, d->lin_blocks);
   gn_stamp<<<1, 1, 0, st>>>(d->stamps.p, 1);
   nodes += 6;
   const Task* fa = d->fa.p;
@@ -1030,66 +1097,71 @@ static int enqueue_iteration(DeviceSolver* d, std::string* err) {
   for (int l = 0; l < L.n_plevels; ++l) {
     const int n_fa = L.fa_ptr[l + 1] - L.fa_ptr[l], n_ff = L.ff_ptr[l + 1] - L.ff_ptr[l],
               n_fb = L.fb_ptr[l + 1] - L.fb_ptr[l];
-    if (n_fa) {
-      sn_k_factor<<<n_fa, kCtaThreads, sizeof(double) * L.fa_smem[l], st>>>(V, fa + L.fa_ptr[l]);
-      ++nodes;
+    // the level's big panels (CTA tasks) and small panels (warp tasks) are independent: two
+    // branches of the graph
+    cudaStream_t side = st;
+    if (n_fa && n_ff) {
+      PGO_CUDA(cudaEventRecord(d->ev_fork, st));
+      PGO_CUDA(cudaStreamWaitEvent(d->aux, d->ev_fork, 0));
+      side = d->aux;
     }
     if (n_ff) {
-      sn_k_fused<<<(n_ff + kWarpsPerCta - 1) / kWarpsPerCta, 32 * kWarpsPerCta,
-                   sizeof(double) * kWarpSmemDoubles * kWarpsPerCta, st>>>(V, ff + L.ff_ptr[l], n_ff);
+      sn_k_fused<<<dim3((n_ff + kWarpsPerCta - 1) / kWarpsPerCta, B), 32 * kWarpsPerCta,
+                   sizeof(double) * kWarpSmemDoubles * kWarpsPerCta, side>>>(V, ff + L.ff_ptr[l], n_ff);
       ++nodes;
     }
+    if (n_fa) {
+      sn_k_factor<<<dim3(n_fa, B), kCtaThreads, sizeof(double) * L.fa_smem[l], st>>>(V, fa + L.fa_ptr[l]);
+      ++nodes;
+    }
+    if (side != st) {
+      PGO_CUDA(cudaEventRecord(d->ev_join, side));
+      PGO_CUDA(cudaStreamWaitEvent(st, d->ev_join, 0));
+    }
     if (n_fb) {
-      sn_k_update<<<n_fb, kCtaThreads, sizeof(double) * L.fb_smem[l], st>>>(V, fb + L.fb_ptr[l]);
+      sn_k_update<<<dim3(n_fb, B), kCtaThreads, sizeof(double) * L.fb_smem[l], st>>>(V, fb + L.fb_ptr[l]);
       ++nodes;
     }
   }
   gn_stamp<<<1, 1, 0, st>>>(d->stamps.p, 2);
   const Task* ss = d->ss.p;
   const Task* sa = d->sa.p;
-  const Task* sf = d->sf.p;
   const Task* sb = d->sb.p;
   const size_t warp_bytes = sizeof(double) * kWarpSmemDoubles * kWarpsPerCta;
-  for (int l = 0; l < L.n_slevels; ++l) {
-    const int n_sa = L.sa_ptr[l + 1] - L.sa_ptr[l], n_ss = L.ss_ptr[l + 1] - L.ss_ptr[l],
-              n_sf = L.sf_ptr[l + 1] - L.sf_ptr[l];
-    if (n_sa) {
-      sn_k_fwd_tri<<<n_sa, kCtaThreads, sizeof(double) * L.sa_smem[l], st>>>(V, sa + L.sa_ptr[l]);
-      ++nodes;
-    }
-    if (n_ss) {
-      sn_k_fwd_small<<<(n_ss + kWarpsPerCta - 1) / kWarpsPerCta, 32 * kWarpsPerCta, warp_bytes, st>>>(
-          V, ss + L.ss_ptr[l], n_ss);
-      ++nodes;
-    }
-    if (n_sf) {
-      sn_k_fwd_rows<<<(n_sf + kWarpsPerCta - 1) / kWarpsPerCta, 32 * kWarpsPerCta, 0, st>>>(
-          V, sf + L.sf_ptr[l], n_sf);
-      ++nodes;
-    }
-  }
   gn_stamp<<<1, 1, 0, st>>>(d->stamps.p, 3);
   for (int l = L.n_slevels - 1; l >= 0; --l) {
     const int n_sa = L.sa_ptr[l + 1] - L.sa_ptr[l], n_ss = L.ss_ptr[l + 1] - L.ss_ptr[l],
               n_sb = L.sb_ptr[l + 1] - L.sb_ptr[l];
-    if (n_sb) {
-      sn_k_bwd_rows<<<(n_sb + kWarpsPerCta - 1) / kWarpsPerCta, 32 * kWarpsPerCta, 0, st>>>(
-          V, sb + L.sb_ptr[l], n_sb);
-      ++nodes;
+    // narrow supernodes (whole, one warp each) next to the wide ones (row gather, then the
+    // triangular part): two branches
+    cudaStream_t side = st;
+    if (n_ss && (n_sb || n_sa)) {
+      PGO_CUDA(cudaEventRecord(d->ev_fork, st));
+      PGO_CUDA(cudaStreamWaitEvent(d->aux, d->ev_fork, 0));
+      side = d->aux;
     }
     if (n_ss) {
-      sn_k_bwd_small<<<(n_ss + kWarpsPerCta - 1) / kWarpsPerCta, 32 * kWarpsPerCta, warp_bytes, st>>>(
+      sn_k_bwd_small<<<dim3((n_ss + kWarpsPerCta - 1) / kWarpsPerCta, B), 32 * kWarpsPerCta, warp_bytes, side>>>(
           V, ss + L.ss_ptr[l], n_ss);
       ++nodes;
     }
-    if (n_sa) {
-      sn_k_bwd_tri<<<n_sa, kCtaThreads, sizeof(double) * L.sa_smem[l], st>>>(V, sa + L.sa_ptr[l]);
+    if (n_sb) {
+      sn_k_bwd_rows<<<dim3((n_sb + kWarpsPerCta - 1) / kWarpsPerCta, B), 32 * kWarpsPerCta, 0, st>>>(
+          V, sb + L.sb_ptr[l], n_sb);
       ++nodes;
+    }
+    if (n_sa) {
+      sn_k_bwd_tri<<<dim3(n_sa, B), kCtaThreads, sizeof(double) * L.sa_smem[l], st>>>(V, sa + L.sa_ptr[l]);
+      ++nodes;
+    }
+    if (side != st) {
+      PGO_CUDA(cudaEventRecord(d->ev_join, side));
+      PGO_CUDA(cudaStreamWaitEvent(st, d->ev_join, 0));
     }
   }
   gn_stamp<<<1, 1, 0, st>>>(d->stamps.p, 4);
-  gn_update<<<(P.n + 255) / 256, 256, 0, st>>>(P);
-  gn_count_iteration<<<1, 1, 0, st>>>(P);
+  gn_update<<<dim3((P.n + 255) / 256, B), 256, 0, st>>>(P);
+  gn_count_iteration<<<1, B, 0, st>>>(P);
   gn_stamp<<<1, 1, 0, st>>>(d->stamps.p, 5);
   nodes += 6;
   d->graph_nodes = nodes;
@@ -1116,6 +1188,7 @@ static int build_iteration_graph(DeviceSolver* d, std::string* err) {
   return PGO_OK;
 }
 
+// chi2_out: [batch][n_iters] (may be null); iters_done: [batch].
 int dev_iterate(DeviceSolver* d, int n_iters, double* chi2_out, int* iters_done, float* ms,
                 std::string* err) {
   if (!d->have_values) {
@@ -1123,7 +1196,8 @@ int dev_iterate(DeviceSolver* d, int n_iters, double* chi2_out, int* iters_done,
     return PGO_ERR_ARG;
   }
   PGO_CUDA(cudaSetDevice(d->device));
-  *iters_done = 0;
+  const int B = d->batch;
+  for (int b = 0; b < B; ++b) iters_done[b] = 0;
   *ms = 0.f;
   if (n_iters <= 0) return PGO_OK;
   if (d->D.world != 1) {
@@ -1134,30 +1208,39 @@ int dev_iterate(DeviceSolver* d, int n_iters, double* chi2_out, int* iters_done,
     const int rc = build_iteration_graph(d, err);
     if (rc != PGO_OK) return rc;
   }
-  int status[4] = {0, 0, 0, 0};
+  std::vector<int> status(4 * static_cast<size_t>(B), 0);
+  std::vector<double> chi2(chi2_out ? static_cast<size_t>(B) * kMaxItersPerCall : 0);
+  bool failed = false;
   PGO_CUDA(cudaEventRecord(d->ev0, d->stream));
-  for (int first = 0; first < n_iters && !status[0]; first += kMaxItersPerCall) {
+  for (int first = 0; first < n_iters && !failed; first += kMaxItersPerCall) {
     const int chunk = std::min(kMaxItersPerCall, n_iters - first);
-    PGO_CUDA(cudaMemsetAsync(d->status.p, 0, 4 * sizeof(int), d->stream));
-    PGO_CUDA(cudaMemsetAsync(d->chi2_out.p, 0, chunk * sizeof(double), d->stream));
+    PGO_CUDA(cudaMemsetAsync(d->status.p, 0, 4 * sizeof(int) * B, d->stream));
+    PGO_CUDA(cudaMemsetAsync(d->chi2_out.p, 0, sizeof(double) * B * kMaxItersPerCall, d->stream));
     for (int it = 0; it < chunk; ++it) PGO_CUDA(cudaGraphLaunch(d->graph_exec, d->stream));
     d->launches += static_cast<uint64_t>(chunk) * d->graph_nodes;
-    PGO_CUDA(cudaMemcpyAsync(status, d->status.p, sizeof status, cudaMemcpyDeviceToHost, d->stream));
+    if (first + chunk >= n_iters) PGO_CUDA(cudaEventRecord(d->ev1, d->stream));
+    PGO_CUDA(cudaMemcpyAsync(status.data(), d->status.p, 4 * sizeof(int) * B, cudaMemcpyDeviceToHost,
+                             d->stream));
     if (chi2_out)
-      PGO_CUDA(cudaMemcpyAsync(chi2_out + first, d->chi2_out.p, chunk * sizeof(double),
+      PGO_CUDA(cudaMemcpyAsync(chi2.data(), d->chi2_out.p, sizeof(double) * B * kMaxItersPerCall,
                                cudaMemcpyDeviceToHost, d->stream));
-    if (first + chunk < n_iters) PGO_CUDA(cudaStreamSynchronize(d->stream));
-    *iters_done += status[1];
+    PGO_CUDA(cudaStreamSynchronize(d->stream));
+    for (int b = 0; b < B; ++b) {
+      iters_done[b] += status[4 * b + 1];
+      failed = failed || status[4 * b] != 0;
+      if (chi2_out)
+        for (int it = 0; it < chunk; ++it)
+          chi2_out[static_cast<size_t>(b) * n_iters + first + it] = chi2[static_cast<size_t>(b) * kMaxItersPerCall + it];
+    }
   }
-  PGO_CUDA(cudaEventRecord(d->ev1, d->stream));
+  if (failed) PGO_CUDA(cudaEventRecord(d->ev1, d->stream));
   unsigned long long st[6] = {0, 0, 0, 0, 0, 0};
   PGO_CUDA(cudaMemcpyAsync(st, d->stamps.p, sizeof st, cudaMemcpyDeviceToHost, d->stream));
   PGO_CUDA(cudaStreamSynchronize(d->stream));
-  if (n_iters <= kMaxItersPerCall) *iters_done = status[1];
   for (int k = 0; k < 5; ++k) d->stage_ms[k] = st[k + 1] > st[k] ? (st[k + 1] - st[k]) * 1e-6 : 0.0;
   PGO_CUDA(cudaEventElapsedTime(ms, d->ev0, d->ev1));
-  d->have_factor = *iters_done > 0;
-  if (status[0]) {
+  d->have_factor = iters_done[0] > 0;
+  if (failed) {
     if (err) *err = "H is not positive definite (a 3x3 pivot failed): is a vertex fixed?";
     return PGO_ERR_NUMERIC;
   }

@@ -50,15 +50,31 @@ struct SNView {
   double* x;        // [n][3] must be zero before the backward substitution
   double* scratch;  // [scratch_blocks][9]
   int* status;      // [0] set to 1 when a pivot block is not positive definite
+  // batch of problem instances with this structure: element strides between instances
+  long long s_M, s_Dinv, s_vec, s_scratch;
 };
+
+// The view of instance b of a batch (blockIdx.y on the device).
+PGO_HD SNView sn_at_instance(SNView V, int b) {
+  V.M += b * V.s_M;
+  V.Dinv += b * V.s_Dinv;
+  V.z += b * V.s_vec;
+  V.u += b * V.s_vec;
+  V.x += b * V.s_vec;
+  V.scratch += b * V.s_scratch;
+  V.status += 4 * b;
+  return V;
+}
 
 // doubles of shared memory a group needs for any task of its kind
 static const int kPairDoubles = (kPanelWidth * (kPanelWidth + 1) / 2 + 1) / 2;  // int table
 static const int kCtaSmemDoubles = kPanelWidth * kPanelWidth * 9 + kPanelWidth * 9 + kPairDoubles +
-                                   3 * kPanelWidth * 3 * kRowChunk;  // factor task
+                                   3 * kPanelWidth +
+                                   3 * kPanelWidth * (3 * kRowChunk + 1);  // factor task
 static const int kSmallPairDoubles = (kSmallWidth * (kSmallWidth + 1) / 2 + 1) / 2;
 static const int kWarpSmemDoubles = kSmallWidth * kSmallWidth * 9 + kSmallWidth * 9 +
-                                    kSmallPairDoubles + 3 * kSmallWidth * 3 * kSmallRows;  // fused
+                                    kSmallPairDoubles + 3 * kSmallWidth +
+                                    3 * kSmallWidth * (3 * kSmallRows + 1);  // fused
 static_assert(kTileBudget * 9 <= kCtaSmemDoubles, "update tiles must fit the CTA's shared memory");
 static_assert(6 * kMaxSuperWidth + kPanelWidth * kPanelWidth * 9 + kPanelWidth * 9 + 3 * 256 <=
                   kCtaSmemDoubles, "a wide supernode's vectors must fit the CTA's shared memory");
@@ -271,25 +287,65 @@ PGO_HD void sn_store_diag(const G& g, const SNView& V, const PanelDesc& pd, cons
     V.Dinv[9 * static_cast<size_t>(pd.c0) + idx] = Di[idx];
 }
 
+// Forward substitution rides along with the factorisation: the right-hand side is one more scalar
+// row of the panel (z^T behaves like a block row of M under the unscaled update rule), staged at
+// row index 3 * nrows of xs. After sn_solve_rows that row holds the final z of the panel's
+// columns; u_t = Dinv_t z_t, and every row a below the panel gets  z_{r_a} -= sum_t M(a,t) u_t.
+template <class G>
+PGO_HD void sn_load_rhs(const G& g, const SNView& V, const PanelDesc& pd, int nrows, int ldx, double* xs) {
+  for (int idx = g.rank(); idx < 3 * pd.w; idx += g.size())
+    xs[idx * ldx + 3 * nrows] = sn_ld(V.z + 3 * static_cast<size_t>(pd.c0) + idx);
+}
+
+template <class G>
+PGO_HD void sn_forward_fused(const G& g, const SNView& V, const PanelDesc& pd, int r0, int nrows,
+                             int ldx, const double* xs, const double* Di, double* us, bool publish) {
+  const int w = pd.w;
+  for (int idx = g.rank(); idx < 3 * w; idx += g.size()) {
+    const int t = idx / 3, k = idx % 3;
+    const double* d = Di + 9 * t + 3 * k;
+    const double v = d[0] * xs[(3 * t) * ldx + 3 * nrows] + d[1] * xs[(3 * t + 1) * ldx + 3 * nrows] +
+                     d[2] * xs[(3 * t + 2) * ldx + 3 * nrows];
+    us[idx] = v;
+    if (publish) V.u[3 * static_cast<size_t>(pd.c0) + idx] = v;
+  }
+  g.sync();
+  const int* rows = V.row_idx + pd.base + w + r0;
+  for (int a = g.rank(); a < nrows; a += g.size()) {
+    const int r = rows[a];
+    double acc[3] = {0.0, 0.0, 0.0};
+    for (int j = 0; j < 3 * w; ++j) {
+      const double uj = us[j];
+      acc[0] += xs[j * ldx + 3 * a] * uj;
+      acc[1] += xs[j * ldx + 3 * a + 1] * uj;
+      acc[2] += xs[j * ldx + 3 * a + 2] * uj;
+    }
+    for (int k = 0; k < 3; ++k) sn_add(V.z + 3 * static_cast<size_t>(r) + k, -acc[k]);
+  }
+}
+
 // ---- factorisation tasks ---------------------------------------------------------------------------
 // fa: factor the diagonal part (every row-chunk task of a panel repeats it: w <= 16, cheap) and
 // finish the rows [r0, r1) below it. The r0 == 0 task publishes the diagonal part and Dinv.
 template <class G>
 PGO_HD void sn_task_factor(const G& g, const SNView& V, const Task& T, double* sm) {
   const PanelDesc pd = V.pn[T.id];
-  const int w = pd.w, nrows = T.r1 - T.r0, ldx = 3 * nrows;
+  const int w = pd.w, nrows = T.r1 - T.r0, ldx = 3 * nrows + 1;
   double* Dg = sm;
   double* Di = Dg + w * w * 9;
   int* pairs = reinterpret_cast<int*>(Di + w * 9);
-  double* xs = Di + w * 9 + kPairDoubles;
+  double* us = Di + w * 9 + kPairDoubles;
+  double* xs = us + 3 * w;
   sn_load_diag(g, V, pd.base, w + pd.m, w, Dg);
   sn_load_rows(g, V, pd, T.r0, nrows, ldx, xs);
+  sn_load_rhs(g, V, pd, nrows, ldx, xs);
   g.sync();
   sn_factor_diag(g, V, w, Dg, Di, pairs);
-  sn_solve_rows(g, w, Dg, xs, ldx, 3 * nrows);
+  sn_solve_rows(g, w, Dg, xs, ldx, 3 * nrows + 1);
   g.sync();
   sn_store_rows(g, V, pd, T.r0, nrows, ldx, xs);
   if (T.r0 == 0) sn_store_diag(g, V, pd, Dg, Di, pd.scratch);
+  sn_forward_fused(g, V, pd, T.r0, nrows, ldx, xs, Di, us, T.r0 == 0);
   g.sync();
 }
 
@@ -377,19 +433,22 @@ PGO_HD void sn_task_update(const G& g, const SNView& V, const Task& T, double* s
 template <class G>
 PGO_HD void sn_task_fused(const G& g, const SNView& V, const Task& T, double* sm) {
   const PanelDesc pd = V.pn[T.id];
-  const int w = pd.w, m = pd.m, ldx = 3 * m;
+  const int w = pd.w, m = pd.m, ldx = 3 * m + 1;
   double* Dg = sm;
   double* Di = Dg + w * w * 9;
   int* pairs = reinterpret_cast<int*>(Di + w * 9);
-  double* xs = Di + w * 9 + kSmallPairDoubles;
+  double* us = Di + w * 9 + kSmallPairDoubles;
+  double* xs = us + 3 * w;
   sn_load_diag(g, V, pd.base, w + m, w, Dg);
   sn_load_rows(g, V, pd, 0, m, ldx, xs);
+  sn_load_rhs(g, V, pd, m, ldx, xs);
   g.sync();
   sn_factor_diag(g, V, w, Dg, Di, pairs);
-  sn_solve_rows(g, w, Dg, xs, ldx, 3 * m);
+  sn_solve_rows(g, w, Dg, xs, ldx, 3 * m + 1);
   g.sync();
   sn_store_rows(g, V, pd, 0, m, ldx, xs);
   sn_store_diag(g, V, pd, Dg, Di, -1);
+  sn_forward_fused(g, V, pd, 0, m, ldx, xs, Di, us, true);
   // outer product straight from shared memory: rank = column b, every rank walks the rows a >= b
   for (int b = g.rank(); b < m; b += g.size()) {
     const int cb = V.colbase[pd.meta + b], to = V.tbl_off[pd.meta + b];
@@ -433,140 +492,6 @@ template <class G>
 PGO_HD void sn_load_dinv(const G& g, const SNView& V, int c0, int w, double* Di) {
   for (int idx = g.rank(); idx < 9 * w; idx += g.size())
     Di[idx] = sn_ld(V.Dinv + 9 * static_cast<size_t>(c0) + idx);
-}
-
-// Triangular part of one panel on staged vectors (all operands in shared memory).
-template <class G>
-PGO_HD void sn_forward_panel(const G& g, int w, const double* Dg, const double* Di, double* zs,
-                             double* us) {
-  for (int t = 0; t < w; ++t) {
-    if (g.rank() == 0) sn_mat_vec(Di + 9 * t, zs + 3 * t, us + 3 * t);
-    g.sync();
-    for (int tp = t + 1 + g.rank(); tp < w; tp += g.size()) {
-      double v[3];
-      sn_mat_vec(Dg + (tp * w + t) * 9, us + 3 * t, v);
-      zs[3 * tp] -= v[0];
-      zs[3 * tp + 1] -= v[1];
-      zs[3 * tp + 2] -= v[2];
-    }
-    g.sync();
-  }
-}
-
-// rows [r0, r1) below the SUPERNODE of panel p:  z_{r_a} -= sum_t M(a,t) u_t  (atomic).
-// us: the supernode's u in shared memory, or null to read it from global memory.
-// Loads are issued four blocks at a time (memory-level parallelism, see sn_gather).
-template <class G>
-PGO_HD void sn_forward_rows(const G& g, const SNView& V, int p, int r0, int r1, const double* us) {
-  const PanelDesc pd = V.pn[p];
-  const SuperDesc sd = V.sn[pd.sn];
-  const int w = pd.w, o = pd.sn_off, len = sd.W + sd.m;
-  for (int a = r0 + g.rank(); a < r1; a += g.size()) {
-    const int r = V.row_idx[sd.base + sd.W + a];
-    double acc[3] = {0.0, 0.0, 0.0};
-    for (int t0 = 0; t0 < w; t0 += 4) {
-      double mb[4][9], uv[4][3];
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-      for (int q = 0; q < 4; ++q) {
-        const int t = t0 + q;
-        if (t < w) {
-          sn_ld9(V.M + 9 * static_cast<size_t>(sn_colpos(sd.base, len, o + t) + (sd.W - o - t) + a), mb[q]);
-          for (int k = 0; k < 3; ++k)
-            uv[q][k] = us ? us[3 * (o + t) + k] : sn_ld(V.u + 3 * static_cast<size_t>(pd.c0 + t) + k);
-        }
-      }
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-      for (int q = 0; q < 4; ++q)
-        if (t0 + q < w) {
-          double v[3];
-          sn_mat_vec(mb[q], uv[q], v);
-          acc[0] += v[0];
-          acc[1] += v[1];
-          acc[2] += v[2];
-        }
-    }
-    for (int k = 0; k < 3; ++k) sn_add(V.z + 3 * static_cast<size_t>(r) + k, -acc[k]);
-  }
-}
-
-// sa (forward): triangular part of a wide supernode, panel by panel, in one group.
-// shared: zs[3W] us[3W] Dg[w*w*9] Di[w*9]
-template <class G>
-PGO_HD void sn_task_forward_tri(const G& g, const SNView& V, const Task& T, double* sm) {
-  const SuperDesc sd = V.sn[T.id];
-  const int W = sd.W, len = sd.W + sd.m;
-  double* zs = sm;
-  double* us = zs + 3 * W;
-  double* Dg = us + 3 * W;
-  double* Di = Dg + kPanelWidth * kPanelWidth * 9;
-  sn_gather(g, 3 * W, [&](int idx, const double** sp, double** dp) {
-    *sp = V.z + 3 * static_cast<size_t>(sd.c0) + idx;
-    *dp = zs + idx;
-  });
-  for (int p = sd.pn_begin; p < sd.pn_end; ++p) {
-    const PanelDesc pd = V.pn[p];
-    const int w = pd.w, o = pd.sn_off;
-    sn_load_diag(g, V, pd.base, w + pd.m, w, Dg);
-    sn_load_dinv(g, V, pd.c0, w, Di);
-    g.sync();
-    sn_forward_panel(g, w, Dg, Di, zs + 3 * o, us + 3 * o);
-    // the supernode's remaining columns are rows of this panel
-    for (int tp = o + w + g.rank(); tp < W; tp += g.size()) {
-      double acc[3] = {0.0, 0.0, 0.0};
-      for (int t0 = 0; t0 < w; t0 += 4) {
-        double mb[4][9];
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-        for (int q = 0; q < 4; ++q)
-          if (t0 + q < w)
-            sn_ld9(V.M + 9 * static_cast<size_t>(sn_colpos(sd.base, len, o + t0 + q) + (tp - o - t0 - q)),
-                   mb[q]);
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-        for (int q = 0; q < 4; ++q)
-          if (t0 + q < w) {
-            double v[3];
-            sn_mat_vec(mb[q], us + 3 * (o + t0 + q), v);
-            acc[0] += v[0];
-            acc[1] += v[1];
-            acc[2] += v[2];
-          }
-      }
-      zs[3 * tp] -= acc[0];
-      zs[3 * tp + 1] -= acc[1];
-      zs[3 * tp + 2] -= acc[2];
-    }
-    g.sync();
-  }
-  for (int idx = g.rank(); idx < 3 * W; idx += g.size()) V.u[3 * static_cast<size_t>(sd.c0) + idx] = us[idx];
-  g.sync();
-}
-
-// ss (forward): a narrow supernode (one panel) including the rows below it.
-// shared: zs[3W] us[3W] Dg[W*W*9] Di[W*9]
-template <class G>
-PGO_HD void sn_task_forward_small(const G& g, const SNView& V, const Task& T, double* sm) {
-  const SuperDesc sd = V.sn[T.id];
-  const int W = sd.W;
-  double* zs = sm;
-  double* us = zs + 3 * W;
-  double* Dg = us + 3 * W;
-  double* Di = Dg + W * W * 9;
-  for (int idx = g.rank(); idx < 3 * W; idx += g.size())
-    zs[idx] = sn_ld(V.z + 3 * static_cast<size_t>(sd.c0) + idx);
-  sn_load_diag(g, V, sd.base, W + sd.m, W, Dg);
-  sn_load_dinv(g, V, sd.c0, W, Di);
-  g.sync();
-  sn_forward_panel(g, W, Dg, Di, zs, us);
-  for (int idx = g.rank(); idx < 3 * W; idx += g.size()) V.u[3 * static_cast<size_t>(sd.c0) + idx] = us[idx];
-  sn_forward_rows(g, V, sd.pn_begin, 0, sd.m, us);
-  g.sync();
 }
 
 // acc += sum over the rows a = first, first + step, ... < end of  M(a, col)^T x_{row(a)}, where the

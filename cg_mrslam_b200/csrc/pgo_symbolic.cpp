@@ -433,7 +433,7 @@ bool build_supernodal(Symbolic& S, std::string* err) {
 
   // substitution: supernode levels and tasks
   std::vector<int> slevel(N.n_super, 0);
-  std::vector<std::pair<int, Task> > ss, sa, sf, sb;
+  std::vector<std::pair<int, Task> > ss, sa, sb;
   for (int s = 0; s < N.n_super; ++s) {
     const int c0 = N.sn_first[s], W = N.sn_first[s + 1] - c0;
     const int base = cp[c0] + W, m = cp[c0 + 1] - base;
@@ -452,10 +452,6 @@ bool build_supernodal(Symbolic& S, std::string* err) {
     const Task t = {s, 0, m, 0};
     sa.push_back(std::make_pair(slevel[s], t));
     for (int p = N.sn_pn_ptr[s]; p < N.sn_pn_ptr[s + 1]; ++p) {
-      for (int r0 = 0; r0 < m; r0 += 32) {
-        const Task x = {p, r0, std::min(m, r0 + 32), 0};
-        sf.push_back(std::make_pair(slevel[s], x));
-      }
       for (int r0 = 0; r0 < m; r0 += 64) {
         const Task x = {p, r0, std::min(m, r0 + 64), 0};
         sb.push_back(std::make_pair(slevel[s], x));
@@ -464,7 +460,6 @@ bool build_supernodal(Symbolic& S, std::string* err) {
   }
   bucket_tasks(ss, N.n_slevels, &N.ss_ptr, &N.ss);
   bucket_tasks(sa, N.n_slevels, &N.sa_ptr, &N.sa);
-  bucket_tasks(sf, N.n_slevels, &N.sf_ptr, &N.sf);
   bucket_tasks(sb, N.n_slevels, &N.sb_ptr, &N.sb);
   return true;
 }
@@ -480,7 +475,6 @@ Supernodal::Lists Supernodal::lists() const {
   L.fb_ptr = fb_ptr;
   L.ss_ptr = ss_ptr;
   L.sa_ptr = sa_ptr;
-  L.sf_ptr = sf_ptr;
   L.sb_ptr = sb_ptr;
   const int pair_doubles = (kPanelWidth * (kPanelWidth + 1) / 2 + 1) / 2;
   L.fa_smem.assign(n_plevels, 0);
@@ -488,7 +482,8 @@ Supernodal::Lists Supernodal::lists() const {
   for (int l = 0; l < n_plevels; ++l) {
     for (int i = fa_ptr[l]; i < fa_ptr[l + 1]; ++i) {
       const int w = pn[fa[i].id].w;
-      L.fa_smem[l] = std::max(L.fa_smem[l], w * w * 9 + w * 9 + pair_doubles + 9 * w * (fa[i].r1 - fa[i].r0));
+      L.fa_smem[l] = std::max(L.fa_smem[l], w * w * 9 + w * 9 + pair_doubles + 3 * w +
+                                                3 * w * (3 * (fa[i].r1 - fa[i].r0) + 1));
     }
     for (int i = fb_ptr[l]; i < fb_ptr[l + 1]; ++i) {
       const int w = pn[fb[i].id].w;

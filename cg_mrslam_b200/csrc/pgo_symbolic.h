@@ -88,14 +88,15 @@ struct Supernodal {
   // CTA tasks for the rest (fa: factor a row chunk; fb: one tile of the outer product)
   std::vector<int> ff_ptr, fa_ptr, fb_ptr;  // n_plevels + 1
   std::vector<Task> ff, fa, fb;
-  // substitution tasks by supernode level: ss = whole small supernode (warp), sa = triangular
-  // part of a wide supernode (CTA), sf / sb = rows below it, forward (chunks of 32) / backward
-  std::vector<int> ss_ptr, sa_ptr, sf_ptr, sb_ptr;  // n_slevels + 1
-  std::vector<Task> ss, sa, sf, sb;
+  // backward-substitution tasks by supernode level (the forward substitution rides along with the
+  // factorisation): ss = whole small supernode (warp), sa = triangular part of a wide supernode
+  // (CTA), sb = gather over the rows below a wide supernode's panel (warp, chunks of 64 rows)
+  std::vector<int> ss_ptr, sa_ptr, sb_ptr;  // n_slevels + 1
+  std::vector<Task> ss, sa, sb;
   // what the host needs to launch the phases: level pointers and per-level shared-memory needs
   struct Lists {
     int n_plevels = 0, n_slevels = 0;
-    std::vector<int> ff_ptr, fa_ptr, fb_ptr, ss_ptr, sa_ptr, sf_ptr, sb_ptr;
+    std::vector<int> ff_ptr, fa_ptr, fb_ptr, ss_ptr, sa_ptr, sb_ptr;
     std::vector<int> fa_smem, fb_smem;  // doubles of shared memory of the largest task per level
     std::vector<int> sa_smem;
   };

@@ -53,6 +53,10 @@ _SIGS = {
     "pgo_analyse_partition": (C.c_int, [C.c_int, C.c_int, _ip, _ip, _bp, C.c_int, _ip,
                                         C.POINTER(C.c_int64)]),
     "pgo_get_stats": (C.c_int, [C.c_void_p, C.POINTER(pgo_stats)]),
+    "pgo_set_batch": (C.c_int, [C.c_void_p, C.c_int]),
+    "pgo_upload_instance": (C.c_int, [C.c_void_p, C.c_int, _dp, _dp, _dp]),
+    "pgo_get_poses_instance": (C.c_int, [C.c_void_p, C.c_int, _dp]),
+    "pgo_iterate_batch": (C.c_int, [C.c_void_p, C.c_int, _dp, _ip]),
     "pgo_stream": (C.c_void_p, [C.c_void_p]),
 }
 
@@ -83,11 +87,14 @@ def _p(a, t):
 class Solver:
     """One SparseOptimizer-like solver on one GPU."""
 
-    def __init__(self, device=0, stream=None):
+    def __init__(self, device=0, stream=None, batch=1):
         self.lib = bind(_lib.load())
         self.h = C.c_void_p()
         self._check(self.lib.pgo_create(C.byref(self.h), device, stream))
         self.n_vertices = self.n_edges = 0
+        self.batch = int(batch)
+        if self.batch != 1:
+            self._check(self.lib.pgo_set_batch(self.h, self.batch))
 
     def _check(self, rc):
         if rc:
@@ -123,6 +130,28 @@ class Solver:
         assert poses.shape == (self.n_vertices, 3) and meas.shape == (self.n_edges, 3) \
             and info6.shape == (self.n_edges, 6)
         self._check(self.lib.pgo_upload(self.h, _p(poses, _dp), _p(meas, _dp), _p(info6, _dp)))
+
+    def upload_instance(self, inst, poses, meas, info6):
+        """Values of one instance of a batch (upload() gives every instance the same values)."""
+        poses, meas, info6 = _d(poses), _d(meas), _d(info6)
+        assert poses.shape == (self.n_vertices, 3) and meas.shape == (self.n_edges, 3) \
+            and info6.shape == (self.n_edges, 6)
+        self._check(self.lib.pgo_upload_instance(self.h, int(inst), _p(poses, _dp), _p(meas, _dp),
+                                                 _p(info6, _dp)))
+
+    def poses_of(self, inst):
+        out = np.empty((self.n_vertices, 3))
+        self._check(self.lib.pgo_get_poses_instance(self.h, int(inst), _p(out, _dp)))
+        return out
+
+    def optimize_batch(self, n_iters):
+        """optimize(n) of every instance: (iterations done [batch], chi2 [batch, n_iters])."""
+        chi2 = np.zeros((self.batch, max(n_iters, 1)))
+        done = np.zeros(self.batch, dtype=np.int32)
+        rc = self.lib.pgo_iterate_batch(self.h, n_iters, _p(chi2, _dp), _p(done, _ip))
+        if rc and rc != PGO_ERR_NUMERIC:
+            self._check(rc)
+        return done, chi2[:, :n_iters]
 
     def set_poses(self, poses):
         poses = _d(poses)

@@ -78,6 +78,21 @@ int pgo_get_poses(pgo_solver* s, double* poses);
  * PGO_ERR_NUMERIC and the estimates are those before the failing iteration). */
 int pgo_iterate(pgo_solver* s, int n_iters, double* poses_out, double* chi2_out, int* iters_done);
 
+/* ---- batch of graphs with one structure --------------------------------------------------------
+ * pgo_set_batch(b) (before pgo_set_graph) makes the solver hold b instances of the graph: same
+ * vertices, edges and fixed set, separate estimates / measurements / information matrices (e.g.
+ * the graphs of several robots sharing a trajectory topology, or resampled measurements). Every
+ * kernel of an iteration then serves all instances, which is what fills the GPU: a single
+ * 50k-vertex factorisation is latency-bound (about a hundred dependent panel levels). pgo_upload
+ * and pgo_set_poses address every instance, the *_instance calls one; pgo_iterate runs all
+ * instances and reports instance 0, pgo_iterate_batch reports all: chi2_out[batch][n_iters] (may be
+ * NULL), iters_done[batch]. Marginals, edge labelling and the initial guess act on instance 0. */
+int pgo_set_batch(pgo_solver* s, int batch);
+int pgo_upload_instance(pgo_solver* s, int inst, const double* poses, const double* meas,
+                        const double* info6);
+int pgo_get_poses_instance(pgo_solver* s, int inst, double* poses);
+int pgo_iterate_batch(pgo_solver* s, int n_iters, double* chi2_out, int* iters_done);
+
 /* EdgeSE2::computeError + chi2() over all edges at the current estimates (computeActiveErrors). */
 int pgo_chi2(pgo_solver* s, double* chi2);
 

@@ -63,6 +63,7 @@ extern "C" int pgo_hostsim_solve(int n, int n_blocks, const int32_t* brow, const
   V.x = x.data();
   V.scratch = scratch.data();
   V.status = &status;
+  V.s_M = V.s_Dinv = V.s_vec = V.s_scratch = 0;
   std::vector<double> sm(kCtaSmemDoubles);
   const SeqGroup g;
   for (int l = 0; l < N.n_plevels; ++l) {
@@ -71,12 +72,6 @@ extern "C" int pgo_hostsim_solve(int n, int n_blocks, const int32_t* brow, const
     for (int i = N.fb_ptr[l]; i < N.fb_ptr[l + 1]; ++i) sn_task_update(g, V, N.fb[i], sm.data());
   }
   if (status) return 2;
-  for (int l = 0; l < N.n_slevels; ++l) {
-    for (int i = N.sa_ptr[l]; i < N.sa_ptr[l + 1]; ++i) sn_task_forward_tri(g, V, N.sa[i], sm.data());
-    for (int i = N.ss_ptr[l]; i < N.ss_ptr[l + 1]; ++i) sn_task_forward_small(g, V, N.ss[i], sm.data());
-    for (int i = N.sf_ptr[l]; i < N.sf_ptr[l + 1]; ++i)
-      sn_forward_rows(g, V, N.sf[i].id, N.sf[i].r0, N.sf[i].r1, nullptr);
-  }
   for (int l = N.n_slevels - 1; l >= 0; --l) {
     for (int i = N.sb_ptr[l]; i < N.sb_ptr[l + 1]; ++i)
       sn_backward_rows(g, V, N.sb[i].id, N.sb[i].r0, N.sb[i].r1);

@@ -188,3 +188,32 @@ def test_full_size_properties():
     err = poses_b[:, :2] - g["truth"][:, :2]
     assert np.sqrt((err ** 2).sum(axis=1)).mean() < 3.0  # only vertex 0 is anchored
     s.close()
+
+
+def test_batch_of_instances_matches_oracle():
+    """pgo_set_batch: three graphs with one structure, different measurements and estimates, are
+    optimised by the same kernels (blockIdx.y = instance); each must match its own oracle run."""
+    g = synth.make_pose_graph(500, 2000, seed=31, box=25.0)
+    rng = np.random.default_rng(9)
+    inst = []
+    for b in range(3):
+        meas = g["meas"] + rng.normal(size=g["meas"].shape) * np.array([0.01, 0.01, 0.002]) * b
+        poses0 = g["poses0"].copy()
+        poses0[1:, :2] += rng.normal(size=(499, 2)) * 0.02 * b
+        inst.append((poses0, meas))
+    s = pgo.Solver(batch=3)
+    s.set_graph(500, g["edge_ij"], g["fixed"])
+    s.upload(g["poses0"], g["meas"], g["info"])          # every instance
+    for b in (1, 2):
+        s.upload_instance(b, inst[b][0], inst[b][1], g["info"])
+    done, chi2 = s.optimize_batch(4)
+    assert list(done) == [4, 4, 4]
+    for b in range(3):
+        ref = po.gauss_newton(inst[b][0], g["edge_ij"], inst[b][1], g["info"], g["fixed"], 4)
+        d = s.poses_of(b) - ref.poses
+        d[:, 2] = po.normalize_theta(d[:, 2])
+        assert np.abs(d).max() < POSE_TOL, b
+        assert np.allclose(chi2[b], ref.chi2, rtol=1e-9), b
+    # the single-instance calls report instance 0
+    assert np.array_equal(s.poses(), s.poses_of(0))
+    s.close()
