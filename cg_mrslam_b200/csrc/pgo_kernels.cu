@@ -464,12 +464,134 @@ __global__ void __launch_bounds__(kCtaThreads) sn_k_factor(SNView V, const Task*
   if (sn_failed(V)) return;
   sn_task_factor(CtaGroup(), V, tasks[blockIdx.x], sm);
 }
-// fb: outer-product tiles, one CTA per tile
+// fb: outer-product tiles, one CTA per tile, on the fp64 tensor cores.
+//   C[3 ti x 3 tj] = A[3 ti x 3 w] * B[3 w x 3 tj],  A = the scaled blocks Y(a,t) = M(a,t) Dinv_t of
+//   the panel's rows a, B = the blocks M(b,t)^T of the rows b;  M(r_a, r_b) -= C(a,b) (fp64 atomics).
+// This is the one true GEMM of the solver (north star: "tensor cores only where it is a true GEMM").
+// mma.sync.m8n8k4.f64 reaches the same 37 TFLOP/s as DFMA on this part (tools/ubench/fp64_rate.cu)
+// with an eighth of the instructions and one shared load per 8x4 fragment instead of two per
+// multiply-add, which is what the scalar version of this kernel was bound by (ncu: fp64 pipe 23 %).
+// Shared memory: As[3 ti][ldk], Bt[3 tj][ldk] (B transposed: both fragments read row-major with
+// the k index fastest; ldk = 4 mod 16 doubles keeps a fragment's 32 loads on distinct banks),
+// tp[ti * tj] scatter positions (-1 = no target).
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gmem_src) {
+  const unsigned sa = static_cast<unsigned>(__cvta_generic_to_shared(smem_dst));
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem_src) : "memory");
+}
+
+template <int NT>  // column tiles of 8 scalars: tj = 8 NT / 3 blocks
+__device__ __forceinline__ void update_tile_mma(const double* As, const double* Bt, const int* tp,
+                                                int ldk, int k4, int mt, int tj, double* M) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+  const int fr = lane >> 2, fk = lane & 3;  // fragment row / k (A, B) ; C: row fr, columns 2 fk, 2 fk + 1
+  for (int mi = warp; mi < mt; mi += n_warps) {
+    double acc[NT][2];
+#pragma unroll
+    for (int ni = 0; ni < NT; ++ni) acc[ni][0] = acc[ni][1] = 0.0;
+    const double* ap = As + (8 * mi + fr) * ldk + fk;
+    const double* bp = Bt + fr * ldk + fk;
+    for (int k0 = 0; k0 < k4; k0 += 4) {
+      const double a = ap[k0];
+#pragma unroll
+      for (int ni = 0; ni < NT; ++ni) dmma884(acc[ni][0], acc[ni][1], a, bp[8 * ni * ldk + k0]);
+    }
+    const int row = 8 * mi + fr, al = row / 3, r = row - 3 * al;
+#pragma unroll
+    for (int ni = 0; ni < NT; ++ni)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int col = 8 * ni + 2 * fk + e, bl = col / 3, c = col - 3 * bl;
+        const int pos = tp[al * tj + bl];
+        if (pos >= 0) atomicAdd(M + 9 * static_cast<size_t>(pos) + 3 * r + c, -acc[ni][e]);
+      }
+  }
+}
+
 __global__ void __launch_bounds__(kCtaThreads) sn_k_update(SNView V, const Task* tasks) {
   extern __shared__ double sm[];
   V = sn_at_instance(V, blockIdx.y);
   if (sn_failed(V)) return;
-  sn_task_update(CtaGroup(), V, tasks[blockIdx.x], sm);
+  const Task T = tasks[blockIdx.x];
+  const PanelDesc pd = V.pn[T.id];
+  const int w = pd.w, m = pd.m, len = w + m;
+  const int i0 = T.r0, j0 = T.r1, ti = T.aux >> 16, tj = T.aux & 0xFFFF;
+  const int ni = min(m - i0, ti), nj = min(m - j0, tj);
+  const int k4 = (3 * w + 3) & ~3, ldk = sn_tile_ld(w);
+  double* As = sm;
+  double* Bt = As + 3 * ti * ldk;
+  int* tp = reinterpret_cast<int*>(Bt + 3 * tj * ldk);
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  if (i0 == 0 && j0 == 0 && pd.scratch >= 0) {  // move a scratch-published diagonal part into place
+    const double* src = V.scratch + 9 * static_cast<size_t>(pd.scratch);
+    for (int idx = tid; idx < w * w * 9; idx += nthr) {
+      const int i = idx / (w * 9), t = (idx / 9) % w, k = idx % 9;
+      if (i >= t) V.M[9 * static_cast<size_t>(sn_colpos(pd.base, len, t) + (i - t)) + k] = __ldcg(src + idx);
+    }
+  }
+  // All staging loops are two-dimensional over (lane, warp): no integer division anywhere (the
+  // first version of this kernel spent more issue slots on index arithmetic than on the products).
+  const int lx = tid & 31, wy = tid >> 5, ny = nthr >> 5;
+  // zero the k padding (3 w .. k4) of both operands
+  for (int c = 3 * w + wy; c < k4; c += ny)
+    for (int row = lx; row < 3 * (ti + tj); row += 32) {
+      if (row < 3 * ti) As[row * ldk + c] = 0.0;
+      else Bt[(row - 3 * ti) * ldk + c] = 0.0;
+    }
+  // A = Y rows (scaled by the panel factorisation), B transposed = M rows: both are plain copies
+  // of 3x3 blocks into row-major [3 block + row][3 t + column], issued as asynchronous 8-byte
+  // global->shared copies so that every block of the tile is in flight at once.
+  for (int t = wy; t < w; t += ny) {
+    const size_t col = static_cast<size_t>(sn_colpos(pd.base, len, t) + (w - t));
+    const double* srca = V.Y + 9 * (col + i0);
+    for (int al = lx; al < ni; al += 32) {
+      double* dst = As + 3 * al * ldk + 3 * t;
+#pragma unroll
+      for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) cp_async8(dst + r * ldk + j, srca + 9 * al + 3 * r + j);
+    }
+    const double* srcb = V.M + 9 * (col + j0);
+    for (int bl = lx; bl < nj; bl += 32) {
+      double* dst = Bt + 3 * bl * ldk + 3 * t;
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) cp_async8(dst + c * ldk + j, srcb + 9 * bl + 3 * c + j);
+    }
+  }
+  // scatter positions of the tile's block pairs: the column's two look-ups once per lane, then one
+  // independent look-up per row
+  {
+    const int bl = lx, b = j0 + bl;
+    if (bl < tj) {
+      int cb = 0, to = 0;
+      if (bl < nj) {
+        cb = V.colbase[pd.meta + b];
+        to = V.tbl_off[pd.meta + b];
+      }
+      for (int al = wy; al < ti; al += ny) {
+        const int a = i0 + al;
+        int pos = -1;
+        if (al < ni && bl < nj && a >= b) pos = cb + V.tbl[to + a];
+        tp[al * tj + bl] = pos;
+      }
+    }
+  }
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncthreads();
+  const int mt = (3 * ni + 7) / 8;
+  switch ((3 * tj) / 8) {
+    case 3: update_tile_mma<3>(As, Bt, tp, ldk, k4, mt, tj, V.M); break;
+    case 6: update_tile_mma<6>(As, Bt, tp, ldk, k4, mt, tj, V.M); break;
+    case 9: update_tile_mma<9>(As, Bt, tp, ldk, k4, mt, tj, V.M); break;
+    default: update_tile_mma<12>(As, Bt, tp, ldk, k4, mt, tj, V.M); break;
+  }
 }
 // ff: small panels start to finish, one warp each
 __global__ void __launch_bounds__(32 * kWarpsPerCta) sn_k_fused(SNView V, const Task* tasks, int n) {
@@ -738,6 +860,7 @@ struct DeviceSolver {
   Buf<SuperDesc> sn_desc;
   Buf<Task> ff, fa, fb, ss, sa, sb;
   Buf<double> diag_scratch;
+  Buf<double> Y;
   Buf<double> many_u, many_x;  // substitution vectors of the marginals (u / x never move)
   // domain decomposition
   DDParams D;
@@ -826,6 +949,7 @@ void dev_destroy(DeviceSolver* d) {
   Buf<Task>* tb[] = {&d->ff, &d->fa, &d->fb, &d->ss, &d->sa, &d->sb};
   for (size_t i = 0; i < sizeof(tb) / sizeof(tb[0]); ++i) tb[i]->release();
   d->diag_scratch.release();
+  d->Y.release();
   d->many_u.release();
   d->many_x.release();
   if (d->graph_exec) cudaGraphExecDestroy(d->graph_exec);
@@ -899,6 +1023,7 @@ int dev_set_structure(DeviceSolver* d, const Symbolic& S, const GraphTables& G, 
   // per-instance stride of the factor storage: a multiple of 32 doubles
   const size_t m_stride = (9 * static_cast<size_t>(S.nnzb) + 3 * n_shared + 8 + 31) / 32 * 32;
   PGO_CUDA(d->M.reserve(B * m_stride));
+  PGO_CUDA(d->Y.reserve(S.world == 1 ? B * m_stride : 1));
   PGO_CUDA(d->owner.upload(S.owner, s));
   PGO_CUDA(d->xfinal_ptr.upload(S.xfinal_ptr, s));
   PGO_CUDA(d->xfinal_cols.upload(S.xfinal_cols, s));
@@ -953,6 +1078,7 @@ int dev_set_structure(DeviceSolver* d, const Symbolic& S, const GraphTables& G, 
   V.tbl_off = d->tbl_off.p;
   V.tbl = d->tbl.p;
   V.M = d->M.p;
+  V.Y = d->Y.p;
   V.Dinv = d->Dinv.p;
   V.z = d->rhs.p;
   V.u = d->u.p;

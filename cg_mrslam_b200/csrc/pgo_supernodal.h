@@ -44,6 +44,8 @@ struct SNView {
   const int* tbl;
   // numeric
   double* M;        // [nnzb][9]
+  double* Y;        // [nnzb][9] Y(a,t) = M(a,t) Dinv_t for the rows below big panels (the scaled
+                    // operand of the outer products, written by the panel factorisation)
   double* Dinv;     // [n][9]
   double* z;        // [n][3] right-hand side, overwritten by the forward substitution
   double* u;        // [n][3]
@@ -57,6 +59,7 @@ struct SNView {
 // The view of instance b of a batch (blockIdx.y on the device).
 PGO_HD SNView sn_at_instance(SNView V, int b) {
   V.M += b * V.s_M;
+  V.Y += b * V.s_M;
   V.Dinv += b * V.s_Dinv;
   V.z += b * V.s_vec;
   V.u += b * V.s_vec;
@@ -75,7 +78,7 @@ static const int kSmallPairDoubles = (kSmallWidth * (kSmallWidth + 1) / 2 + 1) /
 static const int kWarpSmemDoubles = kSmallWidth * kSmallWidth * 9 + kSmallWidth * 9 +
                                     kSmallPairDoubles + 3 * kSmallWidth +
                                     3 * kSmallWidth * (3 * kSmallRows + 1);  // fused
-static_assert(kTileBudget * 9 <= kCtaSmemDoubles, "update tiles must fit the CTA's shared memory");
+static_assert(kTileSmemDoubles <= kCtaSmemDoubles, "update tiles must fit the CTA's shared memory");
 static_assert(6 * kMaxSuperWidth + kPanelWidth * kPanelWidth * 9 + kPanelWidth * 9 + 3 * 256 <=
                   kCtaSmemDoubles, "a wide supernode's vectors must fit the CTA's shared memory");
 
@@ -248,6 +251,23 @@ PGO_HD void sn_store_rows(const G& g, const SNView& V, const PanelDesc& pd, int 
   }
 }
 
+// Y(a,t) = M(a,t) Dinv_t for the staged rows: the scaled operand of the panel's outer products.
+template <class G>
+PGO_HD void sn_store_scaled_rows(const G& g, const SNView& V, const PanelDesc& pd, int r0, int nrows,
+                                 int ldx, const double* xs, const double* Di) {
+  for (int t = 0; t < pd.w; ++t) {
+    double* dst = V.Y + 9 * static_cast<size_t>(sn_colpos(pd.base, pd.w + pd.m, t) + (pd.w - t) + r0);
+    const double* d = Di + 9 * t;
+    for (int a = g.rank(); a < nrows; a += g.size()) {
+      for (int r = 0; r < 3; ++r) {
+        const double m0 = xs[(3 * t) * ldx + 3 * a + r], m1 = xs[(3 * t + 1) * ldx + 3 * a + r],
+                     m2 = xs[(3 * t + 2) * ldx + 3 * a + r];
+        for (int c = 0; c < 3; ++c) dst[9 * a + 3 * r + c] = m0 * d[c] + m1 * d[3 + c] + m2 * d[6 + c];
+      }
+    }
+  }
+}
+
 // M(a,t) -= sum_{s<t} M(a,s) G(s,t), one scalar row per rank.
 template <class G>
 PGO_HD void sn_solve_rows(const G& g, int w, const double* Dg, double* xs, int ldx, int n_scalar) {
@@ -344,6 +364,7 @@ PGO_HD void sn_task_factor(const G& g, const SNView& V, const Task& T, double* s
   sn_solve_rows(g, w, Dg, xs, ldx, 3 * nrows + 1);
   g.sync();
   sn_store_rows(g, V, pd, T.r0, nrows, ldx, xs);
+  sn_store_scaled_rows(g, V, pd, T.r0, nrows, ldx, xs, Di);
   if (T.r0 == 0) sn_store_diag(g, V, pd, Dg, Di, pd.scratch);
   sn_forward_fused(g, V, pd, T.r0, nrows, ldx, xs, Di, us, T.r0 == 0);
   g.sync();
@@ -354,17 +375,18 @@ PGO_HD int sn_target(const SNView& V, int meta, int a, int b) {
 }
 
 // fb: one tile of the panel's outer product
-//   M(r_a, r_b) -= sum_t M(a,t) Dinv_t M(b,t)^T   (a >= b, rows of the panel's below list)
-// T.r0 = first row a, T.r1 = first column b, T.aux = (tile rows << 16) | tile columns. The (0,0)
+//   M(r_a, r_b) -= sum_t Y(a,t) M(b,t)^T,  Y(a,t) = M(a,t) Dinv_t   (a >= b, rows of the panel's
+// below list). T.r0 = first row a, T.r1 = first column b, T.aux = (tile rows << 16) | tile columns. The (0,0)
 // tile also moves a scratch-published diagonal part into place (nothing reads it in this phase).
+// This is the plain statement of the task, used by the host check; the device runs the same task
+// as a tensor-core GEMM (sn_k_update in pgo_kernels.cu).
 template <class G>
 PGO_HD void sn_task_update(const G& g, const SNView& V, const Task& T, double* sm) {
+  (void)sm;
   const PanelDesc pd = V.pn[T.id];
   const int w = pd.w, m = pd.m, len = w + m;
   const int i0 = T.r0, j0 = T.r1, ti = T.aux >> 16, tj = T.aux & 0xFFFF;
   const int ni = m - i0 < ti ? m - i0 : ti, nj = m - j0 < tj ? m - j0 : tj;
-  double* As = sm;               // [(t * 9 + k) * ti + al]
-  double* Ws = As + w * 9 * ti;  // [(t * 9 + k) * tj + bl], W = Dinv_t M(b,t)^T
   if (i0 == 0 && j0 == 0 && pd.scratch >= 0) {
     const double* src = V.scratch + 9 * static_cast<size_t>(pd.scratch);
     for (int idx = g.rank(); idx < w * w * 9; idx += g.size()) {
@@ -372,58 +394,19 @@ PGO_HD void sn_task_update(const G& g, const SNView& V, const Task& T, double* s
       if (i >= t) V.M[9 * static_cast<size_t>(sn_colpos(pd.base, len, t) + (i - t)) + k] = sn_ld(src + idx);
     }
   }
-  {
-    const int per_col = 9 * ni;
-    sn_gather(g, w * per_col, [&](int idx, const double** sp, double** dp) {
-      const int t = idx / per_col, q = idx % per_col;
-      *sp = V.M + 9 * static_cast<size_t>(sn_colpos(pd.base, len, t) + (w - t) + i0) + q;
-      *dp = As + (t * 9 + q % 9) * ti + q / 9;
-    });
-  }
-  for (int idx = g.rank(); idx < w * nj; idx += g.size()) {
-    const int t = idx / nj, bl = idx % nj;
-    const double* mp = V.M + 9 * static_cast<size_t>(sn_colpos(pd.base, len, t) + (w - t) + j0 + bl);
-    const double* dp = V.Dinv + 9 * static_cast<size_t>(pd.c0 + t);
-    double mb[9], d[9];
-    sn_ld9(mp, mb);
-    sn_ld9(dp, d);
-    for (int r = 0; r < 3; ++r)
-      for (int c = 0; c < 3; ++c)
-        Ws[(t * 9 + 3 * r + c) * tj + bl] =
-            d[3 * r] * mb[3 * c] + d[3 * r + 1] * mb[3 * c + 1] + d[3 * r + 2] * mb[3 * c + 2];
-  }
-  g.sync();
-  // 8 x 4 patches of (row, column) pairs per warp: a warp's shared loads touch 8 / 4 consecutive
-  // doubles (ti is a multiple of 8, tj of 4)
-  const int pr = ti >> 3, n_items = (ti * tj);
-  for (int item = g.rank(); item < n_items; item += g.size()) {
-    const int lane = item & 31, q = item >> 5;
-    const int al = (q % pr) * 8 + (lane & 7), bl = (q / pr) * 4 + (lane >> 3);
-    const int a = i0 + al, b = j0 + bl;
-    if (al >= ni || bl >= nj || a < b) continue;
-    // the scatter position's two dependent look-ups overlap with the products below
-    const int tpos = V.colbase[pd.meta + b] + V.tbl[V.tbl_off[pd.meta + b] + a];
+  for (int item = g.rank(); item < ni * nj; item += g.size()) {
+    const int a = i0 + item / nj, b = j0 + item % nj;
+    if (a < b) continue;
     double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     for (int t = 0; t < w; ++t) {
-      double av[9], wv[9];
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-      for (int k = 0; k < 9; ++k) {
-        av[k] = As[(t * 9 + k) * ti + al];
-        wv[k] = Ws[(t * 9 + k) * tj + bl];
-      }
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
+      double mb[9], y[9];
+      sn_ld9(V.Y + 9 * static_cast<size_t>(sn_colpos(pd.base, len, t) + (w - t) + a), y);
+      sn_ld9(V.M + 9 * static_cast<size_t>(sn_colpos(pd.base, len, t) + (w - t) + b), mb);
       for (int r = 0; r < 3; ++r)
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
         for (int c = 0; c < 3; ++c)
-          acc[3 * r + c] += av[3 * r] * wv[c] + av[3 * r + 1] * wv[3 + c] + av[3 * r + 2] * wv[6 + c];
+          acc[3 * r + c] += y[3 * r] * mb[3 * c] + y[3 * r + 1] * mb[3 * c + 1] + y[3 * r + 2] * mb[3 * c + 2];
     }
-    double* dst = V.M + 9 * static_cast<size_t>(tpos);
+    double* dst = V.M + 9 * static_cast<size_t>(sn_target(V, pd.meta, a, b));
     for (int k = 0; k < 9; ++k) sn_add(dst + k, -acc[k]);
   }
   g.sync();

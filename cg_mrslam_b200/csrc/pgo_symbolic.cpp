@@ -412,10 +412,11 @@ bool build_supernodal(Symbolic& S, std::string* err) {
         N.pn_scratch[K] = static_cast<int>(N.scratch_blocks);
         N.scratch_blocks += static_cast<int64_t>(w) * w;
       }
-      // tile shape: (rows + columns) * w blocks are staged in shared memory
-      const int cap = kTileBudget / w;
-      const int tj = std::min((m + 3) / 4 * 4, std::max(8, std::min(64, (cap / 5 + 3) / 4 * 4)));
-      const int ti = std::max(8, std::min(std::min((m + 7) / 8 * 8, (cap - tj) / 8 * 8), 256));
+      // tile shape (see kTileSmemDoubles): as many columns as useful up to 24 (32 for the
+      // narrowest panels), then as many rows as still fit
+      const int tj = std::min((m + 7) / 8 * 8, w <= 2 ? 32 : 24);
+      int ti = std::min((m + 7) / 8 * 8, 256);
+      while (ti > 8 && sn_tile_doubles(w, ti, tj) > kTileSmemDoubles) ti -= 8;
       for (int i0 = 0; i0 < m; i0 += ti)
         for (int j0 = 0; j0 < std::min(m, i0 + ti); j0 += tj) {
           const Task t = {K, i0, j0, (ti << 16) | tj};
@@ -487,7 +488,7 @@ Supernodal::Lists Supernodal::lists() const {
     }
     for (int i = fb_ptr[l]; i < fb_ptr[l + 1]; ++i) {
       const int w = pn[fb[i].id].w;
-      L.fb_smem[l] = std::max(L.fb_smem[l], w * 9 * ((fb[i].aux >> 16) + (fb[i].aux & 0xFFFF)));
+      L.fb_smem[l] = std::max(L.fb_smem[l], sn_tile_doubles(w, fb[i].aux >> 16, fb[i].aux & 0xFFFF));
     }
   }
   L.sa_smem.assign(n_slevels, 0);

@@ -16,6 +16,12 @@
 #include <string>
 #include <vector>
 
+#if defined(__CUDACC__)
+#define PGO_HOST_DEVICE __host__ __device__
+#else
+#define PGO_HOST_DEVICE
+#endif
+
 namespace pgo {
 
 // One block update  M(target) -= M(a) * Dinv(col_of(a)) * M(b)^T.  Updates of one phase are sorted
@@ -39,8 +45,16 @@ static const int kPanelWidth = 16;
 static const int kSmallWidth = 4;    // panels / supernodes this narrow are handled by one warp
 static const int kSmallRows = 32;    // ... if the panel also has at most this many rows below it
 static const int kRowChunk = 64;     // rows below a panel per CTA task of the panel factorisation
-// outer-product tile of one CTA task: (rows + columns) * panel width <= kTileBudget blocks staged
-static const int kTileBudget = 1296;
+// outer-product tile of one CTA task (tensor-core GEMM, pgo_kernels.cu): ti x tj blocks with
+// ti a multiple of 8 and tj in {8, 16, 24, 32}; operands staged as [3 ti][ld] and [3 tj][ld]
+// doubles with ld = sn_tile_ld(w), plus ti * tj scatter positions.
+static const int kTileSmemDoubles = 11600;
+PGO_HOST_DEVICE inline constexpr int sn_tile_ld(int w) {  // >= 3 w rounded up to 4, and = 4 (mod 16)
+  return ((3 * w + 3) & ~3) + ((4 - (((3 * w + 3) & ~3) % 16)) + 16) % 16;
+}
+PGO_HOST_DEVICE inline constexpr int sn_tile_doubles(int w, int ti, int tj) {
+  return 3 * (ti + tj) * sn_tile_ld(w) + (ti * tj + 1) / 2;
+}
 static const int kMaxSuperWidth = 1024;
 
 struct Task {

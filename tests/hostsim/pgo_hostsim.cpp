@@ -56,7 +56,9 @@ extern "C" int pgo_hostsim_solve(int n, int n_blocks, const int32_t* brow, const
   V.colbase = N.colbase.data();
   V.tbl_off = N.tbl_off.data();
   V.tbl = N.tbl.data();
+  std::vector<double> Y(M.size(), 0.0);
   V.M = M.data();
+  V.Y = Y.data();
   V.Dinv = Dinv.data();
   V.z = z.data();
   V.u = u.data();
