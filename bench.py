@@ -45,7 +45,7 @@ def parse():
     ap.add_argument("--cpu-pairs", type=int, default=0, help="pairs in the CPU sample (0 = auto)")
     ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 global, 2 tiled")
     ap.add_argument("--no-gn", action="store_true")
-    ap.add_argument("--gn-batch", type=int, default=16, help="graph instances per GPU in the GN arm")
+    ap.add_argument("--gn-batch", type=int, default=32, help="graph instances per GPU in the GN arm")
     return ap.parse_args()
 
 
