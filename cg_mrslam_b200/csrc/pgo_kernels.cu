@@ -1,20 +1,20 @@
 // CUDA back-end of the SE(2) pose-graph solver (sm_100a). Implements pgo_device.h.
 //
-// One cooperative, persistent kernel (gn_iterations) runs whole Gauss-Newton iterations -- the
-// work of SparseOptimizer::optimize(n) with BlockSolver + LinearSolverCSparse +
-// OptimizationAlgorithmGaussNewton (configured by the reference at
-// src/slam/graph_slam.cpp:44-56) -- with grid-wide barriers between dependent phases:
-//   1. linearise: per free vertex, every incident EdgeSE2 is evaluated (error e, analytic
+// A Gauss-Newton iteration -- the work of SparseOptimizer::optimize(1) with BlockSolver +
+// LinearSolverCSparse + OptimizationAlgorithmGaussNewton (configured by
+// the reference at src/slam/graph_slam.cpp:44-56) -- is one CUDA graph of per-phase kernels:
+//   1. gn_linearise: per free vertex, every incident EdgeSE2 is evaluated (error e, analytic
 //      Jacobians Ji, Jj, C4) and H_pp += Jp^T Om Jp, b_p += Jp^T (-Om e), H_qp += Jq^T Om Jp are
 //      accumulated by the one thread that owns the destination block: no atomics, fixed order
 //      (C5). chi2 = sum e^T Om e is reduced deterministically.
-//   2. factorise: block L D L^T of the permuted H, 3x3 pivots, in elimination-tree level order.
-//      Phase l applies the updates  M(i,j) -= M(i,k) Dinv(k) M(j,k)^T  whose source columns k
-//      became final in phase l-1, from a schedule precomputed on the host (pgo_symbolic.cpp);
-//      each target block is owned by one thread per phase.
-//   3. solve: level-scheduled forward and backward substitution, one warp per block row/column.
-//   4. update: VertexSE2::oplusImpl (C3) on every free vertex.
-// Algorithmic HBM bytes per phase are stated in DESIGN.md section 5.
+//   2. factorise + forward-substitute, bottom-up over the panel levels: supernodal block L D L^T of
+//      the permuted H (pgo_supernodal.h): sn_k_factor / sn_k_fused per level, then sn_k_update, the
+//      outer products on the fp64 tensor cores.
+//   3. back-substitute, top-down over the supernode levels: sn_k_bwd_*.
+//   4. gn_update: VertexSE2::oplusImpl (C3) on every free vertex.
+// The level-by-level kernels further down (phase_forward / phase_backward, pgo_dd.cuh) serve the
+// marginals (multi-right-hand-side solves) and the domain-decomposed multi-GPU iteration.
+// Algorithmic bytes and measured shares per kernel are stated in DESIGN.md section 4.3.
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
