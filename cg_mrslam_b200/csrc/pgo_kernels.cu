@@ -485,30 +485,121 @@ __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gmem_s
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gmem_src) : "memory");
 }
 
+// One tile of an outer product: rows [i0, i0 + ti) x columns [j0, j0 + tj) of the below-row list
+// of the LAST panel of the task's panel range, summed over the columns of all panels of the range
+// (one panel for the updates inside a supernode, all of a supernode's panels for the update of its
+// ancestors), one 16-column chunk staged at a time, accumulators in registers across the chunks.
 template <int NT>  // column tiles of 8 scalars: tj = 8 NT / 3 blocks
-__device__ __forceinline__ void update_tile_mma(const double* As, const double* Bt, const int* tp,
-                                                int ldk, int k4, int mt, int tj, double* M) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
-  const int fr = lane >> 2, fk = lane & 3;  // fragment row / k (A, B) ; C: row fr, columns 2 fk, 2 fk + 1
-  for (int mi = warp; mi < mt; mi += n_warps) {
-    double acc[NT][2];
-#pragma unroll
-    for (int ni = 0; ni < NT; ++ni) acc[ni][0] = acc[ni][1] = 0.0;
-    const double* ap = As + (8 * mi + fr) * ldk + fk;
-    const double* bp = Bt + fr * ldk + fk;
-    for (int k0 = 0; k0 < k4; k0 += 4) {
-      const double a = ap[k0];
-#pragma unroll
-      for (int ni = 0; ni < NT; ++ni) dmma884(acc[ni][0], acc[ni][1], a, bp[8 * ni * ldk + k0]);
+__device__ __forceinline__ void update_tile(const SNView& V, const Task& T, double* sm) {
+  const int ti = T.aux & 0xFF, tj = (T.aux >> 8) & 0xFF, np = (T.aux >> 16) & 0x3F;
+  const int q_last = T.id - ((T.aux >> 22) & 0x3F), q_first = q_last - np + 1;
+  const bool inside = (T.aux >> 28) & 1;  // targets = later columns of the same supernode only
+  const int i0 = T.r0, j0 = T.r1;
+  const PanelDesc last = V.pn[T.id];
+  const int m = last.m;
+  // inside a supernode the columns b stop at the supernode's last column
+  const SuperDesc sd = V.sn[last.sn];
+  const int jlim = inside ? sd.W - last.sn_off - last.w : m;
+  const int ni = min(m - i0, ti), nj = min(jlim - j0, tj);
+  const int ldk = sn_tile_ld(!inside && sd.pn_end - sd.pn_begin > 1 ? kPanelWidth : last.w);
+  double* As = sm;
+  double* Bt = As + 3 * ti * ldk;
+  int* tp = reinterpret_cast<int*>(Bt + 3 * tj * ldk);
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int lx = tid & 31, wy = tid >> 5, ny = nthr >> 5;
+  const int lane = lx, warp = wy, fr = lane >> 2, fk = lane & 3;
+  const int mt = (3 * ni + 7) / 8;
+  if (i0 == 0 && j0 == 0 && q_last == T.id && last.scratch >= 0) {  // move a scratch-published diagonal part into place
+    const int w = last.w, len = w + m;
+    const double* src = V.scratch + 9 * static_cast<size_t>(last.scratch);
+    for (int idx = tid; idx < w * w * 9; idx += nthr) {
+      const int i = idx / (w * 9), t = (idx / 9) % w, k = idx % 9;
+      if (i >= t) V.M[9 * static_cast<size_t>(sn_colpos(last.base, len, t) + (i - t)) + k] = __ldcg(src + idx);
     }
+  }
+  // scatter positions of the tile's block pairs: the column's two look-ups once per lane, then one
+  // independent look-up per row (all staging loops are two-dimensional: no integer division)
+  if (lx < tj) {
+    const int b = j0 + lx;
+    int cb = 0, to = 0;
+    if (lx < nj) {
+      cb = V.colbase[last.meta + b];
+      to = V.tbl_off[last.meta + b];
+    }
+    for (int al = wy; al < ti; al += ny) {
+      const int a = i0 + al;
+      int pos = -1;
+      if (al < ni && lx < nj && a >= b) pos = cb + V.tbl[to + a];
+      tp[al * tj + lx] = pos;
+    }
+  }
+  double acc[2][NT][2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int n = 0; n < NT; ++n) acc[h][n][0] = acc[h][n][1] = 0.0;
+  for (int q = q_first; q <= q_last; ++q) {
+    const PanelDesc pd = V.pn[q];
+    const int w = pd.w, len = w + pd.m;
+    const int off = pd.m - m;  // the last panel's rows start here in this panel's below list
+    const int k4 = (3 * w + 3) & ~3;
+    if (q > q_first) __syncthreads();  // everybody is done with the previous chunk
+    // zero the k padding (3 w .. k4) of both operands
+    for (int c = 3 * w + wy; c < k4; c += ny)
+      for (int row = lx; row < 3 * (ti + tj); row += 32) {
+        if (row < 3 * ti) As[row * ldk + c] = 0.0;
+        else Bt[(row - 3 * ti) * ldk + c] = 0.0;
+      }
+    // A = Y rows (scaled by the panel factorisation), B transposed = M rows: plain copies of 3x3
+    // blocks into row-major [3 block + row][3 t + column], as asynchronous 8-byte global->shared
+    // copies so that every block of the chunk is in flight at once
+    for (int t = wy; t < w; t += ny) {
+      const size_t col = static_cast<size_t>(sn_colpos(pd.base, len, t) + (w - t) + off);
+      const double* srca = V.Y + 9 * (col + i0);
+      for (int al = lx; al < ni; al += 32) {
+        double* dst = As + 3 * al * ldk + 3 * t;
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int j = 0; j < 3; ++j) cp_async8(dst + r * ldk + j, srca + 9 * al + 3 * r + j);
+      }
+      const double* srcb = V.M + 9 * (col + j0);
+      for (int bl = lx; bl < nj; bl += 32) {
+        double* dst = Bt + 3 * bl * ldk + 3 * t;
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+          for (int j = 0; j < 3; ++j) cp_async8(dst + c * ldk + j, srcb + 9 * bl + 3 * c + j);
+      }
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int mi = warp + 8 * h;
+      if (mi < mt) {
+        const double* ap = As + (8 * mi + fr) * ldk + fk;
+        const double* bp = Bt + fr * ldk + fk;
+        for (int k0 = 0; k0 < k4; k0 += 4) {
+          const double a = ap[k0];
+#pragma unroll
+          for (int n = 0; n < NT; ++n) dmma884(acc[h][n][0], acc[h][n][1], a, bp[8 * n * ldk + k0]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int mi = warp + 8 * h;
+    if (mi >= mt) continue;
     const int row = 8 * mi + fr, al = row / 3, r = row - 3 * al;
 #pragma unroll
-    for (int ni = 0; ni < NT; ++ni)
+    for (int n = 0; n < NT; ++n)
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        const int col = 8 * ni + 2 * fk + e, bl = col / 3, c = col - 3 * bl;
+        const int col = 8 * n + 2 * fk + e, bl = col / 3, c = col - 3 * bl;
         const int pos = tp[al * tj + bl];
-        if (pos >= 0) atomicAdd(M + 9 * static_cast<size_t>(pos) + 3 * r + c, -acc[ni][e]);
+        if (pos >= 0) atomicAdd(V.M + 9 * static_cast<size_t>(pos) + 3 * r + c, -acc[h][n][e]);
       }
   }
 }
@@ -518,79 +609,10 @@ __global__ void __launch_bounds__(kCtaThreads) sn_k_update(SNView V, const Task*
   V = sn_at_instance(V, blockIdx.y);
   if (sn_failed(V)) return;
   const Task T = tasks[blockIdx.x];
-  const PanelDesc pd = V.pn[T.id];
-  const int w = pd.w, m = pd.m, len = w + m;
-  const int i0 = T.r0, j0 = T.r1, ti = T.aux >> 16, tj = T.aux & 0xFFFF;
-  const int ni = min(m - i0, ti), nj = min(m - j0, tj);
-  const int k4 = (3 * w + 3) & ~3, ldk = sn_tile_ld(w);
-  double* As = sm;
-  double* Bt = As + 3 * ti * ldk;
-  int* tp = reinterpret_cast<int*>(Bt + 3 * tj * ldk);
-  const int tid = threadIdx.x, nthr = blockDim.x;
-  if (i0 == 0 && j0 == 0 && pd.scratch >= 0) {  // move a scratch-published diagonal part into place
-    const double* src = V.scratch + 9 * static_cast<size_t>(pd.scratch);
-    for (int idx = tid; idx < w * w * 9; idx += nthr) {
-      const int i = idx / (w * 9), t = (idx / 9) % w, k = idx % 9;
-      if (i >= t) V.M[9 * static_cast<size_t>(sn_colpos(pd.base, len, t) + (i - t)) + k] = __ldcg(src + idx);
-    }
-  }
-  // All staging loops are two-dimensional over (lane, warp): no integer division anywhere (the
-  // first version of this kernel spent more issue slots on index arithmetic than on the products).
-  const int lx = tid & 31, wy = tid >> 5, ny = nthr >> 5;
-  // zero the k padding (3 w .. k4) of both operands
-  for (int c = 3 * w + wy; c < k4; c += ny)
-    for (int row = lx; row < 3 * (ti + tj); row += 32) {
-      if (row < 3 * ti) As[row * ldk + c] = 0.0;
-      else Bt[(row - 3 * ti) * ldk + c] = 0.0;
-    }
-  // A = Y rows (scaled by the panel factorisation), B transposed = M rows: both are plain copies
-  // of 3x3 blocks into row-major [3 block + row][3 t + column], issued as asynchronous 8-byte
-  // global->shared copies so that every block of the tile is in flight at once.
-  for (int t = wy; t < w; t += ny) {
-    const size_t col = static_cast<size_t>(sn_colpos(pd.base, len, t) + (w - t));
-    const double* srca = V.Y + 9 * (col + i0);
-    for (int al = lx; al < ni; al += 32) {
-      double* dst = As + 3 * al * ldk + 3 * t;
-#pragma unroll
-      for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int j = 0; j < 3; ++j) cp_async8(dst + r * ldk + j, srca + 9 * al + 3 * r + j);
-    }
-    const double* srcb = V.M + 9 * (col + j0);
-    for (int bl = lx; bl < nj; bl += 32) {
-      double* dst = Bt + 3 * bl * ldk + 3 * t;
-#pragma unroll
-      for (int c = 0; c < 3; ++c)
-#pragma unroll
-        for (int j = 0; j < 3; ++j) cp_async8(dst + c * ldk + j, srcb + 9 * bl + 3 * c + j);
-    }
-  }
-  // scatter positions of the tile's block pairs: the column's two look-ups once per lane, then one
-  // independent look-up per row
-  {
-    const int bl = lx, b = j0 + bl;
-    if (bl < tj) {
-      int cb = 0, to = 0;
-      if (bl < nj) {
-        cb = V.colbase[pd.meta + b];
-        to = V.tbl_off[pd.meta + b];
-      }
-      for (int al = wy; al < ti; al += ny) {
-        const int a = i0 + al;
-        int pos = -1;
-        if (al < ni && bl < nj && a >= b) pos = cb + V.tbl[to + a];
-        tp[al * tj + bl] = pos;
-      }
-    }
-  }
-  asm volatile("cp.async.wait_all;" ::: "memory");
-  __syncthreads();
-  const int mt = (3 * ni + 7) / 8;
-  switch ((3 * tj) / 8) {
-    case 3: update_tile_mma<3>(As, Bt, tp, ldk, k4, mt, tj, V.M); break;
-    case 6: update_tile_mma<6>(As, Bt, tp, ldk, k4, mt, tj, V.M); break;
-    case 9: update_tile_mma<9>(As, Bt, tp, ldk, k4, mt, tj, V.M); break;
-    default: update_tile_mma<12>(As, Bt, tp, ldk, k4, mt, tj, V.M); break;
+  switch ((3 * ((T.aux >> 8) & 0xFF)) / 8) {
+    case 3: update_tile<3>(V, T, sm); break;
+    case 6: update_tile<6>(V, T, sm); break;
+    default: update_tile<9>(V, T, sm); break;
   }
 }
 // ff: small panels start to finish, one warp each

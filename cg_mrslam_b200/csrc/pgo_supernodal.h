@@ -374,39 +374,52 @@ PGO_HD int sn_target(const SNView& V, int meta, int a, int b) {
   return V.colbase[meta + b] + V.tbl[V.tbl_off[meta + b] + a];
 }
 
-// fb: one tile of the panel's outer product
-//   M(r_a, r_b) -= sum_t Y(a,t) M(b,t)^T,  Y(a,t) = M(a,t) Dinv_t   (a >= b, rows of the panel's
-// below list). T.r0 = first row a, T.r1 = first column b, T.aux = (tile rows << 16) | tile columns. The (0,0)
-// tile also moves a scratch-published diagonal part into place (nothing reads it in this phase).
-// This is the plain statement of the task, used by the host check; the device runs the same task
-// as a tensor-core GEMM (sn_k_update in pgo_kernels.cu).
+// fb: one tile of an outer product
+//   M(r_a, r_b) -= sum over the columns t of the panels [T.id - np + 1, T.id] of Y(a,t) M(b,t)^T,
+//   Y(a,t) = M(a,t) Dinv_t,  a >= b rows of the LAST panel's below list.
+// np = 1 and the "inside" flag: the update a panel owes the later columns of its own supernode
+// (needed by the next panel); np = all panels of a supernode: the update the supernode owes its
+// ancestors, applied once with the whole supernode as the inner dimension instead of once per
+// panel (fewer, longer products and a fraction of the atomics).
+// T.r0 = first row a, T.r1 = first column b, T.aux = ti | tj << 8 | np << 16 | inside << 28. The
+// (0,0) tile also moves a scratch-published diagonal part into place (nothing reads it in this
+// phase). This is the plain statement of the task, used by the host check; the device runs the same
+// task as a tensor-core GEMM (sn_k_update in pgo_kernels.cu).
 template <class G>
 PGO_HD void sn_task_update(const G& g, const SNView& V, const Task& T, double* sm) {
   (void)sm;
-  const PanelDesc pd = V.pn[T.id];
-  const int w = pd.w, m = pd.m, len = w + m;
-  const int i0 = T.r0, j0 = T.r1, ti = T.aux >> 16, tj = T.aux & 0xFFFF;
-  const int ni = m - i0 < ti ? m - i0 : ti, nj = m - j0 < tj ? m - j0 : tj;
-  if (i0 == 0 && j0 == 0 && pd.scratch >= 0) {
-    const double* src = V.scratch + 9 * static_cast<size_t>(pd.scratch);
+  const int ti = T.aux & 0xFF, tj = (T.aux >> 8) & 0xFF, np = (T.aux >> 16) & 0x3F;
+  const int q_last = T.id - ((T.aux >> 22) & 0x3F), q_first = q_last - np + 1;
+  const bool inside = (T.aux >> 28) & 1;
+  const PanelDesc last = V.pn[T.id];
+  const int m = last.m, i0 = T.r0, j0 = T.r1;
+  const int jlim = inside ? V.sn[last.sn].W - last.sn_off - last.w : m;
+  const int ni = m - i0 < ti ? m - i0 : ti, nj = jlim - j0 < tj ? jlim - j0 : tj;
+  if (i0 == 0 && j0 == 0 && q_last == T.id && last.scratch >= 0) {
+    const int w = last.w, len = w + m;
+    const double* src = V.scratch + 9 * static_cast<size_t>(last.scratch);
     for (int idx = g.rank(); idx < w * w * 9; idx += g.size()) {
       const int i = idx / (w * 9), t = (idx / 9) % w, k = idx % 9;
-      if (i >= t) V.M[9 * static_cast<size_t>(sn_colpos(pd.base, len, t) + (i - t)) + k] = sn_ld(src + idx);
+      if (i >= t) V.M[9 * static_cast<size_t>(sn_colpos(last.base, len, t) + (i - t)) + k] = sn_ld(src + idx);
     }
   }
   for (int item = g.rank(); item < ni * nj; item += g.size()) {
     const int a = i0 + item / nj, b = j0 + item % nj;
     if (a < b) continue;
     double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    for (int t = 0; t < w; ++t) {
-      double mb[9], y[9];
-      sn_ld9(V.Y + 9 * static_cast<size_t>(sn_colpos(pd.base, len, t) + (w - t) + a), y);
-      sn_ld9(V.M + 9 * static_cast<size_t>(sn_colpos(pd.base, len, t) + (w - t) + b), mb);
-      for (int r = 0; r < 3; ++r)
-        for (int c = 0; c < 3; ++c)
-          acc[3 * r + c] += y[3 * r] * mb[3 * c] + y[3 * r + 1] * mb[3 * c + 1] + y[3 * r + 2] * mb[3 * c + 2];
+    for (int q = q_first; q <= q_last; ++q) {
+      const PanelDesc pd = V.pn[q];
+      const int w = pd.w, len = w + pd.m, off = pd.m - m;
+      for (int t = 0; t < w; ++t) {
+        double mb[9], y[9];
+        sn_ld9(V.Y + 9 * static_cast<size_t>(sn_colpos(pd.base, len, t) + (w - t) + off + a), y);
+        sn_ld9(V.M + 9 * static_cast<size_t>(sn_colpos(pd.base, len, t) + (w - t) + off + b), mb);
+        for (int r = 0; r < 3; ++r)
+          for (int c = 0; c < 3; ++c)
+            acc[3 * r + c] += y[3 * r] * mb[3 * c] + y[3 * r + 1] * mb[3 * c + 1] + y[3 * r + 2] * mb[3 * c + 2];
+      }
     }
-    double* dst = V.M + 9 * static_cast<size_t>(sn_target(V, pd.meta, a, b));
+    double* dst = V.M + 9 * static_cast<size_t>(sn_target(V, last.meta, a, b));
     for (int k = 0; k < 9; ++k) sn_add(dst + k, -acc[k]);
   }
   g.sync();

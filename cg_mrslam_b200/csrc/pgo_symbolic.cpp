@@ -412,16 +412,36 @@ bool build_supernodal(Symbolic& S, std::string* err) {
         N.pn_scratch[K] = static_cast<int>(N.scratch_blocks);
         N.scratch_blocks += static_cast<int64_t>(w) * w;
       }
-      // tile shape (see kTileSmemDoubles): as many columns as useful up to 24 (32 for the
-      // narrowest panels), then as many rows as still fit
-      const int tj = std::min((m + 7) / 8 * 8, w <= 2 ? 32 : 24);
-      int ti = std::min((m + 7) / 8 * 8, 256);
-      while (ti > 8 && sn_tile_doubles(w, ti, tj) > kTileSmemDoubles) ti -= 8;
-      for (int i0 = 0; i0 < m; i0 += ti)
-        for (int j0 = 0; j0 < std::min(m, i0 + ti); j0 += tj) {
-          const Task t = {K, i0, j0, (ti << 16) | tj};
-          fb.push_back(std::make_pair(plevel[K], t));
+      // Outer products. Inside a supernode every panel updates the supernode's later columns
+      // (the next panel needs them); the update of the ANCESTORS (rows x rows below the
+      // supernode) is applied once per supernode, by its last panel's level, with all the
+      // supernode's columns as the inner dimension.
+      const int sn_s = N.pn_sn[K];
+      const int W = N.sn_first[sn_s + 1] - N.sn_first[sn_s], o = c0 - N.sn_first[sn_s];
+      const int w_rest = W - o - w;                         // later columns of the supernode
+      const int np = N.sn_pn_ptr[sn_s + 1] - N.sn_pn_ptr[sn_s];
+      for (int pass = 0; pass < 2; ++pass) {
+        // pass 0: inside the supernode (columns b < w_rest); pass 1 (last panel): the ancestors
+        if (pass == 0 ? w_rest == 0 : w_rest != 0) continue;
+        const int jlim = pass == 0 ? w_rest : m;
+        const int wk = pass == 0 || np == 1 ? w : kPanelWidth;   // widest staged chunk
+        const int tj = std::min((jlim + 7) / 8 * 8, 24);
+        int ti = std::min((m + 7) / 8 * 8, 40);                  // two 8-row strips per warp
+        while (ti > 8 && sn_tile_doubles(wk, ti, tj) > kTileSmemDoubles) ti -= 8;
+        // the inner dimension of an ancestors' update is cut into groups of kUpdateGroup panels
+        // (split-K: the tiles of different groups add into the same targets with atomics anyway)
+        const int n_groups = pass == 0 ? 1 : (np + kUpdateGroup - 1) / kUpdateGroup;
+        for (int gi = 0; gi < n_groups; ++gi) {
+          const int first = pass == 0 ? 0 : np * gi / n_groups, end = pass == 0 ? 1 : np * (gi + 1) / n_groups;
+          const int count = end - first, back = pass == 0 ? 0 : np - end;
+          const int aux = ti | (tj << 8) | (count << 16) | (back << 22) | ((pass == 0 ? 1 : 0) << 28);
+          for (int i0 = 0; i0 < m; i0 += ti)
+            for (int j0 = 0; j0 < std::min(jlim, i0 + ti); j0 += tj) {
+              const Task t = {K, i0, j0, aux};
+              fb.push_back(std::make_pair(plevel[K], t));
+            }
         }
+      }
     }
     const int sn_id = N.pn_sn[K];
     PanelDesc pd = {c0, w, m, cp[c0], N.pn_meta[K], N.pn_scratch[K], c0 - N.sn_first[sn_id], sn_id};
@@ -487,8 +507,9 @@ Supernodal::Lists Supernodal::lists() const {
                                                 3 * w * (3 * (fa[i].r1 - fa[i].r0) + 1));
     }
     for (int i = fb_ptr[l]; i < fb_ptr[l + 1]; ++i) {
-      const int w = pn[fb[i].id].w;
-      L.fb_smem[l] = std::max(L.fb_smem[l], sn_tile_doubles(w, fb[i].aux >> 16, fb[i].aux & 0xFFFF));
+      const int multi = (sn[pn[fb[i].id].sn].pn_end - sn[pn[fb[i].id].sn].pn_begin) > 1 && !((fb[i].aux >> 28) & 1);
+      const int w = multi ? kPanelWidth : pn[fb[i].id].w;
+      L.fb_smem[l] = std::max(L.fb_smem[l], sn_tile_doubles(w, fb[i].aux & 0xFF, (fb[i].aux >> 8) & 0xFF));
     }
   }
   L.sa_smem.assign(n_slevels, 0);

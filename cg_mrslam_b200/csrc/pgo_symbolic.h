@@ -55,12 +55,14 @@ PGO_HOST_DEVICE inline constexpr int sn_tile_ld(int w) {  // >= 3 w rounded up t
 PGO_HOST_DEVICE inline constexpr int sn_tile_doubles(int w, int ti, int tj) {
   return 3 * (ti + tj) * sn_tile_ld(w) + (ti * tj + 1) / 2;
 }
-static const int kMaxSuperWidth = 1024;
+static const int kMaxSuperWidth = 1008;   // at most 63 panels per supernode
+static const int kUpdateGroup = 4;        // panels per tile task of an ancestors' update
 
 struct Task {
   int id;      // panel or supernode
   int r0, r1;  // row range of the below-row list (tile tasks: first row / first column)
-  int aux;     // tile tasks: (tile rows << 16) | tile columns
+  int aux;     // tile tasks: tile rows | tile columns << 8 | panels summed over << 16 |
+               // panels between the last summed one and the task's panel << 22 | inside << 28
 };
 
 // Geometry of a panel / supernode in the block-CSC storage. Because the structure is nested,
