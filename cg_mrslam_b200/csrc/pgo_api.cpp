@@ -121,6 +121,8 @@ int pgo_set_graph(pgo_solver* s, int n_vertices, int n_edges, const int32_t* edg
       free_edges.push_back(std::make_pair(s->hidx[i], s->hidx[j]));
   }
   std::string err;
+  if (s->world > 1 && pgo::dev_batch(s->dev) != 1)
+    return fail(PGO_ERR_ARG, "a domain-decomposed solver holds one graph instance (pgo_set_batch(1))");
   if (!pgo::analyse(n, free_edges, 0, s->world, &s->sym, &err)) return fail(PGO_ERR_CAPACITY, err);
   const pgo::Symbolic& S = s->sym;
 

@@ -68,8 +68,6 @@ struct Params {
   const int* row_pos;
   const int* level_ptr;
   const int* level_cols;
-  const int* phase_ptr;
-  const UpdateOp* ops;
   const int* fwd_ptr;
   const SolveOp* fwd_ops;
   const int* perm_vertex;  // permuted position -> vertex index
@@ -104,11 +102,6 @@ __device__ __forceinline__ Params params_at(Params P, int b) {
 }
 
 // ---- small dense helpers, 3x3 row-major ----------------------------------------------------------
-__device__ __forceinline__ void load9(const double* __restrict__ p, double* m) {
-#pragma unroll
-  for (int i = 0; i < 9; ++i) m[i] = p[i];
-}
-
 // Inverse of a symmetric positive definite 3x3 via Cholesky; false if a pivot is not positive.
 __device__ bool spd_inverse(const double* a, double* inv) {
   const double l00sq = a[0];
@@ -297,19 +290,7 @@ __device__ void phase_linearise(const Params& P, double* scratch, int it) {
   (void)it;
 }
 
-// ---- phase 2: factorise ------------------------------------------------------------------------
-__device__ __forceinline__ void finalise_diag(const Params& P, int col, const double* m) {
-  double inv[9];
-  if (!spd_inverse(m, inv)) {
-    atomicExch(P.status, 1);
-    return;
-  }
-  double* d = P.Dinv + 9 * static_cast<size_t>(col);
-#pragma unroll
-  for (int i = 0; i < 9; ++i) d[i] = inv[i];
-}
-
-// ---- phase 3: solves ---------------------------------------------------------------------------
+// ---- level-by-level substitution (marginals: many right-hand sides against the stored factor) ---
 // Forward substitution works in place on the right-hand side z (initially b):
 //   level-0 rows:  u_j = Dinv_j z_j
 //   phase l >= 1:  z_i -= M(i,k) u_k for the blocks of the columns k of level l-1 (eager, right-
@@ -861,9 +842,8 @@ struct DeviceSolver {
   Params P;
   bool have_structure = false, have_values = false, have_factor = false;
   Buf<int> edge_i, edge_j, vpos, inc_ptr, ff_edges, col_ptr, row_idx, col_of, row_ptr, row_pos,
-      level_ptr, level_cols, phase_ptr, perm_vertex, status, scratch_i;
+      level_ptr, level_cols, perm_vertex, status, scratch_i;
   Buf<Incidence> inc;
-  Buf<UpdateOp> ops;
   Buf<SolveOp> fwd_ops;
   Buf<int> fwd_ptr;
   Buf<unsigned long long> stamps;
@@ -871,25 +851,29 @@ struct DeviceSolver {
   Buf<double> poses, meas, info6, M, Dinv, rhs, u, x, chi2_partial, chi2_out, many_rhs, scratch_d;
   // supernodal tables (single-GPU path)
   SNView V;
-  Supernodal::Lists L;   // host copies of the level pointers (launch geometry)
-  cudaGraph_t graph = nullptr;
-  cudaGraphExec_t graph_exec = nullptr;
-  int graph_nodes = 0;
+  // task lists of one stage: everything (single GPU), or this rank's panels [0] and the shared
+  // separator panels [1] (domain decomposition)
+  struct TaskSet {
+    Supernodal::Lists L;   // host copy: level pointers and launch geometry
+    Buf<Task> ff, fa, fb, ss, sa, sb;
+  } sets[2];
+  // [0]: the whole iteration (single GPU) or the local stage; [1]: the shared stage
+  cudaGraph_t graph[2] = {nullptr, nullptr};
+  cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};
+  int graph_nodes[2] = {0, 0};
   int lin_blocks = 0;
   int batch = 1;  // problem instances sharing this structure
   Buf<int> colbase, tbl_off, tbl;
   Buf<PanelDesc> pn_desc;
   Buf<SuperDesc> sn_desc;
-  Buf<Task> ff, fa, fb, ss, sa, sb;
   Buf<double> diag_scratch;
   Buf<double> Y;
   Buf<double> many_u, many_x;  // substitution vectors of the marginals (u / x never move)
   // domain decomposition
   DDParams D;
-  Buf<int> owner, xfinal_ptr, xfinal_cols;
+  Buf<int> owner;
   Buf<double> pose_x;
   long long exch_first = 0, exch_count = 0;  // doubles, relative to M
-  int dd_iter = 0;
 };
 
 int dev_create(DeviceSolver** out, int device, void* stream, std::string* err) {
@@ -923,7 +907,7 @@ int dev_create(DeviceSolver** out, int device, void* stream, std::string* err) {
     for (size_t i = 0; i < sizeof(warp_kernels) / sizeof(warp_kernels[0]) && e == cudaSuccess; ++i)
       e = cudaFuncSetAttribute(warp_kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, warp_bytes);
   }
-  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gn_dd_local, kThreads, 0);
+  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chi2_only, kThreads, 0);
   if (e == cudaSuccess)
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, solve_many, kThreads, 0);
   if (e == cudaSuccess) {
@@ -959,7 +943,7 @@ void dev_destroy(DeviceSolver* d) {
   if (d->stream) cudaStreamSynchronize(d->stream);
   Buf<int>* ib[] = {&d->edge_i, &d->edge_j, &d->vpos, &d->inc_ptr, &d->ff_edges, &d->col_ptr,
                     &d->row_idx, &d->col_of, &d->row_ptr, &d->row_pos, &d->level_ptr,
-                    &d->level_cols, &d->phase_ptr, &d->perm_vertex, &d->status, &d->scratch_i};
+                    &d->level_cols, &d->perm_vertex, &d->status, &d->scratch_i};
   for (size_t i = 0; i < sizeof(ib) / sizeof(ib[0]); ++i) ib[i]->release();
   Buf<double>* db[] = {&d->poses, &d->meas, &d->info6, &d->M, &d->Dinv, &d->rhs, &d->u, &d->x,
                        &d->chi2_partial, &d->chi2_out, &d->many_rhs, &d->scratch_d};
@@ -968,22 +952,26 @@ void dev_destroy(DeviceSolver* d) {
   d->pn_desc.release();
   d->sn_desc.release();
   for (size_t i = 0; i < sizeof(sb) / sizeof(sb[0]); ++i) sb[i]->release();
-  Buf<Task>* tb[] = {&d->ff, &d->fa, &d->fb, &d->ss, &d->sa, &d->sb};
-  for (size_t i = 0; i < sizeof(tb) / sizeof(tb[0]); ++i) tb[i]->release();
+  for (int k = 0; k < 2; ++k) {
+    Buf<Task>* tb[] = {&d->sets[k].ff, &d->sets[k].fa, &d->sets[k].fb,
+                       &d->sets[k].ss, &d->sets[k].sa, &d->sets[k].sb};
+    for (size_t i = 0; i < sizeof(tb) / sizeof(tb[0]); ++i) tb[i]->release();
+  }
   d->diag_scratch.release();
   d->Y.release();
   d->many_u.release();
   d->many_x.release();
-  if (d->graph_exec) cudaGraphExecDestroy(d->graph_exec);
-  if (d->graph) cudaGraphDestroy(d->graph);
+  for (int k = 0; k < 2; ++k) {
+    if (d->graph_exec[k]) cudaGraphExecDestroy(d->graph_exec[k]);
+    if (d->graph[k]) cudaGraphDestroy(d->graph[k]);
+    d->graph_exec[k] = nullptr;
+    d->graph[k] = nullptr;
+  }
   d->inc.release();
-  d->ops.release();
   d->fwd_ops.release();
   d->fwd_ptr.release();
   d->stamps.release();
   d->owner.release();
-  d->xfinal_ptr.release();
-  d->xfinal_cols.release();
   d->pose_x.release();
   if (d->ev_fork) cudaEventDestroy(d->ev_fork);
   if (d->ev_join) cudaEventDestroy(d->ev_join);
@@ -1015,8 +1003,6 @@ int dev_set_structure(DeviceSolver* d, const Symbolic& S, const GraphTables& G, 
   PGO_CUDA(d->row_pos.upload(S.row_pos, s));
   PGO_CUDA(d->level_ptr.upload(S.level_ptr, s));
   PGO_CUDA(d->level_cols.upload(S.level_cols, s));
-  PGO_CUDA(d->phase_ptr.upload(S.phase_ptr, s));
-  PGO_CUDA(d->ops.upload(S.ops, s));
   PGO_CUDA(d->fwd_ops.upload(S.fwd_ops, s));
   PGO_CUDA(d->fwd_ptr.upload(S.fwd_ptr, s));
   const Supernodal& N = S.sn;
@@ -1025,12 +1011,17 @@ int dev_set_structure(DeviceSolver* d, const Symbolic& S, const GraphTables& G, 
   PGO_CUDA(d->colbase.upload(N.colbase, s));
   PGO_CUDA(d->tbl_off.upload(N.tbl_off, s));
   PGO_CUDA(d->tbl.upload(N.tbl, s));
-  PGO_CUDA(d->ff.upload(N.ff, s));
-  PGO_CUDA(d->fa.upload(N.fa, s));
-  PGO_CUDA(d->fb.upload(N.fb, s));
-  PGO_CUDA(d->ss.upload(N.ss, s));
-  PGO_CUDA(d->sa.upload(N.sa, s));
-  PGO_CUDA(d->sb.upload(N.sb, s));
+  for (int k = 0; k < 2; ++k) {
+    // single GPU: one set with everything; domain decomposition: own panels, then shared panels
+    DeviceSolver::TaskSet& ts = d->sets[k];
+    ts.L = N.lists(S.world == 1 ? (k == 0 ? Supernodal::kAllOwners : -3) : (k == 0 ? G.rank : -1));
+    PGO_CUDA(ts.ff.upload(ts.L.ff, s));
+    PGO_CUDA(ts.fa.upload(ts.L.fa, s));
+    PGO_CUDA(ts.fb.upload(ts.L.fb, s));
+    PGO_CUDA(ts.ss.upload(ts.L.ss, s));
+    PGO_CUDA(ts.sa.upload(ts.L.sa, s));
+    PGO_CUDA(ts.sb.upload(ts.L.sb, s));
+  }
   const size_t scratch_stride = 9 * static_cast<size_t>(N.scratch_blocks) + 9;
   PGO_CUDA(d->diag_scratch.reserve(static_cast<size_t>(d->batch) * scratch_stride));
   std::vector<int> perm_vertex(S.n);
@@ -1045,10 +1036,8 @@ int dev_set_structure(DeviceSolver* d, const Symbolic& S, const GraphTables& G, 
   // per-instance stride of the factor storage: a multiple of 32 doubles
   const size_t m_stride = (9 * static_cast<size_t>(S.nnzb) + 3 * n_shared + 8 + 31) / 32 * 32;
   PGO_CUDA(d->M.reserve(B * m_stride));
-  PGO_CUDA(d->Y.reserve(S.world == 1 ? B * m_stride : 1));
+  PGO_CUDA(d->Y.reserve(B * m_stride));
   PGO_CUDA(d->owner.upload(S.owner, s));
-  PGO_CUDA(d->xfinal_ptr.upload(S.xfinal_ptr, s));
-  PGO_CUDA(d->xfinal_cols.upload(S.xfinal_cols, s));
   PGO_CUDA(d->pose_x.reserve(3 * static_cast<size_t>(G.n_vertices)));
   PGO_CUDA(d->Dinv.reserve(B * 9 * static_cast<size_t>(S.n)));
   PGO_CUDA(d->rhs.reserve(B * 3 * static_cast<size_t>(S.n)));
@@ -1078,8 +1067,6 @@ int dev_set_structure(DeviceSolver* d, const Symbolic& S, const GraphTables& G, 
   P.row_pos = d->row_pos.p;
   P.level_ptr = d->level_ptr.p;
   P.level_cols = d->level_cols.p;
-  P.phase_ptr = d->phase_ptr.p;
-  P.ops = d->ops.p;
   P.fwd_ptr = d->fwd_ptr.p;
   P.fwd_ops = d->fwd_ops.p;
   P.perm_vertex = d->perm_vertex.p;
@@ -1111,7 +1098,6 @@ int dev_set_structure(DeviceSolver* d, const Symbolic& S, const GraphTables& G, 
   V.s_Dinv = 9LL * S.n;
   V.s_vec = 3LL * S.n;
   V.s_scratch = static_cast<long long>(scratch_stride);
-  d->L = N.lists();
   d->lin_blocks = std::max(1, std::min(4 * d->sm_count, (S.n + kThreads - 1) / kThreads));
   PGO_CUDA(d->chi2_out.reserve(B * kMaxItersPerCall));
   PGO_CUDA(d->chi2_partial.reserve(std::max(B * d->lin_blocks, static_cast<size_t>(d->grid))));
@@ -1127,24 +1113,21 @@ int dev_set_structure(DeviceSolver* d, const Symbolic& S, const GraphTables& G, 
   P.s_vec = V.s_vec;
   P.s_partial = d->lin_blocks;
   P.s_chi2 = kMaxItersPerCall;
-  if (d->graph_exec) cudaGraphExecDestroy(d->graph_exec);
-  if (d->graph) cudaGraphDestroy(d->graph);
-  d->graph_exec = nullptr;
-  d->graph = nullptr;
+  for (int k = 0; k < 2; ++k) {
+    if (d->graph_exec[k]) cudaGraphExecDestroy(d->graph_exec[k]);
+    if (d->graph[k]) cudaGraphDestroy(d->graph[k]);
+    d->graph_exec[k] = nullptr;
+    d->graph[k] = nullptr;
+  }
   DDParams& D = d->D;
   D.owner = d->owner.p;
   D.rank = G.rank;
   D.world = S.world;
   D.first_shared = S.first_shared;
-  D.local_levels = S.local_levels;
-  D.shared_min_level = S.shared_min_level;
-  D.xfinal_ptr = d->xfinal_ptr.p;
-  D.xfinal_cols = d->xfinal_cols.p;
   D.tail = d->M.p + 9 * static_cast<size_t>(S.nnzb);
   D.pose_x = d->pose_x.p;
   d->exch_first = 9LL * (S.n > S.first_shared ? S.col_ptr[S.first_shared] : S.nnzb);
   d->exch_count = 9LL * S.nnzb + 3LL * static_cast<long long>(n_shared) + 2 - d->exch_first;
-  d->dd_iter = 0;
   d->have_structure = true;
   return PGO_OK;
 }
@@ -1222,26 +1205,13 @@ int dev_get_poses(DeviceSolver* d, int inst, double* poses, std::string* err) {
   return PGO_OK;
 }
 
-// Records one Gauss-Newton iteration on the solver's stream (captured into a graph by the caller).
-static int enqueue_iteration(DeviceSolver* d, std::string* err) {
+// ---- recording the phases of an iteration on the solver's stream (captured into CUDA graphs) -----
+// Factorisation + forward substitution of one task set, bottom-up over the panel levels.
+static int enqueue_factor(DeviceSolver* d, const DeviceSolver::TaskSet& ts, int* nodes, std::string* err) {
   cudaStream_t st = d->stream;
-  Params P = d->P;
-  P.chi2_out = d->chi2_out.p;
   const SNView V = d->V;
-  const Supernodal::Lists& L = d->L;
-  int nodes = 0;
-  gn_stamp<<<1, 1, 0, st>>>(d->stamps.p, 0);
-  // zero the factor storage (fill positions must start at 0) and the backward accumulators
+  const Supernodal::Lists& L = ts.L;
   const int B = d->batch;
-  PGO_CUDA(cudaMemsetAsync(P.M, 0, sizeof(double) * static_cast<size_t>(P.s_M) * B, st));
-  PGO_CUDA(cudaMemsetAsync(P.x, 0, sizeof(double) * static_cast<size_t>(P.s_vec) * B, st));
-  gn_linearise<<<dim3(d->lin_blocks, B), kThreads, 0, st>>>(P);
-  gn_chi2<<<dim3(1, B), 256, 0, st>>>(P, d->lin_blocks);
-  gn_stamp<<<1, 1, 0, st>>>(d->stamps.p, 1);
-  nodes += 6;
-  const Task* fa = d->fa.p;
-  const Task* ff = d->ff.p;
-  const Task* fb = d->fb.p;
   for (int l = 0; l < L.n_plevels; ++l) {
     const int n_fa = L.fa_ptr[l + 1] - L.fa_ptr[l], n_ff = L.ff_ptr[l + 1] - L.ff_ptr[l],
               n_fb = L.fb_ptr[l + 1] - L.fb_ptr[l];
@@ -1255,28 +1225,33 @@ static int enqueue_iteration(DeviceSolver* d, std::string* err) {
     }
     if (n_ff) {
       sn_k_fused<<<dim3((n_ff + kWarpsPerCta - 1) / kWarpsPerCta, B), 32 * kWarpsPerCta,
-                   sizeof(double) * kWarpSmemDoubles * kWarpsPerCta, side>>>(V, ff + L.ff_ptr[l], n_ff);
-      ++nodes;
+                   sizeof(double) * kWarpSmemDoubles * kWarpsPerCta, side>>>(V, ts.ff.p + L.ff_ptr[l], n_ff);
+      ++*nodes;
     }
     if (n_fa) {
-      sn_k_factor<<<dim3(n_fa, B), kCtaThreads, sizeof(double) * L.fa_smem[l], st>>>(V, fa + L.fa_ptr[l]);
-      ++nodes;
+      sn_k_factor<<<dim3(n_fa, B), kCtaThreads, sizeof(double) * L.fa_smem[l], st>>>(V, ts.fa.p + L.fa_ptr[l]);
+      ++*nodes;
     }
     if (side != st) {
       PGO_CUDA(cudaEventRecord(d->ev_join, side));
       PGO_CUDA(cudaStreamWaitEvent(st, d->ev_join, 0));
     }
     if (n_fb) {
-      sn_k_update<<<dim3(n_fb, B), kCtaThreads, sizeof(double) * L.fb_smem[l], st>>>(V, fb + L.fb_ptr[l]);
-      ++nodes;
+      sn_k_update<<<dim3(n_fb, B), kCtaThreads, sizeof(double) * L.fb_smem[l], st>>>(V, ts.fb.p + L.fb_ptr[l]);
+      ++*nodes;
     }
   }
-  gn_stamp<<<1, 1, 0, st>>>(d->stamps.p, 2);
-  const Task* ss = d->ss.p;
-  const Task* sa = d->sa.p;
-  const Task* sb = d->sb.p;
+  PGO_CUDA(cudaGetLastError());
+  return PGO_OK;
+}
+
+// Backward substitution of one task set, top-down over the supernode levels.
+static int enqueue_backward(DeviceSolver* d, const DeviceSolver::TaskSet& ts, int* nodes, std::string* err) {
+  cudaStream_t st = d->stream;
+  const SNView V = d->V;
+  const Supernodal::Lists& L = ts.L;
+  const int B = d->batch;
   const size_t warp_bytes = sizeof(double) * kWarpSmemDoubles * kWarpsPerCta;
-  gn_stamp<<<1, 1, 0, st>>>(d->stamps.p, 3);
   for (int l = L.n_slevels - 1; l >= 0; --l) {
     const int n_sa = L.sa_ptr[l + 1] - L.sa_ptr[l], n_ss = L.ss_ptr[l + 1] - L.ss_ptr[l],
               n_sb = L.sb_ptr[l + 1] - L.sb_ptr[l];
@@ -1290,40 +1265,88 @@ static int enqueue_iteration(DeviceSolver* d, std::string* err) {
     }
     if (n_ss) {
       sn_k_bwd_small<<<dim3((n_ss + kWarpsPerCta - 1) / kWarpsPerCta, B), 32 * kWarpsPerCta, warp_bytes, side>>>(
-          V, ss + L.ss_ptr[l], n_ss);
-      ++nodes;
+          V, ts.ss.p + L.ss_ptr[l], n_ss);
+      ++*nodes;
     }
     if (n_sb) {
       sn_k_bwd_rows<<<dim3((n_sb + kWarpsPerCta - 1) / kWarpsPerCta, B), 32 * kWarpsPerCta, 0, st>>>(
-          V, sb + L.sb_ptr[l], n_sb);
-      ++nodes;
+          V, ts.sb.p + L.sb_ptr[l], n_sb);
+      ++*nodes;
     }
     if (n_sa) {
-      sn_k_bwd_tri<<<dim3(n_sa, B), kCtaThreads, sizeof(double) * L.sa_smem[l], st>>>(V, sa + L.sa_ptr[l]);
-      ++nodes;
+      sn_k_bwd_tri<<<dim3(n_sa, B), kCtaThreads, sizeof(double) * L.sa_smem[l], st>>>(V, ts.sa.p + L.sa_ptr[l]);
+      ++*nodes;
     }
     if (side != st) {
       PGO_CUDA(cudaEventRecord(d->ev_join, side));
       PGO_CUDA(cudaStreamWaitEvent(st, d->ev_join, 0));
     }
   }
-  gn_stamp<<<1, 1, 0, st>>>(d->stamps.p, 4);
-  gn_update<<<dim3((P.n + 255) / 256, B), 256, 0, st>>>(P);
-  gn_count_iteration<<<1, B, 0, st>>>(P);
-  gn_stamp<<<1, 1, 0, st>>>(d->stamps.p, 5);
-  nodes += 6;
-  d->graph_nodes = nodes;
   PGO_CUDA(cudaGetLastError());
   return PGO_OK;
 }
 
-static int build_iteration_graph(DeviceSolver* d, std::string* err) {
-  if (d->graph_exec) cudaGraphExecDestroy(d->graph_exec);
-  if (d->graph) cudaGraphDestroy(d->graph);
-  d->graph_exec = nullptr;
-  d->graph = nullptr;
+// stage 0: the whole iteration (single GPU) or the local stage of the domain decomposition;
+// stage 1: the shared stage (after the all-reduce)
+static int enqueue_stage(DeviceSolver* d, int stage, std::string* err) {
+  cudaStream_t st = d->stream;
+  Params P = d->P;
+  P.chi2_out = d->chi2_out.p;
+  const int B = d->batch;
+  const bool dd = d->D.world > 1;
+  int nodes = 0, rc = PGO_OK;
+  if (stage == 0) {
+    gn_stamp<<<1, 1, 0, st>>>(d->stamps.p, 0);
+    // zero the factor storage (fill positions must start at 0; with a domain decomposition also
+    // the exchange tail behind it) and the backward accumulators
+    PGO_CUDA(cudaMemsetAsync(P.M, 0, sizeof(double) * static_cast<size_t>(P.s_M) * B, st));
+    PGO_CUDA(cudaMemsetAsync(P.x, 0, sizeof(double) * static_cast<size_t>(P.s_vec) * B, st));
+    if (dd) gn_dd_linearise<<<d->lin_blocks, kThreads, 0, st>>>(P, d->D);
+    else gn_linearise<<<dim3(d->lin_blocks, B), kThreads, 0, st>>>(P);
+    if (!dd) gn_chi2<<<dim3(1, B), 256, 0, st>>>(P, d->lin_blocks);
+    gn_stamp<<<1, 1, 0, st>>>(d->stamps.p, 1);
+    nodes += 6;
+    rc = enqueue_factor(d, d->sets[0], &nodes, err);
+    if (rc != PGO_OK) return rc;
+    if (dd) {
+      gn_dd_pack<<<1, 256, 0, st>>>(P, d->D, d->lin_blocks);
+      ++nodes;
+    }
+    gn_stamp<<<1, 1, 0, st>>>(d->stamps.p, 2);
+  }
+  if (stage == 1 || !dd) {
+    if (dd) {
+      gn_dd_unpack<<<1, 256, 0, st>>>(P, d->D);
+      ++nodes;
+      rc = enqueue_factor(d, d->sets[1], &nodes, err);
+      if (rc != PGO_OK) return rc;
+    }
+    gn_stamp<<<1, 1, 0, st>>>(d->stamps.p, 3);
+    if (dd) {
+      rc = enqueue_backward(d, d->sets[1], &nodes, err);
+      if (rc != PGO_OK) return rc;
+    }
+    rc = enqueue_backward(d, d->sets[0], &nodes, err);
+    if (rc != PGO_OK) return rc;
+    gn_stamp<<<1, 1, 0, st>>>(d->stamps.p, 4);
+    if (dd) gn_dd_update<<<(P.n + 255) / 256, 256, 0, st>>>(P, d->D);
+    else gn_update<<<dim3((P.n + 255) / 256, B), 256, 0, st>>>(P);
+    gn_count_iteration<<<1, B, 0, st>>>(P);
+    gn_stamp<<<1, 1, 0, st>>>(d->stamps.p, 5);
+    nodes += 6;
+  }
+  d->graph_nodes[stage] = nodes;
+  PGO_CUDA(cudaGetLastError());
+  return PGO_OK;
+}
+
+static int build_stage_graph(DeviceSolver* d, int stage, std::string* err) {
+  if (d->graph_exec[stage]) cudaGraphExecDestroy(d->graph_exec[stage]);
+  if (d->graph[stage]) cudaGraphDestroy(d->graph[stage]);
+  d->graph_exec[stage] = nullptr;
+  d->graph[stage] = nullptr;
   PGO_CUDA(cudaStreamBeginCapture(d->stream, cudaStreamCaptureModeThreadLocal));
-  const int rc = enqueue_iteration(d, err);
+  const int rc = enqueue_stage(d, stage, err);
   cudaGraph_t g = nullptr;
   const cudaError_t e = cudaStreamEndCapture(d->stream, &g);
   if (rc != PGO_OK) {
@@ -1331,8 +1354,8 @@ static int build_iteration_graph(DeviceSolver* d, std::string* err) {
     return rc;
   }
   PGO_CUDA(e);
-  d->graph = g;
-  PGO_CUDA(cudaGraphInstantiate(&d->graph_exec, d->graph, 0));
+  d->graph[stage] = g;
+  PGO_CUDA(cudaGraphInstantiate(&d->graph_exec[stage], d->graph[stage], 0));
   return PGO_OK;
 }
 
@@ -1352,8 +1375,8 @@ int dev_iterate(DeviceSolver* d, int n_iters, double* chi2_out, int* iters_done,
     if (err) *err = "this solver was analysed for a domain decomposition: use the pgo_dd_* calls";
     return PGO_ERR_ARG;
   }
-  if (!d->graph_exec) {
-    const int rc = build_iteration_graph(d, err);
+  if (!d->graph_exec[0]) {
+    const int rc = build_stage_graph(d, 0, err);
     if (rc != PGO_OK) return rc;
   }
   std::vector<int> status(4 * static_cast<size_t>(B), 0);
@@ -1364,8 +1387,8 @@ int dev_iterate(DeviceSolver* d, int n_iters, double* chi2_out, int* iters_done,
     const int chunk = std::min(kMaxItersPerCall, n_iters - first);
     PGO_CUDA(cudaMemsetAsync(d->status.p, 0, 4 * sizeof(int) * B, d->stream));
     PGO_CUDA(cudaMemsetAsync(d->chi2_out.p, 0, sizeof(double) * B * kMaxItersPerCall, d->stream));
-    for (int it = 0; it < chunk; ++it) PGO_CUDA(cudaGraphLaunch(d->graph_exec, d->stream));
-    d->launches += static_cast<uint64_t>(chunk) * d->graph_nodes;
+    for (int it = 0; it < chunk; ++it) PGO_CUDA(cudaGraphLaunch(d->graph_exec[0], d->stream));
+    d->launches += static_cast<uint64_t>(chunk) * d->graph_nodes[0];
     if (first + chunk >= n_iters) PGO_CUDA(cudaEventRecord(d->ev1, d->stream));
     PGO_CUDA(cudaMemcpyAsync(status.data(), d->status.p, 4 * sizeof(int) * B, cudaMemcpyDeviceToHost,
                              d->stream));
@@ -1404,40 +1427,33 @@ int dev_dd_begin(DeviceSolver* d, int n_iters, std::string* err) {
   PGO_CUDA(d->chi2_out.reserve(std::max(n_iters, kMaxItersPerCall)));
   PGO_CUDA(cudaMemsetAsync(d->status.p, 0, 4 * sizeof(int), d->stream));
   PGO_CUDA(cudaMemsetAsync(d->chi2_out.p, 0, std::max(n_iters, 1) * sizeof(double), d->stream));
-  d->dd_iter = 0;
   PGO_CUDA(cudaEventRecord(d->ev0, d->stream));
   return PGO_OK;
 }
 
-int dev_dd_local(DeviceSolver* d, std::string* err) {
+static int dd_launch_stage(DeviceSolver* d, int stage, std::string* err) {
   PGO_CUDA(cudaSetDevice(d->device));
-  Params P = d->P;
-  P.chi2_out = d->chi2_out.p;
-  DDParams D = d->D;
-  void* args[] = {&P, &D};
-  PGO_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(gn_dd_local), dim3(d->grid),
-                                       dim3(kThreads), args, 0, d->stream));
-  d->launches++;
+  if (d->D.world < 2) {
+    if (err) *err = "not a domain-decomposed solver (pgo_set_partition first)";
+    return PGO_ERR_ARG;
+  }
+  if (!d->graph_exec[stage]) {
+    const int rc = build_stage_graph(d, stage, err);
+    if (rc != PGO_OK) return rc;
+  }
+  PGO_CUDA(cudaGraphLaunch(d->graph_exec[stage], d->stream));
+  d->launches += d->graph_nodes[stage];
   return PGO_OK;
 }
+
+int dev_dd_local(DeviceSolver* d, std::string* err) { return dd_launch_stage(d, 0, err); }
 
 void dev_dd_exchange(DeviceSolver* d, void** ptr, long long* n_doubles) {
   *ptr = d->M.p + d->exch_first;
   *n_doubles = d->exch_count;
 }
 
-int dev_dd_shared(DeviceSolver* d, std::string* err) {
-  PGO_CUDA(cudaSetDevice(d->device));
-  Params P = d->P;
-  P.chi2_out = d->chi2_out.p;
-  DDParams D = d->D;
-  int it = d->dd_iter++;
-  void* args[] = {&P, &D, &it};
-  PGO_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(gn_dd_shared), dim3(d->grid),
-                                       dim3(kThreads), args, 0, d->stream));
-  d->launches++;
-  return PGO_OK;
-}
+int dev_dd_shared(DeviceSolver* d, std::string* err) { return dd_launch_stage(d, 1, err); }
 
 int dev_dd_end(DeviceSolver* d, int n_iters, double* chi2_out, int* iters_done, float* ms,
                std::string* err) {

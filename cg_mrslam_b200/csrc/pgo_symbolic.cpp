@@ -227,85 +227,6 @@ class Dissector {
   int next_id_ = 0;
 };
 
-// Explicit per-block update schedule of the level-by-level factorisation (domain-decomposed path).
-bool build_update_schedule(Symbolic& S, std::string* err) {
-  const int n = S.n;
-  // ---- update schedule --------------------------------------------------------------------------
-  // Phase l applies every update whose source column has level l - 1. Within a phase the updates
-  // are grouped by target block so that one thread group owns each target (no atomics), in a
-  // fixed order (deterministic rounding).
-  int64_t n_ops = 0;
-  for (int p = 0; p < n; ++p) {
-    const int64_t m = S.col_ptr[p + 1] - S.col_ptr[p] - 1;
-    n_ops += m * (m + 1) / 2;
-  }
-  if (n_ops > 0x3FFFFFF0LL || S.nnzb >= kFinalFlag) {
-    if (err) *err = "more than 2^30 block updates: graph too dense for this solver";
-    return false;
-  }
-  S.n_ops = n_ops;
-  S.ops.resize(n_ops);
-  S.phase_ptr.assign(S.n_levels + 1, 0);
-  std::vector<int> count(S.nnzb, 0), touched;
-  std::vector<UpdateOp> raw;
-  int64_t op_cursor = 0;
-  std::vector<char> fin(n, 0);
-  for (int l = 1; l < S.n_levels; ++l) {
-    S.phase_ptr[l] = static_cast<int>(op_cursor);
-    raw.clear();
-    touched.clear();
-    for (int t = S.level_ptr[l - 1]; t < S.level_ptr[l]; ++t) {
-      const int k = S.level_cols[t];
-      const int base = S.col_ptr[k], m = S.col_ptr[k + 1] - base;  // rows base+1 .. base+m-1
-      for (int b = 1; b < m; ++b) {
-        const int c = S.row_idx[base + b];
-        int w = S.col_ptr[c];  // diagonal of column c == row c
-        for (int a = b; a < m; ++a) {
-          const int r = S.row_idx[base + a];
-          while (S.row_idx[w] != r) ++w;  // struct(k) rows >= c are a subset of struct(c) + {c}
-          UpdateOp x = {w, base + a, base + b};
-          raw.push_back(x);
-          if (count[w]++ == 0) touched.push_back(w);
-        }
-      }
-    }
-    std::sort(touched.begin(), touched.end());
-    // counting sort of the phase's updates by target (stable: generation order within a target)
-    int64_t off = op_cursor;
-    for (size_t i = 0; i < touched.size(); ++i) {
-      const int w = touched[i];
-      const int c = count[w];
-      S.max_run = std::max(S.max_run, c);
-      count[w] = static_cast<int>(off);  // reuse as write cursor
-      off += c;
-    }
-    for (size_t i = 0; i < raw.size(); ++i) {
-      UpdateOp o = raw[i];
-      const int w = o.target;
-      const int col = S.col_of[w];
-      if (S.row_idx[w] == col && S.level[col] == l) {
-        o.target |= kFinalFlag;
-        fin[col] = 1;
-      }
-      S.ops[count[w]++] = o;
-    }
-    for (size_t i = 0; i < touched.size(); ++i) count[touched[i]] = 0;
-    op_cursor = off;
-  }
-  S.phase_ptr[S.n_levels] = static_cast<int>(op_cursor);
-  if (op_cursor != n_ops) {
-    if (err) *err = "internal: update count mismatch";
-    return false;
-  }
-  // every non-leaf column must be finalised by an update of its own phase
-  for (int p = 0; p < n; ++p)
-    if (S.level[p] > 0 && !fin[p]) {
-      if (err) *err = "internal: column without finalising update";
-      return false;
-    }
-  return true;
-}
-
 // Supernodes, panels, scatter tables and task lists of the single-GPU path (pgo_symbolic.h).
 template <typename Key>
 void bucket_tasks(std::vector<std::pair<Key, Task> >& in, int n_levels, std::vector<int>* ptr,
@@ -446,6 +367,7 @@ bool build_supernodal(Symbolic& S, std::string* err) {
     const int sn_id = N.pn_sn[K];
     PanelDesc pd = {c0, w, m, cp[c0], N.pn_meta[K], N.pn_scratch[K], c0 - N.sn_first[sn_id], sn_id};
     N.pn.push_back(pd);
+    N.pn_owner.push_back(S.owner[c0]);
   }
   N.pn_meta[N.n_panels] = static_cast<int>(N.colbase.size());
   bucket_tasks(ff, N.n_plevels, &N.ff_ptr, &N.ff);
@@ -465,6 +387,7 @@ bool build_supernodal(Symbolic& S, std::string* err) {
     N.n_slevels = std::max(N.n_slevels, slevel[s] + 1);
     SuperDesc sd = {c0, W, m, cp[c0], N.sn_pn_ptr[s], N.sn_pn_ptr[s + 1], 0, 0};
     N.sn.push_back(sd);
+    N.sn_owner.push_back(S.owner[c0]);
     if (W <= kSmallWidth) {
       const Task t = {s, 0, m, 0};
       ss.push_back(std::make_pair(slevel[s], t));
@@ -487,35 +410,49 @@ bool build_supernodal(Symbolic& S, std::string* err) {
 
 }  // namespace
 
-Supernodal::Lists Supernodal::lists() const {
+Supernodal::Lists Supernodal::lists(int owner) const {
   Lists L;
   L.n_plevels = n_plevels;
   L.n_slevels = n_slevels;
-  L.ff_ptr = ff_ptr;
-  L.fa_ptr = fa_ptr;
-  L.fb_ptr = fb_ptr;
-  L.ss_ptr = ss_ptr;
-  L.sa_ptr = sa_ptr;
-  L.sb_ptr = sb_ptr;
+  // filter one task list by the owner of its panel / supernode, keeping the level buckets
+  auto filter = [&](const std::vector<int>& ptr, const std::vector<Task>& in, const std::vector<int>& own,
+                    int n_levels, std::vector<int>* out_ptr, std::vector<Task>* out) {
+    out_ptr->assign(n_levels + 1, 0);
+    out->clear();
+    for (int l = 0; l < n_levels; ++l) {
+      for (int i = ptr[l]; i < ptr[l + 1]; ++i)
+        if (owner == kAllOwners || own[in[i].id] == owner) out->push_back(in[i]);
+      (*out_ptr)[l + 1] = static_cast<int>(out->size());
+    }
+  };
+  filter(ff_ptr, ff, pn_owner, n_plevels, &L.ff_ptr, &L.ff);
+  filter(fa_ptr, fa, pn_owner, n_plevels, &L.fa_ptr, &L.fa);
+  filter(fb_ptr, fb, pn_owner, n_plevels, &L.fb_ptr, &L.fb);
+  filter(ss_ptr, ss, sn_owner, n_slevels, &L.ss_ptr, &L.ss);
+  filter(sa_ptr, sa, sn_owner, n_slevels, &L.sa_ptr, &L.sa);
+  filter(sb_ptr, sb, pn_owner, n_slevels, &L.sb_ptr, &L.sb);
   const int pair_doubles = (kPanelWidth * (kPanelWidth + 1) / 2 + 1) / 2;
   L.fa_smem.assign(n_plevels, 0);
   L.fb_smem.assign(n_plevels, 0);
   for (int l = 0; l < n_plevels; ++l) {
-    for (int i = fa_ptr[l]; i < fa_ptr[l + 1]; ++i) {
-      const int w = pn[fa[i].id].w;
+    for (int i = L.fa_ptr[l]; i < L.fa_ptr[l + 1]; ++i) {
+      const Task& t = L.fa[i];
+      const int w = pn[t.id].w;
       L.fa_smem[l] = std::max(L.fa_smem[l], w * w * 9 + w * 9 + pair_doubles + 3 * w +
-                                                3 * w * (3 * (fa[i].r1 - fa[i].r0) + 1));
+                                                3 * w * (3 * (t.r1 - t.r0) + 1));
     }
-    for (int i = fb_ptr[l]; i < fb_ptr[l + 1]; ++i) {
-      const int multi = (sn[pn[fb[i].id].sn].pn_end - sn[pn[fb[i].id].sn].pn_begin) > 1 && !((fb[i].aux >> 28) & 1);
-      const int w = multi ? kPanelWidth : pn[fb[i].id].w;
-      L.fb_smem[l] = std::max(L.fb_smem[l], sn_tile_doubles(w, fb[i].aux & 0xFF, (fb[i].aux >> 8) & 0xFF));
+    for (int i = L.fb_ptr[l]; i < L.fb_ptr[l + 1]; ++i) {
+      const Task& t = L.fb[i];
+      const SuperDesc& sd = sn[pn[t.id].sn];
+      const bool multi = sd.pn_end - sd.pn_begin > 1 && !((t.aux >> 28) & 1);
+      const int w = multi ? kPanelWidth : pn[t.id].w;
+      L.fb_smem[l] = std::max(L.fb_smem[l], sn_tile_doubles(w, t.aux & 0xFF, (t.aux >> 8) & 0xFF));
     }
   }
   L.sa_smem.assign(n_slevels, 0);
   for (int l = 0; l < n_slevels; ++l)
-    for (int i = sa_ptr[l]; i < sa_ptr[l + 1]; ++i)
-      L.sa_smem[l] = std::max(L.sa_smem[l], 6 * sn[sa[i].id].W + kPanelWidth * kPanelWidth * 9 +
+    for (int i = L.sa_ptr[l]; i < L.sa_ptr[l + 1]; ++i)
+      L.sa_smem[l] = std::max(L.sa_smem[l], 6 * sn[L.sa[i].id].W + kPanelWidth * kPanelWidth * 9 +
                                                 kPanelWidth * 9 + 3 * 256);
   return L;
 }
@@ -713,8 +650,7 @@ bool analyse(int n, const std::vector<std::pair<int, int> >& edges, int ordering
       if (S.owner[p] < 0 && !has_shared_child[p]) S.xfinal_cols[cur[S.level[p]]++] = p;
   }
 
-  if (world > 1 && !build_update_schedule(S, err)) return false;
-  if (world == 1) S.phase_ptr.assign(S.n_levels + 1, 0);
+  S.phase_ptr.assign(S.n_levels + 1, 0);
   if (!build_supernodal(S, err)) return false;
   // ---- forward-substitution schedule ------------------------------------------------------------
   {

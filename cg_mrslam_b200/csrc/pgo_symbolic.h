@@ -91,6 +91,7 @@ struct Supernodal {
   std::vector<int> pn_sn;      // n_panels
   std::vector<PanelDesc> pn;   // n_panels
   std::vector<SuperDesc> sn;   // n_super
+  std::vector<int> pn_owner, sn_owner;  // rank that eliminates it, -1 = shared separator (world > 1)
   // scatter tables of the outer-product update. For below-row b of panel K (a block column r_b of
   // some later panel q) and below-row a >= b:  position of M(r_a, r_b) =
   // colbase[pn_meta[K] + b] + tbl[tbl_off[pn_meta[K] + b] + a].
@@ -110,13 +111,17 @@ struct Supernodal {
   std::vector<int> ss_ptr, sa_ptr, sb_ptr;  // n_slevels + 1
   std::vector<Task> ss, sa, sb;
   // what the host needs to launch the phases: level pointers and per-level shared-memory needs
+  // what one stage of an iteration launches: the tasks of the panels / supernodes of one owner
+  // (kAllOwners: everything, the single-GPU case), by level, with per-level shared-memory needs
   struct Lists {
     int n_plevels = 0, n_slevels = 0;
     std::vector<int> ff_ptr, fa_ptr, fb_ptr, ss_ptr, sa_ptr, sb_ptr;
+    std::vector<Task> ff, fa, fb, ss, sa, sb;
     std::vector<int> fa_smem, fb_smem;  // doubles of shared memory of the largest task per level
     std::vector<int> sa_smem;
   };
-  Lists lists() const;
+  static const int kAllOwners = -2;
+  Lists lists(int owner) const;
   int64_t update_blocks = 0;   // target blocks touched by all outer products (atomic 3x3 adds)
   double flops = 0.0;          // of one numeric factorisation
 };
