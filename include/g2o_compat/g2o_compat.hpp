@@ -17,7 +17,9 @@
 #include <fstream>
 #include <iomanip>
 #include <iostream>
+#include <limits>
 #include <map>
+#include <queue>
 #include <memory>
 #include <set>
 #include <sstream>
@@ -329,6 +331,68 @@ struct OptimizationAlgorithmGaussNewton : public OptimizationAlgorithm {
   explicit OptimizationAlgorithmGaussNewton(S* p) {
     delete p;
   }
+};
+
+// ---- HyperDijkstra --------------------------------------------------------------------------------
+// g2o::HyperDijkstra as the reference uses it (vertices_finder.cpp:37-41,46-50,87-93):
+// uniform-cost search from one vertex over ALL edges incident to a vertex (any level, both
+// directions), edge cost from a user functor (max() = impassable), a vertex is reached when the new
+// distance is below its old one and below maxDistance; visited() = every vertex reached, the source
+// included. g2o (recalled) compares with a conditioner, d_new + 1e-3 < d_old, kept as its default
+// parameter. Ties in the queue are broken by vertex id, so the result is deterministic (g2o's own
+// order depends on pointer values; the result SET does not).
+class HyperDijkstra {
+ public:
+  struct CostFunction {
+    virtual double operator()(HyperGraph::Edge* e, HyperGraph::Vertex* from, HyperGraph::Vertex* to) = 0;
+    virtual ~CostFunction() {}
+  };
+  explicit HyperDijkstra(HyperGraph* g) : graph_(g) {}
+  HyperGraph::VertexSet& visited() { return visited_; }
+  double distance(HyperGraph::Vertex* v) const {
+    std::map<HyperGraph::Vertex*, double>::const_iterator it = dist_.find(v);
+    return it == dist_.end() ? std::numeric_limits<double>::max() : it->second;
+  }
+  void shortestPaths(HyperGraph::Vertex* source, CostFunction* cost,
+                     double maxDistance = std::numeric_limits<double>::max(),
+                     double comparisonConditioner = 1e-3, bool directed = false,
+                     double maxEdgeCost = std::numeric_limits<double>::max()) {
+    visited_.clear();
+    dist_.clear();
+    typedef std::pair<double, std::pair<int, HyperGraph::Vertex*> > Entry;  // (distance, id, vertex)
+    std::priority_queue<Entry, std::vector<Entry>, std::greater<Entry> > queue;
+    dist_[source] = 0.0;
+    visited_.insert(source);
+    queue.push(Entry(0.0, std::make_pair(source->id(), source)));
+    while (!queue.empty()) {
+      const Entry top = queue.top();
+      queue.pop();
+      HyperGraph::Vertex* u = top.second.second;
+      if (top.first > dist_[u]) continue;  // stale entry
+      for (HyperGraph::EdgeSet::const_iterator it = u->edges().begin(); it != u->edges().end(); ++it) {
+        HyperGraph::Edge* e = *it;
+        if (directed && e->vertex(0) != u) continue;
+        for (size_t k = 0; k < e->vertices().size(); ++k) {
+          HyperGraph::Vertex* z = e->vertex(k);
+          if (!z || z == u) continue;
+          const double c = (*cost)(e, u, z);
+          if (c == std::numeric_limits<double>::max() || c > maxEdgeCost) continue;
+          const double nd = top.first + c;
+          if (nd + comparisonConditioner < distance(z) && nd < maxDistance) {
+            dist_[z] = nd;
+            visited_.insert(z);
+            queue.push(Entry(nd, std::make_pair(z->id(), z)));
+          }
+        }
+      }
+    }
+    (void)graph_;
+  }
+
+ private:
+  HyperGraph* graph_;
+  HyperGraph::VertexSet visited_;
+  std::map<HyperGraph::Vertex*, double> dist_;
 };
 
 // ---- SparseOptimizer ------------------------------------------------------------------------------

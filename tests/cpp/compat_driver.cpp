@@ -13,12 +13,19 @@
 //   MARG k id_1 ... id_k                             computeMarginals diagonal blocks
 //   STAR gauge k id_1 ... id_k                       CondensedGraphCreator::compute pattern
 //   SAVE path / LOAD path                            g2o text round trip
+//   FINDSM cur                                       VerticesFinder::findVerticesScanMatching
+//   SETS cur                                         ... + findSetsOfVertices + findClosestVertex
+//   NEIGH cur gap k id_1 ... id_k                    addNeighboringVertices
+//   COVGATE cur k id_1 ... id_k                      checkCovariance (marginals on the GPU)
+//   CLOSURES thr nv id_1..id_nv ne (from to dx dy dth)*ne   LoopClosureChecker::init + check
+//   BUFSIM window n (vertex_id n_edges)*n            ClosureBuffer add / updateList / checkList
 #include <cstdio>
 #include <fstream>
 #include <iostream>
 #include <sstream>
 
 #include "cgm/scan_matcher.hpp"
+#include "cgm/slam_frontend.hpp"
 #include "g2o_compat/g2o_compat.hpp"
 
 using namespace g2o;
@@ -190,6 +197,106 @@ int main(int argc, char** argv) {
         v->pop();
         v->setFixed(was_fixed[q++]);
       }
+    } else if (tag == "FINDSM" || tag == "SETS") {
+      int cur;
+      ss >> cur;
+      VerticesFinder vf(&opt);
+      OptimizableGraph::VertexSet vset;
+      vf.findVerticesScanMatching(opt.vertex(cur), vset);
+      if (tag == "FINDSM") {
+        printf("FINDSM %zu", vset.size());
+        for (HyperGraph::Vertex* v : vset) printf(" %d", v->id());
+        printf("\n");
+      } else {
+        std::set<OptimizableGraph::VertexSet> sets;
+        vf.findSetsOfVertices(vset, sets);
+        printf("SETS %zu\n", sets.size());
+        for (OptimizableGraph::VertexSet g : sets) {
+          printf("G %d %zu", vf.findClosestVertex(g, opt.vertex(cur))->id(), g.size());
+          for (HyperGraph::Vertex* v : g) printf(" %d", v->id());
+          printf("\n");
+        }
+      }
+    } else if (tag == "NEIGH" || tag == "COVGATE") {
+      int cur, gap = 0, k;
+      ss >> cur;
+      if (tag == "NEIGH") ss >> gap;
+      ss >> k;
+      OptimizableGraph::VertexSet vset;
+      for (int i = 0; i < k; ++i) {
+        int id;
+        ss >> id;
+        vset.insert(opt.vertex(id));
+      }
+      VertexSE2* last = static_cast<VertexSE2*>(opt.vertex(cur));
+      if (tag == "NEIGH") cgm::addNeighboringVertices(&opt, last, vset, gap);
+      else cgm::checkCovariance(&opt, last, vset);
+      printf("%s %zu", tag.c_str(), vset.size());
+      for (HyperGraph::Vertex* v : vset) printf(" %d", v->id());
+      printf("\n");
+    } else if (tag == "CLOSURES") {
+      double thr;
+      int nv, ne;
+      ss >> thr >> nv;
+      OptimizableGraph::VertexIDMap window;
+      for (int i = 0; i < nv; ++i) {
+        int id;
+        ss >> id;
+        window[id] = opt.vertex(id);
+      }
+      ss >> ne;
+      OptimizableGraph::EdgeSet cand;
+      std::vector<EdgeSE2*> order;
+      for (int i = 0; i < ne; ++i) {
+        int a, b;
+        double dx, dy, dth;
+        ss >> a >> b >> dx >> dy >> dth;
+        EdgeSE2* e = new EdgeSE2();
+        e->vertices()[0] = opt.vertex(a);
+        e->vertices()[1] = opt.vertex(b);
+        e->setMeasurement(SE2(dx, dy, dth));
+        Eigen::Matrix3d info = Eigen::Matrix3d::Identity();
+        info(0, 0) = info(1, 1) = 1000.0;
+        info(2, 2) = 10000.0;  // _SMinf, graph_slam.cpp:75-76
+        e->setInformation(info);
+        e->setSerial(2000000 + i);
+        cand.insert(e);
+        order.push_back(e);
+      }
+      LoopClosureChecker lcc;
+      lcc.init(window, cand, thr);
+      lcc.check();
+      printf("CLOSURES %d %.17g\n", lcc.inliers(), lcc.chi2());
+      for (EdgeSE2* e : order) printf("C %.17g\n", lcc.closures()[e]);
+      for (EdgeSE2* e : order) delete e;
+    } else if (tag == "BUFSIM") {
+      int window, n;
+      ss >> window >> n;
+      ClosureBuffer buf;
+      std::vector<EdgeSE2*> owned;
+      for (int step = 0; step < n; ++step) {
+        int vid, ne;
+        ss >> vid >> ne;
+        if (ne > 0) {  // GraphSLAM::addClosures: the candidates of this keyframe + the keyframe
+          OptimizableGraph::EdgeSet es;
+          for (int i = 0; i < ne; ++i) {
+            EdgeSE2* e = new EdgeSE2();
+            e->vertices()[0] = opt.vertices().begin()->second;
+            e->vertices()[1] = opt.vertex(vid);
+            e->setSerial(3000000 + static_cast<long long>(owned.size()));
+            owned.push_back(e);
+            es.insert(e);
+          }
+          buf.addEdgeSet(es);
+          buf.addVertex(opt.vertex(vid));
+        }
+        const bool vote = buf.checkList(window);  // GraphSLAM::checkClosures, then updateClosures
+        buf.updateList(window);
+        printf("B %d %zu %zu", vote ? 1 : 0, buf.edgeSet().size(), buf.vertices().size());
+        for (const VertexTime& vt : buf.vertexList()) printf(" %d:%d", vt.v->id(), vt.time);
+        printf("\n");
+      }
+      for (EdgeSE2* e : owned) delete e;
     } else if (tag == "SAVE") {
       std::string path;
       ss >> path;

@@ -182,3 +182,39 @@ def test_cpp_api_matches_oracles(driver, tmp_path, oracle_lib):
     # push/pop around the condensed-graph computation restores the estimates
     second = np.array([[float(x) for x in lines[i].split()[2:]] for i in blocks[len(verts):]])
     assert np.array_equal(first, second)
+
+
+@pytest.mark.gpu
+def test_covariance_gate_matches_oracle(driver, tmp_path):
+    """GraphSLAM::checkCovariance (graph_slam.cpp:311-354) through CovarianceEstimator: the whole
+    graph re-optimised once with the current vertex as the gauge, marginal blocks from the GPU
+    solver, chi2 gate on the xy offset. The surviving candidate ids must equal the oracle's."""
+    from oracle import frontend_oracle as fo
+    g = synth.make_pose_graph(300, 1100, seed=17, box=19.0, init="truth_noisy")
+    n = len(g["poses0"])
+    ids = [20000 + k for k in range(n)]
+    cur = n - 1
+    d = np.hypot(*(g["poses0"][:n - 1, :2] - g["poses0"][cur, :2]).T)
+    cand = sorted(set(np.argsort(d)[:30].tolist()) | set(range(1, n - 1, 23)))   # near ones + far ones
+    path = str(tmp_path / "s.txt")
+    with open(path, "w") as f:
+        for k in range(n):
+            p = g["poses0"][k]
+            f.write("V %d %.17g %.17g %.17g %d 0 0 0 8\n" % (ids[k], p[0], p[1], p[2], 1 if k == 0 else 0))
+        for (a, b), z, w in zip(g["edge_ij"], g["meas"], g["info"]):
+            f.write("E %d %d %.17g %.17g %.17g %s\n" % (ids[a], ids[b], z[0], z[1], z[2],
+                                                      " ".join("%.17g" % x for x in w)))
+        f.write("COVGATE %d %d %s\nPOSES\n" % (ids[cur], len(cand), " ".join(str(ids[k]) for k in cand)))
+    lines, _ = _run(driver, path)
+    got = [int(x) for x in lines[0].split()[2:]]
+    # oracle: gauge = current vertex, spanning-tree guess, one GN iteration, marginals of that H
+    guess = po.initial_guess(g["poses0"], g["edge_ij"], g["meas"], [cur])
+    res = po.gauss_newton(guess, g["edge_ij"], g["meas"], g["info"], [cur], 1)
+    hidx = po.hessian_index(n, [cur])
+    covs = po.marginals(res, hidx, [(k, k) for k in cand])
+    poses = {ids[k]: g["poses0"][k] for k in range(n)}       # the gate uses the LIVE estimates (popState)
+    want = fo.check_covariance(poses, [ids[k] for k in cand], ids[cur], {ids[k]: c for k, c in zip(cand, covs)})
+    assert got == want and 0 < len(want) < len(cand)
+    # GraphManipulator::popState left the estimates untouched
+    after = np.array([[float(x) for x in ln.split()[2:]] for ln in lines if ln.startswith("P ")])
+    assert np.array_equal(after, g["poses0"])
