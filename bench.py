@@ -45,7 +45,7 @@ def parse():
     ap.add_argument("--cpu-pairs", type=int, default=0, help="pairs in the CPU sample (0 = auto)")
     ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 global, 2 tiled")
     ap.add_argument("--no-gn", action="store_true")
-    ap.add_argument("--gn-batch", type=int, default=32, help="graph instances per GPU in the GN arm")
+    ap.add_argument("--gn-batch", type=int, default=64, help="graph instances per GPU in the GN arm")
     return ap.parse_args()
 
 
@@ -293,12 +293,18 @@ def gn_ours(args, local, world, barrier):
                                "truth+noise start, vertex 0 fixed; %d instances per GPU with one "
                                "structure and re-drawn measurements, every kernel of an iteration "
                                "serves all instances" % (st["n_vertices"], st["n_edges"], B),
-                   "batch": B, "factor_blocks": st["factor_blocks"], "levels": st["n_levels"],
+                   "batch": B, "factor_blocks": st["factor_blocks"], "elimination_tree_height": st["n_levels"],
+                   "supernodes": st["n_supernodes"], "panels": st["n_panels"],
+                   "panel_levels": st["n_panel_levels"], "supernode_levels": st["n_supernode_levels"],
                    "analyse_seconds": analyse_s, "stage_ms_last_iter": st["stage_ms"]},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                      "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_kind": pk_kind,
                      "kernel": "iteration graph (sn_k_factor / sn_k_update / sn_k_bwd_* + linearise)",
                      "algorithmic_bytes": nbytes,
+                     "fp64": {"flops_per_iteration": st.get("factor_flops", 0.0),
+                              "achieved_tflops": st.get("factor_flops", 0.0) / (per_iter_ms * 1e-3) / 1e12,
+                              "peak_tflops": 37.1,
+                              "peak_kind": "measured on this part: profiles/r01_ubench_fp64_rate.txt"},
                      "note": "bytes per instance-iteration = 152 E + 120 V + 4 x 72 B x factor blocks "
                              "(SURVEY 8d direct form); the factorisation itself is bound by fp64 "
                              "issue and dependent-level latency, not by HBM"},

@@ -454,6 +454,12 @@ int pgo_get_stats(const pgo_solver* s, pgo_stats* out) {
   out->last_iterate_ms = s->last_ms;
   out->kernel_launches = static_cast<int64_t>(pgo::dev_launches(s->dev));
   for (int k = 0; k < 5; ++k) out->stage_ms[k] = pgo::dev_stage_ms(s->dev)[k];
+  out->factor_flops = s->sym.sn.flops;
+  out->n_supernodes = s->sym.sn.n_super;
+  out->n_panels = s->sym.sn.n_panels;
+  out->n_panel_levels = s->sym.sn.n_plevels;
+  out->n_supernode_levels = s->sym.sn.n_slevels;
+  out->batch = pgo::dev_batch(s->dev);
   return PGO_OK;
 }
 

@@ -189,14 +189,15 @@ PGO_HD void sn_load_diag(const G& g, const SNView& V, int base, int len, int w, 
 
 // In-place block LDL^T of the diagonal part. On return (after a sync):
 //   Dg[i][t], i >= t : final M(c0+i, c0+t);  Dg[s][t], s < t : G(s,t) = Dinv_s M(t,s)^T;  Di[t].
-// pairs: scratch table of w (w + 1) / 2 ints, (i << 8) | t per lower-triangular block.
+// pairs: scratch table of w (w + 1) / 2 ints, (i << 8) | t per lower-triangular block, COLUMN by
+// column, so that the blocks still alive at step s (t > s) are a suffix of the table.
 template <class G>
 PGO_HD void sn_factor_diag(const G& g, const SNView& V, int w, double* Dg, double* Di, int* pairs) {
   const int n_pairs = w * (w + 1) / 2;
   for (int p = g.rank(); p < n_pairs; p += g.size()) {
-    int i = 0;
-    while ((i + 1) * (i + 2) / 2 <= p) ++i;
-    pairs[p] = (i << 8) | (p - i * (i + 1) / 2);
+    int t = 0;
+    while ((t + 1) * w - (t + 1) * t / 2 <= p) ++t;  // column t starts at t w - t (t - 1) / 2
+    pairs[p] = ((t + p - (t * w - t * (t - 1) / 2)) << 8) | t;
   }
   for (int s = 0; s < w; ++s) {
     if (g.rank() == 0) {
@@ -209,9 +210,9 @@ PGO_HD void sn_factor_diag(const G& g, const SNView& V, int w, double* Dg, doubl
     // one pass over the blocks (i, t), i >= t > s: the diagonal ones also publish G(s,t) into the
     // upper part; everybody forms the column of G it needs on the fly
     const double* d = Di + 9 * s;
-    for (int idx = g.rank(); idx < n_pairs * 9; idx += g.size()) {
+    const int first = (s + 1) * w - (s + 1) * s / 2;  // first pair of column s + 1
+    for (int idx = 9 * first + g.rank(); idx < n_pairs * 9; idx += g.size()) {
       const int pr = pairs[idx / 9], i = pr >> 8, t = pr & 255;
-      if (t <= s) continue;
       const int k = idx % 9, r = k / 3, c = k % 3;
       const double* m = Dg + (t * w + s) * 9;  // M(t,s)
       if (i == t)

@@ -20,7 +20,11 @@ class pgo_stats(C.Structure):
                 ("n_levels", C.c_int32), ("factor_blocks", C.c_int64), ("update_ops", C.c_int64),
                 ("hessian_blocks", C.c_int64), ("analyse_seconds", C.c_double),
                 ("last_iterate_ms", C.c_double), ("kernel_launches", C.c_int64),
-                ("stage_ms", C.c_double * 5)]
+                ("stage_ms", C.c_double * 5),
+                ("factor_flops", C.c_double),
+                ("n_supernodes", C.c_int32), ("n_panels", C.c_int32),
+                ("n_panel_levels", C.c_int32), ("n_supernode_levels", C.c_int32),
+                ("batch", C.c_int32)]
 
 
 class SolverError(RuntimeError):

@@ -48,6 +48,9 @@ typedef struct pgo_stats {
   double last_iterate_ms;                /* device time of the last pgo_iterate call             */
   int64_t kernel_launches;               /* kernels launched by this solver so far               */
   double stage_ms[5];                    /* last GN iteration: linearise, factor, forward, backward, update */
+  double factor_flops;                   /* fp64 flops of one numeric factorisation (supernodal count) */
+  int32_t n_supernodes, n_panels, n_panel_levels, n_supernode_levels;
+  int32_t batch;                         /* graph instances held by the solver */
 } pgo_stats;
 
 const char* pgo_last_error(void);
