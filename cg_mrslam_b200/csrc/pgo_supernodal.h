@@ -207,22 +207,23 @@ PGO_HD void sn_factor_diag(const G& g, const SNView& V, int w, double* Dg, doubl
       }
     }
     g.sync();
-    // one pass over the blocks (i, t), i >= t > s: the diagonal ones also publish G(s,t) into the
-    // upper part; everybody forms the column of G it needs on the fly
+    // G(s,t) = Dinv_s M(t,s)^T for t > s, into the upper part
     const double* d = Di + 9 * s;
+    const int rem = w - s - 1;
+    for (int idx = g.rank(); idx < rem * 9; idx += g.size()) {
+      const int t = s + 1 + idx / 9, k = idx % 9, r = k / 3, c = k % 3;
+      const double* m = Dg + (t * w + s) * 9;
+      Dg[(s * w + t) * 9 + k] = d[3 * r] * m[3 * c] + d[3 * r + 1] * m[3 * c + 1] + d[3 * r + 2] * m[3 * c + 2];
+    }
+    g.sync();
+    // trailing update of the blocks (i, t), i >= t > s (a suffix of the pair table)
     const int first = (s + 1) * w - (s + 1) * s / 2;  // first pair of column s + 1
     for (int idx = 9 * first + g.rank(); idx < n_pairs * 9; idx += g.size()) {
       const int pr = pairs[idx / 9], i = pr >> 8, t = pr & 255;
       const int k = idx % 9, r = k / 3, c = k % 3;
-      const double* m = Dg + (t * w + s) * 9;  // M(t,s)
-      if (i == t)
-        Dg[(s * w + t) * 9 + k] =
-            d[3 * r] * m[3 * c] + d[3 * r + 1] * m[3 * c + 1] + d[3 * r + 2] * m[3 * c + 2];
       const double* a = Dg + (i * w + s) * 9;
-      const double g0 = d[0] * m[3 * c] + d[1] * m[3 * c + 1] + d[2] * m[3 * c + 2];
-      const double g1 = d[3] * m[3 * c] + d[4] * m[3 * c + 1] + d[5] * m[3 * c + 2];
-      const double g2 = d[6] * m[3 * c] + d[7] * m[3 * c + 1] + d[8] * m[3 * c + 2];
-      Dg[(i * w + t) * 9 + k] -= a[3 * r] * g0 + a[3 * r + 1] * g1 + a[3 * r + 2] * g2;
+      const double* gg = Dg + (s * w + t) * 9;
+      Dg[(i * w + t) * 9 + k] -= a[3 * r] * gg[c] + a[3 * r + 1] * gg[3 + c] + a[3 * r + 2] * gg[6 + c];
     }
     g.sync();
   }
