@@ -1329,8 +1329,8 @@ static int enqueue_stage(DeviceSolver* d, int stage, std::string* err) {
     rc = enqueue_backward(d, d->sets[0], &nodes, err);
     if (rc != PGO_OK) return rc;
     gn_stamp<<<1, 1, 0, st>>>(d->stamps.p, 4);
-    if (dd) gn_dd_update<<<(P.n + 255) / 256, 256, 0, st>>>(P, d->D);
-    else gn_update<<<dim3((P.n + 255) / 256, B), 256, 0, st>>>(P);
+    if (dd) gn_dd_update<<<std::max(1, (P.n + 255) / 256), 256, 0, st>>>(P, d->D);
+    else gn_update<<<dim3(std::max(1, (P.n + 255) / 256), B), 256, 0, st>>>(P);
     gn_count_iteration<<<1, B, 0, st>>>(P);
     gn_stamp<<<1, 1, 0, st>>>(d->stamps.p, 5);
     nodes += 6;

@@ -217,3 +217,47 @@ def test_batch_of_instances_matches_oracle():
     # the single-instance calls report instance 0
     assert np.array_equal(s.poses(), s.poses_of(0))
     s.close()
+
+
+def test_degenerate_graphs():
+    """Edge cases of the structure analysis and the task lists: a graph with every vertex fixed, a
+    two-vertex graph, a free vertex without any edge (singular H: reported, not silently solved),
+    two components, and re-use of one solver for growing graphs (the keyframe loop)."""
+    info = np.array([[100.0, 0, 0, 100.0, 0, 1000.0]])
+    # all fixed: nothing to solve, chi2 still reported
+    s = pgo.Solver()
+    s.set_graph(2, [(0, 1)], [0, 1])
+    s.upload(np.array([[0, 0, 0], [1.1, 0, 0.0]]), np.array([[1.0, 0, 0]]), info)
+    done, chi2, poses = s.optimize(2)
+    assert done == 2 and np.allclose(chi2, 100.0 * 0.1 ** 2) and np.array_equal(poses[1], [1.1, 0, 0])
+    # two vertices, one free: one GN step lands on the measurement
+    s.set_graph(2, [(0, 1)], [0])
+    s.upload(np.array([[0, 0, 0], [1.3, 0.2, 0.1]]), np.array([[1.0, 0, 0]]), info)
+    done, chi2, poses = s.optimize(3)
+    assert done == 3 and np.abs(poses[1] - [1.0, 0, 0]).max() < 1e-9
+    # an isolated free vertex makes H singular: g2o's linear solver fails, so do we
+    s.set_graph(3, [(0, 1)], [0])
+    s.upload(np.zeros((3, 3)), np.array([[1.0, 0, 0]]), info)
+    done, _, _ = s.optimize(2)
+    assert done == 0
+    # two components, one fixed vertex each
+    g = synth.make_pose_graph(150, 500, seed=2, box=14.0)
+    e2 = np.concatenate([g["edge_ij"], g["edge_ij"] + 150])
+    p2 = np.concatenate([g["poses0"], g["poses0"] + [3.0, 1.0, 0.0]])
+    s.set_graph(300, e2, [0, 150])
+    s.upload(p2, np.concatenate([g["meas"]] * 2), np.concatenate([g["info"]] * 2))
+    done, chi2, poses = s.optimize(4)
+    ref = po.gauss_newton(g["poses0"], g["edge_ij"], g["meas"], g["info"], g["fixed"], 4)
+    assert done == 4 and np.abs(poses[:150] - ref.poses).max() < POSE_TOL
+    assert np.abs(poses[150:] - [3.0, 1.0, 0.0] - ref.poses)[:, :2].max() < POSE_TOL
+    # the same solver, growing graph (one structure analysis per call, as in the keyframe loop)
+    for n in (20, 60, 150):
+        keep = (g["edge_ij"] < n).all(axis=1)
+        s.set_graph(n, g["edge_ij"][keep], [0])
+        s.upload(g["poses0"][:n], g["meas"][keep], g["info"][keep])
+        done, _, poses = s.optimize(3)
+        ref = po.gauss_newton(g["poses0"][:n], g["edge_ij"][keep], g["meas"][keep], g["info"][keep], [0], 3)
+        d = poses - ref.poses
+        d[:, 2] = po.normalize_theta(d[:, 2])
+        assert done == 3 and np.abs(d).max() < POSE_TOL, n
+    s.close()
