@@ -58,6 +58,7 @@ int main(int argc, char** argv) {
            v->estimate().translation().y(), v->estimate().rotation().angle());
   }
   printf("EDGES %zu\n", gslam.graph()->edges().size());
+  if (argc > 2) printf("SAVE %d\n", gslam.saveGraph(argv[2]) ? 1 : 0);  // g2o text, graph_slam.cpp:620-623
   printf("END\n");
   return 0;
 }

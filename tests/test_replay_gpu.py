@@ -32,8 +32,8 @@ def replay_exe(tmp_path_factory):
     return exe
 
 
-def run_mirror(exe, path):
-    out = subprocess.run([exe, path], capture_output=True, text=True, timeout=900)
+def run_mirror(exe, path, save=None):
+    out = subprocess.run([exe, path] + ([save] if save else []), capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stderr[-3000:]
     lines = out.stdout.splitlines()
     assert "BEGIN" in lines and lines[-1] == "END", out.stdout[-2000:] + out.stderr[-2000:]
@@ -87,7 +87,8 @@ def test_bag_replay_matches_oracle(replay_exe, oracle_lib, tmp_path, n, min_inli
         for k in range(n):
             f.write("%.17g %.17g %.17g " % tuple(fx["odom"][k]))
             f.write(" ".join("%.9g" % r for r in fx["ranges"][k]) + "\n")
-    got_frames, got_poses = run_mirror(replay_exe, path)
+    g2o_path = str(tmp_path / "robot-0.g2o")
+    got_frames, got_poses = run_mirror(replay_exe, path, g2o_path)
     want_frames, want_poses = run_oracle(fx, n, min_inliers, oracle_lib)
     assert len(got_frames) == len(want_frames) == n
     kinds = {}
@@ -109,3 +110,29 @@ def test_bag_replay_matches_oracle(replay_exe, oracle_lib, tmp_path, n, min_inli
     if n > 120:
         assert kinds.get("L", 0) > 0 and kinds.get("A", 0) > 0, kinds   # candidates and accepted closures
     print("replay", n, "keyframes:", kinds, "max |pose - oracle| = %.2e" % worst)
+    if n > 120:
+        condensed_graph_on_replayed_graph(g2o_path, got_poses)
+
+
+def condensed_graph_on_replayed_graph(g2o_path, mirror_poses):
+    """BASELINE cfg 1, the per-robot half: the graph the replay saved (g2o text, as saveGraph
+    writes it) is reduced to a condensed star on a set of separator vertices, as
+    CondensedGraphBuffer::computeCondensedGraph does for a peer robot
+    (condensed_graph_buffer.cpp:437-485): gauge = separator nearest the centroid, optimise with the
+    gauge fixed, one labelled EdgeSE2 gauge -> v per separator. GPU solver vs oracle."""
+    from cg_mrslam_b200 import pgo
+    from oracle import pgo_oracle as po
+    g = po.read_g2o(g2o_path)
+    ids = list(g["ids"])
+    assert sorted(ids) == sorted(mirror_poses)
+    for k, v in enumerate(ids):                       # the text round trip keeps 17 digits
+        assert np.abs(g["poses"][k] - mirror_poses[v]).max() < 1e-12
+    seps = [k for k in range(5, len(ids), 17)]        # vertices a peer robot would have matched
+    gauge = po.select_gauge_centroid(g["poses"], seps)
+    zr, omr, vs_r = po.condensed_star(g["poses"], g["edge_ij"], g["meas"], g["info"], gauge, seps)
+    z, om, vs = pgo.condensed_star(pgo.Solver, g["poses"], g["edge_ij"], g["meas"], g["info"], gauge, seps)
+    assert vs == vs_r and len(vs) == len(seps) - 1
+    dz = z - zr
+    dz[:, 2] = (dz[:, 2] + np.pi) % (2 * np.pi) - np.pi
+    assert np.abs(dz).max() < TOL
+    assert np.allclose(om, omr, rtol=1e-6, atol=1e-6 * np.abs(omr).max())
