@@ -496,7 +496,14 @@ def ours(args):
                 "pairs_with_match": found, "kernel": args.kernel},
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_kind": pk_kind,
+                "frac": achieved / pk["hbm_gbs"],
+                # ncu dram__bytes_read + write of a 300-pair launch of the same kernel
+                # (profiles/r01_ncu_score_tiled_s3.txt: 34.39 MB + 0.05 MB), scaled per pair
+                "traffic": (34.391040e6 + 54.016e3) / 300.0 * n if args.kernel != 1 else None,
+                "on_chip": {"alu_pipe_pct": 64.0, "shared_wavefronts_pct": 55.7, "issue_active_pct": 59.8,
+                            "source": "profiles/r01_ncu_score_tiled_s3.txt (the limiter is the "
+                                      "shared-memory gather + integer pipe, not HBM)"},
+                "peak_kind": pk_kind,
                 "kernel": "score_tiled" if args.kernel != 1 else "score_global",
                 "kernel_ms": score_ms, "algorithmic_bytes": alg_bytes,
                 "note": "algorithmic bytes = sum over candidates of k_theta x 1 B + 4 B per score "
