@@ -432,6 +432,7 @@ struct WarpGroup {
 };
 
 const int kCtaThreads = 256;   // CTA tasks
+const int kUpdateThreads = 128;  // outer-product tiles: 4 warps, two 8-row strips each
 const int kWarpsPerCta = 4;    // warp tasks: 4 per CTA
 
 __device__ __forceinline__ bool sn_failed(const SNView& V) {
@@ -557,7 +558,7 @@ __device__ __forceinline__ void update_tile(const SNView& V, const Task& T, doub
     __syncthreads();
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      const int mi = warp + 8 * h;
+      const int mi = warp + ny * h;
       if (mi < mt) {
         const double* ap = As + (8 * mi + fr) * ldk + fk;
         const double* bp = Bt + fr * ldk + fk;
@@ -571,7 +572,7 @@ __device__ __forceinline__ void update_tile(const SNView& V, const Task& T, doub
   }
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
-    const int mi = warp + 8 * h;
+    const int mi = warp + ny * h;
     if (mi >= mt) continue;
     const int row = 8 * mi + fr, al = row / 3, r = row - 3 * al;
 #pragma unroll
@@ -585,7 +586,7 @@ __device__ __forceinline__ void update_tile(const SNView& V, const Task& T, doub
   }
 }
 
-__global__ void __launch_bounds__(kCtaThreads) sn_k_update(SNView V, const Task* tasks) {
+__global__ void __launch_bounds__(kUpdateThreads, 5) sn_k_update(SNView V, const Task* tasks) {
   extern __shared__ double sm[];
   V = sn_at_instance(V, blockIdx.y);
   if (sn_failed(V)) return;
@@ -1237,7 +1238,7 @@ static int enqueue_factor(DeviceSolver* d, const DeviceSolver::TaskSet& ts, int*
       PGO_CUDA(cudaStreamWaitEvent(st, d->ev_join, 0));
     }
     if (n_fb) {
-      sn_k_update<<<dim3(n_fb, B), kCtaThreads, sizeof(double) * L.fb_smem[l], st>>>(V, ts.fb.p + L.fb_ptr[l]);
+      sn_k_update<<<dim3(n_fb, B), kUpdateThreads, sizeof(double) * L.fb_smem[l], st>>>(V, ts.fb.p + L.fb_ptr[l]);
       ++*nodes;
     }
   }

@@ -346,8 +346,8 @@ bool build_supernodal(Symbolic& S, std::string* err) {
         if (pass == 0 ? w_rest == 0 : w_rest != 0) continue;
         const int jlim = pass == 0 ? w_rest : m;
         const int wk = pass == 0 || np == 1 ? w : kPanelWidth;   // widest staged chunk
-        const int tj = std::min((jlim + 7) / 8 * 8, 24);
-        int ti = std::min((m + 7) / 8 * 8, 40);                  // two 8-row strips per warp
+        const int tj = std::min((jlim + 7) / 8 * 8, 16);
+        int ti = std::min((m + 7) / 8 * 8, 16);                  // two 8-row strips per warp (4 warps)
         while (ti > 8 && sn_tile_doubles(wk, ti, tj) > kTileSmemDoubles) ti -= 8;
         // the inner dimension of an ancestors' update is cut into groups of kUpdateGroup panels
         // (split-K: the tiles of different groups add into the same targets with atomics anyway)
