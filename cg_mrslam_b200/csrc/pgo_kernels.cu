@@ -12,8 +12,9 @@
 //      outer products on the fp64 tensor cores.
 //   3. back-substitute, top-down over the supernode levels: sn_k_bwd_*.
 //   4. gn_update: VertexSE2::oplusImpl (C3) on every free vertex.
-// The level-by-level kernels further down (phase_forward / phase_backward, pgo_dd.cuh) serve the
-// marginals (multi-right-hand-side solves) and the domain-decomposed multi-GPU iteration.
+// Marginal covariance blocks are extra right-hand sides against the stored factor (stand-alone
+// forward + backward substitution with the same task functions); pgo_dd.cuh holds what the
+// domain-decomposed multi-GPU iteration adds (owned-edge linearisation, exchange packing).
 // Algorithmic bytes and measured shares per kernel are stated in DESIGN.md section 4.3.
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
@@ -59,17 +60,9 @@ struct Params {
   const double* meas;
   const double* info6;
   // factor structure
-  int n_levels;
   long long nnzb;
   const int* col_ptr;
   const int* row_idx;
-  const int* col_of;
-  const int* row_ptr;
-  const int* row_pos;
-  const int* level_ptr;
-  const int* level_cols;
-  const int* fwd_ptr;
-  const SolveOp* fwd_ops;
   const int* perm_vertex;  // permuted position -> vertex index
   // numeric
   double* M;      // [nnzb][9]
@@ -290,129 +283,6 @@ __device__ void phase_linearise(const Params& P, double* scratch, int it) {
   (void)it;
 }
 
-// ---- level-by-level substitution (marginals: many right-hand sides against the stored factor) ---
-// Forward substitution works in place on the right-hand side z (initially b):
-//   level-0 rows:  u_j = Dinv_j z_j
-//   phase l >= 1:  z_i -= M(i,k) u_k for the blocks of the columns k of level l-1 (eager, right-
-//                  looking timing), one thread per target row (left-looking ownership); a row of
-//                  level l is complete after this phase: u_i = Dinv_i z_i.
-__device__ __forceinline__ void finish_row(const Params& P, int row, const double* z, double* u) {
-  const double* d = P.Dinv + 9 * static_cast<size_t>(row);
-  u[0] = d[0] * z[0] + d[1] * z[1] + d[2] * z[2];
-  u[1] = d[3] * z[0] + d[4] * z[1] + d[5] * z[2];
-  u[2] = d[6] * z[0] + d[7] * z[1] + d[8] * z[2];
-}
-
-__device__ void phase_forward_leaves(const Params& P, int nrhs, double* z, size_t stride) {
-  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
-  const int n0 = P.level_ptr[1] - P.level_ptr[0];
-  for (int t = tid; t < n0 * nrhs; t += nthreads) {
-    const int j = P.level_cols[P.level_ptr[0] + t % n0], r = t / n0;
-    finish_row(P, j, z + r * stride + 3 * static_cast<size_t>(j),
-               P.u + r * stride + 3 * static_cast<size_t>(j));
-  }
-}
-
-__device__ void phase_forward(const Params& P, int l, int nrhs, double* z, size_t stride) {
-  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
-  const int begin = P.fwd_ptr[l], end = P.fwd_ptr[l + 1];
-  for (int i = begin + tid; i < end; i += nthreads) {
-    const SolveOp first = P.fwd_ops[i];
-    if (i > begin && P.fwd_ops[i - 1].row == first.row) continue;  // not the head of its run
-    const int row = first.row & ~kFinalFlag;
-    for (int r = 0; r < nrhs; ++r) {
-      double* zz = z + r * stride + 3 * static_cast<size_t>(row);
-      const double* uu = P.u + r * stride;
-      double z0 = zz[0], z1 = zz[1], z2 = zz[2];
-      int j = i;
-      SolveOp op = first;
-      while (true) {
-        const double* m = P.M + 9 * static_cast<size_t>(op.pos);
-        const double* v = uu + 3 * static_cast<size_t>(P.col_of[op.pos]);
-        const double v0 = v[0], v1 = v[1], v2 = v[2];
-        z0 -= m[0] * v0 + m[1] * v1 + m[2] * v2;
-        z1 -= m[3] * v0 + m[4] * v1 + m[5] * v2;
-        z2 -= m[6] * v0 + m[7] * v1 + m[8] * v2;
-        ++j;
-        if (j >= end) break;
-        op = P.fwd_ops[j];
-        if (op.row != first.row) break;
-      }
-      zz[0] = z0;
-      zz[1] = z1;
-      zz[2] = z2;
-      if (first.row & kFinalFlag) {
-        const double zf[3] = {z0, z1, z2};
-        finish_row(P, row, zf, P.u + r * stride + 3 * static_cast<size_t>(row));
-      }
-    }
-  }
-}
-
-// backward, level l: x_j = u_j - Dinv_j sum_{i>j} M(i,j)^T x_i. A column's blocks are contiguous,
-// so the lanes of the group that owns column j read consecutive 72-byte blocks. Narrow levels (the
-// separator chains) give each column a whole CTA, wide levels a warp.
-__device__ __forceinline__ void backward_store(const Params& P, int j, int r, size_t stride,
-                                               double s0, double s1, double s2) {
-  const double* d = P.Dinv + 9 * static_cast<size_t>(j);
-  const double* uj = P.u + r * stride + 3 * static_cast<size_t>(j);
-  double* out = P.x + r * stride + 3 * static_cast<size_t>(j);
-  out[0] = uj[0] - (d[0] * s0 + d[1] * s1 + d[2] * s2);
-  out[1] = uj[1] - (d[3] * s0 + d[4] * s1 + d[5] * s2);
-  out[2] = uj[2] - (d[6] * s0 + d[7] * s1 + d[8] * s2);
-}
-
-__device__ void phase_backward(const Params& P, int l, int nrhs, size_t stride, double* scratch) {
-  const int lane = threadIdx.x & 31;
-  const int n_cols = P.level_ptr[l + 1] - P.level_ptr[l];
-  const int n_items = n_cols * nrhs;
-  const bool cta_mode = n_items <= static_cast<int>(gridDim.x);
-  const int group = cta_mode ? blockDim.x : 32;
-  const int gid = cta_mode ? blockIdx.x : ((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
-  const int n_groups = cta_mode ? gridDim.x : ((gridDim.x * blockDim.x) >> 5);
-  const int rank = cta_mode ? threadIdx.x : lane;
-  for (int w = gid; w < n_items; w += n_groups) {
-    const int j = P.level_cols[P.level_ptr[l] + w % n_cols], r = w / n_cols;
-    const double* xx = P.x + r * stride;
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-    for (int t = P.col_ptr[j] + 1 + rank; t < P.col_ptr[j + 1]; t += group) {
-      const double* m = P.M + 9 * static_cast<size_t>(t);
-      const double* v = xx + 3 * static_cast<size_t>(P.row_idx[t]);
-      const double v0 = v[0], v1 = v[1], v2 = v[2];
-      s0 += m[0] * v0 + m[3] * v1 + m[6] * v2;
-      s1 += m[1] * v0 + m[4] * v1 + m[7] * v2;
-      s2 += m[2] * v0 + m[5] * v1 + m[8] * v2;
-    }
-    for (int o = 16; o; o >>= 1) {
-      s0 += __shfl_down_sync(0xffffffffu, s0, o);
-      s1 += __shfl_down_sync(0xffffffffu, s1, o);
-      s2 += __shfl_down_sync(0xffffffffu, s2, o);
-    }
-    if (!cta_mode) {
-      if (lane == 0) backward_store(P, j, r, stride, s0, s1, s2);
-    } else {
-      const int warp = threadIdx.x >> 5, n_warps = (blockDim.x + 31) >> 5;
-      if (lane == 0) {
-        scratch[3 * warp] = s0;
-        scratch[3 * warp + 1] = s1;
-        scratch[3 * warp + 2] = s2;
-      }
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        double t0 = 0.0, t1 = 0.0, t2 = 0.0;
-        for (int q = 0; q < n_warps; ++q) {
-          t0 += scratch[3 * q];
-          t1 += scratch[3 * q + 1];
-          t2 += scratch[3 * q + 2];
-        }
-        backward_store(P, j, r, stride, t0, t1, t2);
-      }
-      __syncthreads();
-    }
-  }
-}
-
-// ---- the persistent kernels ----------------------------------------------------------------------
 const int kThreads = 256;
 
 // ---- supernodal single-GPU iteration (pgo_supernodal.h) ------------------------------------------
@@ -626,6 +496,26 @@ __global__ void __launch_bounds__(kCtaThreads) sn_k_bwd_tri(SNView V, const Task
   sn_task_backward_tri(CtaGroup(), V, tasks[blockIdx.x], sm);
 }
 
+// stand-alone forward substitution (right-hand sides solved after the factorisation: marginals)
+__global__ void __launch_bounds__(kCtaThreads) sn_k_fwd_tri(SNView V, const Task* tasks) {
+  extern __shared__ double sm[];
+  V = sn_at_instance(V, blockIdx.y);
+  sn_task_forward_tri(CtaGroup(), V, tasks[blockIdx.x], sm);
+}
+__global__ void __launch_bounds__(32 * kWarpsPerCta) sn_k_fwd_small(SNView V, const Task* tasks, int n) {
+  extern __shared__ double sm[];
+  const int i = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  V = sn_at_instance(V, blockIdx.y);
+  if (i >= n) return;
+  sn_task_forward_small(WarpGroup(), V, tasks[i], sm + (threadIdx.x >> 5) * kWarpSmemDoubles);
+}
+__global__ void __launch_bounds__(32 * kWarpsPerCta) sn_k_fwd_rows(SNView V, const Task* tasks, int n) {
+  const int i = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+  V = sn_at_instance(V, blockIdx.y);
+  if (i >= n) return;
+  sn_forward_rows(WarpGroup(), V, tasks[i].id, tasks[i].r0, tasks[i].r1, nullptr);
+}
+
 // linearise + chi2 (phase 1) as plain kernels
 __global__ void __launch_bounds__(kThreads) gn_linearise(Params P) {
   __shared__ double scratch[32];
@@ -663,23 +553,6 @@ __global__ void gn_stamp(unsigned long long* stamps, int k) {
   unsigned long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   stamps[k] = t;
-}
-
-// H X = E for nrhs right-hand sides already placed in P.rhs-like storage `rhs` ([nrhs][n][3]).
-__global__ void __launch_bounds__(kThreads) solve_many(Params P, double* rhs, int nrhs) {
-  cg::grid_group grid = cg::this_grid();
-  __shared__ double scratch[32];
-  const size_t stride = 3 * static_cast<size_t>(P.n);
-  phase_forward_leaves(P, nrhs, rhs, stride);
-  grid.sync();
-  for (int l = 1; l < P.n_levels; ++l) {
-    phase_forward(P, l, nrhs, rhs, stride);
-    grid.sync();
-  }
-  for (int l = P.n_levels - 1; l >= 0; --l) {
-    phase_backward(P, l, nrhs, stride, scratch);
-    grid.sync();
-  }
 }
 
 #include "pgo_dd.cuh"
@@ -842,11 +715,8 @@ struct DeviceSolver {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   Params P;
   bool have_structure = false, have_values = false, have_factor = false;
-  Buf<int> edge_i, edge_j, vpos, inc_ptr, ff_edges, col_ptr, row_idx, col_of, row_ptr, row_pos,
-      level_ptr, level_cols, perm_vertex, status, scratch_i;
+  Buf<int> edge_i, edge_j, vpos, inc_ptr, ff_edges, col_ptr, row_idx, perm_vertex, status, scratch_i;
   Buf<Incidence> inc;
-  Buf<SolveOp> fwd_ops;
-  Buf<int> fwd_ptr;
   Buf<unsigned long long> stamps;
   double stage_ms[5] = {0, 0, 0, 0, 0};
   Buf<double> poses, meas, info6, M, Dinv, rhs, u, x, chi2_partial, chi2_out, many_rhs, scratch_d;
@@ -856,7 +726,7 @@ struct DeviceSolver {
   // separator panels [1] (domain decomposition)
   struct TaskSet {
     Supernodal::Lists L;   // host copy: level pointers and launch geometry
-    Buf<Task> ff, fa, fb, ss, sa, sb;
+    Buf<Task> ff, fa, fb, ss, sa, sf, sb;
   } sets[2];
   // [0]: the whole iteration (single GPU) or the local stage; [1]: the shared stage
   cudaGraph_t graph[2] = {nullptr, nullptr};
@@ -895,24 +765,22 @@ int dev_create(DeviceSolver** out, int device, void* stream, std::string* err) {
   DeviceSolver* d = new DeviceSolver();
   d->device = device;
   cudaDeviceGetAttribute(&d->sm_count, cudaDevAttrMultiProcessorCount, device);
-  int per_sm = 0, per_sm2 = 0;
+  int per_sm = 0;
   cudaError_t e = cudaSuccess;
   {
     const int cta_bytes = static_cast<int>(sizeof(double) * kCtaSmemDoubles);
     const int warp_bytes = static_cast<int>(sizeof(double) * kWarpSmemDoubles * kWarpsPerCta);
     const void* cta_kernels[] = {reinterpret_cast<const void*>(sn_k_factor), reinterpret_cast<const void*>(sn_k_update),
-                                 reinterpret_cast<const void*>(sn_k_bwd_tri)};
+                                 reinterpret_cast<const void*>(sn_k_bwd_tri), reinterpret_cast<const void*>(sn_k_fwd_tri)};
     for (size_t i = 0; i < sizeof(cta_kernels) / sizeof(cta_kernels[0]) && e == cudaSuccess; ++i)
       e = cudaFuncSetAttribute(cta_kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, cta_bytes);
-    const void* warp_kernels[] = {reinterpret_cast<const void*>(sn_k_fused),                                   reinterpret_cast<const void*>(sn_k_bwd_small)};
+    const void* warp_kernels[] = {reinterpret_cast<const void*>(sn_k_fused),                                   reinterpret_cast<const void*>(sn_k_bwd_small), reinterpret_cast<const void*>(sn_k_fwd_small)};
     for (size_t i = 0; i < sizeof(warp_kernels) / sizeof(warp_kernels[0]) && e == cudaSuccess; ++i)
       e = cudaFuncSetAttribute(warp_kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, warp_bytes);
   }
   if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, chi2_only, kThreads, 0);
-  if (e == cudaSuccess)
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm2, solve_many, kThreads, 0);
   if (e == cudaSuccess) {
-    per_sm = std::max(1, std::min(per_sm, per_sm2));
+    per_sm = std::max(1, per_sm);
     d->grid = d->sm_count * per_sm;
     if (stream) {
       d->stream = static_cast<cudaStream_t>(stream);
@@ -942,9 +810,8 @@ void dev_destroy(DeviceSolver* d) {
   if (!d) return;
   cudaSetDevice(d->device);
   if (d->stream) cudaStreamSynchronize(d->stream);
-  Buf<int>* ib[] = {&d->edge_i, &d->edge_j, &d->vpos, &d->inc_ptr, &d->ff_edges, &d->col_ptr,
-                    &d->row_idx, &d->col_of, &d->row_ptr, &d->row_pos, &d->level_ptr,
-                    &d->level_cols, &d->perm_vertex, &d->status, &d->scratch_i};
+  Buf<int>* ib[] = {&d->edge_i, &d->edge_j, &d->vpos,        &d->inc_ptr, &d->ff_edges,
+                    &d->col_ptr, &d->row_idx, &d->perm_vertex, &d->status,  &d->scratch_i};
   for (size_t i = 0; i < sizeof(ib) / sizeof(ib[0]); ++i) ib[i]->release();
   Buf<double>* db[] = {&d->poses, &d->meas, &d->info6, &d->M, &d->Dinv, &d->rhs, &d->u, &d->x,
                        &d->chi2_partial, &d->chi2_out, &d->many_rhs, &d->scratch_d};
@@ -954,8 +821,8 @@ void dev_destroy(DeviceSolver* d) {
   d->sn_desc.release();
   for (size_t i = 0; i < sizeof(sb) / sizeof(sb[0]); ++i) sb[i]->release();
   for (int k = 0; k < 2; ++k) {
-    Buf<Task>* tb[] = {&d->sets[k].ff, &d->sets[k].fa, &d->sets[k].fb,
-                       &d->sets[k].ss, &d->sets[k].sa, &d->sets[k].sb};
+    Buf<Task>* tb[] = {&d->sets[k].ff, &d->sets[k].fa, &d->sets[k].fb, &d->sets[k].ss,
+                       &d->sets[k].sa, &d->sets[k].sf, &d->sets[k].sb};
     for (size_t i = 0; i < sizeof(tb) / sizeof(tb[0]); ++i) tb[i]->release();
   }
   d->diag_scratch.release();
@@ -969,8 +836,6 @@ void dev_destroy(DeviceSolver* d) {
     d->graph[k] = nullptr;
   }
   d->inc.release();
-  d->fwd_ops.release();
-  d->fwd_ptr.release();
   d->stamps.release();
   d->owner.release();
   d->pose_x.release();
@@ -999,13 +864,6 @@ int dev_set_structure(DeviceSolver* d, const Symbolic& S, const GraphTables& G, 
   PGO_CUDA(d->ff_edges.upload(G.ff_edges, s));
   PGO_CUDA(d->col_ptr.upload(S.col_ptr, s));
   PGO_CUDA(d->row_idx.upload(S.row_idx, s));
-  PGO_CUDA(d->col_of.upload(S.col_of, s));
-  PGO_CUDA(d->row_ptr.upload(S.row_ptr, s));
-  PGO_CUDA(d->row_pos.upload(S.row_pos, s));
-  PGO_CUDA(d->level_ptr.upload(S.level_ptr, s));
-  PGO_CUDA(d->level_cols.upload(S.level_cols, s));
-  PGO_CUDA(d->fwd_ops.upload(S.fwd_ops, s));
-  PGO_CUDA(d->fwd_ptr.upload(S.fwd_ptr, s));
   const Supernodal& N = S.sn;
   PGO_CUDA(d->pn_desc.upload(N.pn, s));
   PGO_CUDA(d->sn_desc.upload(N.sn, s));
@@ -1021,6 +879,7 @@ int dev_set_structure(DeviceSolver* d, const Symbolic& S, const GraphTables& G, 
     PGO_CUDA(ts.fb.upload(ts.L.fb, s));
     PGO_CUDA(ts.ss.upload(ts.L.ss, s));
     PGO_CUDA(ts.sa.upload(ts.L.sa, s));
+    PGO_CUDA(ts.sf.upload(ts.L.sf, s));
     PGO_CUDA(ts.sb.upload(ts.L.sb, s));
   }
   const size_t scratch_stride = 9 * static_cast<size_t>(N.scratch_blocks) + 9;
@@ -1059,17 +918,9 @@ int dev_set_structure(DeviceSolver* d, const Symbolic& S, const GraphTables& G, 
   P.poses = d->poses.p;
   P.meas = d->meas.p;
   P.info6 = d->info6.p;
-  P.n_levels = S.n_levels;
   P.nnzb = S.nnzb;
   P.col_ptr = d->col_ptr.p;
   P.row_idx = d->row_idx.p;
-  P.col_of = d->col_of.p;
-  P.row_ptr = d->row_ptr.p;
-  P.row_pos = d->row_pos.p;
-  P.level_ptr = d->level_ptr.p;
-  P.level_cols = d->level_cols.p;
-  P.fwd_ptr = d->fwd_ptr.p;
-  P.fwd_ops = d->fwd_ops.p;
   P.perm_vertex = d->perm_vertex.p;
   P.M = d->M.p;
   P.Dinv = d->Dinv.p;
@@ -1099,6 +950,7 @@ int dev_set_structure(DeviceSolver* d, const Symbolic& S, const GraphTables& G, 
   V.s_Dinv = 9LL * S.n;
   V.s_vec = 3LL * S.n;
   V.s_scratch = static_cast<long long>(scratch_stride);
+  V.s_status = 4;
   d->lin_blocks = std::max(1, std::min(4 * d->sm_count, (S.n + kThreads - 1) / kThreads));
   PGO_CUDA(d->chi2_out.reserve(B * kMaxItersPerCall));
   PGO_CUDA(d->chi2_partial.reserve(std::max(B * d->lin_blocks, static_cast<size_t>(d->grid))));
@@ -1247,11 +1099,10 @@ static int enqueue_factor(DeviceSolver* d, const DeviceSolver::TaskSet& ts, int*
 }
 
 // Backward substitution of one task set, top-down over the supernode levels.
-static int enqueue_backward(DeviceSolver* d, const DeviceSolver::TaskSet& ts, int* nodes, std::string* err) {
+static int enqueue_backward(DeviceSolver* d, const DeviceSolver::TaskSet& ts, const SNView& V, int B,
+                            int* nodes, std::string* err) {
   cudaStream_t st = d->stream;
-  const SNView V = d->V;
   const Supernodal::Lists& L = ts.L;
-  const int B = d->batch;
   const size_t warp_bytes = sizeof(double) * kWarpSmemDoubles * kWarpsPerCta;
   for (int l = L.n_slevels - 1; l >= 0; --l) {
     const int n_sa = L.sa_ptr[l + 1] - L.sa_ptr[l], n_ss = L.ss_ptr[l + 1] - L.ss_ptr[l],
@@ -1281,6 +1132,34 @@ static int enqueue_backward(DeviceSolver* d, const DeviceSolver::TaskSet& ts, in
     if (side != st) {
       PGO_CUDA(cudaEventRecord(d->ev_join, side));
       PGO_CUDA(cudaStreamWaitEvent(st, d->ev_join, 0));
+    }
+  }
+  PGO_CUDA(cudaGetLastError());
+  return PGO_OK;
+}
+
+// Stand-alone forward substitution of B right-hand sides (marginals), bottom-up.
+static int enqueue_forward(DeviceSolver* d, const DeviceSolver::TaskSet& ts, const SNView& V, int B,
+                           int* nodes, std::string* err) {
+  cudaStream_t st = d->stream;
+  const Supernodal::Lists& L = ts.L;
+  const size_t warp_bytes = sizeof(double) * kWarpSmemDoubles * kWarpsPerCta;
+  for (int l = 0; l < L.n_slevels; ++l) {
+    const int n_sa = L.sa_ptr[l + 1] - L.sa_ptr[l], n_ss = L.ss_ptr[l + 1] - L.ss_ptr[l],
+              n_sf = L.sf_ptr[l + 1] - L.sf_ptr[l];
+    if (n_ss) {
+      sn_k_fwd_small<<<dim3((n_ss + kWarpsPerCta - 1) / kWarpsPerCta, B), 32 * kWarpsPerCta, warp_bytes, st>>>(
+          V, ts.ss.p + L.ss_ptr[l], n_ss);
+      ++*nodes;
+    }
+    if (n_sa) {
+      sn_k_fwd_tri<<<dim3(n_sa, B), kCtaThreads, sizeof(double) * L.sa_smem[l], st>>>(V, ts.sa.p + L.sa_ptr[l]);
+      ++*nodes;
+    }
+    if (n_sf) {
+      sn_k_fwd_rows<<<dim3((n_sf + kWarpsPerCta - 1) / kWarpsPerCta, B), 32 * kWarpsPerCta, 0, st>>>(
+          V, ts.sf.p + L.sf_ptr[l], n_sf);
+      ++*nodes;
     }
   }
   PGO_CUDA(cudaGetLastError());
@@ -1324,10 +1203,10 @@ static int enqueue_stage(DeviceSolver* d, int stage, std::string* err) {
     }
     gn_stamp<<<1, 1, 0, st>>>(d->stamps.p, 3);
     if (dd) {
-      rc = enqueue_backward(d, d->sets[1], &nodes, err);
+      rc = enqueue_backward(d, d->sets[1], d->V, d->batch, &nodes, err);
       if (rc != PGO_OK) return rc;
     }
-    rc = enqueue_backward(d, d->sets[0], &nodes, err);
+    rc = enqueue_backward(d, d->sets[0], d->V, d->batch, &nodes, err);
     if (rc != PGO_OK) return rc;
     gn_stamp<<<1, 1, 0, st>>>(d->stamps.p, 4);
     if (dd) gn_dd_update<<<std::max(1, (P.n + 255) / 256), 256, 0, st>>>(P, d->D);
@@ -1517,6 +1396,10 @@ int dev_marginals(DeviceSolver* d, int n, const int* col_p, const int* row_p, do
     return PGO_ERR_ARG;
   }
   if (n <= 0) return PGO_OK;
+  if (d->D.world != 1) {
+    if (err) *err = "marginals need the whole factor: not available on a domain-decomposed solver";
+    return PGO_ERR_ARG;
+  }
   PGO_CUDA(cudaSetDevice(d->device));
   // distinct columns -> right-hand sides
   std::vector<int> cols(col_p, col_p + n);
@@ -1553,17 +1436,24 @@ int dev_marginals(DeviceSolver* d, int n, const int* col_p, const int* row_p, do
     PGO_CUDA(cudaMemcpyAsync(d_rhs_of, local_rhs.data(), nb * sizeof(int), cudaMemcpyHostToDevice, d->stream));
     PGO_CUDA(cudaMemsetAsync(d->many_rhs.p, 0, 3 * nc * stride * sizeof(double), d->stream));
     set_unit_rhs<<<(3 * nc + 127) / 128, 128, 0, d->stream>>>(d->many_rhs.p, stride, d_cols, nc);
-    Params P = d->P;
-    P.u = d->many_u.p;
-    P.x = d->many_x.p;
-    double* rhs = d->many_rhs.p;
-    int nrhs = 3 * nc;
-    void* args[] = {&P, &rhs, &nrhs};
-    PGO_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(solve_many), dim3(d->grid),
-                                         dim3(kThreads), args, 0, d->stream));
+    // the right-hand sides play the role of batch instances that share one factor
+    SNView V = d->V;
+    V.z = d->many_rhs.p;
+    V.u = d->many_u.p;
+    V.x = d->many_x.p;
+    V.s_M = V.s_Dinv = V.s_scratch = 0;
+    V.s_vec = static_cast<long long>(stride);
+    V.s_status = 0;
+    const int nrhs = 3 * nc;
+    PGO_CUDA(cudaMemsetAsync(d->many_x.p, 0, nrhs * stride * sizeof(double), d->stream));
+    int nodes = 0;
+    int rc = enqueue_forward(d, d->sets[0], V, nrhs, &nodes, err);
+    if (rc == PGO_OK) rc = enqueue_backward(d, d->sets[0], V, nrhs, &nodes, err);
+    if (rc != PGO_OK) return rc;
+    d->launches += nodes;
     gather_blocks<<<(9 * nb + 127) / 128, 128, 0, d->stream>>>(d->many_x.p, stride, d_rows, d_rhs_of, nb,
                                                               d->scratch_d.p);
-    d->launches += 3;
+    d->launches += 2;
     PGO_CUDA(cudaGetLastError());
     std::vector<double> part(9 * static_cast<size_t>(nb));
     PGO_CUDA(cudaMemcpyAsync(part.data(), d->scratch_d.p, part.size() * sizeof(double),

@@ -54,6 +54,7 @@ struct SNView {
   int* status;      // [0] set to 1 when a pivot block is not positive definite
   // batch of problem instances with this structure: element strides between instances
   long long s_M, s_Dinv, s_vec, s_scratch;
+  int s_status;     // 4 for a batch of graphs, 0 when the "instances" are right-hand sides of one graph
 };
 
 // The view of instance b of a batch (blockIdx.y on the device).
@@ -65,7 +66,7 @@ PGO_HD SNView sn_at_instance(SNView V, int b) {
   V.u += b * V.s_vec;
   V.x += b * V.s_vec;
   V.scratch += b * V.s_scratch;
-  V.status += 4 * b;
+  V.status += b * V.s_status;
   return V;
 }
 
@@ -490,6 +491,146 @@ template <class G>
 PGO_HD void sn_load_dinv(const G& g, const SNView& V, int c0, int w, double* Di) {
   for (int idx = g.rank(); idx < 9 * w; idx += g.size())
     Di[idx] = sn_ld(V.Dinv + 9 * static_cast<size_t>(c0) + idx);
+}
+
+// ---- stand-alone forward substitution ---------------------------------------------------------------
+// During an iteration the forward substitution rides along with the factorisation (sn_forward_fused).
+// Further right-hand sides against the stored factor -- the unit block columns of the marginal
+// covariances (SparseOptimizer::computeMarginals) -- go through these tasks, bottom-up
+// over the supernode levels: sa / ss as in the backward direction, sf = rows below a wide
+// supernode's panel (warp, chunks of 32 rows).
+// Triangular part of one panel on staged vectors (all operands in shared memory).
+template <class G>
+PGO_HD void sn_forward_panel(const G& g, int w, const double* Dg, const double* Di, double* zs,
+                             double* us) {
+  for (int t = 0; t < w; ++t) {
+    if (g.rank() == 0) sn_mat_vec(Di + 9 * t, zs + 3 * t, us + 3 * t);
+    g.sync();
+    for (int tp = t + 1 + g.rank(); tp < w; tp += g.size()) {
+      double v[3];
+      sn_mat_vec(Dg + (tp * w + t) * 9, us + 3 * t, v);
+      zs[3 * tp] -= v[0];
+      zs[3 * tp + 1] -= v[1];
+      zs[3 * tp + 2] -= v[2];
+    }
+    g.sync();
+  }
+}
+
+// rows [r0, r1) below the SUPERNODE of panel p:  z_{r_a} -= sum_t M(a,t) u_t  (atomic).
+// us: the supernode's u in shared memory, or null to read it from global memory.
+// Loads are issued four blocks at a time (memory-level parallelism, see sn_gather).
+template <class G>
+PGO_HD void sn_forward_rows(const G& g, const SNView& V, int p, int r0, int r1, const double* us) {
+  const PanelDesc pd = V.pn[p];
+  const SuperDesc sd = V.sn[pd.sn];
+  const int w = pd.w, o = pd.sn_off, len = sd.W + sd.m;
+  for (int a = r0 + g.rank(); a < r1; a += g.size()) {
+    const int r = V.row_idx[sd.base + sd.W + a];
+    double acc[3] = {0.0, 0.0, 0.0};
+    for (int t0 = 0; t0 < w; t0 += 4) {
+      double mb[4][9], uv[4][3];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+      for (int q = 0; q < 4; ++q) {
+        const int t = t0 + q;
+        if (t < w) {
+          sn_ld9(V.M + 9 * static_cast<size_t>(sn_colpos(sd.base, len, o + t) + (sd.W - o - t) + a), mb[q]);
+          for (int k = 0; k < 3; ++k)
+            uv[q][k] = us ? us[3 * (o + t) + k] : sn_ld(V.u + 3 * static_cast<size_t>(pd.c0 + t) + k);
+        }
+      }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+      for (int q = 0; q < 4; ++q)
+        if (t0 + q < w) {
+          double v[3];
+          sn_mat_vec(mb[q], uv[q], v);
+          acc[0] += v[0];
+          acc[1] += v[1];
+          acc[2] += v[2];
+        }
+    }
+    for (int k = 0; k < 3; ++k) sn_add(V.z + 3 * static_cast<size_t>(r) + k, -acc[k]);
+  }
+}
+
+// sa (forward): triangular part of a wide supernode, panel by panel, in one group.
+// shared: zs[3W] us[3W] Dg[w*w*9] Di[w*9]
+template <class G>
+PGO_HD void sn_task_forward_tri(const G& g, const SNView& V, const Task& T, double* sm) {
+  const SuperDesc sd = V.sn[T.id];
+  const int W = sd.W, len = sd.W + sd.m;
+  double* zs = sm;
+  double* us = zs + 3 * W;
+  double* Dg = us + 3 * W;
+  double* Di = Dg + kPanelWidth * kPanelWidth * 9;
+  sn_gather(g, 3 * W, [&](int idx, const double** sp, double** dp) {
+    *sp = V.z + 3 * static_cast<size_t>(sd.c0) + idx;
+    *dp = zs + idx;
+  });
+  for (int p = sd.pn_begin; p < sd.pn_end; ++p) {
+    const PanelDesc pd = V.pn[p];
+    const int w = pd.w, o = pd.sn_off;
+    sn_load_diag(g, V, pd.base, w + pd.m, w, Dg);
+    sn_load_dinv(g, V, pd.c0, w, Di);
+    g.sync();
+    sn_forward_panel(g, w, Dg, Di, zs + 3 * o, us + 3 * o);
+    // the supernode's remaining columns are rows of this panel
+    for (int tp = o + w + g.rank(); tp < W; tp += g.size()) {
+      double acc[3] = {0.0, 0.0, 0.0};
+      for (int t0 = 0; t0 < w; t0 += 4) {
+        double mb[4][9];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int q = 0; q < 4; ++q)
+          if (t0 + q < w)
+            sn_ld9(V.M + 9 * static_cast<size_t>(sn_colpos(sd.base, len, o + t0 + q) + (tp - o - t0 - q)),
+                   mb[q]);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int q = 0; q < 4; ++q)
+          if (t0 + q < w) {
+            double v[3];
+            sn_mat_vec(mb[q], us + 3 * (o + t0 + q), v);
+            acc[0] += v[0];
+            acc[1] += v[1];
+            acc[2] += v[2];
+          }
+      }
+      zs[3 * tp] -= acc[0];
+      zs[3 * tp + 1] -= acc[1];
+      zs[3 * tp + 2] -= acc[2];
+    }
+    g.sync();
+  }
+  for (int idx = g.rank(); idx < 3 * W; idx += g.size()) V.u[3 * static_cast<size_t>(sd.c0) + idx] = us[idx];
+  g.sync();
+}
+
+// ss (forward): a narrow supernode (one panel) including the rows below it.
+// shared: zs[3W] us[3W] Dg[W*W*9] Di[W*9]
+template <class G>
+PGO_HD void sn_task_forward_small(const G& g, const SNView& V, const Task& T, double* sm) {
+  const SuperDesc sd = V.sn[T.id];
+  const int W = sd.W;
+  double* zs = sm;
+  double* us = zs + 3 * W;
+  double* Dg = us + 3 * W;
+  double* Di = Dg + W * W * 9;
+  for (int idx = g.rank(); idx < 3 * W; idx += g.size())
+    zs[idx] = sn_ld(V.z + 3 * static_cast<size_t>(sd.c0) + idx);
+  sn_load_diag(g, V, sd.base, W + sd.m, W, Dg);
+  sn_load_dinv(g, V, sd.c0, W, Di);
+  g.sync();
+  sn_forward_panel(g, W, Dg, Di, zs, us);
+  for (int idx = g.rank(); idx < 3 * W; idx += g.size()) V.u[3 * static_cast<size_t>(sd.c0) + idx] = us[idx];
+  sn_forward_rows(g, V, sd.pn_begin, 0, sd.m, us);
+  g.sync();
 }
 
 // acc += sum over the rows a = first, first + step, ... < end of  M(a, col)^T x_{row(a)}, where the

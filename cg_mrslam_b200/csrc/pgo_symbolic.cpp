@@ -376,7 +376,7 @@ bool build_supernodal(Symbolic& S, std::string* err) {
 
   // substitution: supernode levels and tasks
   std::vector<int> slevel(N.n_super, 0);
-  std::vector<std::pair<int, Task> > ss, sa, sb;
+  std::vector<std::pair<int, Task> > ss, sa, sf, sb;
   for (int s = 0; s < N.n_super; ++s) {
     const int c0 = N.sn_first[s], W = N.sn_first[s + 1] - c0;
     const int base = cp[c0] + W, m = cp[c0 + 1] - base;
@@ -396,6 +396,10 @@ bool build_supernodal(Symbolic& S, std::string* err) {
     const Task t = {s, 0, m, 0};
     sa.push_back(std::make_pair(slevel[s], t));
     for (int p = N.sn_pn_ptr[s]; p < N.sn_pn_ptr[s + 1]; ++p) {
+      for (int r0 = 0; r0 < m; r0 += 32) {
+        const Task x = {p, r0, std::min(m, r0 + 32), 0};
+        sf.push_back(std::make_pair(slevel[s], x));
+      }
       for (int r0 = 0; r0 < m; r0 += 64) {
         const Task x = {p, r0, std::min(m, r0 + 64), 0};
         sb.push_back(std::make_pair(slevel[s], x));
@@ -404,6 +408,7 @@ bool build_supernodal(Symbolic& S, std::string* err) {
   }
   bucket_tasks(ss, N.n_slevels, &N.ss_ptr, &N.ss);
   bucket_tasks(sa, N.n_slevels, &N.sa_ptr, &N.sa);
+  bucket_tasks(sf, N.n_slevels, &N.sf_ptr, &N.sf);
   bucket_tasks(sb, N.n_slevels, &N.sb_ptr, &N.sb);
   return true;
 }
@@ -430,6 +435,7 @@ Supernodal::Lists Supernodal::lists(int owner) const {
   filter(fb_ptr, fb, pn_owner, n_plevels, &L.fb_ptr, &L.fb);
   filter(ss_ptr, ss, sn_owner, n_slevels, &L.ss_ptr, &L.ss);
   filter(sa_ptr, sa, sn_owner, n_slevels, &L.sa_ptr, &L.sa);
+  filter(sf_ptr, sf, pn_owner, n_slevels, &L.sf_ptr, &L.sf);
   filter(sb_ptr, sb, pn_owner, n_slevels, &L.sb_ptr, &L.sb);
   const int pair_doubles = (kPanelWidth * (kPanelWidth + 1) / 2 + 1) / 2;
   L.fa_smem.assign(n_plevels, 0);
@@ -574,29 +580,14 @@ bool analyse(int n, const std::vector<std::pair<int, int> >& edges, int ordering
     return false;
   }
   S.row_idx.resize(S.nnzb);
-  S.col_of.resize(S.nnzb);
+  S.n_ops = 0;
   for (int p = 0; p < n; ++p) {
     int w = S.col_ptr[p];
-    S.row_idx[w] = p;
-    S.col_of[w++] = p;
-    for (size_t i = 0; i < cols[p].size(); ++i) {
-      S.row_idx[w] = cols[p][i];
-      S.col_of[w++] = p;
-    }
+    S.row_idx[w++] = p;
+    for (size_t i = 0; i < cols[p].size(); ++i) S.row_idx[w++] = cols[p][i];
+    S.n_ops += static_cast<int64_t>(cols[p].size()) * (static_cast<int64_t>(cols[p].size()) + 1) / 2;
     std::vector<int>().swap(cols[p]);
   }
-  // row view of the strictly lower part
-  S.row_ptr.assign(n + 1, 0);
-  for (int p = 0; p < n; ++p)
-    for (int w = S.col_ptr[p] + 1; w < S.col_ptr[p + 1]; ++w) ++S.row_ptr[S.row_idx[w] + 1];
-  for (int p = 0; p < n; ++p) S.row_ptr[p + 1] += S.row_ptr[p];
-  S.row_pos.resize(S.row_ptr[n]);
-  {
-    std::vector<int> cur(S.row_ptr.begin(), S.row_ptr.end() - 1);
-    for (int p = 0; p < n; ++p)
-      for (int w = S.col_ptr[p] + 1; w < S.col_ptr[p + 1]; ++w) S.row_pos[cur[S.row_idx[w]]++] = w;
-  }
-
   // ---- levels -----------------------------------------------------------------------------------
   S.level.assign(n, 0);
   S.n_levels = n ? 1 : 0;
@@ -605,15 +596,6 @@ bool analyse(int n, const std::vector<std::pair<int, int> >& edges, int ordering
     if (par >= 0) S.level[par] = std::max(S.level[par], S.level[p] + 1);
     S.n_levels = std::max(S.n_levels, S.level[p] + 1);
   }
-  S.level_ptr.assign(S.n_levels + 1, 0);
-  for (int p = 0; p < n; ++p) ++S.level_ptr[S.level[p] + 1];
-  for (int l = 0; l < S.n_levels; ++l) S.level_ptr[l + 1] += S.level_ptr[l];
-  S.level_cols.resize(n);
-  {
-    std::vector<int> cur(S.level_ptr.begin(), S.level_ptr.end() - 1);
-    for (int p = 0; p < n; ++p) S.level_cols[cur[S.level[p]]++] = p;
-  }
-
   // ---- partition bookkeeping -----------------------------------------------------------------------
   S.local_levels = 0;
   S.shared_min_level = S.n_levels;
@@ -633,64 +615,7 @@ bool analyse(int n, const std::vector<std::pair<int, int> >& edges, int ordering
       return false;
     }
   }
-  {
-    // shared columns whose diagonal no shared-source update completes at their own level
-    std::vector<char> has_shared_child(n, 0);
-    for (int p = 0; p < n; ++p) {
-      const int par = S.parent[p];
-      if (par >= 0 && S.owner[p] < 0 && S.level[p] + 1 == S.level[par]) has_shared_child[par] = 1;
-    }
-    S.xfinal_ptr.assign(S.n_levels + 1, 0);
-    for (int p = 0; p < n; ++p)
-      if (S.owner[p] < 0 && !has_shared_child[p]) ++S.xfinal_ptr[S.level[p] + 1];
-    for (int l = 0; l < S.n_levels; ++l) S.xfinal_ptr[l + 1] += S.xfinal_ptr[l];
-    S.xfinal_cols.resize(S.xfinal_ptr[S.n_levels]);
-    std::vector<int> cur(S.xfinal_ptr.begin(), S.xfinal_ptr.end() - 1);
-    for (int p = 0; p < n; ++p)
-      if (S.owner[p] < 0 && !has_shared_child[p]) S.xfinal_cols[cur[S.level[p]]++] = p;
-  }
-
-  S.phase_ptr.assign(S.n_levels + 1, 0);
   if (!build_supernodal(S, err)) return false;
-  // ---- forward-substitution schedule ------------------------------------------------------------
-  {
-    S.fwd_ptr.assign(S.n_levels + 1, 0);
-    S.fwd_ops.resize(S.nnzb - n);
-    std::vector<int> cnt(n, 0), rows_touched;
-    int64_t cursor = 0;
-    for (int l = 1; l < S.n_levels; ++l) {
-      S.fwd_ptr[l] = static_cast<int>(cursor);
-      rows_touched.clear();
-      for (int t = S.level_ptr[l - 1]; t < S.level_ptr[l]; ++t) {
-        const int k = S.level_cols[t];
-        for (int w = S.col_ptr[k] + 1; w < S.col_ptr[k + 1]; ++w)
-          if (cnt[S.row_idx[w]]++ == 0) rows_touched.push_back(S.row_idx[w]);
-      }
-      std::sort(rows_touched.begin(), rows_touched.end());
-      int64_t off = cursor;
-      for (size_t i = 0; i < rows_touched.size(); ++i) {
-        const int r = rows_touched[i];
-        const int c = cnt[r];
-        cnt[r] = static_cast<int>(off);
-        off += c;
-      }
-      for (int t = S.level_ptr[l - 1]; t < S.level_ptr[l]; ++t) {
-        const int k = S.level_cols[t];
-        for (int w = S.col_ptr[k] + 1; w < S.col_ptr[k + 1]; ++w) {
-          const int r = S.row_idx[w];
-          SolveOp o = {S.level[r] == l ? (r | kFinalFlag) : r, w};
-          S.fwd_ops[cnt[r]++] = o;
-        }
-      }
-      for (size_t i = 0; i < rows_touched.size(); ++i) cnt[rows_touched[i]] = 0;
-      cursor = off;
-    }
-    S.fwd_ptr[S.n_levels] = static_cast<int>(cursor);
-    if (cursor != S.nnzb - n) {
-      if (err) *err = "internal: forward schedule count mismatch";
-      return false;
-    }
-  }
   S.analyse_seconds =
       std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
   return true;

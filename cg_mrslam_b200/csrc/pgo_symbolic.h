@@ -5,10 +5,11 @@
 // the unknowns are eliminated. This file does the same job for the GPU factorisation:
 //   * fill-reducing ordering of the free vertices (nested dissection on the block graph; g2o
 //     uses scalar AMD, SURVEY C8 -- the ordering changes rounding only, not the solution);
-//   * elimination tree, block structure of the factor, column levels;
-//   * an explicit, ordered list of every block update  M(i,j) -= M(i,k) D(k)^-1 M(j,k)^T  grouped
-//     by the phase in which its source column k becomes final ("inspector"), which the kernels in
-//     pgo_kernels.cu execute without searching and without atomics ("executor").
+//   * elimination tree, block structure of the factor;
+//   * supernodes, panels, the scatter tables of the panels' outer products and the task lists per
+//     level that the kernels in pgo_kernels.cu execute without searching ("inspector / executor");
+//   * for world > 1, the cut of the top dissection levels into shared separators and the owner
+//     of every other column.
 #ifndef CGM_PGO_SYMBOLIC_H
 #define CGM_PGO_SYMBOLIC_H
 
@@ -23,17 +24,6 @@
 #endif
 
 namespace pgo {
-
-// One block update  M(target) -= M(a) * Dinv(col_of(a)) * M(b)^T.  Updates of one phase are sorted
-// by target; a thread owns a maximal run of equal targets (runs are short: the sources of one
-// phase rarely share a target). kFinalFlag marks runs that complete the diagonal block of a
-// column whose level equals the phase: the owner then also inverts it.
-struct UpdateOp {
-  int target;  // position of M(i,j) | kFinalFlag
-  int a;       // position of M(i,k)
-  int b;       // position of M(j,k)
-};
-static const int kFinalFlag = 0x40000000;
 
 // ---- supernodal view (single-GPU factorisation and solves) -------------------------------------
 // A SUPERNODE is a maximal chain of columns with nested structure (column q+1 is q's parent and
@@ -105,18 +95,20 @@ struct Supernodal {
   // CTA tasks for the rest (fa: factor a row chunk; fb: one tile of the outer product)
   std::vector<int> ff_ptr, fa_ptr, fb_ptr;  // n_plevels + 1
   std::vector<Task> ff, fa, fb;
-  // backward-substitution tasks by supernode level (the forward substitution rides along with the
-  // factorisation): ss = whole small supernode (warp), sa = triangular part of a wide supernode
-  // (CTA), sb = gather over the rows below a wide supernode's panel (warp, chunks of 64 rows)
-  std::vector<int> ss_ptr, sa_ptr, sb_ptr;  // n_slevels + 1
-  std::vector<Task> ss, sa, sb;
+  // substitution tasks by supernode level: ss = whole small supernode (warp), sa = triangular part
+  // of a wide supernode (CTA), sb = backward gather over the rows below a wide supernode's panel
+  // (warp, chunks of 64 rows), sf = forward scatter over the same rows (chunks of 32; only for
+  // right-hand sides solved after the factorisation: during an iteration the forward substitution
+  // rides along with the factorisation)
+  std::vector<int> ss_ptr, sa_ptr, sf_ptr, sb_ptr;  // n_slevels + 1
+  std::vector<Task> ss, sa, sf, sb;
   // what the host needs to launch the phases: level pointers and per-level shared-memory needs
   // what one stage of an iteration launches: the tasks of the panels / supernodes of one owner
   // (kAllOwners: everything, the single-GPU case), by level, with per-level shared-memory needs
   struct Lists {
     int n_plevels = 0, n_slevels = 0;
-    std::vector<int> ff_ptr, fa_ptr, fb_ptr, ss_ptr, sa_ptr, sb_ptr;
-    std::vector<Task> ff, fa, fb, ss, sa, sb;
+    std::vector<int> ff_ptr, fa_ptr, fb_ptr, ss_ptr, sa_ptr, sf_ptr, sb_ptr;
+    std::vector<Task> ff, fa, fb, ss, sa, sf, sb;
     std::vector<int> fa_smem, fb_smem;  // doubles of shared memory of the largest task per level
     std::vector<int> sa_smem;
   };
@@ -124,11 +116,6 @@ struct Supernodal {
   Lists lists(int owner) const;
   int64_t update_blocks = 0;   // target blocks touched by all outer products (atomic 3x3 adds)
   double flops = 0.0;          // of one numeric factorisation
-};
-
-struct SolveOp {
-  int row;  // target block row | kFinalFlag
-  int pos;  // position of M(row, k)
 };
 
 struct Symbolic {
@@ -141,37 +128,19 @@ struct Symbolic {
   // factor structure, block CSC, diagonal first, rows ascending
   std::vector<int> col_ptr;     // n + 1
   std::vector<int> row_idx;     // nnzb
-  std::vector<int> col_of;      // nnzb: column of each position
-  // the same structure by rows (strictly lower part), for the forward substitution
-  std::vector<int> row_ptr;     // n + 1
-  std::vector<int> row_pos;     // position of M(j,k) for each k < j in row j, k ascending
-  // columns grouped by level
-  std::vector<int> level_ptr;   // n_levels + 1
-  std::vector<int> level_cols;  // n
-  // update schedule: phase l (1 <= l < n_levels) applies ops [phase_ptr[l], phase_ptr[l+1])
-  std::vector<int> phase_ptr;   // n_levels + 1 (phase 0 is empty)
-  std::vector<UpdateOp> ops;
-  // forward-substitution schedule, same idea: phase l applies  z(i) -= M(i,k) u(k)  for every
-  // off-diagonal block of the columns k of level l - 1, sorted by target row i; kFinalFlag marks
-  // the runs after which row i (of level l) is complete
-  std::vector<int> fwd_ptr;     // n_levels + 1
-  std::vector<SolveOp> fwd_ops;
   // multi-GPU domain decomposition (world > 1): owner[p] = rank that eliminates column p, or -1
   // for the shared top separators, which are ordered last: columns [first_shared, n) are shared.
   // A column's elimination-tree descendants all have the same owner; no edge connects two
-  // different owners. explicit_final lists, per level, the shared columns that no shared-source
-  // update completes (their children are all owned by ranks).
+  // different owners.
   int world = 1;
   std::vector<int> owner;          // n
   int first_shared = 0;            // == n when world == 1
   int local_levels = 0;            // 1 + max level of an owned column
   int shared_min_level = 0;        // min level of a shared column (n_levels if none)
-  std::vector<int> xfinal_ptr;     // n_levels + 1
-  std::vector<int> xfinal_cols;
   Supernodal sn;
   // statistics
-  int64_t nnzb = 0, n_ops = 0;
-  int max_run = 0;              // longest run of updates sharing one target within a phase
+  int64_t nnzb = 0;
+  int64_t n_ops = 0;            // 3x3 block products of one factorisation (sum over columns of m (m + 1) / 2)
   double analyse_seconds = 0.0;
 };
 

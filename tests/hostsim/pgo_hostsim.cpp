@@ -66,6 +66,7 @@ extern "C" int pgo_hostsim_solve(int n, int n_blocks, const int32_t* brow, const
   V.scratch = scratch.data();
   V.status = &status;
   V.s_M = V.s_Dinv = V.s_vec = V.s_scratch = 0;
+  V.s_status = 0;
   std::vector<double> sm(kCtaSmemDoubles);
   const SeqGroup g;
   for (int l = 0; l < N.n_plevels; ++l) {
@@ -82,6 +83,29 @@ extern "C" int pgo_hostsim_solve(int n, int n_blocks, const int32_t* brow, const
   }
   for (int p = 0; p < n; ++p)
     for (int k = 0; k < 3; ++k) x_out[3 * static_cast<size_t>(S.perm[p]) + k] = x[3 * static_cast<size_t>(p) + k];
+  // the stand-alone forward substitution (marginals path) on the same right-hand side must give the
+  // same solution: x2 is returned behind x
+  {
+    std::vector<double> z2(3 * static_cast<size_t>(n)), x2(3 * static_cast<size_t>(n), 0.0);
+    for (int p = 0; p < n; ++p)
+      for (int k = 0; k < 3; ++k) z2[3 * static_cast<size_t>(p) + k] = rhs[3 * static_cast<size_t>(S.perm[p]) + k];
+    V.z = z2.data();
+    V.x = x2.data();
+    for (int l = 0; l < N.n_slevels; ++l) {
+      for (int i = N.sa_ptr[l]; i < N.sa_ptr[l + 1]; ++i) sn_task_forward_tri(g, V, N.sa[i], sm.data());
+      for (int i = N.ss_ptr[l]; i < N.ss_ptr[l + 1]; ++i) sn_task_forward_small(g, V, N.ss[i], sm.data());
+      for (int i = N.sf_ptr[l]; i < N.sf_ptr[l + 1]; ++i)
+        sn_forward_rows(g, V, N.sf[i].id, N.sf[i].r0, N.sf[i].r1, nullptr);
+    }
+    for (int l = N.n_slevels - 1; l >= 0; --l) {
+      for (int i = N.sb_ptr[l]; i < N.sb_ptr[l + 1]; ++i) sn_backward_rows(g, V, N.sb[i].id, N.sb[i].r0, N.sb[i].r1);
+      for (int i = N.ss_ptr[l]; i < N.ss_ptr[l + 1]; ++i) sn_task_backward_small(g, V, N.ss[i], sm.data());
+      for (int i = N.sa_ptr[l]; i < N.sa_ptr[l + 1]; ++i) sn_task_backward_tri(g, V, N.sa[i], sm.data());
+    }
+    for (int p = 0; p < n; ++p)
+      for (int k = 0; k < 3; ++k)
+        x_out[3 * static_cast<size_t>(n) + 3 * static_cast<size_t>(S.perm[p]) + k] = x2[3 * static_cast<size_t>(p) + k];
+  }
   if (stats) {
     stats[0] = N.n_super;
     stats[1] = N.n_panels;
