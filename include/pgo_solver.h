@@ -40,9 +40,9 @@ typedef struct pgo_solver pgo_solver;
 
 typedef struct pgo_stats {
   int32_t n_vertices, n_edges, n_free;   /* as given / non-fixed vertices                        */
-  int32_t n_levels;                      /* elimination-tree height = phases per factorisation   */
+  int32_t n_levels;                      /* elimination-tree height (the kernels run per PANEL level) */
   int64_t factor_blocks;                 /* 3x3 blocks in the factor (incl. diagonal)            */
-  int64_t update_ops;                    /* block updates per factorisation                      */
+  int64_t update_ops;                    /* 3x3 block products of one factorisation               */
   int64_t hessian_blocks;                /* non-zero 3x3 blocks of H (lower triangle + diagonal) */
   double analyse_seconds;                /* host time of the structure analysis                  */
   double last_iterate_ms;                /* device time of the last pgo_iterate call             */
@@ -61,7 +61,7 @@ void pgo_destroy(pgo_solver* s);
 
 /* SparseOptimizer::initializeOptimization + BlockSolver::buildStructure + the symbolic part of
  * LinearSolverCSparse: active set, hessian indices (fixed -> -1, the others
- * 0..n-1 in vertex order), fill-reducing ordering, factor structure, update schedule.
+ * 0..n-1 in vertex order), fill-reducing ordering, factor structure, supernodes / panels, task lists.
  * fixed[v] != 0 marks a fixed vertex. At least one vertex must be fixed per connected component,
  * exactly as with g2o (otherwise H is singular and pgo_iterate reports PGO_ERR_NUMERIC). */
 int pgo_set_graph(pgo_solver* s, int n_vertices, int n_edges, const int32_t* edge_i,
