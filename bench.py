@@ -455,12 +455,16 @@ def ours(args):
         t0 = time.perf_counter()
         m.batch_stage(cur_np, cur_counts, regions, reg_counts, step, MAX_SCORE, BINS,
                       map_pts=map_np, map_counts=map_counts)
+        ta = time.perf_counter()
         m.batch_launch()
+        tb = time.perf_counter()
         res, n_out = m.batch_collect(cap=4)
         torch.cuda.synchronize()
         t1 = time.perf_counter()
         if it >= args.warmup:
             e2e_t.append(t1 - t0)
+            e2e_split = {"stage_ms": (ta - t0) * 1e3, "launch_ms": (tb - ta) * 1e3,
+                         "collect_ms": (t1 - tb) * 1e3}
     clocks = sampler.stop() if rank == 0 else None
     d2h = int(n_out.sum()) * 16 + 32
     e2e_sec = sum(e2e_t)
@@ -510,7 +514,8 @@ def ours(args):
                         "(SURVEY 8d); the gathers hit shared memory, not DRAM, so frac may exceed 1",
                 "step_split_ms": kms[-1]},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms_max / args.steps},
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms_max / args.steps,
+                    "host_split_last_step": e2e_split},
             "gpu_launches": int(launches2 - launches1),
             "clocks": clocks,
         }
