@@ -62,6 +62,10 @@ class Dissector {
  public:
   Dissector(const Graph& g, int leaf, int world)
       : g_(g), leaf_(leaf), mark_(g.n, -1), dist_(g.n, -1), owner_(g.n, 0), load_(world, 0) {
+    for (int f = 0; f < 4; ++f) d4_[f].assign(g.n, -1);
+    pos_.assign(g.n, 0);
+    part_.assign(g.n, 0);
+    lock_.assign(g.n, 0);
     cut_depth_ = 0;
     while ((1 << cut_depth_) < world) ++cut_depth_;
   }
@@ -149,53 +153,12 @@ class Dissector {
       }
       return;
     }
-    // pseudo-peripheral start: repeat BFS from the farthest vertex
-    int start = visit.back();
-    for (int rep = 0; rep < 2; ++rep) {
-      for (size_t i = 0; i < s.size(); ++i) dist_[s[i]] = -1;
-      bfs(start, id, &visit);
-      start = visit.back();
-    }
-    const int depth_bfs = dist_[visit.back()];
-    if (depth_bfs < 2) {  // (nearly) a clique: nothing to dissect
+    const double bal = deciding ? kBalanceDeciding : kBalanceFill;
+    std::vector<int> a, b, sep;
+    if (!separate(s, id, bal, &a, &b, &sep)) {  // (nearly) a clique: nothing to dissect
       if (deciding) assign(s, depth, path);
       order_->insert(order_->end(), s.begin(), s.end());
       return;
-    }
-    std::vector<int> level_size(depth_bfs + 1, 0);
-    for (size_t i = 0; i < s.size(); ++i) ++level_size[dist_[s[i]]];
-    // separator = the smallest level whose removal leaves both sides >= kBalance (else the median)
-    const double total = static_cast<double>(s.size());
-    const double bal = deciding ? kBalanceDeciding : kBalanceFill;
-    int best = -1, below = 0, median = 1;
-    for (int m = 0; m <= depth_bfs; ++m) {
-      const int above = static_cast<int>(s.size()) - below - level_size[m];
-      if (m >= 1 && m < depth_bfs) {
-        if (below >= bal * total && above >= bal * total &&
-            (best < 0 || level_size[m] < level_size[best]))
-          best = m;
-      }
-      if (below + level_size[m] / 2 <= total / 2) median = std::max(1, std::min(m, depth_bfs - 1));
-      below += level_size[m];
-    }
-    const int cut = best >= 0 ? best : median;
-    std::vector<int> a, b, sep;
-    for (size_t i = 0; i < visit.size(); ++i) {
-      const int v = visit[i];
-      if (dist_[v] < cut) {
-        a.push_back(v);
-      } else if (dist_[v] > cut) {
-        b.push_back(v);
-      } else {
-        // thin the separator: a level-`cut` vertex without a neighbour beyond it joins side A
-        bool touches_b = false;
-        for (int t = g_.ptr[v]; t < g_.ptr[v + 1] && !touches_b; ++t) {
-          const int w = g_.adj[t];
-          touches_b = mark_[w] == id && dist_[w] > cut;
-        }
-        if (touches_b) sep.push_back(v);
-        else a.push_back(v);
-      }
     }
     if (a.empty() || b.empty()) {
       if (deciding) assign(s, depth, path);
@@ -218,9 +181,255 @@ class Dissector {
     order_->insert(order_->end(), sep.begin(), sep.end());
   }
 
+
+  // BFS inside subset `id` from `start` writing hop counts into `d` (entries of the subset must
+  // be -1 on entry); returns the last vertex reached.
+  int bfs_dist(int start, int id, std::vector<int>& d) {
+    queue_.clear();
+    queue_.push_back(start);
+    d[start] = 0;
+    for (size_t h = 0; h < queue_.size(); ++h) {
+      const int v = queue_[h];
+      for (int t = g_.ptr[v]; t < g_.ptr[v + 1]; ++t) {
+        const int w = g_.adj[t];
+        if (mark_[w] == id && d[w] < 0) {
+          d[w] = d[v] + 1;
+          queue_.push_back(w);
+        }
+      }
+    }
+    return queue_.back();
+  }
+
+  // Vertex separator of the connected subset s (mark_ == id).
+  //   1. four hop-distance fields: from a pseudo-peripheral pair (p, q) and from a second pair
+  //      (u, w) chosen off the p-q axis; the differences x = d_p - d_q, y = d_u - d_w act as two
+  //      coordinates of an embedding. Candidate sweeps: x, y, x + y, x - y, d_p, d_q.
+  //   2. per sweep: sort, and for every cut position inside the balance window count the
+  //      boundary vertices of either side (difference arrays); keep the smallest.
+  //   3. vertex Fiduccia-Mattheyses refinement of the winner (move a separator vertex to one
+  //      side, pull its neighbours on the other side into the separator; hill-climbing with
+  //      roll-back).
+  bool separate(const std::vector<int>& s, int id, double bal, std::vector<int>* a,
+                std::vector<int>* b, std::vector<int>* sep) {
+    const int n = static_cast<int>(s.size());
+    for (int f = 0; f < 4; ++f)
+      for (int i = 0; i < n; ++i) d4_[f][s[i]] = -1;
+    int p = bfs_dist(s[0], id, d4_[0]);
+    for (int i = 0; i < n; ++i) d4_[0][s[i]] = -1;
+    int q = bfs_dist(p, id, d4_[0]);
+    for (int i = 0; i < n; ++i) d4_[0][s[i]] = -1;
+    p = bfs_dist(q, id, d4_[0]);   // d4_[0] = hops from q ... (q, p) is the pseudo-peripheral pair
+    std::swap(p, q);               // now d4_[0] is the distance from p
+    if (d4_[0][q] < 2) return false;
+    bfs_dist(q, id, d4_[1]);
+    int u = s[0];
+    long long best_sum = -1;
+    for (int i = 0; i < n; ++i) {
+      const int v = s[i];
+      // far from the p-q axis, and not next to either end
+      const long long off = static_cast<long long>(d4_[0][v]) + d4_[1][v] -
+                            std::abs(d4_[0][v] - d4_[1][v]);
+      if (off > best_sum) {
+        best_sum = off;
+        u = v;
+      }
+    }
+    const int w = bfs_dist(u, id, d4_[2]);
+    bfs_dist(w, id, d4_[3]);
+
+    int lo = std::max(1, static_cast<int>(bal * n)), hi = std::min(n - 1, n - lo);
+    std::vector<std::pair<long long, int> > keyed(n);
+    std::vector<int> diff_a(n + 2), diff_b(n + 2), best_order;
+    int best_cost = n + 1, best_k = -1;
+    bool best_from_a = true;
+    // no admissible cut inside the balance window (small, dense subsets): widen the window
+    for (int attempt = 0; attempt < 3 && best_k < 0; ++attempt, lo = attempt == 1 ? std::max(1, lo / 2) : 1, hi = n - lo)
+    for (int cand = 0; cand < 6; ++cand) {
+      for (int i = 0; i < n; ++i) {
+        const int v = s[i];
+        const long long x = d4_[0][v] - d4_[1][v], y = d4_[2][v] - d4_[3][v];
+        long long k1, k2;
+        switch (cand) {
+          case 0: k1 = x; k2 = y; break;
+          case 1: k1 = y; k2 = x; break;
+          case 2: k1 = x + y; k2 = x - y; break;
+          case 3: k1 = x - y; k2 = x + y; break;
+          case 4: k1 = d4_[0][v]; k2 = y; break;
+          default: k1 = d4_[1][v]; k2 = y; break;
+        }
+        keyed[i] = std::make_pair(k1 * (1LL << 24) + k2, v);
+      }
+      std::sort(keyed.begin(), keyed.end());
+      for (int i = 0; i < n; ++i) pos_[keyed[i].second] = i;
+      std::fill(diff_a.begin(), diff_a.end(), 0);
+      std::fill(diff_b.begin(), diff_b.end(), 0);
+      for (int i = 0; i < n; ++i) {
+        const int v = keyed[i].second;
+        int mx = i, mn = i;
+        for (int t = g_.ptr[v]; t < g_.ptr[v + 1]; ++t) {
+          const int x = g_.adj[t];
+          if (mark_[x] != id) continue;
+          mx = std::max(mx, pos_[x]);
+          mn = std::min(mn, pos_[x]);
+        }
+        // with A = [0, k): v is on A's boundary for i < k <= mx, on B's boundary for mn < k <= i
+        ++diff_a[i + 1];
+        --diff_a[mx + 1];
+        ++diff_b[mn + 1];
+        --diff_b[i + 1];
+      }
+      int ca = 0, cb = 0;
+      for (int k = 1; k <= hi; ++k) {
+        ca += diff_a[k];
+        cb += diff_b[k];
+        if (k < lo) continue;
+        // the separator is taken out of one side: that side must stay above the balance bound
+        const int cost_a = k - ca >= lo ? ca : n + 1, cost_b = n - k - cb >= lo ? cb : n + 1;
+        const int c = std::min(cost_a, cost_b);
+        if (c < best_cost) {
+          best_cost = c;
+          best_k = k;
+          best_from_a = cost_a <= cost_b;
+          best_order.resize(n);
+          for (int i = 0; i < n; ++i) best_order[i] = keyed[i].second;
+        }
+      }
+    }
+    if (best_k < 0) return false;
+    // part: 0 = A, 1 = B, 2 = separator
+    for (int i = 0; i < n; ++i) part_[best_order[i]] = i < best_k ? 0 : 1;
+    for (int i = 0; i < n; ++i) {
+      const int v = best_order[i];
+      if ((i < best_k) != best_from_a) continue;
+      const int other = best_from_a ? 1 : 0;
+      for (int t = g_.ptr[v]; t < g_.ptr[v + 1]; ++t) {
+        const int x = g_.adj[t];
+        if (mark_[x] == id && part_[x] == other) {
+          part_[v] = 2;
+          break;
+        }
+      }
+    }
+    refine(s, id, lo);
+    a->clear();
+    b->clear();
+    sep->clear();
+    for (int i = 0; i < n; ++i) {
+      const int v = best_order[i];
+      (part_[v] == 0 ? a : part_[v] == 1 ? b : sep)->push_back(v);
+    }
+    return !a->empty() && !b->empty();
+  }
+
+  // Vertex-separator FM on part_ (0 / 1 / 2) of subset `id`; both sides keep >= lo vertices.
+  void refine(const std::vector<int>& s, int id, int lo) {
+    const int n = static_cast<int>(s.size());
+    std::vector<int> sepv;
+    int size[3] = {0, 0, 0};
+    for (int i = 0; i < n; ++i) {
+      ++size[part_[s[i]]];
+      if (part_[s[i]] == 2) sepv.push_back(s[i]);
+      lock_[s[i]] = 0;
+    }
+    struct Move { int v, to, n_pulled; };
+    std::vector<Move> log;
+    std::vector<int> pulled;
+    for (int pass = 0; pass < 8; ++pass) {
+      log.clear();
+      pulled.clear();
+      const int start_sep = size[2];
+      int best_sep = size[2], best_at = 0, best_imb = std::abs(size[0] - size[1]);
+      const int patience = 40 + size[2] / 4;
+      std::vector<int> touched;
+      while (true) {
+        int bv = -1, bto = 0, bgain = -(1 << 30), bslot = -1;
+        for (size_t i = 0; i < sepv.size(); ++i) {
+          const int v = sepv[i];
+          if (part_[v] != 2 || lock_[v]) continue;
+          int nb[2] = {0, 0};
+          for (int t = g_.ptr[v]; t < g_.ptr[v + 1]; ++t) {
+            const int x = g_.adj[t];
+            if (mark_[x] == id && part_[x] < 2) ++nb[part_[x]];
+          }
+          for (int to = 0; to < 2; ++to) {
+            const int pull = nb[1 - to];
+            if (size[1 - to] - pull < lo) continue;
+            const int gain = 1 - pull;
+            // ties: towards the smaller side
+            const bool better = gain > bgain || (gain == bgain && size[to] < size[bto]);
+            if (better) {
+              bgain = gain;
+              bv = v;
+              bto = to;
+              bslot = static_cast<int>(i);
+            }
+          }
+        }
+        if (bv < 0) break;
+        (void)bslot;
+        // apply
+        part_[bv] = bto;
+        lock_[bv] = 1;
+        touched.push_back(bv);
+        ++size[bto];
+        --size[2];
+        int n_pulled = 0;
+        for (int t = g_.ptr[bv]; t < g_.ptr[bv + 1]; ++t) {
+          const int x = g_.adj[t];
+          if (mark_[x] == id && part_[x] == 1 - bto) {
+            part_[x] = 2;
+            --size[1 - bto];
+            ++size[2];
+            sepv.push_back(x);
+            pulled.push_back(x);
+            ++n_pulled;
+          }
+        }
+        const Move m = {bv, bto, n_pulled};
+        log.push_back(m);
+        const int imb = std::abs(size[0] - size[1]);
+        if (size[2] < best_sep || (size[2] == best_sep && imb < best_imb)) {
+          best_sep = size[2];
+          best_imb = imb;
+          best_at = static_cast<int>(log.size());
+        }
+        if (static_cast<int>(log.size()) - best_at > patience) break;
+      }
+      // roll back to the best prefix
+      while (static_cast<int>(log.size()) > best_at) {
+        const Move m = log.back();
+        log.pop_back();
+        for (int k = 0; k < m.n_pulled; ++k) {
+          const int x = pulled.back();
+          pulled.pop_back();
+          part_[x] = 1 - m.to;
+          ++size[1 - m.to];
+          --size[2];
+        }
+        part_[m.v] = 2;
+        --size[m.to];
+        ++size[2];
+      }
+      for (size_t i = 0; i < touched.size(); ++i) lock_[touched[i]] = 0;
+      // compact the separator list
+      size_t wr = 0;
+      for (size_t i = 0; i < sepv.size(); ++i)
+        if (part_[sepv[i]] == 2 && !lock_[sepv[i]]) {
+          lock_[sepv[i]] = 2;  // de-duplicate
+          sepv[wr++] = sepv[i];
+        }
+      sepv.resize(wr);
+      for (size_t i = 0; i < sepv.size(); ++i) lock_[sepv[i]] = 0;
+      if (size[2] >= start_sep && pass > 0) break;
+      if (best_at == 0) break;
+    }
+  }
+
   const Graph& g_;
   int leaf_;
   std::vector<int> mark_, dist_, owner_;
+  std::vector<int> d4_[4], pos_, part_, lock_, queue_;
   std::vector<long long> load_;
   int cut_depth_ = 0;
   std::vector<int>* order_ = nullptr;
