@@ -244,8 +244,8 @@ class Dissector {
     int best_cost = n + 1, best_k = -1;
     bool best_from_a = true;
     // no admissible cut inside the balance window (small, dense subsets): widen the window
-    for (int attempt = 0; attempt < 3 && best_k < 0; ++attempt, lo = attempt == 1 ? std::max(1, lo / 2) : 1, hi = n - lo)
-    for (int cand = 0; cand < 6; ++cand) {
+    int best_cand = 0;
+    auto sweep = [&](int cand) {
       for (int i = 0; i < n; ++i) {
         const int v = s[i];
         const long long x = d4_[0][v] - d4_[1][v], y = d4_[2][v] - d4_[3][v];
@@ -261,42 +261,50 @@ class Dissector {
         keyed[i] = std::make_pair(k1 * (1LL << 24) + k2, v);
       }
       std::sort(keyed.begin(), keyed.end());
-      for (int i = 0; i < n; ++i) pos_[keyed[i].second] = i;
-      std::fill(diff_a.begin(), diff_a.end(), 0);
-      std::fill(diff_b.begin(), diff_b.end(), 0);
-      for (int i = 0; i < n; ++i) {
-        const int v = keyed[i].second;
-        int mx = i, mn = i;
-        for (int t = g_.ptr[v]; t < g_.ptr[v + 1]; ++t) {
-          const int x = g_.adj[t];
-          if (mark_[x] != id) continue;
-          mx = std::max(mx, pos_[x]);
-          mn = std::min(mn, pos_[x]);
+    };
+    // no admissible cut inside the balance window (small, dense subsets): widen the window
+    for (int attempt = 0; attempt < 3 && best_k < 0;
+         ++attempt, lo = attempt == 1 ? std::max(1, lo / 2) : 1, hi = n - lo)
+      for (int cand = 0; cand < 6; ++cand) {
+        sweep(cand);
+        for (int i = 0; i < n; ++i) pos_[keyed[i].second] = i;
+        std::fill(diff_a.begin(), diff_a.end(), 0);
+        std::fill(diff_b.begin(), diff_b.end(), 0);
+        for (int i = 0; i < n; ++i) {
+          const int v = keyed[i].second;
+          int mx = i, mn = i;
+          for (int t = g_.ptr[v]; t < g_.ptr[v + 1]; ++t) {
+            const int x = g_.adj[t];
+            if (mark_[x] != id) continue;
+            mx = std::max(mx, pos_[x]);
+            mn = std::min(mn, pos_[x]);
+          }
+          // with A = [0, k): v is on A's boundary for i < k <= mx, on B's boundary for mn < k <= i
+          ++diff_a[i + 1];
+          --diff_a[mx + 1];
+          ++diff_b[mn + 1];
+          --diff_b[i + 1];
         }
-        // with A = [0, k): v is on A's boundary for i < k <= mx, on B's boundary for mn < k <= i
-        ++diff_a[i + 1];
-        --diff_a[mx + 1];
-        ++diff_b[mn + 1];
-        --diff_b[i + 1];
-      }
-      int ca = 0, cb = 0;
-      for (int k = 1; k <= hi; ++k) {
-        ca += diff_a[k];
-        cb += diff_b[k];
-        if (k < lo) continue;
-        // the separator is taken out of one side: that side must stay above the balance bound
-        const int cost_a = k - ca >= lo ? ca : n + 1, cost_b = n - k - cb >= lo ? cb : n + 1;
-        const int c = std::min(cost_a, cost_b);
-        if (c < best_cost) {
-          best_cost = c;
-          best_k = k;
-          best_from_a = cost_a <= cost_b;
-          best_order.resize(n);
-          for (int i = 0; i < n; ++i) best_order[i] = keyed[i].second;
+        int ca = 0, cb = 0;
+        for (int k = 1; k <= hi; ++k) {
+          ca += diff_a[k];
+          cb += diff_b[k];
+          if (k < lo) continue;
+          // the separator is taken out of one side: that side must stay above the balance bound
+          const int cost_a = k - ca >= lo ? ca : n + 1, cost_b = n - k - cb >= lo ? cb : n + 1;
+          const int c = std::min(cost_a, cost_b);
+          if (c < best_cost) {
+            best_cost = c;
+            best_k = k;
+            best_from_a = cost_a <= cost_b;
+            best_cand = cand;
+          }
         }
       }
-    }
     if (best_k < 0) return false;
+    sweep(best_cand);
+    best_order.resize(n);
+    for (int i = 0; i < n; ++i) best_order[i] = keyed[i].second;
     // part: 0 = A, 1 = B, 2 = separator
     for (int i = 0; i < n; ++i) part_[best_order[i]] = i < best_k ? 0 : 1;
     for (int i = 0; i < n; ++i) {
