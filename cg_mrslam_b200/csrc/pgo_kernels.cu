@@ -468,12 +468,13 @@ __global__ void __launch_bounds__(kUpdateThreads, 5) sn_k_update(SNView V, const
   }
 }
 // ff: small panels start to finish, one warp each
-__global__ void __launch_bounds__(32 * kWarpsPerCta) sn_k_fused(SNView V, const Task* tasks, int n) {
+// (stride = shared-memory doubles per warp: the largest task of the level)
+__global__ void __launch_bounds__(32 * kWarpsPerCta, 8) sn_k_fused(SNView V, const Task* tasks, int n, int stride) {
   extern __shared__ double sm[];
   const int i = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
   V = sn_at_instance(V, blockIdx.y);
   if (i >= n || sn_failed(V)) return;
-  sn_task_fused(WarpGroup(), V, tasks[i], sm + (threadIdx.x >> 5) * kWarpSmemDoubles);
+  sn_task_fused(WarpGroup(), V, tasks[i], sm + (threadIdx.x >> 5) * stride);
 }
 // backward substitution
 __global__ void __launch_bounds__(32 * kWarpsPerCta) sn_k_bwd_rows(SNView V, const Task* tasks, int n) {
@@ -487,9 +488,9 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) sn_k_bwd_small(SNView V, co
   const int i = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
   V = sn_at_instance(V, blockIdx.y);
   if (i >= n || sn_failed(V)) return;
-  sn_task_backward_small(WarpGroup(), V, tasks[i], sm + (threadIdx.x >> 5) * kWarpSmemDoubles);
+  sn_task_backward_small(WarpGroup(), V, tasks[i], sm + (threadIdx.x >> 5) * kWarpSubstDoubles);
 }
-__global__ void __launch_bounds__(kCtaThreads) sn_k_bwd_tri(SNView V, const Task* tasks) {
+__global__ void __launch_bounds__(kCtaThreads, 2) sn_k_bwd_tri(SNView V, const Task* tasks) {
   extern __shared__ double sm[];
   V = sn_at_instance(V, blockIdx.y);
   if (sn_failed(V)) return;
@@ -507,7 +508,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) sn_k_fwd_small(SNView V, co
   const int i = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
   V = sn_at_instance(V, blockIdx.y);
   if (i >= n) return;
-  sn_task_forward_small(WarpGroup(), V, tasks[i], sm + (threadIdx.x >> 5) * kWarpSmemDoubles);
+  sn_task_forward_small(WarpGroup(), V, tasks[i], sm + (threadIdx.x >> 5) * kWarpSubstDoubles);
 }
 __global__ void __launch_bounds__(32 * kWarpsPerCta) sn_k_fwd_rows(SNView V, const Task* tasks, int n) {
   const int i = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
@@ -1077,8 +1078,9 @@ static int enqueue_factor(DeviceSolver* d, const DeviceSolver::TaskSet& ts, int*
       side = d->aux;
     }
     if (n_ff) {
+      const int stride = (L.ff_smem[l] + 1) & ~1;
       sn_k_fused<<<dim3((n_ff + kWarpsPerCta - 1) / kWarpsPerCta, B), 32 * kWarpsPerCta,
-                   sizeof(double) * kWarpSmemDoubles * kWarpsPerCta, side>>>(V, ts.ff.p + L.ff_ptr[l], n_ff);
+                   sizeof(double) * stride * kWarpsPerCta, side>>>(V, ts.ff.p + L.ff_ptr[l], n_ff, stride);
       ++*nodes;
     }
     if (n_fa) {
@@ -1103,7 +1105,7 @@ static int enqueue_backward(DeviceSolver* d, const DeviceSolver::TaskSet& ts, co
                             int* nodes, std::string* err) {
   cudaStream_t st = d->stream;
   const Supernodal::Lists& L = ts.L;
-  const size_t warp_bytes = sizeof(double) * kWarpSmemDoubles * kWarpsPerCta;
+  const size_t warp_bytes = sizeof(double) * kWarpSubstDoubles * kWarpsPerCta;
   for (int l = L.n_slevels - 1; l >= 0; --l) {
     const int n_sa = L.sa_ptr[l + 1] - L.sa_ptr[l], n_ss = L.ss_ptr[l + 1] - L.ss_ptr[l],
               n_sb = L.sb_ptr[l + 1] - L.sb_ptr[l];
@@ -1143,7 +1145,7 @@ static int enqueue_forward(DeviceSolver* d, const DeviceSolver::TaskSet& ts, con
                            int* nodes, std::string* err) {
   cudaStream_t st = d->stream;
   const Supernodal::Lists& L = ts.L;
-  const size_t warp_bytes = sizeof(double) * kWarpSmemDoubles * kWarpsPerCta;
+  const size_t warp_bytes = sizeof(double) * kWarpSubstDoubles * kWarpsPerCta;
   for (int l = 0; l < L.n_slevels; ++l) {
     const int n_sa = L.sa_ptr[l + 1] - L.sa_ptr[l], n_ss = L.ss_ptr[l + 1] - L.ss_ptr[l],
               n_sf = L.sf_ptr[l + 1] - L.sf_ptr[l];

@@ -79,6 +79,12 @@ static const int kSmallPairDoubles = (kSmallWidth * (kSmallWidth + 1) / 2 + 1) /
 static const int kWarpSmemDoubles = kSmallWidth * kSmallWidth * 9 + kSmallWidth * 9 +
                                     kSmallPairDoubles + 3 * kSmallWidth +
                                     3 * kSmallWidth * (3 * kSmallRows + 1);  // fused
+// warp tasks of the substitutions: xs[3W] us[3W] Dg[W*W*9] Di[W*9] red[3 * 32]
+static const int kWarpSubstDoubles = 6 * kSmallWidth + kSmallWidth * kSmallWidth * 9 + kSmallWidth * 9 + 3 * 32;
+// shared memory of one fused task (sn_task_fused)
+PGO_HD int sn_fused_doubles(int w, int m) {
+  return w * w * 9 + w * 9 + kSmallPairDoubles + 3 * w + 3 * w * (3 * m + 1);
+}
 static_assert(kTileSmemDoubles <= kCtaSmemDoubles, "update tiles must fit the CTA's shared memory");
 static_assert(6 * kMaxSuperWidth + kPanelWidth * kPanelWidth * 9 + kPanelWidth * 9 + 3 * 256 <=
                   kCtaSmemDoubles, "a wide supernode's vectors must fit the CTA's shared memory");
@@ -448,11 +454,17 @@ PGO_HD void sn_task_fused(const G& g, const SNView& V, const Task& T, double* sm
   sn_store_rows(g, V, pd, 0, m, ldx, xs);
   sn_store_diag(g, V, pd, Dg, Di, -1);
   sn_forward_fused(g, V, pd, 0, m, ldx, xs, Di, us, true);
-  // outer product straight from shared memory: rank = column b, every rank walks the rows a >= b
-  for (int b = g.rank(); b < m; b += g.size()) {
-    const int cb = V.colbase[pd.meta + b], to = V.tbl_off[pd.meta + b];
-    for (int a = b; a < m; ++a) {
-      const int tpos = cb + V.tbl[to + a];
+  // outer product straight from shared memory: one (a, b) block pair, a >= b, per rank and turn
+  // (pairs numbered column by column: column b holds the rows b .. m-1)
+  for (int p = g.rank(); p < m * (m + 1) / 2; p += g.size()) {
+    int b = 0, a = p;
+    while (a >= m - b) {
+      a -= m - b;
+      ++b;
+    }
+    a += b;
+    {
+      const int tpos = V.colbase[pd.meta + b] + V.tbl[V.tbl_off[pd.meta + b] + a];
       double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
       for (int t = 0; t < w; ++t) {
         double av[9], y[9], bv[9];

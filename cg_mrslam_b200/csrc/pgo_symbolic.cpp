@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 
@@ -57,6 +58,7 @@ Graph build_graph(int n, const std::vector<std::pair<int, int> >& edges) {
 // each side of a cut keeps at least this share of the vertices: tighter while ranks are being
 // carved out (load balance), looser below (smaller separators, less fill)
 const double kBalanceDeciding = 0.38, kBalanceFill = 0.30;
+const int kLeafSize = 4;
 
 class Dissector {
  public:
@@ -72,6 +74,7 @@ class Dissector {
 
   // owner (per original vertex): rank, or -1 for the shared separators of the top cut_depth levels
   const std::vector<int>& owner() const { return owner_; }
+  const std::vector<std::vector<int> >& groups() const { return groups_; }
 
   void run(std::vector<int>* order) {
     order_ = order;
@@ -116,7 +119,7 @@ class Dissector {
     const bool deciding = depth < cut_depth_;
     if (static_cast<int>(s.size()) <= leaf_) {
       if (deciding) assign(s, depth, path);
-      order_->insert(order_->end(), s.begin(), s.end());
+      emit_leaf(s);
       return;
     }
     const int id = next_id_++;
@@ -155,12 +158,7 @@ class Dissector {
     }
     const double bal = deciding ? kBalanceDeciding : kBalanceFill;
     std::vector<int> a, b, sep;
-    if (!separate(s, id, bal, &a, &b, &sep)) {  // (nearly) a clique: nothing to dissect
-      if (deciding) assign(s, depth, path);
-      order_->insert(order_->end(), s.begin(), s.end());
-      return;
-    }
-    if (a.empty() || b.empty()) {
+    if (!separate(s, id, bal, &a, &b, &sep) || a.empty() || b.empty()) {  // (nearly) a clique
       if (deciding) assign(s, depth, path);
       order_->insert(order_->end(), s.begin(), s.end());
       return;
@@ -181,6 +179,26 @@ class Dissector {
     order_->insert(order_->end(), sep.begin(), sep.end());
   }
 
+
+  // A leaf of the dissection is eliminated as ONE supernode: its connected pieces are recorded as
+  // groups, and analyse() makes every column of a group carry the union of the group's boundary
+  // (explicit zero blocks inside the leaf's columns; no fill is added above the leaf, whose boundary
+  // becomes a clique either way). One dense trapezoid per leaf instead of a handful of one-column
+  // panels: a fraction of the tasks and of the scattered atomic updates.
+  void emit_leaf(const std::vector<int>& s) {
+    const int id = next_id_++;
+    for (size_t i = 0; i < s.size(); ++i) {
+      mark_[s[i]] = id;
+      dist_[s[i]] = -1;
+    }
+    std::vector<int> visit;
+    for (size_t i = 0; i < s.size(); ++i) {
+      if (dist_[s[i]] >= 0) continue;
+      bfs(s[i], id, &visit);
+      order_->insert(order_->end(), visit.begin(), visit.end());
+      if (visit.size() > 1) groups_.push_back(visit);
+    }
+  }
 
   // BFS inside subset `id` from `start` writing hop counts into `d` (entries of the subset must
   // be -1 on entry); returns the last vertex reached.
@@ -438,6 +456,7 @@ class Dissector {
   int leaf_;
   std::vector<int> mark_, dist_, owner_;
   std::vector<int> d4_[4], pos_, part_, lock_, queue_;
+  std::vector<std::vector<int> > groups_;
   std::vector<long long> load_;
   int cut_depth_ = 0;
   std::vector<int>* order_ = nullptr;
@@ -657,7 +676,14 @@ Supernodal::Lists Supernodal::lists(int owner) const {
   const int pair_doubles = (kPanelWidth * (kPanelWidth + 1) / 2 + 1) / 2;
   L.fa_smem.assign(n_plevels, 0);
   L.fb_smem.assign(n_plevels, 0);
+  L.ff_smem.assign(n_plevels, 0);
   for (int l = 0; l < n_plevels; ++l) {
+    for (int i = L.ff_ptr[l]; i < L.ff_ptr[l + 1]; ++i) {
+      const PanelDesc& pd = pn[L.ff[i].id];
+      const int w = pd.w, m = pd.m;  // = sn_fused_doubles(w, m) of pgo_supernodal.h
+      const int pair_small = (kSmallWidth * (kSmallWidth + 1) / 2 + 1) / 2;
+      L.ff_smem[l] = std::max(L.ff_smem[l], w * w * 9 + w * 9 + pair_small + 3 * w + 3 * w * (3 * m + 1));
+    }
     for (int i = L.fa_ptr[l]; i < L.fa_ptr[l + 1]; ++i) {
       const Task& t = L.fa[i];
       const int w = pn[t.id].w;
@@ -691,7 +717,7 @@ bool analyse(int n, const std::vector<std::pair<int, int> >& edges, int ordering
       if (err) *err = "edge endpoint outside the free-vertex range";
       return false;
     }
-  const Graph g = build_graph(n, edges);
+  Graph g = build_graph(n, edges);
 
   // ---- ordering -------------------------------------------------------------------------------
   if (world < 1 || (world & (world - 1)) != 0) {
@@ -708,9 +734,33 @@ bool analyse(int n, const std::vector<std::pair<int, int> >& edges, int ordering
     S.perm.resize(n);
     std::iota(S.perm.begin(), S.perm.end(), 0);
   } else {
-    Dissector d(g, 8, world);
+    int leaf = kLeafSize;
+    if (const char* ev = std::getenv("CGM_PGO_LEAF")) leaf = std::max(1, std::atoi(ev));  // tuning aid
+    Dissector d(g, leaf, world);
     d.run(&S.perm);
     vertex_owner = d.owner();
+    // leaf groups become supernodes: clique inside the group, every member tied to the whole
+    // boundary of the group (structure only; the numeric blocks of these pairs start at zero)
+    std::vector<std::pair<int, int> > all(edges);
+    std::vector<int> in_group(n, -1), boundary;
+    const std::vector<std::vector<int> >& groups = d.groups();
+    for (size_t gi = 0; gi < groups.size(); ++gi) {
+      const std::vector<int>& L = groups[gi];
+      boundary.clear();
+      for (size_t i = 0; i < L.size(); ++i) in_group[L[i]] = static_cast<int>(gi);
+      for (size_t i = 0; i < L.size(); ++i)
+        for (int t = g.ptr[L[i]]; t < g.ptr[L[i] + 1]; ++t) {
+          const int x = g.adj[t];
+          if (in_group[x] != static_cast<int>(gi)) boundary.push_back(x);
+        }
+      std::sort(boundary.begin(), boundary.end());
+      boundary.erase(std::unique(boundary.begin(), boundary.end()), boundary.end());
+      for (size_t i = 0; i < L.size(); ++i) {
+        for (size_t j = i + 1; j < L.size(); ++j) all.push_back(std::make_pair(L[i], L[j]));
+        for (size_t j = 0; j < boundary.size(); ++j) all.push_back(std::make_pair(L[i], boundary[j]));
+      }
+    }
+    if (!groups.empty()) g = build_graph(n, all);
   }
   if (static_cast<int>(S.perm.size()) != n) {
     if (err) *err = "internal: ordering lost vertices";

@@ -110,6 +110,7 @@ struct Supernodal {
     std::vector<int> ff_ptr, fa_ptr, fb_ptr, ss_ptr, sa_ptr, sf_ptr, sb_ptr;
     std::vector<Task> ff, fa, fb, ss, sa, sf, sb;
     std::vector<int> fa_smem, fb_smem;  // doubles of shared memory of the largest task per level
+    std::vector<int> ff_smem;           // ... per warp task of the fused kernel
     std::vector<int> sa_smem;
   };
   static const int kAllOwners = -2;
