@@ -71,11 +71,12 @@ struct Params {
   double* u;      // [nrhs][n][3]
   double* x;      // [nrhs][n][3]
   double* chi2_partial;  // [gridDim.x]
+  double* trig;          // [n_vertices + n_edges][2]: sin, cos of every pose angle / measurement angle
   double* chi2_out;      // [n_iters]
   int* status;           // [0] error flag, [1] iterations done
   unsigned long long* stamps;  // [6] globaltimer at the stage boundaries of the last iteration
   // batch of problem instances with this structure: element strides between instances
-  long long s_poses, s_meas, s_info, s_M, s_Dinv, s_vec, s_partial, s_chi2;
+  long long s_poses, s_meas, s_info, s_M, s_Dinv, s_vec, s_partial, s_chi2, s_trig;
 };
 
 // Instance b of a batch (blockIdx.y in the kernels of the iteration graph).
@@ -89,6 +90,7 @@ __device__ __forceinline__ Params params_at(Params P, int b) {
   P.u += b * P.s_vec;
   P.x += b * P.s_vec;
   P.chi2_partial += b * P.s_partial;
+  P.trig += b * P.s_trig;
   P.chi2_out += b * P.s_chi2;
   P.status += 4 * b;
   return P;
@@ -204,6 +206,54 @@ __device__ void linearise_edge(const Params& P, int edge, EdgeLin* L) {
   L->om[8] = w[5];
 }
 
+// The same with the sines / cosines taken from P.trig (gn_trig runs first): an iteration evaluates
+// every edge from both of its ends, and each evaluation needs the rotations of theta_i, -theta_i,
+// theta_z and -theta_z; with the table an iteration costs V + E sincos instead of ~10 E.
+__device__ void linearise_edge_tab(const Params& P, int edge, EdgeLin* L) {
+  const int vi = P.edge_i[edge], vj = P.edge_j[edge];
+  const SE2d xi = load_pose(P.poses, vi);
+  const SE2d xj = load_pose(P.poses, vj);
+  const double si = P.trig[2 * vi], ci = P.trig[2 * vi + 1];
+  const double* tz = P.trig + 2 * (static_cast<size_t>(P.n_vertices) + edge);
+  const double sz = -tz[0], cz = tz[1];  // rotation of Z^-1
+  const SE2d z = {P.meas[3 * edge], P.meas[3 * edge + 1], P.meas[3 * edge + 2]};
+  SE2d zinv, ixi, d;
+  zinv.th = normalize_theta(-z.th);
+  zinv.x = cz * (-z.x) - sz * (-z.y);
+  zinv.y = sz * (-z.x) + cz * (-z.y);
+  {
+    const double s = -si, c = ci;  // rotation of Xi^-1
+    ixi.th = normalize_theta(-xi.th);
+    ixi.x = c * (-xi.x) - s * (-xi.y);
+    ixi.y = s * (-xi.x) + c * (-xi.y);
+    d.x = ixi.x + (c * xj.x - s * xj.y);
+    d.y = ixi.y + (s * xj.x + c * xj.y);
+    d.th = normalize_theta(ixi.th + xj.th);
+  }
+  L->e[0] = zinv.x + (cz * d.x - sz * d.y);
+  L->e[1] = zinv.y + (sz * d.x + cz * d.y);
+  L->e[2] = normalize_theta(zinv.th + d.th);
+  const double dx = xj.x - xi.x, dy = xj.y - xi.y;
+  const double a[9] = {-ci, -si, -si * dx + ci * dy, si, -ci, -ci * dx - si * dy, 0.0, 0.0, -1.0};
+  const double b[9] = {ci, si, 0.0, -si, ci, 0.0, 0.0, 0.0, 1.0};
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    L->ji[c] = cz * a[c] - sz * a[3 + c];
+    L->ji[3 + c] = sz * a[c] + cz * a[3 + c];
+    L->ji[6 + c] = a[6 + c];
+    L->jj[c] = cz * b[c] - sz * b[3 + c];
+    L->jj[3 + c] = sz * b[c] + cz * b[3 + c];
+    L->jj[6 + c] = b[6 + c];
+  }
+  const double* w = P.info6 + 6 * static_cast<size_t>(edge);
+  L->om[0] = w[0];
+  L->om[1] = L->om[3] = w[1];
+  L->om[2] = L->om[6] = w[2];
+  L->om[4] = w[3];
+  L->om[5] = L->om[7] = w[4];
+  L->om[8] = w[5];
+}
+
 __device__ __forceinline__ double edge_chi2(const EdgeLin& L) {
   double c = 0.0;
 #pragma unroll
@@ -230,6 +280,7 @@ __device__ double block_sum(double v, double* scratch) {
 }
 
 // ---- phase 1: linearise ------------------------------------------------------------------------
+template <bool kTab>
 __device__ void phase_linearise(const Params& P, double* scratch, int it) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
   double chi = 0.0;
@@ -239,7 +290,8 @@ __device__ void phase_linearise(const Params& P, double* scratch, int it) {
       const Incidence inc = P.inc[t];
       const int edge = inc.edge_role >> 1, role = inc.edge_role & 1;
       EdgeLin L;
-      linearise_edge(P, edge, &L);
+      if (kTab) linearise_edge_tab(P, edge, &L);
+      else linearise_edge(P, edge, &L);
       const double* jo = role ? L.jj : L.ji;  // this vertex
       const double* jx = role ? L.ji : L.jj;  // the other one
       double A[9];                            // Jo^T Omega
@@ -275,7 +327,8 @@ __device__ void phase_linearise(const Params& P, double* scratch, int it) {
   }
   for (int t = tid; t < P.n_ff; t += nthreads) {
     EdgeLin L;
-    linearise_edge(P, P.ff_edges[t], &L);
+    if (kTab) linearise_edge_tab(P, P.ff_edges[t], &L);
+    else linearise_edge(P, P.ff_edges[t], &L);
     chi += edge_chi2(L);
   }
   const double s = block_sum(chi, scratch);
@@ -522,7 +575,20 @@ __global__ void __launch_bounds__(kThreads) gn_linearise(Params P) {
   __shared__ double scratch[32];
   P = params_at(P, blockIdx.y);
   if (*reinterpret_cast<volatile int*>(P.status) != 0) return;
-  phase_linearise(P, scratch, 0);
+  phase_linearise<true>(P, scratch, 0);
+}
+// sin / cos of every pose angle and every measurement angle of this iteration (see linearise_edge_tab)
+__global__ void gn_trig(Params P) {
+  P = params_at(P, blockIdx.y);
+  if (*reinterpret_cast<volatile int*>(P.status) != 0) return;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= P.n_vertices + P.n_edges) return;
+  const double th = t < P.n_vertices ? P.poses[3 * static_cast<size_t>(t) + 2]
+                                     : P.meas[3 * static_cast<size_t>(t - P.n_vertices) + 2];
+  double sn, cs;
+  sincos(th, &sn, &cs);
+  P.trig[2 * static_cast<size_t>(t)] = sn;
+  P.trig[2 * static_cast<size_t>(t) + 1] = cs;
 }
 __global__ void gn_chi2(Params P, int n_partials) {
   __shared__ double scratch[32];
@@ -720,7 +786,7 @@ struct DeviceSolver {
   Buf<Incidence> inc;
   Buf<unsigned long long> stamps;
   double stage_ms[5] = {0, 0, 0, 0, 0};
-  Buf<double> poses, meas, info6, M, Dinv, rhs, u, x, chi2_partial, chi2_out, many_rhs, scratch_d;
+  Buf<double> poses, meas, info6, M, Dinv, rhs, u, x, chi2_partial, chi2_out, many_rhs, scratch_d, trig;
   // supernodal tables (single-GPU path)
   SNView V;
   // task lists of one stage: everything (single GPU), or this rank's panels [0] and the shared
@@ -770,7 +836,7 @@ int dev_create(DeviceSolver** out, int device, void* stream, std::string* err) {
   cudaError_t e = cudaSuccess;
   {
     const int cta_bytes = static_cast<int>(sizeof(double) * kCtaSmemDoubles);
-    const int warp_bytes = static_cast<int>(sizeof(double) * kWarpSmemDoubles * kWarpsPerCta);
+    const int warp_bytes = static_cast<int>(sizeof(double) * (kWarpSmemDoubles + 1) * kWarpsPerCta);
     const void* cta_kernels[] = {reinterpret_cast<const void*>(sn_k_factor), reinterpret_cast<const void*>(sn_k_update),
                                  reinterpret_cast<const void*>(sn_k_bwd_tri), reinterpret_cast<const void*>(sn_k_fwd_tri)};
     for (size_t i = 0; i < sizeof(cta_kernels) / sizeof(cta_kernels[0]) && e == cudaSuccess; ++i)
@@ -815,7 +881,7 @@ void dev_destroy(DeviceSolver* d) {
                     &d->col_ptr, &d->row_idx, &d->perm_vertex, &d->status,  &d->scratch_i};
   for (size_t i = 0; i < sizeof(ib) / sizeof(ib[0]); ++i) ib[i]->release();
   Buf<double>* db[] = {&d->poses, &d->meas, &d->info6, &d->M, &d->Dinv, &d->rhs, &d->u, &d->x,
-                       &d->chi2_partial, &d->chi2_out, &d->many_rhs, &d->scratch_d};
+                       &d->chi2_partial, &d->chi2_out, &d->many_rhs, &d->scratch_d, &d->trig};
   for (size_t i = 0; i < sizeof(db) / sizeof(db[0]); ++i) db[i]->release();
   Buf<int>* sb[] = {&d->colbase, &d->tbl_off, &d->tbl};
   d->pn_desc.release();
@@ -967,6 +1033,9 @@ int dev_set_structure(DeviceSolver* d, const Symbolic& S, const GraphTables& G, 
   P.s_vec = V.s_vec;
   P.s_partial = d->lin_blocks;
   P.s_chi2 = kMaxItersPerCall;
+  P.s_trig = 2LL * (static_cast<long long>(G.n_vertices) + G.n_edges);
+  PGO_CUDA(d->trig.reserve(B * static_cast<size_t>(P.s_trig)));
+  P.trig = d->trig.p;
   for (int k = 0; k < 2; ++k) {
     if (d->graph_exec[k]) cudaGraphExecDestroy(d->graph_exec[k]);
     if (d->graph[k]) cudaGraphDestroy(d->graph[k]);
@@ -1184,7 +1253,11 @@ static int enqueue_stage(DeviceSolver* d, int stage, std::string* err) {
     PGO_CUDA(cudaMemsetAsync(P.M, 0, sizeof(double) * static_cast<size_t>(P.s_M) * B, st));
     PGO_CUDA(cudaMemsetAsync(P.x, 0, sizeof(double) * static_cast<size_t>(P.s_vec) * B, st));
     if (dd) gn_dd_linearise<<<d->lin_blocks, kThreads, 0, st>>>(P, d->D);
-    else gn_linearise<<<dim3(d->lin_blocks, B), kThreads, 0, st>>>(P);
+    else {
+      gn_trig<<<dim3((P.n_vertices + P.n_edges + 255) / 256, B), 256, 0, st>>>(P);
+      gn_linearise<<<dim3(d->lin_blocks, B), kThreads, 0, st>>>(P);
+      ++nodes;
+    }
     if (!dd) gn_chi2<<<dim3(1, B), 256, 0, st>>>(P, d->lin_blocks);
     gn_stamp<<<1, 1, 0, st>>>(d->stamps.p, 1);
     nodes += 6;
