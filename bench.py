@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--cpu-pairs", type=int, default=0, help="pairs in the CPU sample (0 = auto)")
     ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 global, 2 tiled")
     ap.add_argument("--no-gn", action="store_true")
+    ap.add_argument("--e2e-chunks", type=int, default=4,
+                    help="handles / host threads the end-to-end step is pipelined over")
     ap.add_argument("--gn-batch", type=int, default=64, help="graph instances per GPU in the GN arm")
     return ap.parse_args()
 
@@ -259,19 +261,46 @@ def gn_ours(args, local, world, barrier):
     st = s.stats()
     dev_ms = st["last_iterate_ms"]
     iters = int(done.sum())
-    # end to end: every step uploads estimates + measurements of every instance and reads all
-    # estimates back
+    # end to end: every step uploads estimates + measurements of every instance, runs one iteration
+    # and reads all estimates back. The instances are served by K solver handles (B / K instances,
+    # one stream and one host thread each): the uploads of handle k+1 overlap the kernels of handle k.
+    s.close()
+    K = max(1, min(args.e2e_chunks, B))
+    bounds = [B * k // K for k in range(K + 1)]
+    parts = []
+    for k in range(K):
+        sk = pgo.Solver(device=local, batch=bounds[k + 1] - bounds[k])
+        sk.set_graph(nv, g["edge_ij"], g["fixed"])
+        parts.append(sk)
+    outs = [torch.empty((nv, 3), dtype=torch.float64).pin_memory().numpy() for _ in range(B)]
+    up_lock = threading.Lock()
+    e2e_done = np.zeros(B, dtype=np.int32)
+
+    def part_step(k):
+        sk = parts[k]
+        with up_lock:
+            for b in range(bounds[k], bounds[k + 1]):
+                sk.upload_instance(b - bounds[k], poses0, inst_meas[b], info)
+        d, _ = sk.optimize_batch(1)
+        e2e_done[bounds[k]:bounds[k + 1]] = d
+        for b in range(bounds[k], bounds[k + 1]):
+            sk.poses_of(b - bounds[k], out=outs[b])
+
     times = []
     for it in range(args.warmup + args.steps):
         barrier()
         t0 = time.perf_counter()
-        for b in range(B):
-            s.upload_instance(b, poses0, inst_meas[b], info)
-        s.optimize_batch(1)
-        outs = [s.poses_of(b) for b in range(B)]
+        ths = [threading.Thread(target=part_step, args=(k,)) for k in range(K)]
+        for th in ths:
+            th.start()
+        for th in ths:
+            th.join()
         t1 = time.perf_counter()
         if it >= args.warmup:
             times.append(t1 - t0)
+    assert int(e2e_done.sum()) == B, e2e_done
+    for sk in parts:
+        sk.close()
     t = torch.tensor([dev_ms, sum(times) * 1e3, single_ms], dtype=torch.float64, device="cuda")
     if world > 1:
         import torch.distributed as dist
@@ -310,11 +339,10 @@ def gn_ours(args, local, world, barrier):
                              "issue and dependent-level latency, not by HBM"},
         "e2e": {"value": world * args.steps * B / (float(t[1]) * 1e-3), "unit": "iters/s",
                 "h2d_bytes_per_step": int(B * (poses0.nbytes + inst_meas[0].nbytes + info.nbytes)),
-                "d2h_bytes_per_step": int(B * poses0.nbytes)},
+                "d2h_bytes_per_step": int(B * poses0.nbytes), "chunks": K},
         "chi2_first_last": [float(chi2[0, 0]), float(chi2[0, -1])] if chi2.size else None,
         "gpu_launches": int(launches_per_iter * args.steps),
     }
-    s.close()
     if world > 1:
         out["dd"] = gn_domain_decomposed(args, g, local, world, barrier, poses0, inst_meas[0], info,
                                          float(chi2_warm[0]) if len(chi2_warm) else None)
@@ -448,28 +476,62 @@ def ours(args):
     found = int((n_out > 0).sum())
 
     # ---- end-to-end arm: host buffers in, host results out, every step -------------------------
+    # The step's pairs are cut into K chunks, one cgm_matcher handle + stream + host thread each
+    # (the reference's own search runs on up to 4 OpenMP threads, chargrid.cpp:223-227): chunk
+    # k+1's host planning and H2D copies overlap chunk k's kernels. Every step still stages every
+    # pair from the pinned host buffers and collects every result list on the host.
+    K = max(1, min(args.e2e_chunks, n))
+    bounds = [n * k // K for k in range(K + 1)]
+    map_off = np.concatenate([[0], np.cumsum(map_counts)])
+    cur_off = np.concatenate([[0], np.cumsum(cur_counts)])
+    m.close()
+    chunk_m, chunk_streams = [], []
+    for k in range(K):
+        cs = torch.cuda.Stream()
+        cm = matcher.Matcher(LC["ll"], LC["ur"], LC["res"], LC["kernel_range"],
+                             n_slots=bounds[k + 1] - bounds[k], device=local, stream=cs.cuda_stream)
+        cm.set_kernel(args.kernel)
+        chunk_m.append(cm)
+        chunk_streams.append(cs)
+    n_out = np.zeros(n, dtype=np.int32)
+    stage_lock = threading.Lock()
+
+    def chunk_step(k):
+        a, b = bounds[k], bounds[k + 1]
+        cm = chunk_m[k]
+        with stage_lock:   # one chunk at a time on the copy engine
+            cm.batch_stage(cur_np[cur_off[a]:cur_off[b]], cur_counts[a:b], regions[a:b], reg_counts[a:b],
+                           step, MAX_SCORE, BINS, map_pts=map_np[map_off[a]:map_off[b]],
+                           map_counts=map_counts[a:b])
+            cm.batch_launch()
+        _, no = cm.batch_collect(cap=4)
+        n_out[a:b] = no
+
     e2e_t = []
     h2d = (map_np.nbytes + cur_np.nbytes + regions.nbytes + 2 * map_counts.nbytes)
     for it in range(args.warmup + args.steps):
         barrier()
         t0 = time.perf_counter()
-        m.batch_stage(cur_np, cur_counts, regions, reg_counts, step, MAX_SCORE, BINS,
-                      map_pts=map_np, map_counts=map_counts)
-        ta = time.perf_counter()
-        m.batch_launch()
-        tb = time.perf_counter()
-        res, n_out = m.batch_collect(cap=4)
+        if K == 1:
+            chunk_step(0)
+        else:
+            ths = [threading.Thread(target=chunk_step, args=(k,)) for k in range(K)]
+            for th in ths:
+                th.start()
+            for th in ths:
+                th.join()
         torch.cuda.synchronize()
         t1 = time.perf_counter()
         if it >= args.warmup:
             e2e_t.append(t1 - t0)
-            e2e_split = {"stage_ms": (ta - t0) * 1e3, "launch_ms": (tb - ta) * 1e3,
-                         "collect_ms": (t1 - tb) * 1e3}
+    e2e_found = int((n_out > 0).sum())
+    assert e2e_found == found, (e2e_found, found)   # same answers as the one-handle run
     clocks = sampler.stop() if rank == 0 else None
     d2h = int(n_out.sum()) * 16 + 32
     e2e_sec = sum(e2e_t)
 
-    m.close()
+    for cm in chunk_m:
+        cm.close()
     gn = None if args.no_gn else gn_ours(args, local, world, barrier)
 
     cand = stats["candidates"]
@@ -515,7 +577,9 @@ def ours(args):
                 "step_split_ms": kms[-1]},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms_max / args.steps,
-                    "host_split_last_step": e2e_split},
+                    "chunks": K,
+                    "note": "%d chunks of pairs, one matcher handle + stream + host thread each: host "
+                            "planning and H2D of a chunk overlap the kernels of the previous one" % K},
             "gpu_launches": int(launches2 - launches1),
             "clocks": clocks,
         }

@@ -143,8 +143,12 @@ class Solver:
         self._check(self.lib.pgo_upload_instance(self.h, int(inst), _p(poses, _dp), _p(meas, _dp),
                                                  _p(info6, _dp)))
 
-    def poses_of(self, inst):
-        out = np.empty((self.n_vertices, 3))
+    def poses_of(self, inst, out=None):
+        """Estimates of one instance; `out` (C-contiguous float64 [n_vertices, 3], e.g. pinned) is
+        filled in place when given."""
+        if out is None:
+            out = np.empty((self.n_vertices, 3))
+        assert out.shape == (self.n_vertices, 3) and out.dtype == np.float64 and out.flags.c_contiguous
         self._check(self.lib.pgo_get_poses_instance(self.h, int(inst), _p(out, _dp)))
         return out
 
