@@ -72,9 +72,13 @@ PGO_HD SNView sn_at_instance(SNView V, int b) {
 
 // doubles of shared memory a group needs for any task of its kind
 static const int kPairDoubles = (kPanelWidth * (kPanelWidth + 1) / 2 + 1) / 2;  // int table
-static const int kCtaSmemDoubles = kPanelWidth * kPanelWidth * 9 + kPanelWidth * 9 + kPairDoubles +
-                                   3 * kPanelWidth +
-                                   3 * kPanelWidth * (3 * kRowChunk + 1);  // factor task
+static const int kFactorSmemDoubles = kPanelWidth * kPanelWidth * 9 + kPanelWidth * 9 + kPairDoubles +
+                                      3 * kPanelWidth +
+                                      3 * kPanelWidth * (3 * kRowChunk + 1);  // factor task
+static const int kTriSmemDoubles = 6 * kMaxSuperWidth + kPanelWidth * kPanelWidth * 9 + kPanelWidth * 9 +
+                                   3 * 256;  // a wide supernode's vectors (substitution)
+PGO_HD constexpr int sn_max3(int a, int b, int c) { return a > b ? (a > c ? a : c) : (b > c ? b : c); }
+static const int kCtaSmemDoubles = sn_max3(kFactorSmemDoubles, kTileSmemDoubles, kTriSmemDoubles);
 static const int kSmallPairDoubles = (kSmallWidth * (kSmallWidth + 1) / 2 + 1) / 2;
 static const int kWarpSmemDoubles = kSmallWidth * kSmallWidth * 9 + kSmallWidth * 9 +
                                     kSmallPairDoubles + 3 * kSmallWidth +
@@ -85,9 +89,6 @@ static const int kWarpSubstDoubles = 6 * kSmallWidth + kSmallWidth * kSmallWidth
 PGO_HD int sn_fused_doubles(int w, int m) {
   return w * w * 9 + w * 9 + kSmallPairDoubles + 3 * w + 3 * w * (3 * m + 1);
 }
-static_assert(kTileSmemDoubles <= kCtaSmemDoubles, "update tiles must fit the CTA's shared memory");
-static_assert(6 * kMaxSuperWidth + kPanelWidth * kPanelWidth * 9 + kPanelWidth * 9 + 3 * 256 <=
-                  kCtaSmemDoubles, "a wide supernode's vectors must fit the CTA's shared memory");
 
 struct SeqGroup {  // host: one thread plays every rank in turn
   PGO_HD int rank() const { return 0; }
