@@ -778,8 +778,8 @@ struct DeviceSolver {
   int grid = 0;  // co-resident CTAs of the cooperative kernels
   uint64_t launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  cudaStream_t aux = nullptr;  // second branch while capturing the iteration graph
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaStream_t aux = nullptr, aux2 = nullptr;  // further branches while capturing the iteration graph
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr;
   Params P;
   bool have_structure = false, have_values = false, have_factor = false;
   Buf<int> edge_i, edge_j, vpos, inc_ptr, ff_edges, col_ptr, row_idx, perm_vertex, status, scratch_i;
@@ -857,8 +857,10 @@ int dev_create(DeviceSolver** out, int device, void* stream, std::string* err) {
     }
   }
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d->aux, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d->aux2, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->ev_fork, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->ev_join, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->ev_join2, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreate(&d->ev0);
   if (e == cudaSuccess) e = cudaEventCreate(&d->ev1);
   if (e == cudaSuccess) e = d->status.reserve(4);
@@ -908,7 +910,9 @@ void dev_destroy(DeviceSolver* d) {
   d->pose_x.release();
   if (d->ev_fork) cudaEventDestroy(d->ev_fork);
   if (d->ev_join) cudaEventDestroy(d->ev_join);
+  if (d->ev_join2) cudaEventDestroy(d->ev_join2);
   if (d->aux) cudaStreamDestroy(d->aux);
+  if (d->aux2) cudaStreamDestroy(d->aux2);
   if (d->ev0) cudaEventDestroy(d->ev0);
   if (d->ev1) cudaEventDestroy(d->ev1);
   if (d->own_stream && d->stream) cudaStreamDestroy(d->stream);
@@ -1138,27 +1142,40 @@ static int enqueue_factor(DeviceSolver* d, const DeviceSolver::TaskSet& ts, int*
   for (int l = 0; l < L.n_plevels; ++l) {
     const int n_fa = L.fa_ptr[l + 1] - L.fa_ptr[l], n_ff = L.ff_ptr[l + 1] - L.ff_ptr[l],
               n_fb = L.fb_ptr[l + 1] - L.fb_ptr[l];
-    // the level's big panels (CTA tasks) and small panels (warp tasks) are independent: two
+    // the level's big panels (CTA tasks), its small panels (warp tasks) and the few small panels
+    // with many rows (warp tasks with a large shared-memory stride) are independent: up to three
     // branches of the graph
-    cudaStream_t side = st;
-    if (n_fa && n_ff) {
-      PGO_CUDA(cudaEventRecord(d->ev_fork, st));
-      PGO_CUDA(cudaStreamWaitEvent(d->aux, d->ev_fork, 0));
-      side = d->aux;
-    }
-    if (n_ff) {
+    const int n_ffl = L.ff_large[l], n_ffs = n_ff - n_ffl;
+    cudaStream_t s_small = st, s_large = st;
+    if (n_ffs && (n_fa || n_ffl)) s_small = d->aux;
+    if (n_ffl && n_fa) s_large = d->aux2;
+    if (s_small != st || s_large != st) PGO_CUDA(cudaEventRecord(d->ev_fork, st));
+    if (s_small != st) PGO_CUDA(cudaStreamWaitEvent(s_small, d->ev_fork, 0));
+    if (s_large != st) PGO_CUDA(cudaStreamWaitEvent(s_large, d->ev_fork, 0));
+    if (n_ffl) {
       const int stride = (L.ff_smem[l] + 1) & ~1;
-      sn_k_fused<<<dim3((n_ff + kWarpsPerCta - 1) / kWarpsPerCta, B), 32 * kWarpsPerCta,
-                   sizeof(double) * stride * kWarpsPerCta, side>>>(V, ts.ff.p + L.ff_ptr[l], n_ff, stride);
+      sn_k_fused<<<dim3((n_ffl + kWarpsPerCta - 1) / kWarpsPerCta, B), 32 * kWarpsPerCta,
+                   sizeof(double) * stride * kWarpsPerCta, s_large>>>(V, ts.ff.p + L.ff_ptr[l], n_ffl, stride);
+      ++*nodes;
+    }
+    if (n_ffs) {
+      const int stride = (L.ff_smem_small[l] + 1) & ~1;
+      sn_k_fused<<<dim3((n_ffs + kWarpsPerCta - 1) / kWarpsPerCta, B), 32 * kWarpsPerCta,
+                   sizeof(double) * stride * kWarpsPerCta, s_small>>>(V, ts.ff.p + L.ff_ptr[l] + n_ffl, n_ffs,
+                                                                      stride);
       ++*nodes;
     }
     if (n_fa) {
       sn_k_factor<<<dim3(n_fa, B), kCtaThreads, sizeof(double) * L.fa_smem[l], st>>>(V, ts.fa.p + L.fa_ptr[l]);
       ++*nodes;
     }
-    if (side != st) {
-      PGO_CUDA(cudaEventRecord(d->ev_join, side));
+    if (s_small != st) {
+      PGO_CUDA(cudaEventRecord(d->ev_join, s_small));
       PGO_CUDA(cudaStreamWaitEvent(st, d->ev_join, 0));
+    }
+    if (s_large != st) {
+      PGO_CUDA(cudaEventRecord(d->ev_join2, s_large));
+      PGO_CUDA(cudaStreamWaitEvent(st, d->ev_join2, 0));
     }
     if (n_fb) {
       sn_k_update<<<dim3(n_fb, B), kUpdateThreads, sizeof(double) * L.fb_smem[l], st>>>(V, ts.fb.p + L.fb_ptr[l]);

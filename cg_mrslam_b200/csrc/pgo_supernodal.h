@@ -119,6 +119,22 @@ PGO_HD void sn_fail(int* status) {
 #endif
 }
 
+// Asynchronous 8-byte global -> shared copy (cp.async) and the wait for all of a thread's copies;
+// the host stand-in copies at once. dst must point into the task's shared memory.
+PGO_HD void sn_copy_async(double* dst, const double* src) {
+#if defined(__CUDA_ARCH__)
+  const unsigned sa = static_cast<unsigned>(__cvta_generic_to_shared(dst));
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(src) : "memory");
+#else
+  *dst = *src;
+#endif
+}
+PGO_HD void sn_copy_wait() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.wait_all;" ::: "memory");
+#endif
+}
+
 // first position of column t of a chain whose first column starts at `base` with `len` blocks
 PGO_HD int sn_colpos(int base, int len, int t) { return base + t * len - t * (t - 1) / 2; }
 
@@ -237,16 +253,21 @@ PGO_HD void sn_factor_diag(const G& g, const SNView& V, int w, double* Dg, doubl
   }
 }
 
-// Rows below the diagonal part, staged as scalar rows: xs[(3 t + c) * ldx + 3 a + r] = M(a,t)[r][c].
+// Rows below the diagonal part, staged as scalar rows: xs[(3 t + c) * ldx + 3 a + r] = M(a,t)[r][c],
+// as asynchronous copies, column by column (no division by a run-time value): the caller overlaps
+// them with the factorisation of the diagonal part and calls sn_copy_wait() + sync before the rows
+// are used.
 template <class G>
-PGO_HD void sn_load_rows(const G& g, const SNView& V, const PanelDesc& pd, int r0, int nrows, int ldx,
-                         double* xs) {
-  const int per_col = 9 * nrows;
-  sn_gather(g, pd.w * per_col, [&](int idx, const double** sp, double** dp) {
-    const int t = idx / per_col, q = idx % per_col, a = q / 9, k = q % 9;
-    *sp = V.M + 9 * static_cast<size_t>(sn_colpos(pd.base, pd.w + pd.m, t) + (pd.w - t) + r0) + q;
-    *dp = xs + (3 * t + k % 3) * ldx + 3 * a + k / 3;
-  });
+PGO_HD void sn_load_rows_async(const G& g, const SNView& V, const PanelDesc& pd, int r0, int nrows, int ldx,
+                               double* xs) {
+  for (int t = 0; t < pd.w; ++t) {
+    const double* src = V.M + 9 * static_cast<size_t>(sn_colpos(pd.base, pd.w + pd.m, t) + (pd.w - t) + r0);
+    double* dst = xs + 3 * t * ldx;
+    for (int q = g.rank(); q < 9 * nrows; q += g.size()) {
+      const int a = q / 9, k = q - 9 * a, r = k / 3, c = k - 3 * r;
+      sn_copy_async(dst + c * ldx + 3 * a + r, src + q);
+    }
+  }
 }
 
 template <class G>
@@ -366,11 +387,13 @@ PGO_HD void sn_task_factor(const G& g, const SNView& V, const Task& T, double* s
   int* pairs = reinterpret_cast<int*>(Di + w * 9);
   double* us = Di + w * 9 + kPairDoubles;
   double* xs = us + 3 * w;
+  sn_load_rows_async(g, V, pd, T.r0, nrows, ldx, xs);  // in flight during the diagonal factorisation
   sn_load_diag(g, V, pd.base, w + pd.m, w, Dg);
-  sn_load_rows(g, V, pd, T.r0, nrows, ldx, xs);
   sn_load_rhs(g, V, pd, nrows, ldx, xs);
   g.sync();
   sn_factor_diag(g, V, w, Dg, Di, pairs);
+  sn_copy_wait();
+  g.sync();
   sn_solve_rows(g, w, Dg, xs, ldx, 3 * nrows + 1);
   g.sync();
   sn_store_rows(g, V, pd, T.r0, nrows, ldx, xs);
@@ -445,11 +468,13 @@ PGO_HD void sn_task_fused(const G& g, const SNView& V, const Task& T, double* sm
   int* pairs = reinterpret_cast<int*>(Di + w * 9);
   double* us = Di + w * 9 + kSmallPairDoubles;
   double* xs = us + 3 * w;
+  sn_load_rows_async(g, V, pd, 0, m, ldx, xs);  // in flight during the diagonal factorisation
   sn_load_diag(g, V, pd.base, w + m, w, Dg);
-  sn_load_rows(g, V, pd, 0, m, ldx, xs);
   sn_load_rhs(g, V, pd, m, ldx, xs);
   g.sync();
   sn_factor_diag(g, V, w, Dg, Di, pairs);
+  sn_copy_wait();
+  g.sync();
   sn_solve_rows(g, w, Dg, xs, ldx, 3 * m + 1);
   g.sync();
   sn_store_rows(g, V, pd, 0, m, ldx, xs);

@@ -677,12 +677,24 @@ Supernodal::Lists Supernodal::lists(int owner) const {
   L.fa_smem.assign(n_plevels, 0);
   L.fb_smem.assign(n_plevels, 0);
   L.ff_smem.assign(n_plevels, 0);
+  L.ff_smem_small.assign(n_plevels, 0);
+  L.ff_large.assign(n_plevels, 0);
+  const int pair_small = (kSmallWidth * (kSmallWidth + 1) / 2 + 1) / 2;
+  auto fused_need = [&](const Task& t) {  // = sn_fused_doubles(w, m) of pgo_supernodal.h
+    const PanelDesc& pd = pn[t.id];
+    return pd.w * pd.w * 9 + pd.w * 9 + pair_small + 3 * pd.w + 3 * pd.w * (3 * pd.m + 1);
+  };
   for (int l = 0; l < n_plevels; ++l) {
+    std::stable_partition(L.ff.begin() + L.ff_ptr[l], L.ff.begin() + L.ff_ptr[l + 1],
+                          [&](const Task& t) { return fused_need(t) > kFusedSmallDoubles; });
     for (int i = L.ff_ptr[l]; i < L.ff_ptr[l + 1]; ++i) {
-      const PanelDesc& pd = pn[L.ff[i].id];
-      const int w = pd.w, m = pd.m;  // = sn_fused_doubles(w, m) of pgo_supernodal.h
-      const int pair_small = (kSmallWidth * (kSmallWidth + 1) / 2 + 1) / 2;
-      L.ff_smem[l] = std::max(L.ff_smem[l], w * w * 9 + w * 9 + pair_small + 3 * w + 3 * w * (3 * m + 1));
+      const int need = fused_need(L.ff[i]);
+      if (need > kFusedSmallDoubles) {
+        ++L.ff_large[l];
+        L.ff_smem[l] = std::max(L.ff_smem[l], need);
+      } else {
+        L.ff_smem_small[l] = std::max(L.ff_smem_small[l], need);
+      }
     }
     for (int i = L.fa_ptr[l]; i < L.fa_ptr[l + 1]; ++i) {
       const Task& t = L.fa[i];

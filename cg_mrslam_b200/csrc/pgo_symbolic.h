@@ -34,6 +34,7 @@ namespace pgo {
 static const int kPanelWidth = 16;
 static const int kSmallWidth = 4;    // panels / supernodes this narrow are handled by one warp
 static const int kSmallRows = 32;    // ... if the panel also has at most this many rows below it
+static const int kFusedSmallDoubles = 704;  // 5.5 kB per warp: 8+ CTAs of 4 warps per SM
 static const int kRowChunk = 64;     // rows below a panel per CTA task of the panel factorisation
 // outer-product tile of one CTA task (tensor-core GEMM, pgo_kernels.cu): ti x tj blocks with
 // ti a multiple of 8 and tj in {8, 16, 24, 32}; operands staged as [3 ti][ld] and [3 tj][ld]
@@ -110,7 +111,10 @@ struct Supernodal {
     std::vector<int> ff_ptr, fa_ptr, fb_ptr, ss_ptr, sa_ptr, sf_ptr, sb_ptr;
     std::vector<Task> ff, fa, fb, ss, sa, sf, sb;
     std::vector<int> fa_smem, fb_smem;  // doubles of shared memory of the largest task per level
-    std::vector<int> ff_smem;           // ... per warp task of the fused kernel
+    // fused warp tasks: per level the few tasks needing more than kFusedSmallDoubles of shared
+    // memory come first (ff_large[l] of them, stride ff_smem[l]) and are launched apart from the
+    // many small ones (stride ff_smem_small[l]), which then run at full occupancy
+    std::vector<int> ff_smem, ff_smem_small, ff_large;
     std::vector<int> sa_smem;
   };
   static const int kAllOwners = -2;
