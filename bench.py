@@ -604,10 +604,17 @@ def ours(args):
 
 def main():
     args = parse()
+    # stdout carries exactly ONE JSON line: everything libraries print there (NCCL's version banner
+    # at communicator creation, for one) goes to stderr instead
+    sys.stdout.flush()
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
     if args.impl == "reference":
         reference_arm(args)
     else:
         ours(args)
+    real_stdout.flush()
 
 
 if __name__ == "__main__":
