@@ -457,7 +457,9 @@ __device__ __forceinline__ void update_tile(const SNView& V, const Task& T, doub
       }
     // A = Y rows (scaled by the panel factorisation), B transposed = M rows: plain copies of 3x3
     // blocks into row-major [3 block + row][3 t + column], as asynchronous 8-byte global->shared
-    // copies so that every block of the chunk is in flight at once
+    // copies so that every block of the chunk is in flight at once. (Lanes run over the blocks of a
+    // column: a patch-shaped mapping with conflict-free shared-memory writes was measured 5 % slower,
+    // its global reads being scattered over eight blocks per instruction.)
     for (int t = wy; t < w; t += ny) {
       const size_t col = static_cast<size_t>(sn_colpos(pd.base, len, t) + (w - t) + off);
       const double* srca = V.Y + 9 * (col + i0);
@@ -479,16 +481,21 @@ __device__ __forceinline__ void update_tile(const SNView& V, const Task& T, doub
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int mi = warp + ny * h;
-      if (mi < mt) {
-        const double* ap = As + (8 * mi + fr) * ldk + fk;
+    {
+      const int m0 = warp, m1 = warp + ny;
+      const bool two = m1 < mt;  // warp-uniform
+      if (m0 < mt) {
+        const double* ap0 = As + (8 * m0 + fr) * ldk + fk;
+        const double* ap1 = As + (8 * (two ? m1 : m0) + fr) * ldk + fk;
         const double* bp = Bt + fr * ldk + fk;
         for (int k0 = 0; k0 < k4; k0 += 4) {
-          const double a = ap[k0];
+          const double a0 = ap0[k0], a1 = ap1[k0];
 #pragma unroll
-          for (int n = 0; n < NT; ++n) dmma884(acc[h][n][0], acc[h][n][1], a, bp[8 * n * ldk + k0]);
+          for (int n = 0; n < NT; ++n) {
+            const double bb = bp[8 * n * ldk + k0];   // one B fragment feeds both row strips
+            dmma884(acc[0][n][0], acc[0][n][1], a0, bb);
+            if (two) dmma884(acc[1][n][0], acc[1][n][1], a1, bb);
+          }
         }
       }
     }
