@@ -457,45 +457,42 @@ __device__ __forceinline__ void update_tile(const SNView& V, const Task& T, doub
       }
     // A = Y rows (scaled by the panel factorisation), B transposed = M rows: plain copies of 3x3
     // blocks into row-major [3 block + row][3 t + column], as asynchronous 8-byte global->shared
-    // copies so that every block of the chunk is in flight at once. (Lanes run over the blocks of a
-    // column: a patch-shaped mapping with conflict-free shared-memory writes was measured 5 % slower,
-    // its global reads being scattered over eight blocks per instruction.)
-    for (int t = wy; t < w; t += ny) {
-      const size_t col = static_cast<size_t>(sn_colpos(pd.base, len, t) + (w - t) + off);
-      const double* srca = V.Y + 9 * (col + i0);
-      for (int al = lx; al < ni; al += 32) {
-        double* dst = As + 3 * al * ldk + 3 * t;
+    // copies so that every block of the chunk is in flight at once. A warp instruction covers 8
+    // consecutive blocks of 4 consecutive columns, a half-warp 4 x 4: with ldk = 4 (mod 16) the
+    // block stride is 12 and the column stride 3 (mod 16 doubles), so the 16 writes of a half-warp
+    // fall on 16 different banks, and each column's blocks are one contiguous run in global memory.
+    {
+      const int al_l = (lx & 3) | ((lx >> 4) << 2), t_l = (lx >> 2) & 3;
+      const int nga = (ni + 7) >> 3, ngb = (nj + 7) >> 3;
+      for (int gidx = wy; gidx < nga + ngb; gidx += ny) {
+        const bool is_a = gidx < nga;
+        const int blk = 8 * (is_a ? gidx : gidx - nga) + al_l;
+        if (blk >= (is_a ? ni : nj)) continue;
+        const double* base = (is_a ? V.Y + 9 * static_cast<size_t>(i0) : V.M + 9 * static_cast<size_t>(j0)) + 9 * blk;
+        double* drow = (is_a ? As : Bt) + 3 * blk * ldk;
+        for (int t = t_l; t < w; t += 4) {
+          const size_t col = static_cast<size_t>(sn_colpos(pd.base, len, t) + (w - t) + off);
+          const double* src = base + 9 * col;
+          double* dst = drow + 3 * t;
 #pragma unroll
-        for (int r = 0; r < 3; ++r)
+          for (int r = 0; r < 3; ++r)
 #pragma unroll
-          for (int j = 0; j < 3; ++j) cp_async8(dst + r * ldk + j, srca + 9 * al + 3 * r + j);
-      }
-      const double* srcb = V.M + 9 * (col + j0);
-      for (int bl = lx; bl < nj; bl += 32) {
-        double* dst = Bt + 3 * bl * ldk + 3 * t;
-#pragma unroll
-        for (int c = 0; c < 3; ++c)
-#pragma unroll
-          for (int j = 0; j < 3; ++j) cp_async8(dst + c * ldk + j, srcb + 9 * bl + 3 * c + j);
+            for (int j = 0; j < 3; ++j) cp_async8(dst + r * ldk + j, src + 3 * r + j);
+        }
       }
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
-    {
-      const int m0 = warp, m1 = warp + ny;
-      const bool two = m1 < mt;  // warp-uniform
-      if (m0 < mt) {
-        const double* ap0 = As + (8 * m0 + fr) * ldk + fk;
-        const double* ap1 = As + (8 * (two ? m1 : m0) + fr) * ldk + fk;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int mi = warp + ny * h;
+      if (mi < mt) {
+        const double* ap = As + (8 * mi + fr) * ldk + fk;
         const double* bp = Bt + fr * ldk + fk;
         for (int k0 = 0; k0 < k4; k0 += 4) {
-          const double a0 = ap0[k0], a1 = ap1[k0];
+          const double a = ap[k0];
 #pragma unroll
-          for (int n = 0; n < NT; ++n) {
-            const double bb = bp[8 * n * ldk + k0];   // one B fragment feeds both row strips
-            dmma884(acc[0][n][0], acc[0][n][1], a0, bb);
-            if (two) dmma884(acc[1][n][0], acc[1][n][1], a1, bb);
-          }
+          for (int n = 0; n < NT; ++n) dmma884(acc[h][n][0], acc[h][n][1], a, bp[8 * n * ldk + k0]);
         }
       }
     }
