@@ -118,3 +118,24 @@ extern "C" int pgo_hostsim_solve(int n, int n_blocks, const int32_t* brow, const
   }
   return 0;
 }
+
+// Structure analysis alone: out = {factor blocks, MFLOP of one factorisation, panel levels,
+// supernode levels, supernodes, shared (top separator) columns}. Returns 0, or 1 with the analysis
+// refusing the graph (its own checks: every edge inside one owner or touching a shared separator,
+// descendants of a column owned like the column).
+extern "C" int pgo_hostsim_analyse(int n, int n_edges, const int32_t* ei, const int32_t* ej, int world,
+                                   int64_t* out /*[6]*/) {
+  std::vector<std::pair<int, int> > edges(n_edges);
+  for (int k = 0; k < n_edges; ++k) edges[k] = std::make_pair(ei[k], ej[k]);
+  Symbolic S;
+  std::string err;
+  if (!analyse(n, edges, 0, world, &S, &err)) return 1;
+  out[0] = S.nnzb;
+  out[1] = static_cast<int64_t>(S.sn.flops / 1e6);
+  out[2] = S.sn.n_plevels;
+  out[3] = S.sn.n_slevels;
+  out[4] = S.sn.n_super;
+  out[5] = S.n - S.first_shared;
+  return 0;
+}
+
