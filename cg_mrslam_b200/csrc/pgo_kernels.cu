@@ -337,6 +337,9 @@ __device__ void phase_linearise(const Params& P, double* scratch, int it) {
 }
 
 const int kThreads = 256;
+// linearise: one vertex per thread, degrees differ by several times: small CTAs keep the wait for
+// the heaviest vertex of a CTA (its chi2 reduction is a barrier) short
+const int kLinThreads = 128;
 
 // ---- supernodal single-GPU iteration (pgo_supernodal.h) ------------------------------------------
 // One Gauss-Newton iteration is a CUDA graph of small kernels, one per phase and panel / supernode
@@ -540,12 +543,12 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) sn_k_bwd_rows(SNView V, con
   if (i >= n || sn_failed(V)) return;
   sn_backward_rows(WarpGroup(), V, tasks[i].id, tasks[i].r0, tasks[i].r1);
 }
-__global__ void __launch_bounds__(32 * kWarpsPerCta) sn_k_bwd_small(SNView V, const Task* tasks, int n) {
+__global__ void __launch_bounds__(32 * kWarpsPerCta) sn_k_bwd_small(SNView V, const Task* tasks, int n, int stride) {
   extern __shared__ double sm[];
   const int i = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
   V = sn_at_instance(V, blockIdx.y);
   if (i >= n || sn_failed(V)) return;
-  sn_task_backward_small(WarpGroup(), V, tasks[i], sm + (threadIdx.x >> 5) * kWarpSubstDoubles);
+  sn_task_backward_small(WarpGroup(), V, tasks[i], sm + (threadIdx.x >> 5) * stride);
 }
 __global__ void __launch_bounds__(kCtaThreads, 2) sn_k_bwd_tri(SNView V, const Task* tasks) {
   extern __shared__ double sm[];
@@ -560,12 +563,12 @@ __global__ void __launch_bounds__(kCtaThreads) sn_k_fwd_tri(SNView V, const Task
   V = sn_at_instance(V, blockIdx.y);
   sn_task_forward_tri(CtaGroup(), V, tasks[blockIdx.x], sm);
 }
-__global__ void __launch_bounds__(32 * kWarpsPerCta) sn_k_fwd_small(SNView V, const Task* tasks, int n) {
+__global__ void __launch_bounds__(32 * kWarpsPerCta) sn_k_fwd_small(SNView V, const Task* tasks, int n, int stride) {
   extern __shared__ double sm[];
   const int i = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
   V = sn_at_instance(V, blockIdx.y);
   if (i >= n) return;
-  sn_task_forward_small(WarpGroup(), V, tasks[i], sm + (threadIdx.x >> 5) * kWarpSubstDoubles);
+  sn_task_forward_small(WarpGroup(), V, tasks[i], sm + (threadIdx.x >> 5) * stride);
 }
 __global__ void __launch_bounds__(32 * kWarpsPerCta) sn_k_fwd_rows(SNView V, const Task* tasks, int n) {
   const int i = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
@@ -575,7 +578,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) sn_k_fwd_rows(SNView V, con
 }
 
 // linearise + chi2 (phase 1) as plain kernels
-__global__ void __launch_bounds__(kThreads) gn_linearise(Params P) {
+__global__ void __launch_bounds__(kLinThreads) gn_linearise(Params P) {
   __shared__ double scratch[32];
   P = params_at(P, blockIdx.y);
   if (*reinterpret_cast<volatile int*>(P.status) != 0) return;
@@ -840,7 +843,8 @@ int dev_create(DeviceSolver** out, int device, void* stream, std::string* err) {
   cudaError_t e = cudaSuccess;
   {
     const int cta_bytes = static_cast<int>(sizeof(double) * kCtaSmemDoubles);
-    const int warp_bytes = static_cast<int>(sizeof(double) * (kWarpSmemDoubles + 1) * kWarpsPerCta);
+    const int warp_bytes = static_cast<int>(sizeof(double) * (std::max(kWarpSmemDoubles, kWarpSubstDoubles) + 1) *
+                                            kWarpsPerCta);
     const void* cta_kernels[] = {reinterpret_cast<const void*>(sn_k_factor), reinterpret_cast<const void*>(sn_k_update),
                                  reinterpret_cast<const void*>(sn_k_bwd_tri), reinterpret_cast<const void*>(sn_k_fwd_tri)};
     for (size_t i = 0; i < sizeof(cta_kernels) / sizeof(cta_kernels[0]) && e == cudaSuccess; ++i)
@@ -1026,7 +1030,7 @@ int dev_set_structure(DeviceSolver* d, const Symbolic& S, const GraphTables& G, 
   V.s_vec = 3LL * S.n;
   V.s_scratch = static_cast<long long>(scratch_stride);
   V.s_status = 4;
-  d->lin_blocks = std::max(1, std::min(4 * d->sm_count, (S.n + kThreads - 1) / kThreads));
+  d->lin_blocks = std::max(1, std::min(4 * d->sm_count, (S.n + kLinThreads - 1) / kLinThreads));
   PGO_CUDA(d->chi2_out.reserve(B * kMaxItersPerCall));
   PGO_CUDA(d->chi2_partial.reserve(std::max(B * d->lin_blocks, static_cast<size_t>(d->grid))));
   PGO_CUDA(d->status.reserve(4 * B));
@@ -1195,7 +1199,6 @@ static int enqueue_backward(DeviceSolver* d, const DeviceSolver::TaskSet& ts, co
                             int* nodes, std::string* err) {
   cudaStream_t st = d->stream;
   const Supernodal::Lists& L = ts.L;
-  const size_t warp_bytes = sizeof(double) * kWarpSubstDoubles * kWarpsPerCta;
   for (int l = L.n_slevels - 1; l >= 0; --l) {
     const int n_sa = L.sa_ptr[l + 1] - L.sa_ptr[l], n_ss = L.ss_ptr[l + 1] - L.ss_ptr[l],
               n_sb = L.sb_ptr[l + 1] - L.sb_ptr[l];
@@ -1207,9 +1210,18 @@ static int enqueue_backward(DeviceSolver* d, const DeviceSolver::TaskSet& ts, co
       PGO_CUDA(cudaStreamWaitEvent(d->aux, d->ev_fork, 0));
       side = d->aux;
     }
-    if (n_ss) {
-      sn_k_bwd_small<<<dim3((n_ss + kWarpsPerCta - 1) / kWarpsPerCta, B), 32 * kWarpsPerCta, warp_bytes, side>>>(
-          V, ts.ss.p + L.ss_ptr[l], n_ss);
+    const int n_ssl = L.ss_large[l];
+    if (n_ssl) {  // single-panel supernodes of 5 .. 16 columns
+      const int stride = (L.ss_smem[l] + 1) & ~1;
+      sn_k_bwd_small<<<dim3((n_ssl + kWarpsPerCta - 1) / kWarpsPerCta, B), 32 * kWarpsPerCta,
+                       sizeof(double) * stride * kWarpsPerCta, side>>>(V, ts.ss.p + L.ss_ptr[l], n_ssl, stride);
+      ++*nodes;
+    }
+    if (n_ss > n_ssl) {
+      const int stride = (L.ss_smem_small[l] + 1) & ~1;
+      sn_k_bwd_small<<<dim3((n_ss - n_ssl + kWarpsPerCta - 1) / kWarpsPerCta, B), 32 * kWarpsPerCta,
+                       sizeof(double) * stride * kWarpsPerCta, side>>>(V, ts.ss.p + L.ss_ptr[l] + n_ssl,
+                                                                       n_ss - n_ssl, stride);
       ++*nodes;
     }
     if (n_sb) {
@@ -1235,13 +1247,21 @@ static int enqueue_forward(DeviceSolver* d, const DeviceSolver::TaskSet& ts, con
                            int* nodes, std::string* err) {
   cudaStream_t st = d->stream;
   const Supernodal::Lists& L = ts.L;
-  const size_t warp_bytes = sizeof(double) * kWarpSubstDoubles * kWarpsPerCta;
   for (int l = 0; l < L.n_slevels; ++l) {
     const int n_sa = L.sa_ptr[l + 1] - L.sa_ptr[l], n_ss = L.ss_ptr[l + 1] - L.ss_ptr[l],
               n_sf = L.sf_ptr[l + 1] - L.sf_ptr[l];
-    if (n_ss) {
-      sn_k_fwd_small<<<dim3((n_ss + kWarpsPerCta - 1) / kWarpsPerCta, B), 32 * kWarpsPerCta, warp_bytes, st>>>(
-          V, ts.ss.p + L.ss_ptr[l], n_ss);
+    const int n_ssl = L.ss_large[l];
+    if (n_ssl) {
+      const int stride = (L.ss_smem[l] + 1) & ~1;
+      sn_k_fwd_small<<<dim3((n_ssl + kWarpsPerCta - 1) / kWarpsPerCta, B), 32 * kWarpsPerCta,
+                       sizeof(double) * stride * kWarpsPerCta, st>>>(V, ts.ss.p + L.ss_ptr[l], n_ssl, stride);
+      ++*nodes;
+    }
+    if (n_ss > n_ssl) {
+      const int stride = (L.ss_smem_small[l] + 1) & ~1;
+      sn_k_fwd_small<<<dim3((n_ss - n_ssl + kWarpsPerCta - 1) / kWarpsPerCta, B), 32 * kWarpsPerCta,
+                       sizeof(double) * stride * kWarpsPerCta, st>>>(V, ts.ss.p + L.ss_ptr[l] + n_ssl, n_ss - n_ssl,
+                                                                     stride);
       ++*nodes;
     }
     if (n_sa) {
@@ -1276,7 +1296,7 @@ static int enqueue_stage(DeviceSolver* d, int stage, std::string* err) {
     if (dd) gn_dd_linearise<<<d->lin_blocks, kThreads, 0, st>>>(P, d->D);
     else {
       gn_trig<<<dim3((P.n_vertices + P.n_edges + 255) / 256, B), 256, 0, st>>>(P);
-      gn_linearise<<<dim3(d->lin_blocks, B), kThreads, 0, st>>>(P);
+      gn_linearise<<<dim3(d->lin_blocks, B), kLinThreads, 0, st>>>(P);
       ++nodes;
     }
     if (!dd) gn_chi2<<<dim3(1, B), 256, 0, st>>>(P, d->lin_blocks);

@@ -84,7 +84,7 @@ static const int kWarpSmemDoubles = kSmallWidth * kSmallWidth * 9 + kSmallWidth 
                                     kSmallPairDoubles + 3 * kSmallWidth +
                                     3 * kSmallWidth * (3 * kSmallRows + 1);  // fused
 // warp tasks of the substitutions: xs[3W] us[3W] Dg[W*W*9] Di[W*9] red[3 * 32]
-static const int kWarpSubstDoubles = 6 * kSmallWidth + kSmallWidth * kSmallWidth * 9 + kSmallWidth * 9 + 3 * 32;
+static const int kWarpSubstDoubles = 6 * kSubstWarpWidth + kSubstWarpWidth * kSubstWarpWidth * 9 + kSubstWarpWidth * 9 + 3 * 32;
 // shared memory of one fused task (sn_task_fused)
 PGO_HD int sn_fused_doubles(int w, int m) {
   return w * w * 9 + w * 9 + kSmallPairDoubles + 3 * w + 3 * w * (3 * m + 1);

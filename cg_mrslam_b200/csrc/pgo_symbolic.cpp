@@ -624,7 +624,7 @@ bool build_supernodal(Symbolic& S, std::string* err) {
     SuperDesc sd = {c0, W, m, cp[c0], N.sn_pn_ptr[s], N.sn_pn_ptr[s + 1], 0, 0};
     N.sn.push_back(sd);
     N.sn_owner.push_back(S.owner[c0]);
-    if (W <= kSmallWidth) {
+    if (W <= kSubstWarpWidth) {
       const Task t = {s, 0, m, 0};
       ss.push_back(std::make_pair(slevel[s], t));
       continue;
@@ -708,6 +708,27 @@ Supernodal::Lists Supernodal::lists(int owner) const {
       const bool multi = sd.pn_end - sd.pn_begin > 1 && !((t.aux >> 28) & 1);
       const int w = multi ? kPanelWidth : pn[t.id].w;
       L.fb_smem[l] = std::max(L.fb_smem[l], sn_tile_doubles(w, t.aux & 0xFF, (t.aux >> 8) & 0xFF));
+    }
+  }
+  // xs[3W] us[3W] Dg[W*W*9] Di[W*9] red[3 * 32] (sn_task_backward_small / _forward_small)
+  auto subst_need = [&](const Task& t) {
+    const int W = sn[t.id].W;
+    return 6 * W + 9 * W * W + 9 * W + 96;
+  };
+  L.ss_smem.assign(n_slevels, 0);
+  L.ss_smem_small.assign(n_slevels, 0);
+  L.ss_large.assign(n_slevels, 0);
+  for (int l = 0; l < n_slevels; ++l) {
+    std::stable_partition(L.ss.begin() + L.ss_ptr[l], L.ss.begin() + L.ss_ptr[l + 1],
+                          [&](const Task& t) { return subst_need(t) > kSubstSmallDoubles; });
+    for (int i = L.ss_ptr[l]; i < L.ss_ptr[l + 1]; ++i) {
+      const int need = subst_need(L.ss[i]);
+      if (need > kSubstSmallDoubles) {
+        ++L.ss_large[l];
+        L.ss_smem[l] = std::max(L.ss_smem[l], need);
+      } else {
+        L.ss_smem_small[l] = std::max(L.ss_smem_small[l], need);
+      }
     }
   }
   L.sa_smem.assign(n_slevels, 0);

@@ -33,6 +33,8 @@ namespace pgo {
 // (factor the panel, then subtract its outer product from every later column with atomics).
 static const int kPanelWidth = 16;
 static const int kSmallWidth = 4;    // panels / supernodes this narrow are handled by one warp
+static const int kSubstWarpWidth = 16;  // substitutions: single-panel supernodes are warp tasks
+static const int kSubstSmallDoubles = 320;  // ... launched apart from the narrow ones above this need
 static const int kSmallRows = 32;    // ... if the panel also has at most this many rows below it
 static const int kFusedSmallDoubles = 704;  // 5.5 kB per warp: 8+ CTAs of 4 warps per SM
 static const int kRowChunk = 64;     // rows below a panel per CTA task of the panel factorisation
@@ -116,6 +118,9 @@ struct Supernodal {
     // many small ones (stride ff_smem_small[l]), which then run at full occupancy
     std::vector<int> ff_smem, ff_smem_small, ff_large;
     std::vector<int> sa_smem;
+    // warp substitution tasks (ss): per level the wider ones first (ss_large[l] of them, stride
+    // ss_smem[l] doubles per warp), then the narrow ones (stride ss_smem_small[l])
+    std::vector<int> ss_smem, ss_smem_small, ss_large;
   };
   static const int kAllOwners = -2;
   Lists lists(int owner) const;
