@@ -33,7 +33,9 @@ namespace pgo {
 // (factor the panel, then subtract its outer product from every later column with atomics).
 static const int kPanelWidth = 16;
 static const int kSmallWidth = 4;    // panels / supernodes this narrow are handled by one warp
-static const int kSubstWarpWidth = 16;  // substitutions: single-panel supernodes are warp tasks
+static const int kSubstWarpWidth = 4;   // substitutions: supernodes this narrow are warp tasks (16, i.e. every
+                                        // single-panel supernode, was measured: the row gather of a 16-column
+                                        // supernode is too long for one warp, 0.2 ms slower for one graph)
 static const int kSubstSmallDoubles = 320;  // ... launched apart from the narrow ones above this need
 static const int kSmallRows = 32;    // ... if the panel also has at most this many rows below it
 static const int kFusedSmallDoubles = 704;  // 5.5 kB per warp: 8+ CTAs of 4 warps per SM
