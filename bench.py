@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--no-gn", action="store_true")
     ap.add_argument("--e2e-chunks", type=int, default=4,
                     help="handles / host threads the end-to-end step is pipelined over")
-    ap.add_argument("--gn-batch", type=int, default=64, help="graph instances per GPU in the GN arm")
+    ap.add_argument("--gn-batch", type=int, default=128, help="graph instances per GPU in the GN arm")
     return ap.parse_args()
 
 
