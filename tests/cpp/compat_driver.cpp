@@ -19,11 +19,14 @@
 //   COVGATE cur k id_1 ... id_k                      checkCovariance (marginals on the GPU)
 //   CLOSURES thr nv id_1..id_nv ne (from to dx dy dth)*ne   LoopClosureChecker::init + check
 //   BUFSIM window n (vertex_id n_edges)*n            ClosureBuffer add / updateList / checkList
+//   CGB robot optimal k id_1 ... id_k                CondensedGraphBuffer::insertOutClosure + computeCondensedGraph
+//   CGIN robot n (from to dx dy dth I11..I33)*n      CondensedGraphBuffer::insertEdgesFromRobot
 #include <cstdio>
 #include <fstream>
 #include <iostream>
 #include <sstream>
 
+#include "cgm/condensed_graph.hpp"
 #include "cgm/scan_matcher.hpp"
 #include "cgm/slam_frontend.hpp"
 #include "g2o_compat/g2o_compat.hpp"
@@ -44,6 +47,7 @@ int main(int argc, char** argv) {
   opt.setAlgorithm(new OptimizationAlgorithmGaussNewton(std::move(blockSolver)));
   opt.setVerbose(false);
 
+  CondensedGraphBuffer condensedGraphs(&opt);   // as MRGraphSLAM holds one (mr_graph_slam.cpp:32)
   ScanMatcher closeMatcher, lcMatcher;
   bool matchers_ready = false;
   auto ready = [&]() {
@@ -197,6 +201,57 @@ int main(int argc, char** argv) {
         v->pop();
         v->setFixed(was_fixed[q++]);
       }
+    } else if (tag == "CGB") {
+      // the star another robot gets over the vertices it asked about (condensed_graph_buffer.cpp:437-485)
+      int robot, optimal, k;
+      ss >> robot >> optimal >> k;
+      OptimizableGraph::VertexIDMap asked;
+      for (int i = 0; i < k; ++i) {
+        int id;
+        ss >> id;
+        asked.insert(std::make_pair(id, opt.vertex(id)));
+      }
+      condensedGraphs.insertOutClosure(robot, asked);
+      condensedGraphs.computeCondensedGraph(robot, optimal != 0);
+      OptimizableGraph::EdgeSet star = condensedGraphs.outCondensedGraph(robot);
+      const int gauge = star.empty() ? -1 : (*star.begin())->vertex(0)->id();
+      int at_level = 0;
+      for (HyperGraph::Edge* he : opt.edges())
+        at_level += static_cast<OptimizableGraph::Edge*>(he)->level() == robot + 1;
+      printf("CGB %d %zu %zu %zu %d %zu\n", gauge, star.size(), opt.edges().size(),
+             condensedGraphs.getMyEdges().size(), at_level, condensedGraphs.outClosures(robot)->size());
+      for (HyperGraph::Edge* he : star) {
+        EdgeSE2* e = static_cast<EdgeSE2*>(he);
+        printf("C %d %.17g %.17g %.17g", e->vertex(1)->id(), e->measurement().translation().x(),
+               e->measurement().translation().y(), e->measurement().rotation().angle());
+        for (int i = 0; i < 3; ++i)
+          for (int j = 0; j < 3; ++j) printf(" %.17g", e->information()(i, j));
+        printf("\n");
+      }
+    } else if (tag == "CGIN") {
+      // a star received from another robot replaces the previous one (condensed_graph_buffer.cpp:487-510)
+      int robot, n;
+      ss >> robot >> n;
+      OptimizableGraph::EdgeSet eset;
+      for (int i = 0; i < n; ++i) {
+        int a, b;
+        double x, y, th, w[6];
+        ss >> a >> b >> x >> y >> th;
+        for (int q = 0; q < 6; ++q) ss >> w[q];
+        EdgeSE2* e = new EdgeSE2();
+        e->vertices()[0] = opt.vertex(a);
+        e->vertices()[1] = opt.vertex(b);
+        e->setMeasurement(SE2(x, y, th));
+        Eigen::Matrix3d m;
+        m(0, 0) = w[0]; m(0, 1) = m(1, 0) = w[1]; m(0, 2) = m(2, 0) = w[2];
+        m(1, 1) = w[3]; m(1, 2) = m(2, 1) = w[4]; m(2, 2) = w[5];
+        e->setInformation(m);
+        e->setSerial(2000000 + i);
+        eset.insert(e);
+      }
+      condensedGraphs.insertEdgesFromRobot(robot, eset);
+      printf("CGIN %zu %zu %zu\n", condensedGraphs.inCondensedGraph(robot).size(), opt.edges().size(),
+             condensedGraphs.getMyEdges().size());
     } else if (tag == "FINDSM" || tag == "SETS") {
       int cur;
       ss >> cur;

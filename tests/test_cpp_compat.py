@@ -218,3 +218,85 @@ def test_covariance_gate_matches_oracle(driver, tmp_path):
     # GraphManipulator::popState left the estimates untouched
     after = np.array([[float(x) for x in ln.split()[2:]] for ln in lines if ln.startswith("P ")])
     assert np.array_equal(after, g["poses0"])
+
+
+@pytest.mark.gpu
+def test_condensed_graph_buffer_matches_oracle(driver, tmp_path):
+    """CondensedGraphBuffer (condensed_graph_buffer.cpp:94-510) + CondensedGraphCreator
+    (condensed_graph_creator.cpp:33-66) through their C++ mirrors: the star a peer robot gets over
+    the vertices it asked about -- centroid gauge and 'optimal' gauge (argmin of sum det(Omega^-1)
+    over all candidate gauges) --, its replacement on the next request, the bookkeeping of a star
+    received from a peer, and that neither kind of star leaks into 'my own edges'."""
+    g = synth.make_pose_graph(260, 950, seed=23, box=17.0, init="truth_noisy")
+    n = len(g["poses0"])
+    ids = [10000 + k for k in range(n)]
+    asked = [12, 57, 58, 131, 190, 244]
+    more = [77, 131, 203]                       # a later request: 131 is already listed
+    peer_star = [(57, 190, (0.4, -0.2, 0.05)), (57, 12, (-1.0, 0.3, -0.4))]
+    path = str(tmp_path / "cgb.txt")
+    with open(path, "w") as f:
+        for k in range(n):
+            p = g["poses0"][k]
+            f.write("V %d %.17g %.17g %.17g %d 0 0 0 8\n" % (ids[k], p[0], p[1], p[2], 1 if k == 0 else 0))
+        for (a, b), z, w in zip(g["edge_ij"], g["meas"], g["info"]):
+            f.write("E %d %d %.17g %.17g %.17g %s\n" % (ids[a], ids[b], z[0], z[1], z[2],
+                                                      " ".join("%.17g" % x for x in w)))
+        f.write("CGB 1 0 %d %s\n" % (len(asked), " ".join(str(ids[k]) for k in asked)))
+        f.write("CGIN 1 %d %s\n" % (len(peer_star), " ".join(
+            "%d %d %.17g %.17g %.17g 500 0 0 500 0 5000" % (ids[a], ids[b], z[0], z[1], z[2])
+            for a, b, z in peer_star)))
+        f.write("CGB 1 0 %d %s\n" % (len(more), " ".join(str(ids[k]) for k in more)))
+        f.write("CGB 2 1 %d %s\n" % (len(asked[:4]), " ".join(str(ids[k]) for k in asked[:4])))
+        f.write("POSES\n")
+    lines, _ = _run(driver, path)
+    heads = [i for i, ln in enumerate(lines) if ln.startswith("CGB ")]
+    n_e = len(g["edge_ij"])
+
+    def star_of(i):
+        head = [int(x) for x in lines[heads[i]].split()[1:]]
+        rows = []
+        for ln in lines[heads[i] + 1:]:
+            if not ln.startswith("C "):
+                break
+            rows.append([float(x) for x in ln.split()[1:]])
+        return head, np.array(rows)
+
+    def check(rows, seps, gauge, edge_ij, meas, info):
+        z, om, vs = po.condensed_star(g["poses0"], edge_ij, meas, info, gauge, sorted(seps))
+        assert [int(r[0]) for r in rows] == [ids[v] for v in vs]
+        dz = rows[:, 1:4] - z
+        dz[:, 2] = po.normalize_theta(dz[:, 2])
+        assert np.abs(dz).max() < 1e-6
+        assert np.abs(rows[:, 4:].reshape(-1, 3, 3) - om).max() < 1e-6 * np.abs(om).max()
+        return om
+
+    # 1. first request of robot 1: centroid gauge, star over the asked vertices, level-2 edges
+    head, rows = star_of(0)
+    gauge = po.select_gauge_centroid(g["poses0"], sorted(asked))
+    assert head == [ids[gauge], len(asked) - 1, n_e + len(asked) - 1, n_e, len(asked) - 1, len(asked)]
+    check(rows, asked, gauge, g["edge_ij"], g["meas"], g["info"])
+    # 2. the peer's star arrives: level-0 edges in the graph, but not among "my own edges"
+    assert [int(x) for x in lines[[i for i, ln in enumerate(lines) if ln.startswith("CGIN ")][0]].split()[1:]] == \
+        [len(peer_star), n_e + len(asked) - 1 + len(peer_star), n_e]
+    # 3. a later request adds two vertices; the old star is replaced; the star is computed from
+    #    this robot's own edges only (the peer's star does not enter)
+    head, rows = star_of(1)
+    union = sorted(set(asked) | set(more))
+    gauge = po.select_gauge_centroid(g["poses0"], union)
+    assert head == [ids[gauge], len(union) - 1, n_e + len(union) - 1 + len(peer_star), n_e, len(union) - 1,
+                    len(union)]
+    check(rows, union, gauge, g["edge_ij"], g["meas"], g["info"])
+    # 4. robot 2, optimal gauge: every candidate's star is computed, the least uncertain one wins
+    head, rows = star_of(2)
+    cand = sorted(asked[:4])
+    cost = []
+    for c in cand:
+        _, om, _ = po.condensed_star(g["poses0"], g["edge_ij"], g["meas"], g["info"], c, cand)
+        cost.append(sum(np.linalg.det(np.linalg.inv(o)) for o in om))
+    best = cand[int(np.argmin(cost))]
+    assert head[0] == ids[best] and head[1] == len(cand) - 1 and head[4] == len(cand) - 1
+    check(rows, cand, best, g["edge_ij"], g["meas"], g["info"])
+    # push / pop inside the creator left every estimate untouched
+    after = np.array([[float(x) for x in ln.split()[2:]] for ln in lines if ln.startswith("P ")])
+    assert np.array_equal(after, g["poses0"])
+
