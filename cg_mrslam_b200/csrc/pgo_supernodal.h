@@ -80,15 +80,8 @@ static const int kTriSmemDoubles = 6 * kMaxSuperWidth + kPanelWidth * kPanelWidt
 PGO_HD constexpr int sn_max3(int a, int b, int c) { return a > b ? (a > c ? a : c) : (b > c ? b : c); }
 static const int kCtaSmemDoubles = sn_max3(kFactorSmemDoubles, kTileSmemDoubles, kTriSmemDoubles);
 static const int kSmallPairDoubles = (kSmallWidth * (kSmallWidth + 1) / 2 + 1) / 2;
-static const int kWarpSmemDoubles = kSmallWidth * kSmallWidth * 9 + kSmallWidth * 9 +
-                                    kSmallPairDoubles + 3 * kSmallWidth +
-                                    3 * kSmallWidth * (3 * kSmallRows + 1);  // fused
-// warp tasks of the substitutions: xs[3W] us[3W] Dg[W*W*9] Di[W*9] red[3 * 32]
-static const int kWarpSubstDoubles = 6 * kSubstWarpWidth + kSubstWarpWidth * kSubstWarpWidth * 9 + kSubstWarpWidth * 9 + 3 * 32;
-// shared memory of one fused task (sn_task_fused)
-PGO_HD int sn_fused_doubles(int w, int m) {
-  return w * w * 9 + w * 9 + kSmallPairDoubles + 3 * w + 3 * w * (3 * m + 1);
-}
+static const int kWarpSmemDoubles = sn_fused_doubles(kSmallWidth, kSmallRows);  // fused
+static const int kWarpSubstDoubles = sn_subst_doubles(kSubstWarpWidth);
 
 struct SeqGroup {  // host: one thread plays every rank in turn
   PGO_HD int rank() const { return 0; }

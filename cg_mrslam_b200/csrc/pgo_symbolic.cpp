@@ -3,7 +3,6 @@
 
 #include <algorithm>
 #include <chrono>
-#include <cstdlib>
 #include <cstring>
 #include <numeric>
 
@@ -679,11 +678,7 @@ Supernodal::Lists Supernodal::lists(int owner) const {
   L.ff_smem.assign(n_plevels, 0);
   L.ff_smem_small.assign(n_plevels, 0);
   L.ff_large.assign(n_plevels, 0);
-  const int pair_small = (kSmallWidth * (kSmallWidth + 1) / 2 + 1) / 2;
-  auto fused_need = [&](const Task& t) {  // = sn_fused_doubles(w, m) of pgo_supernodal.h
-    const PanelDesc& pd = pn[t.id];
-    return pd.w * pd.w * 9 + pd.w * 9 + pair_small + 3 * pd.w + 3 * pd.w * (3 * pd.m + 1);
-  };
+  auto fused_need = [&](const Task& t) { return sn_fused_doubles(pn[t.id].w, pn[t.id].m); };
   for (int l = 0; l < n_plevels; ++l) {
     std::stable_partition(L.ff.begin() + L.ff_ptr[l], L.ff.begin() + L.ff_ptr[l + 1],
                           [&](const Task& t) { return fused_need(t) > kFusedSmallDoubles; });
@@ -710,11 +705,7 @@ Supernodal::Lists Supernodal::lists(int owner) const {
       L.fb_smem[l] = std::max(L.fb_smem[l], sn_tile_doubles(w, t.aux & 0xFF, (t.aux >> 8) & 0xFF));
     }
   }
-  // xs[3W] us[3W] Dg[W*W*9] Di[W*9] red[3 * 32] (sn_task_backward_small / _forward_small)
-  auto subst_need = [&](const Task& t) {
-    const int W = sn[t.id].W;
-    return 6 * W + 9 * W * W + 9 * W + 96;
-  };
+  auto subst_need = [&](const Task& t) { return sn_subst_doubles(sn[t.id].W); };
   L.ss_smem.assign(n_slevels, 0);
   L.ss_smem_small.assign(n_slevels, 0);
   L.ss_large.assign(n_slevels, 0);
@@ -767,9 +758,7 @@ bool analyse(int n, const std::vector<std::pair<int, int> >& edges, int ordering
     S.perm.resize(n);
     std::iota(S.perm.begin(), S.perm.end(), 0);
   } else {
-    int leaf = kLeafSize;
-    if (const char* ev = std::getenv("CGM_PGO_LEAF")) leaf = std::max(1, std::atoi(ev));  // tuning aid
-    Dissector d(g, leaf, world);
+    Dissector d(g, kLeafSize, world);
     d.run(&S.perm);
     vertex_owner = d.owner();
     // leaf groups become supernodes: clique inside the group, every member tied to the whole

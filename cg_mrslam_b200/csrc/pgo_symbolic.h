@@ -50,6 +50,13 @@ PGO_HOST_DEVICE inline constexpr int sn_tile_ld(int w) {  // >= 3 w rounded up t
 PGO_HOST_DEVICE inline constexpr int sn_tile_doubles(int w, int ti, int tj) {
   return 3 * (ti + tj) * sn_tile_ld(w) + (ti * tj + 1) / 2;
 }
+// shared memory (doubles) of one warp task: a fused small panel (sn_task_fused: Dg[w*w*9] Di[w*9]
+// pair table, us[3w], xs[3w][3m+1]) and a narrow supernode of the substitutions
+// (sn_task_backward_small / _forward_small: xs[3W] us[3W] Dg[W*W*9] Di[W*9] red[3 * 32])
+PGO_HOST_DEVICE inline constexpr int sn_fused_doubles(int w, int m) {
+  return w * w * 9 + w * 9 + (kSmallWidth * (kSmallWidth + 1) / 2 + 1) / 2 + 3 * w + 3 * w * (3 * m + 1);
+}
+PGO_HOST_DEVICE inline constexpr int sn_subst_doubles(int W) { return 6 * W + 9 * W * W + 9 * W + 96; }
 static const int kMaxSuperWidth = 1008;   // at most 63 panels per supernode
 static const int kUpdateGroup = 4;        // panels per tile task of an ancestors' update
 
