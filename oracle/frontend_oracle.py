@@ -185,3 +185,58 @@ class ClosureWindow:
                 self.vertices = [vt for vt in self.vertices if vt[0] != v]
         ids = {v for v, _ in self.vertices}
         return vote, len(self.edges), len(ids), [tuple(vt) for vt in self.vertices]
+
+
+class MRClosureWindows:
+    """MRClosureBuffer (mr_closure_buffer.cpp:30-118): one ClosureBuffer per peer robot. State per
+    peer: vertex list [[id, age]] in insertion order (a re-inserted vertex is listed again with
+    age 0, closure_buffer.cpp addVertex), the id map, and the candidate edges (serial, vertex)."""
+
+    def __init__(self):
+        self.peers = {}
+        self.serial = 0
+        self.edges_of = {}
+
+    def _remove_vertex(self, st, v):
+        if v not in st["ids"]:
+            return
+        st["ids"].discard(v)
+        st["edges"] = [(s, ev) for (s, ev) in st["edges"] if ev != v]
+        st["list"] = [vt for vt in st["list"] if vt[0] != v]
+
+    def insert(self, robot, vertex, n_edges):
+        new = []
+        for _ in range(n_edges):
+            new.append((self.serial, vertex))
+            self.serial += 1
+        self.edges_of.setdefault(vertex, []).extend(new)
+        st = self.peers.setdefault(robot, {"list": [], "ids": set(), "edges": []})
+        st["list"].append([vertex, 0])
+        st["ids"].add(vertex)
+        st["edges"].extend(new)
+
+    def remove(self, robot, vertex):
+        st = self.peers.get(robot)
+        if st is None:
+            return
+        self._remove_vertex(st, vertex)
+        gone = set(self.edges_of.get(vertex, []))
+        st["edges"] = [e for e in st["edges"] if e not in gone]
+        if not st["ids"]:
+            del self.peers[robot]
+
+    def update(self, window):
+        for robot in sorted(self.peers):
+            st = self.peers[robot]
+            for vt in st["list"]:
+                vt[1] += 1
+            for v, t in list(st["list"]):
+                if t >= window:
+                    self._remove_vertex(st, v)
+            if not st["ids"]:
+                del self.peers[robot]
+
+    def state(self):
+        return [(r, len(set(st["edges"])), len(st["ids"]), [tuple(vt) for vt in st["list"]])
+                for r, st in sorted(self.peers.items())]
+

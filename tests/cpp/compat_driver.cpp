@@ -19,6 +19,7 @@
 //   COVGATE cur k id_1 ... id_k                      checkCovariance (marginals on the GPU)
 //   CLOSURES thr nv id_1..id_nv ne (from to dx dy dth)*ne   LoopClosureChecker::init + check
 //   BUFSIM window n (vertex_id n_edges)*n            ClosureBuffer add / updateList / checkList
+//   MRBUF window n (op robot vertex_id n_edges)*n    MRClosureBuffer insert (I) / remove (R) / update (U)
 //   CGB robot optimal k id_1 ... id_k                CondensedGraphBuffer::insertOutClosure + computeCondensedGraph
 //   CGIN robot n (from to dx dy dth I11..I33)*n      CondensedGraphBuffer::insertEdgesFromRobot
 #include <cstdio>
@@ -27,6 +28,7 @@
 #include <sstream>
 
 #include "cgm/condensed_graph.hpp"
+#include "cgm/mr_closure_buffer.hpp"
 #include "cgm/scan_matcher.hpp"
 #include "cgm/slam_frontend.hpp"
 #include "g2o_compat/g2o_compat.hpp"
@@ -201,6 +203,47 @@ int main(int argc, char** argv) {
         v->pop();
         v->setFixed(was_fixed[q++]);
       }
+    } else if (tag == "MRBUF") {
+      // the per-peer windows as MRGraphSLAM drives them (mr_graph_slam.cpp:233-247,310-327)
+      int window, n;
+      ss >> window >> n;
+      MRClosureBuffer mr;
+      std::vector<EdgeSE2*> owned;
+      std::map<int, std::vector<EdgeSE2*> > edges_of;   // by vertex id
+      for (int step = 0; step < n; ++step) {
+        std::string op;
+        int robot, vid, ne;
+        ss >> op >> robot >> vid >> ne;
+        if (op == "I") {
+          ClosureBuffer c;
+          c.addVertex(opt.vertex(vid));
+          for (int i = 0; i < ne; ++i) {
+            EdgeSE2* e = new EdgeSE2();
+            e->vertices()[0] = opt.vertices().begin()->second;
+            e->vertices()[1] = opt.vertex(vid);
+            e->setSerial(4000000 + static_cast<long long>(owned.size()));
+            owned.push_back(e);
+            edges_of[vid].push_back(e);
+            c.addEdge(e);
+          }
+          mr.insert(c, robot);
+        } else if (op == "R") {
+          ClosureBuffer c;
+          c.addVertex(opt.vertex(vid));
+          for (EdgeSE2* e : edges_of[vid]) c.addEdge(e);
+          mr.remove(c, robot);
+        } else {
+          mr.update(window);
+        }
+        MRClosureBuffer snapshot = mr;   // findInterRobotConstraints iterates over a copy (mr_graph_slam.cpp:270)
+        printf("MR %u", snapshot.size());
+        for (auto& kv : snapshot.mrClosures) {
+          printf(" | %d %zu %zu", kv.first, kv.second->edgeSet().size(), kv.second->vertices().size());
+          for (const VertexTime& vt : kv.second->vertexList()) printf(" %d:%d", vt.v->id(), vt.time);
+        }
+        printf("\n");
+      }
+      for (EdgeSE2* e : owned) delete e;
     } else if (tag == "CGB") {
       // the star another robot gets over the vertices it asked about (condensed_graph_buffer.cpp:437-485)
       int robot, optimal, k;

@@ -134,3 +134,36 @@ def test_closure_buffer_window(driver, tmp_path):
         assert int(tok[2]) == n_edges and int(tok[3]) == n_vertices
         assert [tuple(int(x) for x in t.split(":")) for t in tok[4:]] == vl
     assert any(ln.split()[1] == "1" for ln in lines)
+
+
+def test_mr_closure_buffer(driver, tmp_path):
+    """MRClosureBuffer (mr_closure_buffer.cpp:30-118): per-peer windows under insert / remove /
+    update, incl. a vertex inserted twice, removal of the last vertex of a peer, and ageing out."""
+    g, ids, poses, edges = graph(60, 120, seed=4, box=9.0)
+    ops = [("I", 1, ids[5], 1), ("I", 2, ids[7], 0), ("I", 1, ids[6], 2), ("U", 0, 0, 0),
+           ("I", 1, ids[5], 0), ("I", 3, ids[9], 1), ("R", 2, ids[7], 0), ("U", 0, 0, 0),
+           ("R", 1, ids[6], 0), ("U", 0, 0, 0), ("I", 2, ids[8], 3), ("U", 0, 0, 0), ("U", 0, 0, 0),
+           ("R", 4, ids[5], 0), ("U", 0, 0, 0), ("U", 0, 0, 0), ("U", 0, 0, 0)]
+    cmd = "MRBUF 3 %d %s" % (len(ops), " ".join("%s %d %d %d" % o for o in ops))
+    path = str(tmp_path / "s.txt")
+    write(path, g, ids, [cmd])
+    lines = run(driver, path)
+    mr = fo.MRClosureWindows()
+    seen_sizes = set()
+    for ln, (op, robot, v, ne) in zip(lines, ops):
+        if op == "I":
+            mr.insert(robot, v, ne)
+        elif op == "R":
+            mr.remove(robot, v)
+        else:
+            mr.update(3)
+        want = mr.state()
+        parts = ln.split(" | ")
+        assert parts[0] == "MR %d" % len(want), (ln, want)
+        for part, (r, n_edges, n_vertices, vl) in zip(parts[1:], want):
+            tok = part.split()
+            assert [int(tok[0]), int(tok[1]), int(tok[2])] == [r, n_edges, n_vertices], (ln, want)
+            assert [tuple(int(x) for x in t.split(":")) for t in tok[3:]] == vl, (ln, want)
+        seen_sizes.add(len(want))
+    assert seen_sizes >= {0, 1, 2, 3}
+
