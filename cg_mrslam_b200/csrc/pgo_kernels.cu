@@ -281,7 +281,7 @@ __device__ double block_sum(double v, double* scratch) {
 
 // ---- phase 1: linearise ------------------------------------------------------------------------
 template <bool kTab>
-__device__ void phase_linearise(const Params& P, double* scratch, int it) {
+__device__ void phase_linearise(const Params& P) {
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
   double chi = 0.0;
   for (int p = tid; p < P.n; p += nthreads) {
@@ -331,9 +331,11 @@ __device__ void phase_linearise(const Params& P, double* scratch, int it) {
     else linearise_edge(P, P.ff_edges[t], &L);
     chi += edge_chi2(L);
   }
-  const double s = block_sum(chi, scratch);
-  if (threadIdx.x == 0) P.chi2_partial[blockIdx.x] = s;
-  (void)it;
+  // one partial per WARP, in a fixed order: no CTA barrier, a warp retires as soon as its own
+  // vertices are done (degrees differ by several times)
+  for (int o = 16; o; o >>= 1) chi += __shfl_down_sync(0xffffffffu, chi, o);
+  if ((threadIdx.x & 31) == 0) P.chi2_partial[blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)] = chi;
+
 }
 
 const int kThreads = 256;
@@ -579,10 +581,9 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) sn_k_fwd_rows(SNView V, con
 
 // linearise + chi2 (phase 1) as plain kernels
 __global__ void __launch_bounds__(kLinThreads) gn_linearise(Params P) {
-  __shared__ double scratch[32];
   P = params_at(P, blockIdx.y);
   if (*reinterpret_cast<volatile int*>(P.status) != 0) return;
-  phase_linearise<true>(P, scratch, 0);
+  phase_linearise<true>(P);
 }
 // sin / cos of every pose angle and every measurement angle of this iteration (see linearise_edge_tab)
 __global__ void gn_trig(Params P) {
@@ -1032,7 +1033,7 @@ int dev_set_structure(DeviceSolver* d, const Symbolic& S, const GraphTables& G, 
   V.s_status = 4;
   d->lin_blocks = std::max(1, std::min(4 * d->sm_count, (S.n + kLinThreads - 1) / kLinThreads));
   PGO_CUDA(d->chi2_out.reserve(B * kMaxItersPerCall));
-  PGO_CUDA(d->chi2_partial.reserve(std::max(B * d->lin_blocks, static_cast<size_t>(d->grid))));
+  PGO_CUDA(d->chi2_partial.reserve(std::max(B * d->lin_blocks * (kLinThreads / 32), static_cast<size_t>(d->grid))));
   PGO_CUDA(d->status.reserve(4 * B));
   P.chi2_partial = d->chi2_partial.p;
   P.status = d->status.p;
@@ -1043,7 +1044,7 @@ int dev_set_structure(DeviceSolver* d, const Symbolic& S, const GraphTables& G, 
   P.s_M = V.s_M;
   P.s_Dinv = V.s_Dinv;
   P.s_vec = V.s_vec;
-  P.s_partial = d->lin_blocks;
+  P.s_partial = d->lin_blocks * (kLinThreads / 32);
   P.s_chi2 = kMaxItersPerCall;
   P.s_trig = 2LL * (static_cast<long long>(G.n_vertices) + G.n_edges);
   PGO_CUDA(d->trig.reserve(B * static_cast<size_t>(P.s_trig)));
@@ -1299,7 +1300,7 @@ static int enqueue_stage(DeviceSolver* d, int stage, std::string* err) {
       gn_linearise<<<dim3(d->lin_blocks, B), kLinThreads, 0, st>>>(P);
       ++nodes;
     }
-    if (!dd) gn_chi2<<<dim3(1, B), 256, 0, st>>>(P, d->lin_blocks);
+    if (!dd) gn_chi2<<<dim3(1, B), 256, 0, st>>>(P, d->lin_blocks * (kLinThreads / 32));
     gn_stamp<<<1, 1, 0, st>>>(d->stamps.p, 1);
     nodes += 6;
     rc = enqueue_factor(d, d->sets[0], &nodes, err);
