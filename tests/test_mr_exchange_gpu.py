@@ -1,0 +1,107 @@
+"""Two MRGraphSLAM mirrors (include/cgm/mr_graph_slam.hpp) exchange condensed graphs through the
+float32 wire format, as cg_mrslam.cpp:236-259 / graph_comm.cpp:126-154 do over UDP: B asks A about
+the A-vertices it closed loops with, A computes the star on the GPU and answers, B optimises with
+the star. Checked against the pose-graph oracle: datagram sizes, the star (1e-6, and exactly
+float32-representable: it crossed the wire), B's estimates after optimize(5) (1e-6)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from cg_mrslam_b200 import synth
+from oracle import pgo_oracle as po
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIBDIR = os.path.join(ROOT, "cg_mrslam_b200", "lib")
+
+
+@pytest.fixture(scope="module")
+def driver(tmp_path_factory):
+    import __graft_entry__ as g
+    if not os.path.exists(os.path.join(LIBDIR, "libcgmrslam_b200.so")):
+        g.build()
+    exe = str(tmp_path_factory.mktemp("cpp") / "mr_exchange")
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O1", "-Wall", "-Werror",
+                           "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "mr_exchange.cpp"), "-o", exe,
+                           "-L" + LIBDIR, "-lcgmrslam_b200", "-Wl,-rpath," + LIBDIR])
+    return exe
+
+
+@pytest.mark.gpu
+def test_condensed_graph_exchange(driver, tmp_path):
+    rng = np.random.default_rng(31)
+    ga = synth.make_pose_graph(200, 720, seed=41, box=15.0, init="truth_noisy")
+    gb = synth.make_pose_graph(180, 640, seed=42, box=15.0, init="truth_noisy")
+    na, nb = len(ga["poses0"]), len(gb["poses0"])
+    ida = list(range(na))                       # robot 0: ids 0 .. (id / 10000 == 0)
+    idb = [10000 + k for k in range(nb)]        # robot 1
+    asked = [23, 88, 141, 190]                  # A's vertices B closed loops with
+    partners = [15, 60, 99, 170]                # ... from these B vertices
+    # B's copies of A's vertices: A's estimate seen with some error; inter-robot closure edges
+    copies = ga["poses0"][asked] + rng.normal(size=(len(asked), 3)) * [0.05, 0.05, 0.01]
+    ir_meas = []
+    for p, c in zip(partners, copies):
+        rel = po.se2_mul(po.se2_inv(gb["poses0"][p]), c)[0]
+        ir_meas.append(po.se2_mul(rel, rng.normal(0, [0.02, 0.02, 0.005]))[0])
+    ir_info = [100.0, 0.0, 0.0, 100.0, 0.0, 1000.0]
+    path = str(tmp_path / "mr.txt")
+    with open(path, "w") as f:
+        for r, g, ids in ((0, ga, ida), (1, gb, idb)):
+            for k, vid in enumerate(ids):
+                p = g["poses0"][k]
+                f.write("V %d %d %.17g %.17g %.17g %d\n" % (r, vid, p[0], p[1], p[2], 1 if k == 0 else 0))
+            for (a, b), z, w in zip(g["edge_ij"], g["meas"], g["info"]):
+                f.write("E %d %d %d %.17g %.17g %.17g %s\n" % (r, ids[a], ids[b], z[0], z[1], z[2],
+                                                             " ".join("%.17g" % x for x in w)))
+        for a, c in zip(asked, copies):
+            f.write("V 1 %d %.17g %.17g %.17g 0\n" % (ida[a], c[0], c[1], c[2]))
+        for p, a, z in zip(partners, asked, ir_meas):
+            f.write("E 1 %d %d %.17g %.17g %.17g %s\n" % (idb[p], ida[a], z[0], z[1], z[2],
+                                                        " ".join("%.17g" % x for x in ir_info)))
+        f.write("WANT 1 0 %d %s\n" % (len(asked), " ".join(str(ida[a]) for a in asked)))
+    out = subprocess.run([driver, path], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    lines = out.stdout.splitlines()
+    lines = lines[lines.index("BEGIN") + 1:lines.index("END")]
+    msgs = [ln.split() for ln in lines if ln.startswith("MSG ")]
+    n_star = len(asked) - 1
+    # B -> A: header 8 + edge count 8 + closure count 8 + 4 ids; A -> B: the star, no requests
+    assert msgs[0] == ["MSG", "1", "0", str(8 + 8 + 8 + 4 * len(asked)), "closures", str(len(asked)), "edges", "0"]
+    assert msgs[1] == ["MSG", "0", "1", str(8 + 8 + n_star * (8 + 9 * 4) + 8), "closures", "0", "edges", str(n_star)]
+    # the star A computed: centroid gauge, its own edges only
+    gauge = po.select_gauge_centroid(ga["poses0"], sorted(asked))
+    z, om, vs = po.condensed_star(ga["poses0"], ga["edge_ij"], ga["meas"], ga["info"], gauge, sorted(asked))
+    rows = np.array([[float(x) for x in ln.split()[1:]] for ln in lines if ln.startswith("C ")])
+    assert [ln.split()[:3] for ln in lines if ln.startswith("STAR ")][0] == \
+        ["STAR", str(n_star), str(len(gb["edge_ij"]) + len(asked) + n_star)]
+    assert [int(r[0]) for r in rows] == [ida[gauge]] * n_star and [int(r[1]) for r in rows] == [ida[v] for v in vs]
+    got_z, got_om = rows[:, 2:5], rows[:, 5:].reshape(-1, 3, 3)
+    dz = got_z - z
+    dz[:, 2] = po.normalize_theta(dz[:, 2])
+    assert np.abs(dz).max() < 1e-6
+    assert np.abs(got_om - om).max() < 1e-6 * np.abs(om).max()
+    f32 = lambda a: a.astype(np.float32).astype(np.float64)
+    assert np.array_equal(got_z, f32(got_z)) and np.array_equal(got_om, f32(got_om))   # it crossed the wire
+    assert np.array_equal(got_om, np.transpose(got_om, (0, 2, 1)))
+    # B's optimisation: its own graph + the closures + the star as received
+    idx = {vid: k for k, vid in enumerate(idb)}
+    for j, a in enumerate(asked):
+        idx[ida[a]] = nb + j
+    poses0 = np.vstack([gb["poses0"], copies])
+    e_ij = [list(e) for e in gb["edge_ij"]] + [[idx[idb[p]], idx[ida[a]]] for p, a in zip(partners, asked)] + \
+        [[idx[int(r[0])], idx[int(r[1])]] for r in rows]
+    meas = np.vstack([gb["meas"], np.array(ir_meas), got_z])
+    info = np.vstack([gb["info"], np.tile(ir_info, (len(asked), 1)),
+                      np.array([[o[0, 0], o[0, 1], o[0, 2], o[1, 1], o[1, 2], o[2, 2]] for o in got_om])])
+    ref = po.gauss_newton(poses0, np.array(e_ij, dtype=np.int64), meas, info, [0], 5)
+    got_p = {int(ln.split()[1]): [float(x) for x in ln.split()[2:]] for ln in lines if ln.startswith("P ")}
+    got = np.array([got_p[vid] for vid in sorted(idx, key=idx.get)])
+    d = got - ref.poses
+    d[:, 2] = po.normalize_theta(d[:, 2])
+    assert np.abs(d).max() < 1e-6
+    assert np.abs(got - poses0).max() > 1e-3          # the optimisation moved something
+    # second round: the star is replaced on both sides, nothing is duplicated
+    assert [ln.split()[1:] for ln in lines if ln.startswith("AGAIN ")][0] == \
+        [str(n_star), str(len(gb["edge_ij"]) + len(asked) + n_star), str(len(ga["edge_ij"]) + n_star)]
