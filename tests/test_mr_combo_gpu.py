@@ -64,7 +64,7 @@ def f32(a):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("seed,ref,max_score", [(5, 14, 0.3), (8, 3, 0.3), (11, 20, 0.12)])
+@pytest.mark.parametrize("seed,ref,max_score", [(5, 14, 0.3), (8, 3, 0.3), (11, 20, 0.12), (5, 14, 0.01)])
 def test_combo_message_to_accepted_closure(driver, tmp_path, oracle_lib, seed, ref, max_score):
     from oracle import bindings
     from oracle import scan_matcher_oracle as smo
@@ -126,6 +126,7 @@ def test_combo_message_to_accepted_closure(driver, tmp_path, oracle_lib, seed, r
             frm, to, t = rounds[0]["cands"][0]
             assert (frm, to) == (a[-1]["id"], last["id"]) and np.array_equal(t, t2)
             matched_from = a[-1]["id"]
+    # (seeds 5 and 8 match on arrival, seed 11 only on the retry, max_score 0.01 never)
     ask = lines[[i for i, ln in enumerate(lines) if ln.startswith("ASK ")][0]].split()
     repeat = state("REPEAT")[0]
     if matched_from is not None:
