@@ -90,68 +90,46 @@ struct CondensedGraphBuffer {
     return mine;
   }
 
-  // argmin over the candidate gauges of sum_e det(Omega_e^-1) of the star it yields; the first of
-  // equal candidates (ascending id) wins
+  // Gauge selection: argmin of a cost over the candidate vertices, ascending id, the first of equal
+  // candidates wins (strict < in condensed_graph_buffer.cpp:270,305,337).
+  //   optimal:  sum over the star it would yield of det(Omega_e^-1)   (:252-288)
+  //   plain:    summed distance to the other candidates               (:290-316)
+  //   centroid: distance to the centroid of the candidates            (:318-345)
   g2o::OptimizableGraph::Vertex* selectOptimalGauge(VertexIDMap* vertices) {
-    g2o::OptimizableGraph::Vertex* bestGauge = 0;
-    double bestUncertainty = std::numeric_limits<double>::max();
-    EdgeSet myOwnEdges = getMyEdges();
-    g2o::OptimizableGraph::VertexSet vset;
-    for (auto& kv : *vertices) vset.insert(kv.second);
-    for (auto& kv : *vertices) {
-      g2o::OptimizableGraph::Vertex* candidateGauge = ovx(kv.second);
-      CondensedGraphCreator cgc(_optimizer);
-      cgc.setVertices(vset);
-      cgc.setGauge(candidateGauge);
-      cgc.setEdges(myOwnEdges);
-      cgc.compute();
-      EdgeSet labeledEdges = cgc.getCondensedGraph();
-      const double totalUncertainty = computeOverallUncertainty(labeledEdges);
-      for (g2o::HyperGraph::Edge* e : labeledEdges) delete e;   // (the reference leaks them)
-      if (totalUncertainty < bestUncertainty) {
-        bestUncertainty = totalUncertainty;
-        bestGauge = candidateGauge;
-      }
-    }
-    return bestGauge;
+    EdgeSet own = getMyEdges();
+    g2o::OptimizableGraph::VertexSet all;
+    for (auto& kv : *vertices) all.insert(kv.second);
+    return cheapest(vertices, [&](g2o::VertexSE2* candidate) {
+      CondensedGraphCreator creator(_optimizer);
+      creator.setVertices(all);
+      creator.setGauge(candidate);
+      creator.setEdges(own);
+      creator.compute();
+      EdgeSet star = creator.getCondensedGraph();
+      const double cost = computeOverallUncertainty(star);
+      for (g2o::HyperGraph::Edge* e : star) delete e;   // (the reference leaks them)
+      return cost;
+    });
   }
-  // argmin of the summed distances to the other vertices
   g2o::OptimizableGraph::Vertex* selectGauge(VertexIDMap* vertices) {
-    g2o::OptimizableGraph::Vertex* bestGauge = 0;
-    double bestDistance = std::numeric_limits<double>::max();
-    for (auto& a : *vertices) {
-      g2o::VertexSE2* va = static_cast<g2o::VertexSE2*>(a.second);
-      double currentDistance = 0;
-      for (auto& b : *vertices) {
-        g2o::VertexSE2* vb = static_cast<g2o::VertexSE2*>(b.second);
-        if (vb->id() == va->id()) continue;
-        const g2o::SE2 dt = va->estimate().inverse() * vb->estimate();
-        currentDistance += dt.translation().norm();
+    return cheapest(vertices, [&](g2o::VertexSE2* candidate) {
+      double sum = 0;
+      for (auto& kv : *vertices) {
+        g2o::VertexSE2* other = static_cast<g2o::VertexSE2*>(kv.second);
+        if (other->id() != candidate->id())
+          sum += (candidate->estimate().inverse() * other->estimate()).translation().norm();
       }
-      if (currentDistance < bestDistance) {
-        bestDistance = currentDistance;
-        bestGauge = va;
-      }
-    }
-    return bestGauge;
+      return sum;
+    });
   }
-  // the vertex closest to the centroid of the translations
   g2o::OptimizableGraph::Vertex* selectGaugeCentroid(VertexIDMap* vertices) {
-    g2o::OptimizableGraph::Vertex* bestGauge = 0;
-    double bestDistance = std::numeric_limits<double>::max();
     Eigen::Vector2d sum(.0, .0);
     for (auto& kv : *vertices) sum += static_cast<g2o::VertexSE2*>(kv.second)->estimate().translation();
     const Eigen::Vector2d centroid(sum.x() / vertices->size(), sum.y() / vertices->size());
-    for (auto& kv : *vertices) {
-      g2o::VertexSE2* v = static_cast<g2o::VertexSE2*>(kv.second);
-      const Eigen::Vector2d vdist = v->estimate().translation() - centroid;
-      const double currentDistance = vdist.norm();
-      if (currentDistance < bestDistance) {
-        bestDistance = currentDistance;
-        bestGauge = v;
-      }
-    }
-    return bestGauge;
+    return cheapest(vertices, [&](g2o::VertexSE2* candidate) {
+      const Eigen::Vector2d d = candidate->estimate().translation() - centroid;
+      return d.norm();
+    });
   }
 
   // The star robot `robot` gets: over the vertices it asked about (insertOutClosure), from this
@@ -223,6 +201,20 @@ struct CondensedGraphBuffer {
  protected:
   static g2o::OptimizableGraph::Vertex* ovx(g2o::HyperGraph::Vertex* v) {
     return static_cast<g2o::OptimizableGraph::Vertex*>(v);
+  }
+  template <class Cost>
+  static g2o::OptimizableGraph::Vertex* cheapest(VertexIDMap* vertices, Cost cost) {
+    g2o::OptimizableGraph::Vertex* best = 0;
+    double best_cost = std::numeric_limits<double>::max();
+    for (auto& kv : *vertices) {
+      g2o::VertexSE2* candidate = static_cast<g2o::VertexSE2*>(kv.second);
+      const double c = cost(candidate);
+      if (c < best_cost) {
+        best_cost = c;
+        best = candidate;
+      }
+    }
+    return best;
   }
   static void merge(std::map<int, VertexIDMap*>& into, int robot, VertexIDMap& vidmap) {
     std::map<int, VertexIDMap*>::iterator it = into.find(robot);
