@@ -786,8 +786,8 @@ struct DeviceSolver {
   int grid = 0;  // co-resident CTAs of the cooperative kernels
   uint64_t launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  cudaStream_t aux = nullptr, aux2 = nullptr;  // further branches while capturing the iteration graph
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr;
+  cudaStream_t aux = nullptr, aux2 = nullptr, aux3 = nullptr;  // further branches while capturing the iteration graph
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr, ev_join3 = nullptr;
   Params P;
   bool have_structure = false, have_values = false, have_factor = false;
   Buf<int> edge_i, edge_j, vpos, inc_ptr, ff_edges, col_ptr, row_idx, perm_vertex, status, scratch_i;
@@ -867,9 +867,11 @@ int dev_create(DeviceSolver** out, int device, void* stream, std::string* err) {
   }
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d->aux, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d->aux2, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d->aux3, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->ev_fork, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->ev_join, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->ev_join2, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->ev_join3, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreate(&d->ev0);
   if (e == cudaSuccess) e = cudaEventCreate(&d->ev1);
   if (e == cudaSuccess) e = d->status.reserve(4);
@@ -920,8 +922,10 @@ void dev_destroy(DeviceSolver* d) {
   if (d->ev_fork) cudaEventDestroy(d->ev_fork);
   if (d->ev_join) cudaEventDestroy(d->ev_join);
   if (d->ev_join2) cudaEventDestroy(d->ev_join2);
+  if (d->ev_join3) cudaEventDestroy(d->ev_join3);
   if (d->aux) cudaStreamDestroy(d->aux);
   if (d->aux2) cudaStreamDestroy(d->aux2);
+  if (d->aux3) cudaStreamDestroy(d->aux3);
   if (d->ev0) cudaEventDestroy(d->ev0);
   if (d->ev1) cudaEventDestroy(d->ev1);
   if (d->own_stream && d->stream) cudaStreamDestroy(d->stream);
@@ -1174,9 +1178,26 @@ static int enqueue_factor(DeviceSolver* d, const DeviceSolver::TaskSet& ts, int*
                                                                       stride);
       ++*nodes;
     }
-    if (n_fa) {
-      sn_k_factor<<<dim3(n_fa, B), kCtaThreads, sizeof(double) * L.fa_smem[l], st>>>(V, ts.fa.p + L.fa_ptr[l]);
+    // wide panels on the main branch, narrow ones (less shared memory: more CTAs per SM) beside them
+    const int n_fal = L.fa_large[l], n_fas = n_fa - n_fal;
+    cudaStream_t s_fas = st;
+    if (n_fas && n_fal) {
+      if (s_small == st && s_large == st) PGO_CUDA(cudaEventRecord(d->ev_fork, st));
+      PGO_CUDA(cudaStreamWaitEvent(d->aux3, d->ev_fork, 0));
+      s_fas = d->aux3;
+    }
+    if (n_fal) {
+      sn_k_factor<<<dim3(n_fal, B), kCtaThreads, sizeof(double) * L.fa_smem[l], st>>>(V, ts.fa.p + L.fa_ptr[l]);
       ++*nodes;
+    }
+    if (n_fas) {
+      sn_k_factor<<<dim3(n_fas, B), kCtaThreads, sizeof(double) * L.fa_smem_small[l], s_fas>>>(
+          V, ts.fa.p + L.fa_ptr[l] + n_fal);
+      ++*nodes;
+    }
+    if (s_fas != st) {
+      PGO_CUDA(cudaEventRecord(d->ev_join3, s_fas));
+      PGO_CUDA(cudaStreamWaitEvent(st, d->ev_join3, 0));
     }
     if (s_small != st) {
       PGO_CUDA(cudaEventRecord(d->ev_join, s_small));

@@ -674,6 +674,8 @@ Supernodal::Lists Supernodal::lists(int owner) const {
   filter(sb_ptr, sb, pn_owner, n_slevels, &L.sb_ptr, &L.sb);
   const int pair_doubles = (kPanelWidth * (kPanelWidth + 1) / 2 + 1) / 2;
   L.fa_smem.assign(n_plevels, 0);
+  L.fa_smem_small.assign(n_plevels, 0);
+  L.fa_large.assign(n_plevels, 0);
   L.fb_smem.assign(n_plevels, 0);
   L.ff_smem.assign(n_plevels, 0);
   L.ff_smem_small.assign(n_plevels, 0);
@@ -691,11 +693,20 @@ Supernodal::Lists Supernodal::lists(int owner) const {
         L.ff_smem_small[l] = std::max(L.ff_smem_small[l], need);
       }
     }
-    for (int i = L.fa_ptr[l]; i < L.fa_ptr[l + 1]; ++i) {
-      const Task& t = L.fa[i];
+    auto factor_need = [&](const Task& t) {
       const int w = pn[t.id].w;
-      L.fa_smem[l] = std::max(L.fa_smem[l], w * w * 9 + w * 9 + pair_doubles + 3 * w +
-                                                3 * w * (3 * (t.r1 - t.r0) + 1));
+      return w * w * 9 + w * 9 + pair_doubles + 3 * w + 3 * w * (3 * (t.r1 - t.r0) + 1);
+    };
+    std::stable_partition(L.fa.begin() + L.fa_ptr[l], L.fa.begin() + L.fa_ptr[l + 1],
+                          [&](const Task& t) { return factor_need(t) > kFactorSmallDoubles; });
+    for (int i = L.fa_ptr[l]; i < L.fa_ptr[l + 1]; ++i) {
+      const int need = factor_need(L.fa[i]);
+      if (need > kFactorSmallDoubles) {
+        ++L.fa_large[l];
+        L.fa_smem[l] = std::max(L.fa_smem[l], need);
+      } else {
+        L.fa_smem_small[l] = std::max(L.fa_smem_small[l], need);
+      }
     }
     for (int i = L.fb_ptr[l]; i < L.fb_ptr[l + 1]; ++i) {
       const Task& t = L.fb[i];

@@ -39,6 +39,7 @@ static const int kSubstWarpWidth = 4;   // substitutions: supernodes this narrow
 static const int kSubstSmallDoubles = 320;  // ... launched apart from the narrow ones above this need
 static const int kSmallRows = 32;    // ... if the panel also has at most this many rows below it
 static const int kFusedSmallDoubles = 704;  // 5.5 kB per warp: 8+ CTAs of 4 warps per SM
+static const int kFactorSmallDoubles = 5400;  // 43 kB: a panel of <= 8 columns with a full row chunk
 static const int kRowChunk = 64;     // rows below a panel per CTA task of the panel factorisation
 // outer-product tile of one CTA task (tensor-core GEMM, pgo_kernels.cu): ti x tj blocks with
 // ti a multiple of 8 and tj in {8, 16, 24, 32}; operands staged as [3 ti][ld] and [3 tj][ld]
@@ -122,6 +123,10 @@ struct Supernodal {
     std::vector<int> ff_ptr, fa_ptr, fb_ptr, ss_ptr, sa_ptr, sf_ptr, sb_ptr;
     std::vector<Task> ff, fa, fb, ss, sa, sf, sb;
     std::vector<int> fa_smem, fb_smem;  // doubles of shared memory of the largest task per level
+    // factor tasks: per level the ones needing more than kFactorSmallDoubles come first
+    // (fa_large[l] of them, fa_smem[l]); the rest (narrow panels) are launched apart with
+    // fa_smem_small[l], so that four of them fit an SM instead of two
+    std::vector<int> fa_smem_small, fa_large;
     // fused warp tasks: per level the few tasks needing more than kFusedSmallDoubles of shared
     // memory come first (ff_large[l] of them, stride ff_smem[l]) and are launched apart from the
     // many small ones (stride ff_smem_small[l]), which then run at full occupancy
