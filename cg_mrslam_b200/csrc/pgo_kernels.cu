@@ -1191,7 +1191,7 @@ static int enqueue_factor(DeviceSolver* d, const DeviceSolver::TaskSet& ts, int*
       ++*nodes;
     }
     if (n_fas) {
-      sn_k_factor<<<dim3(n_fas, B), kCtaThreads, sizeof(double) * L.fa_smem_small[l], s_fas>>>(
+      sn_k_factor<<<dim3(n_fas, B), kCtaThreads / 2, sizeof(double) * L.fa_smem_small[l], s_fas>>>(
           V, ts.fa.p + L.fa_ptr[l] + n_fal);
       ++*nodes;
     }
