@@ -9,6 +9,9 @@
 // Input (one file):  V robot id x y th fixed | E robot i j dx dy dth I11 I12 I13 I22 I23 I33 |
 //                    WANT robot peer k id_1 ... id_k   (robot's "in" closures of that peer)
 // Output: the datagram sizes, the star as B received it, B's estimates after optimize(5).
+// With a second argument "graph" the robots use GraphMessages instead (constructGraphMessage, the
+// alternative the reference keeps next to the condensed graphs, graph_comm.cpp:147): A answers
+// with its whole own graph, B adds A's vertices and edges to its graph.
 #include <cstdio>
 #include <fstream>
 #include <sstream>
@@ -73,19 +76,34 @@ int main(int argc, char** argv) {
       robots[r].buffer().insertInClosure(peer, want);
     }
   }
+  const bool whole_graph = argc > 2 && std::string(argv[2]) == "graph";
   printf("BEGIN\n");
-  char buf[MAX_LENGTH_MSG];
+  static char buf[MAX_LENGTH_MSG];
   // one exchange: from -> to
   auto send = [&](int from, int to) -> bool {
-    CondensedGraphMessage* out = robots[from].constructCondensedGraphMessage(to);
-    if (!out) {
-      printf("MSG %d %d none\n", from, to);
-      return false;
+    size_t n = 0;
+    if (whole_graph) {
+      GraphMessage* out = robots[from].constructGraphMessage(to);
+      if (!out) {
+        printf("MSG %d %d none\n", from, to);
+        return false;
+      }
+      char* end = out->toCharArray(buf, MAX_LENGTH_MSG);
+      n = end ? static_cast<size_t>(end - buf) : 0;
+      printf("MSG %d %d %zu closures %zu edges %zu vertices %zu\n", from, to, n, out->closures.size(),
+             out->edgeVector.size(), out->vertexVector.size());
+      delete out;
+    } else {
+      CondensedGraphMessage* out = robots[from].constructCondensedGraphMessage(to);
+      if (!out) {
+        printf("MSG %d %d none\n", from, to);
+        return false;
+      }
+      char* end = out->toCharArray(buf, MAX_LENGTH_MSG);
+      n = end ? static_cast<size_t>(end - buf) : 0;
+      printf("MSG %d %d %zu closures %zu edges %zu\n", from, to, n, out->closures.size(), out->edgeVector.size());
+      delete out;
     }
-    char* end = out->toCharArray(buf, MAX_LENGTH_MSG);
-    const size_t n = end ? static_cast<size_t>(end - buf) : 0;
-    printf("MSG %d %d %zu closures %zu edges %zu\n", from, to, n, out->closures.size(), out->edgeVector.size());
-    delete out;
     if (!n) return false;
     RobotMessage* in = robots[to].createMsgfromCharArray(buf, n);
     if (!in) return false;

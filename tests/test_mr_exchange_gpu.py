@@ -29,8 +29,7 @@ def driver(tmp_path_factory):
     return exe
 
 
-@pytest.mark.gpu
-def test_condensed_graph_exchange(driver, tmp_path):
+def scenario(path):
     rng = np.random.default_rng(31)
     ga = synth.make_pose_graph(200, 720, seed=41, box=15.0, init="truth_noisy")
     gb = synth.make_pose_graph(180, 640, seed=42, box=15.0, init="truth_noisy")
@@ -46,7 +45,6 @@ def test_condensed_graph_exchange(driver, tmp_path):
         rel = po.se2_mul(po.se2_inv(gb["poses0"][p]), c)[0]
         ir_meas.append(po.se2_mul(rel, rng.normal(0, [0.02, 0.02, 0.005]))[0])
     ir_info = [100.0, 0.0, 0.0, 100.0, 0.0, 1000.0]
-    path = str(tmp_path / "mr.txt")
     with open(path, "w") as f:
         for r, g, ids in ((0, ga, ida), (1, gb, idb)):
             for k, vid in enumerate(ids):
@@ -61,6 +59,14 @@ def test_condensed_graph_exchange(driver, tmp_path):
             f.write("E 1 %d %d %.17g %.17g %.17g %s\n" % (idb[p], ida[a], z[0], z[1], z[2],
                                                         " ".join("%.17g" % x for x in ir_info)))
         f.write("WANT 1 0 %d %s\n" % (len(asked), " ".join(str(ida[a]) for a in asked)))
+    return ga, gb, ida, idb, asked, partners, copies, ir_meas, ir_info
+
+
+@pytest.mark.gpu
+def test_condensed_graph_exchange(driver, tmp_path):
+    path = str(tmp_path / "mr.txt")
+    ga, gb, ida, idb, asked, partners, copies, ir_meas, ir_info = scenario(path)
+    na, nb = len(ga["poses0"]), len(gb["poses0"])
     out = subprocess.run([driver, path], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr
     lines = out.stdout.splitlines()
@@ -105,3 +111,49 @@ def test_condensed_graph_exchange(driver, tmp_path):
     # second round: the star is replaced on both sides, nothing is duplicated
     assert [ln.split()[1:] for ln in lines if ln.startswith("AGAIN ")][0] == \
         [str(n_star), str(len(gb["edge_ij"]) + len(asked) + n_star), str(len(ga["edge_ij"]) + n_star)]
+
+
+@pytest.mark.gpu
+def test_whole_graph_exchange(driver, tmp_path):
+    """The GraphMessage alternative (mr_graph_slam.cpp:397-483, 672-739): A answers B's request with
+    its whole own graph; B creates A's vertices (float32 estimates), refreshes the copies it had,
+    takes A's edges as level-0 edges and optimises the union."""
+    path = str(tmp_path / "mr.txt")
+    ga, gb, ida, idb, asked, partners, copies, ir_meas, ir_info = scenario(path)
+    na, nb = len(ga["poses0"]), len(gb["poses0"])
+    out = subprocess.run([driver, path, "graph"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    lines = out.stdout.splitlines()
+    lines = lines[lines.index("BEGIN") + 1:lines.index("END")]
+    msgs = [ln.split() for ln in lines if ln.startswith("MSG ")]
+    n_ea = len(ga["edge_ij"])
+    # B -> A: only the request (A has not been asked before: no vertices, no edges)
+    assert msgs[0] == ["MSG", "1", "0", str(8 + 8 + 8 + 8 + 4 * len(asked)), "closures", str(len(asked)),
+                       "edges", "0", "vertices", "0"]
+    # A -> B: every vertex and every own edge of A (its star for B, level 2, is not among them)
+    assert msgs[1] == ["MSG", "0", "1", str(8 + 8 + na * 16 + 8 + n_ea * 44 + 8), "closures", "0",
+                       "edges", str(n_ea), "vertices", str(na)]
+    f32 = lambda a: np.asarray(a, dtype=np.float64).astype(np.float32).astype(np.float64)
+    # B's union graph: its own vertices, then A's (all of them now), estimates as they crossed the wire
+    idx = {vid: k for k, vid in enumerate(idb)}
+    for k, vid in enumerate(ida):
+        idx[vid] = nb + k
+    poses0 = np.vstack([gb["poses0"], f32(ga["poses0"])])
+    info_a = f32(ga["info"])
+    e_ij = [list(e) for e in gb["edge_ij"]] + [[idx[idb[p]], idx[ida[a]]] for p, a in zip(partners, asked)] + \
+        [[nb + a, nb + b] for a, b in ga["edge_ij"]]
+    meas = np.vstack([gb["meas"], np.array(ir_meas), f32(ga["meas"])])
+    info = np.vstack([gb["info"], np.tile(ir_info, (len(asked), 1)), info_a])
+    ref = po.gauss_newton(poses0, np.array(e_ij, dtype=np.int64), meas, info, [0], 5)
+    got_p = {int(ln.split()[1]): [float(x) for x in ln.split()[2:]] for ln in lines if ln.startswith("P ")}
+    assert sorted(got_p) == sorted(idx)
+    got = np.array([got_p[vid] for vid in sorted(idx, key=idx.get)])
+    d = got - ref.poses
+    d[:, 2] = po.normalize_theta(d[:, 2])
+    assert np.abs(d).max() < 1e-6
+    star = [ln.split() for ln in lines if ln.startswith("STAR ")][0]
+    assert star[1:] == [str(n_ea), str(len(gb["edge_ij"]) + len(asked) + n_ea)]
+    # second round: A's edges replace the ones B already had; nothing is duplicated
+    assert [ln.split()[1:] for ln in lines if ln.startswith("AGAIN ")][0] == \
+        [str(n_ea), str(len(gb["edge_ij"]) + len(asked) + n_ea), str(n_ea + len(asked) - 1)]
+
