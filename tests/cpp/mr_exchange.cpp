@@ -135,6 +135,25 @@ int main(int argc, char** argv) {
   send(0, 1);
   printf("AGAIN %zu %zu %zu\n", robots[1].buffer().inCondensedGraph(0).size(), robots[1].graph()->edges().size(),
          robots[0].graph()->edges().size());
+  // if A asked B about vertices as well, B's star has reached A by now: A optimises with it
+  OptimizableGraph::EdgeSet back = robots[0].buffer().inCondensedGraph(1);
+  printf("BACK %zu\n", back.size());
+  for (HyperGraph::Edge* he : back) {
+    EdgeSE2* e = static_cast<EdgeSE2*>(he);
+    printf("D %d %d %.17g %.17g %.17g", e->vertex(0)->id(), e->vertex(1)->id(), e->measurement().translation().x(),
+           e->measurement().translation().y(), e->measurement().rotation().angle());
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) printf(" %.17g", e->information()(i, j));
+    printf("\n");
+  }
+  if (!back.empty()) {
+    robots[0].optimize(5);
+    for (auto& kv : robots[0].graph()->vertices()) {
+      const VertexSE2* v = static_cast<const VertexSE2*>(kv.second);
+      printf("Q %d %.17g %.17g %.17g\n", v->id(), v->estimate().translation().x(), v->estimate().translation().y(),
+             v->estimate().rotation().angle());
+    }
+  }
   printf("END\n");
   return 0;
 }

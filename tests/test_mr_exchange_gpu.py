@@ -157,3 +157,99 @@ def test_whole_graph_exchange(driver, tmp_path):
     assert [ln.split()[1:] for ln in lines if ln.startswith("AGAIN ")][0] == \
         [str(n_ea), str(len(gb["edge_ij"]) + len(asked) + n_ea), str(n_ea + len(asked) - 1)]
 
+
+@pytest.mark.gpu
+def test_two_robots_2k_nodes_8k_edges(driver, tmp_path):
+    """BASELINE cfg 2 in synthetic form: two robots with 1000 poses / 4000 edges each, six
+    inter-robot closures either way; each asks the other about the vertices it closed loops with,
+    each computes the other's star on the GPU from its own edges (closures to the peer included),
+    the stars cross the wire, both optimise. Stars and both robots' estimates against the oracle."""
+    rng = np.random.default_rng(77)
+    g = [synth.make_pose_graph(1000, 4000, seed=51 + r, box=35.0, init="truth_noisy") for r in range(2)]
+    ids = [[10000 * r + k for k in range(1000)] for r in range(2)]
+    # robot r closed loops between its vertices mine[r] and the peer's vertices theirs[r]
+    mine = [[40, 300, 301, 640, 777, 910], [15, 220, 480, 481, 700, 950]]
+    theirs = [[100, 250, 400, 555, 800, 990], [60, 333, 334, 500, 720, 880]]
+    ir_info = [100.0, 0.0, 0.0, 100.0, 0.0, 1000.0]
+    copies, ir_meas = [], []
+    for r in range(2):
+        peer = 1 - r
+        c = g[peer]["poses0"][theirs[r]] + rng.normal(size=(len(theirs[r]), 3)) * [0.05, 0.05, 0.01]
+        copies.append(c)
+        zs = []
+        for p, cc in zip(mine[r], c):
+            rel = po.se2_mul(po.se2_inv(g[r]["poses0"][p]), cc)[0]
+            zs.append(po.se2_mul(rel, rng.normal(0, [0.02, 0.02, 0.005]))[0])
+        ir_meas.append(np.array(zs))
+    path = str(tmp_path / "mr2k.txt")
+    with open(path, "w") as f:
+        for r in range(2):
+            for k, vid in enumerate(ids[r]):
+                p = g[r]["poses0"][k]
+                f.write("V %d %d %.17g %.17g %.17g %d\n" % (r, vid, p[0], p[1], p[2], 1 if k == 0 else 0))
+            for (a, b), z, w in zip(g[r]["edge_ij"], g[r]["meas"], g[r]["info"]):
+                f.write("E %d %d %d %.17g %.17g %.17g %s\n" % (r, ids[r][a], ids[r][b], z[0], z[1], z[2],
+                                                             " ".join("%.17g" % x for x in w)))
+        for r in range(2):
+            peer = 1 - r
+            for a, c in zip(theirs[r], copies[r]):
+                f.write("V %d %d %.17g %.17g %.17g 0\n" % (r, ids[peer][a], c[0], c[1], c[2]))
+            for p, a, z in zip(mine[r], theirs[r], ir_meas[r]):
+                f.write("E %d %d %d %.17g %.17g %.17g %s\n" % (r, ids[r][p], ids[peer][a], z[0], z[1], z[2],
+                                                             " ".join("%.17g" % x for x in ir_info)))
+            f.write("WANT %d %d %d %s\n" % (r, peer, len(theirs[r]), " ".join(str(ids[peer][a]) for a in theirs[r])))
+    out = subprocess.run([driver, path], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr
+    lines = out.stdout.splitlines()
+    lines = lines[lines.index("BEGIN") + 1:lines.index("END")]
+
+    def local_graph(r):
+        """robot r's graph as the oracle sees it: own vertices, then the peer copies; own edges + closures"""
+        peer = 1 - r
+        idx = {vid: k for k, vid in enumerate(ids[r])}
+        for j, a in enumerate(theirs[r]):
+            idx[ids[peer][a]] = 1000 + j
+        poses = np.vstack([g[r]["poses0"], copies[r]])
+        e_ij = np.array([list(e) for e in g[r]["edge_ij"]] +
+                        [[idx[ids[r][p]], idx[ids[peer][a]]] for p, a in zip(mine[r], theirs[r])], dtype=np.int64)
+        meas = np.vstack([g[r]["meas"], ir_meas[r]])
+        info = np.vstack([g[r]["info"], np.tile(ir_info, (len(mine[r]), 1))])
+        return idx, poses, e_ij, meas, info
+
+    def check_star(rows, r, asked_by_peer):
+        """the star robot r computed over its vertices the peer asked about, as the peer received it"""
+        idx, poses, e_ij, meas, info = local_graph(r)
+        seps = sorted(asked_by_peer)
+        gauge = po.select_gauge_centroid(poses, seps)
+        z, om, vs = po.condensed_star(poses, e_ij, meas, info, gauge, seps)
+        assert [int(x[0]) for x in rows] == [ids[r][gauge]] * len(vs)
+        assert [int(x[1]) for x in rows] == [ids[r][v] for v in vs]
+        dz = rows[:, 2:5] - z
+        dz[:, 2] = po.normalize_theta(dz[:, 2])
+        assert np.abs(dz).max() < 1e-6
+        got_om = rows[:, 5:].reshape(-1, 3, 3)
+        assert np.abs(got_om - om).max() < 1e-6 * np.abs(om).max()
+        return rows[:, 2:5], got_om
+
+    def check_poses(tag, r, star_rows):
+        """robot r after optimize(5): its local graph + the peer's star between the peer copies"""
+        idx, poses, e_ij, meas, info = local_graph(r)
+        z, om = star_rows[:, 2:5], star_rows[:, 5:].reshape(-1, 3, 3)
+        e2 = np.vstack([e_ij, np.array([[idx[int(x[0])], idx[int(x[1])]] for x in star_rows], dtype=np.int64)])
+        m2 = np.vstack([meas, z])
+        i2 = np.vstack([info, np.array([[o[0, 0], o[0, 1], o[0, 2], o[1, 1], o[1, 2], o[2, 2]] for o in om])])
+        ref = po.gauss_newton(poses, e2, m2, i2, [0], 5)
+        got_p = {int(ln.split()[1]): [float(x) for x in ln.split()[2:]] for ln in lines if ln.startswith(tag + " ")}
+        got = np.array([got_p[vid] for vid in sorted(idx, key=idx.get)])
+        d = got - ref.poses
+        d[:, 2] = po.normalize_theta(d[:, 2])
+        assert np.abs(d).max() < 1e-6, np.abs(d).max()
+
+    rows_c = np.array([[float(x) for x in ln.split()[1:]] for ln in lines if ln.startswith("C ")])
+    rows_d = np.array([[float(x) for x in ln.split()[1:]] for ln in lines if ln.startswith("D ")])
+    assert len(rows_c) == 5 and len(rows_d) == 5
+    check_star(rows_c, 0, theirs[1])       # A's star over the A-vertices B asked about, as B got it
+    check_star(rows_d, 1, theirs[0])       # B's star over the B-vertices A asked about, as A got it
+    check_poses("P", 1, rows_c)
+    check_poses("Q", 0, rows_d)
+
