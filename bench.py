@@ -327,7 +327,10 @@ def gn_ours(args, local, world, barrier):
                    "panel_levels": st["n_panel_levels"], "supernode_levels": st["n_supernode_levels"],
                    "analyse_seconds": analyse_s, "stage_ms_last_iter": st["stage_ms"]},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                     "frac": achieved / pk["hbm_gbs"], "traffic": None, "peak_kind": pk_kind,
+                     "frac": achieved / pk["hbm_gbs"],
+                     # DRAM bytes per instance-iteration summed over the kernels of one iteration
+                     # (ncu dram__bytes_read + write, 16 instances): profiles/r01_gn_dram_traffic_batch16.txt
+                     "traffic": 957.6e6, "peak_kind": pk_kind,
                      "kernel": "iteration graph (sn_k_factor / sn_k_update / sn_k_bwd_* + linearise)",
                      "algorithmic_bytes": nbytes,
                      "fp64": {"flops_per_iteration": st.get("factor_flops", 0.0),
