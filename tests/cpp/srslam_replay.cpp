@@ -5,9 +5,11 @@
 // windowLoopClosure 10, maxScore 0.15, inlierThreshold 2, minInliers 7). Prints every decision and
 // the final estimates; tests/test_replay_gpu.py compares them with the CPU oracle pipeline.
 //
+// usage:  srslam_replay keyframes.txt [graph.g2o [id_robot]]
 // input:  n_beams first_angle step max_range laser_x laser_y laser_th min_inliers
 //         then one line per keyframe: odom_x odom_y odom_th r_1 ... r_n
 #include <cstdio>
+#include <cstdlib>
 #include <fstream>
 #include <sstream>
 
@@ -23,7 +25,7 @@ int main(int argc, char** argv) {
   double first, step, maxr, lx, ly, lth;
   f >> nb >> first >> step >> maxr >> lx >> ly >> lth >> min_inliers;
   GraphSLAM gslam;
-  gslam.setIdRobot(0);
+  gslam.setIdRobot(argc > 3 ? std::atoi(argv[3]) : 0);   // vertex ids = id_robot * 10000 + k (graph_slam.cpp:384-386)
   gslam.setBaseId(10000);
   gslam.init(0.025, 0.2, 10, 0.15, 2.0, min_inliers);
   printf("BEGIN\n");

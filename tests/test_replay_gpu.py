@@ -1,5 +1,5 @@
-"""BASELINE config 0/1 as a parity case: keyframes of robot_0 from the reference's own
-2robots-hospital bag (tests/golden/bag_2robots_robot0_kf160.npz, made by
+"""BASELINE config 0/1 as a parity case: keyframes of robot_0 and of robot_1 from the reference's
+own 2robots-hospital bag (tests/golden/bag_2robots_robot{0,1}_kf160.npz, made by
 tools/extract_bag_keyframes.py) replayed through the GPU-backed GraphSLAM mirror
 (include/cgm/graph_slam.hpp: addDataSM -> findConstraints -> optimize(5), the loop of
 src/srslam.cpp:190-221 with its default parameters) and through the CPU oracle pipeline
@@ -14,7 +14,7 @@ import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIBDIR = os.path.join(ROOT, "cg_mrslam_b200", "lib")
-FIXTURE = os.path.join(ROOT, "tests", "golden", "bag_2robots_robot0_kf160.npz")
+FIXTURES = [os.path.join(ROOT, "tests", "golden", "bag_2robots_robot%d_kf160.npz" % r) for r in range(2)]
 LASER_POSE = (0.05, 0.0, 0.0)      # base_link -> base_laser_link in the bag's /tf
 TOL = 1e-6
 
@@ -32,8 +32,8 @@ def replay_exe(tmp_path_factory):
     return exe
 
 
-def run_mirror(exe, path, save=None):
-    out = subprocess.run([exe, path] + ([save] if save else []), capture_output=True, text=True, timeout=900)
+def run_mirror(exe, path, save, robot):
+    out = subprocess.run([exe, path, save, str(robot)], capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stderr[-3000:]
     lines = out.stdout.splitlines()
     assert "BEGIN" in lines and lines[-1] == "END", out.stdout[-2000:] + out.stderr[-2000:]
@@ -49,12 +49,12 @@ def run_mirror(exe, path, save=None):
     return frames, poses
 
 
-def run_oracle(fx, n, min_inliers, oracle_lib):
+def run_oracle(fx, n, min_inliers, oracle_lib, robot):
     from oracle import bindings
     from oracle.graph_slam_oracle import GraphSlamOracle
     lib = bindings.MatcherLib("reference") if bindings.have_reference() else oracle_lib
     geom = (float(fx["first_angle"]), float(fx["angular_step"]), float(fx["max_range"]))
-    gs = GraphSlamOracle(lib, oracle_lib, geom, LASER_POSE, min_inliers=min_inliers)
+    gs = GraphSlamOracle(lib, oracle_lib, geom, LASER_POSE, min_inliers=min_inliers, id_robot=robot)
     frames = []
     for k in range(n):
         ranges = fx["ranges"][k].astype(np.float64)
@@ -73,12 +73,14 @@ def angle_diff(a, b):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("n,min_inliers", [(60, 7), (160, 7)])
-def test_bag_replay_matches_oracle(replay_exe, oracle_lib, tmp_path, n, min_inliers):
-    """60 keyframes: the outbound leg (odometry refinement + close edges). 160 keyframes: through
-    the first revisit (keyframe 118 closes on keyframe 56); the vote accepts its first seven
-    closures at keyframe 127 with the reference's default quorum of 7 inliers."""
-    fx = np.load(FIXTURE)
+@pytest.mark.parametrize("robot,n,min_inliers", [(0, 60, 7), (0, 160, 7), (1, 160, 7), (1, 160, 4)])
+def test_bag_replay_matches_oracle(replay_exe, oracle_lib, tmp_path, robot, n, min_inliers):
+    """robot_0, 60 keyframes: the outbound leg (odometry refinement + close edges). 160 keyframes:
+    through the first revisit (keyframe 118 closes on keyframe 56); the vote accepts its first seven
+    closures at keyframe 127 with the reference's default quorum of 7 inliers. robot_1 (vertex ids
+    10000 + k): 59 loop-closure candidates from keyframe 110 on; the default quorum accepts none of
+    them within 160 keyframes, a quorum of 4 accepts its first four at keyframe 127."""
+    fx = np.load(FIXTURES[robot])
     path = str(tmp_path / "kf.txt")
     with open(path, "w") as f:
         f.write("%d %.17g %.17g %.17g %.17g %.17g %.17g %d\n" % (
@@ -87,9 +89,9 @@ def test_bag_replay_matches_oracle(replay_exe, oracle_lib, tmp_path, n, min_inli
         for k in range(n):
             f.write("%.17g %.17g %.17g " % tuple(fx["odom"][k]))
             f.write(" ".join("%.9g" % r for r in fx["ranges"][k]) + "\n")
-    g2o_path = str(tmp_path / "robot-0.g2o")
-    got_frames, got_poses = run_mirror(replay_exe, path, g2o_path)
-    want_frames, want_poses = run_oracle(fx, n, min_inliers, oracle_lib)
+    g2o_path = str(tmp_path / ("robot-%d.g2o" % robot))
+    got_frames, got_poses = run_mirror(replay_exe, path, g2o_path, robot)
+    want_frames, want_poses = run_oracle(fx, n, min_inliers, oracle_lib, robot)
     assert len(got_frames) == len(want_frames) == n
     kinds = {}
     for k, (g, w) in enumerate(zip(got_frames, want_frames)):
@@ -108,9 +110,10 @@ def test_bag_replay_matches_oracle(replay_exe, oracle_lib, tmp_path, n, min_inli
     assert worst < TOL, worst
     assert kinds.get("S", 0) > n // 2            # odometry edges refined by the matcher
     if n > 120:
-        assert kinds.get("L", 0) > 0 and kinds.get("A", 0) > 0, kinds   # candidates and accepted closures
-    print("replay", n, "keyframes:", kinds, "max |pose - oracle| = %.2e" % worst)
-    if n > 120:
+        assert kinds.get("L", 0) > 0, kinds                               # loop-closure candidates
+        assert (kinds.get("A", 0) > 0) == ((robot, min_inliers) != (1, 7)), kinds   # accepted closures
+    print("replay robot", robot, n, "keyframes:", kinds, "max |pose - oracle| = %.2e" % worst)
+    if n > 120 and robot == 0:
         condensed_graph_on_replayed_graph(g2o_path, got_poses)
 
 
