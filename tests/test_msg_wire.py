@@ -74,6 +74,54 @@ def test_buffer_too_small_and_bad_input(product):
     assert product.unpack(huge) is None
 
 
+def test_garbled_datagrams_never_crash(product):
+    """Datagrams arrive from the network: truncated, extended and bit-flipped versions of valid
+    messages, and pure noise, must parse to a message of exactly the datagram's length or be
+    refused -- never crash, never read past the buffer (counts are checked against the bytes left)."""
+    rng = np.random.default_rng(99)
+    valid = [product.pack(mw.random_message(k, rng, big=b)) for k in mw.TYPES for b in (False, True)]
+    accepted = refused = 0
+    for trial in range(3000):
+        d = bytearray(valid[trial % len(valid)])
+        kind = trial % 4
+        if kind == 0 and len(d) > 1:
+            d = d[:int(rng.integers(0, len(d)))]
+        elif kind == 1:
+            d += bytes(rng.integers(0, 256, size=int(rng.integers(1, 40)), dtype=np.uint8))
+        elif kind == 2:
+            for _ in range(int(rng.integers(1, 6))):
+                d[int(rng.integers(0, len(d)))] ^= 1 << int(rng.integers(0, 8))
+        else:
+            d = bytearray(rng.integers(0, 256, size=int(rng.integers(0, 200)), dtype=np.uint8))
+            if len(d) >= 4 and trial % 8 == 3:
+                d[:4] = struct.pack("<i", [1, 2, 4, 5, 6, 7, 8][trial % 7])
+        back = product.unpack(bytes(d), cap=1 << 16)
+        if back is None:
+            refused += 1
+        else:
+            accepted += 1
+            assert back["consumed"] == len(d)
+    assert refused > 1000 and accepted > 100, (accepted, refused)
+
+
+def test_parser_under_sanitizers(tmp_path):
+    """The same kind of input through a C++ harness built with AddressSanitizer + UBSan, every
+    datagram in a heap buffer of exactly its size."""
+    import subprocess
+    exe = str(tmp_path / "wire_fuzz")
+    build = subprocess.run(["/usr/bin/g++", "-std=c++17", "-O1", "-g", "-fsanitize=address,undefined",
+                            "-fno-omit-frame-pointer", "-I" + os.path.join(mw.ROOT, "include"),
+                            os.path.join(mw.ROOT, "tests", "cpp", "wire_fuzz.cpp"), "-o", exe],
+                           capture_output=True, text=True)
+    if build.returncode != 0 and "sanitize" in build.stderr.lower():
+        pytest.skip("sanitizer runtime not available")
+    assert build.returncode == 0, build.stderr
+    run = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert run.returncode == 0 and "Sanitizer" not in run.stderr and "runtime error" not in run.stderr, run.stderr[-2000:]
+    accepted, refused = [int(x) for x in run.stdout.split()[1::2]]
+    assert accepted > 10000 and refused > 10000
+
+
 @pytest.mark.skipif(not os.path.exists(mw.REF_SO), reason="verbatim reference build not present")
 def test_against_reference_build(product):
     ref = mw.Wire(mw.REF_SO)
