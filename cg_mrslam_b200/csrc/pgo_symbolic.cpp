@@ -67,6 +67,8 @@ class Dissector {
     pos_.assign(g.n, 0);
     part_.assign(g.n, 0);
     lock_.assign(g.n, 0);
+    nbc_[0].assign(g.n, 0);
+    nbc_[1].assign(g.n, 0);
     cut_depth_ = 0;
     while ((1 << cut_depth_) < world) ++cut_depth_;
   }
@@ -232,12 +234,9 @@ class Dissector {
     const int n = static_cast<int>(s.size());
     for (int f = 0; f < 4; ++f)
       for (int i = 0; i < n; ++i) d4_[f][s[i]] = -1;
-    int p = bfs_dist(s[0], id, d4_[0]);
+    const int p = bfs_dist(s[0], id, d4_[0]);      // far from an arbitrary start
     for (int i = 0; i < n; ++i) d4_[0][s[i]] = -1;
-    int q = bfs_dist(p, id, d4_[0]);
-    for (int i = 0; i < n; ++i) d4_[0][s[i]] = -1;
-    p = bfs_dist(q, id, d4_[0]);   // d4_[0] = hops from q ... (q, p) is the pseudo-peripheral pair
-    std::swap(p, q);               // now d4_[0] is the distance from p
+    const int q = bfs_dist(p, id, d4_[0]);         // d4_[0] = hops from p; q is farthest from p
     if (d4_[0][q] < 2) return false;
     bfs_dist(q, id, d4_[1]);
     int u = s[0];
@@ -256,12 +255,14 @@ class Dissector {
     bfs_dist(w, id, d4_[3]);
 
     int lo = std::max(1, static_cast<int>(bal * n)), hi = std::min(n - 1, n - lo);
-    std::vector<std::pair<long long, int> > keyed(n);
+    // sort keys packed into one word: primary key, secondary key, position in s (all three are
+    // small: hop-distance differences and a subset index)
+    std::vector<uint64_t> keyed(n);
     std::vector<int> diff_a(n + 2), diff_b(n + 2), best_order;
     int best_cost = n + 1, best_k = -1;
     bool best_from_a = true;
-    // no admissible cut inside the balance window (small, dense subsets): widen the window
     int best_cand = 0;
+    const long long kBias = 1LL << 20;   // |keys| < 2^20: hop counts of a subset of < 2^19 vertices, doubled
     auto sweep = [&](int cand) {
       for (int i = 0; i < n; ++i) {
         const int v = s[i];
@@ -275,20 +276,22 @@ class Dissector {
           case 4: k1 = d4_[0][v]; k2 = y; break;
           default: k1 = d4_[1][v]; k2 = y; break;
         }
-        keyed[i] = std::make_pair(k1 * (1LL << 24) + k2, v);
+        keyed[i] = (static_cast<uint64_t>(k1 + kBias) << 42) | (static_cast<uint64_t>(k2 + kBias) << 21) |
+                   static_cast<uint64_t>(i);
       }
       std::sort(keyed.begin(), keyed.end());
+      for (int i = 0; i < n; ++i) keyed[i] = static_cast<uint64_t>(s[keyed[i] & ((1u << 21) - 1)]);
     };
     // no admissible cut inside the balance window (small, dense subsets): widen the window
     for (int attempt = 0; attempt < 3 && best_k < 0;
          ++attempt, lo = attempt == 1 ? std::max(1, lo / 2) : 1, hi = n - lo)
       for (int cand = 0; cand < 6; ++cand) {
         sweep(cand);
-        for (int i = 0; i < n; ++i) pos_[keyed[i].second] = i;
+        for (int i = 0; i < n; ++i) pos_[keyed[i]] = i;
         std::fill(diff_a.begin(), diff_a.end(), 0);
         std::fill(diff_b.begin(), diff_b.end(), 0);
         for (int i = 0; i < n; ++i) {
-          const int v = keyed[i].second;
+          const int v = static_cast<int>(keyed[i]);
           int mx = i, mn = i;
           for (int t = g_.ptr[v]; t < g_.ptr[v + 1]; ++t) {
             const int x = g_.adj[t];
@@ -321,7 +324,7 @@ class Dissector {
     if (best_k < 0) return false;
     sweep(best_cand);
     best_order.resize(n);
-    for (int i = 0; i < n; ++i) best_order[i] = keyed[i].second;
+    for (int i = 0; i < n; ++i) best_order[i] = static_cast<int>(keyed[i]);
     // part: 0 = A, 1 = B, 2 = separator
     for (int i = 0; i < n; ++i) part_[best_order[i]] = i < best_k ? 0 : 1;
     for (int i = 0; i < n; ++i) {
@@ -360,9 +363,20 @@ class Dissector {
     struct Move { int v, to, n_pulled; };
     std::vector<Move> log;
     std::vector<int> pulled;
+    // neighbours of a separator vertex on side 0 / 1, kept up to date move by move
+    auto count_sides = [&](int v) {
+      int nb[2] = {0, 0};
+      for (int t = g_.ptr[v]; t < g_.ptr[v + 1]; ++t) {
+        const int x = g_.adj[t];
+        if (mark_[x] == id && part_[x] < 2) ++nb[part_[x]];
+      }
+      nbc_[0][v] = nb[0];
+      nbc_[1][v] = nb[1];
+    };
     for (int pass = 0; pass < 8; ++pass) {
       log.clear();
       pulled.clear();
+      for (size_t i = 0; i < sepv.size(); ++i) count_sides(sepv[i]);
       const int start_sep = size[2];
       int best_sep = size[2], best_at = 0, best_imb = std::abs(size[0] - size[1]);
       const int patience = 40 + size[2] / 4;
@@ -372,13 +386,8 @@ class Dissector {
         for (size_t i = 0; i < sepv.size(); ++i) {
           const int v = sepv[i];
           if (part_[v] != 2 || lock_[v]) continue;
-          int nb[2] = {0, 0};
-          for (int t = g_.ptr[v]; t < g_.ptr[v + 1]; ++t) {
-            const int x = g_.adj[t];
-            if (mark_[x] == id && part_[x] < 2) ++nb[part_[x]];
-          }
           for (int to = 0; to < 2; ++to) {
-            const int pull = nb[1 - to];
+            const int pull = nbc_[1 - to][v];
             if (size[1 - to] - pull < lo) continue;
             const int gain = 1 - pull;
             // ties: towards the smaller side
@@ -402,7 +411,10 @@ class Dissector {
         int n_pulled = 0;
         for (int t = g_.ptr[bv]; t < g_.ptr[bv + 1]; ++t) {
           const int x = g_.adj[t];
-          if (mark_[x] == id && part_[x] == 1 - bto) {
+          if (mark_[x] != id) continue;
+          if (part_[x] == 2) {
+            ++nbc_[bto][x];  // bv now sits on side bto
+          } else if (part_[x] == 1 - bto) {
             part_[x] = 2;
             --size[1 - bto];
             ++size[2];
@@ -411,6 +423,16 @@ class Dissector {
             ++n_pulled;
           }
         }
+        // the pulled vertices left side 1 - bto: their separator neighbours lose one there, and
+        // they get counts of their own
+        for (int k = 0; k < n_pulled; ++k) {
+          const int x = pulled[pulled.size() - 1 - k];
+          for (int t = g_.ptr[x]; t < g_.ptr[x + 1]; ++t) {
+            const int z = g_.adj[t];
+            if (mark_[z] == id && part_[z] == 2) --nbc_[1 - bto][z];
+          }
+        }
+        for (int k = 0; k < n_pulled; ++k) count_sides(pulled[pulled.size() - 1 - k]);
         const Move m = {bv, bto, n_pulled};
         log.push_back(m);
         const int imb = std::abs(size[0] - size[1]);
@@ -454,7 +476,7 @@ class Dissector {
   const Graph& g_;
   int leaf_;
   std::vector<int> mark_, dist_, owner_;
-  std::vector<int> d4_[4], pos_, part_, lock_, queue_;
+  std::vector<int> d4_[4], pos_, part_, lock_, queue_, nbc_[2];
   std::vector<std::vector<int> > groups_;
   std::vector<long long> load_;
   int cut_depth_ = 0;
