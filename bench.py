@@ -170,6 +170,10 @@ def cpu_run(n_pairs, n_threads, repeat=1):
     return kind, cand, times
 
 
+WORKLOAD = ("cfg5 scan matcher: %d pairs per GPU per step, 1081-beam scans, one 100x100x101 = "
+            "1.01M-candidate window per pair, LC grid 700x700 res 0.1, raster + score + compact")
+
+
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -188,9 +192,9 @@ def reference_arm(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec / len(timed),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32",
         "data": "synthetic",
-        "config": {"workload": "cfg5 scan matcher: 1081-beam pairs, 100x100x101 window, LC grid "
-                               "700x700 res 0.1 (CPU sample of the same workload)",
-                   "pairs_per_step": n_pairs},
+        # the GPU arm's workload; each CPU step is a bounded sample of it (sample_pairs_per_step)
+        "config": {"workload": WORKLOAD % args.pairs, "pairs_per_gpu": args.pairs,
+                   "sample_pairs_per_step": n_pairs},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": n_threads, "kind": kind,
                          "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -556,9 +560,7 @@ def ours(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "u8/int32", "data": "synthetic",
             "config": {
-                "workload": "cfg5 scan matcher: %d pairs per GPU per step, 1081-beam scans, one "
-                            "100x100x101 = 1.01M-candidate window per pair, LC grid 700x700 res "
-                            "0.1, raster + score + compact" % n,
+                "workload": WORKLOAD % n,
                 "pairs_per_gpu": n, "candidates_per_step_per_gpu": cand,
                 "mean_k": stats["cell_reads"] / max(cand, 1),
                 "l2": "inputs larger than L2 (%.1f GB of grids per GPU)" % (n * 700 * 704 / 1e9),
