@@ -177,6 +177,60 @@ int cgm_matcher_raster(cgm_matcher* m, int slot, const double* map_xy, int n) {
   return rc ? fail(rc, err) : CGM_OK;
 }
 
+int cgm_matcher_set_stamp(cgm_matcher* m, const uint8_t* stamp_colmajor, int dim) {
+  if (!m || !stamp_colmajor || dim <= 0 || dim % 2 == 0 || dim > 255)
+    return fail(CGM_ERR_ARG, "bad stamp (odd dimension 1..255 expected)");
+  std::string err;
+  const int rc = cgm::dev_set_stamp(m->dev, stamp_colmajor, dim, &err);
+  if (rc) return fail(rc, err);
+  m->stamp.assign(stamp_colmajor, stamp_colmajor + static_cast<size_t>(dim) * dim);
+  m->stamp_dim = dim;
+  // stamping takes minima: a cell never exceeds what it held before, so the bound only has to
+  // cover cells written by fills / uploads; it is kept as it is
+  return CGM_OK;
+}
+
+namespace {
+// every cell of `slot` <- value, then the points are stamped: one launch
+int fill_and_raster(cgm_matcher* m, int slot, int value, const double* map_xy, int n) {
+  std::string err;
+  // cells hold `value` or less from now on; other slots of a multi-slot matcher keep their bound
+  const int bound = m->n_slots == 1 ? value : std::max(m->geom.max_cell, value);
+  m->geom.fill_value = value;
+  m->geom.max_cell = std::max(bound, 1);
+  cgm::dev_set_bounds(m->dev, value, m->geom.max_cell);
+  int rc = cgm::dev_stage_map(m->dev, slot, 1, map_xy, &n, true, &err);
+  if (!rc) rc = cgm::dev_launch_map(m->dev, &err);
+  if (!rc) rc = cgm::dev_sync(m->dev, &err);
+  cgm::dev_clear_map_stage(m->dev);
+  return rc ? fail(rc, err) : CGM_OK;
+}
+}  // namespace
+
+int cgm_matcher_fill(cgm_matcher* m, int slot, int value) {
+  if (!m || !slot_ok(m, slot, 1) || value < 0 || value > 255) return fail(CGM_ERR_ARG, "bad argument");
+  return fill_and_raster(m, slot, value, nullptr, 0);
+}
+
+int cgm_matcher_fill_raster(cgm_matcher* m, int slot, int value, const double* map_xy, int n) {
+  if (!m || !slot_ok(m, slot, 1) || value < 0 || value > 255 || n < 0 || (n && !map_xy))
+    return fail(CGM_ERR_ARG, "bad argument");
+  return fill_and_raster(m, slot, value, map_xy, n);
+}
+
+int cgm_matcher_copy_grid(cgm_matcher* dst, int dst_slot, cgm_matcher* src, int src_slot) {
+  if (!dst || !src || !slot_ok(dst, dst_slot, 1) || !slot_ok(src, src_slot, 1))
+    return fail(CGM_ERR_ARG, "bad argument");
+  if (dst->geom.rows != src->geom.rows || dst->geom.cols != src->geom.cols)
+    return fail(CGM_ERR_ARG, "grid copy between different geometries");
+  std::string err;
+  const int rc = cgm::dev_copy_grid(dst->dev, dst_slot, src->dev, src_slot, &err);
+  if (rc) return fail(rc, err);
+  dst->geom.max_cell = std::max(dst->geom.max_cell, src->geom.max_cell);
+  cgm::dev_set_bounds(dst->dev, dst->geom.fill_value, dst->geom.max_cell);
+  return CGM_OK;
+}
+
 int cgm_matcher_raster_batch(cgm_matcher* m, int first_slot, int n, const double* map_xy,
                              const int* counts) {
   if (!m || !slot_ok(m, first_slot, n) || !counts) return fail(CGM_ERR_ARG, "bad argument");
@@ -226,16 +280,12 @@ int cgm_matcher_search(cgm_matcher* m, int slot, const double* pts_xy, int n_pts
   return CGM_OK;
 }
 
-int cgm_matcher_hierarchical_search(cgm_matcher* m, int slot, const double* pts_xy, int n_pts,
-                                    const float* regions, int n_regions, double theta_res,
-                                    double max_score, double bin_x, double bin_y, double bin_theta,
-                                    int n_levels, cgm_result* out, int cap, int* n_out) {
-  if (!m || !slot_ok(m, slot, 1) || n_pts < 0 || n_regions < 0 || (n_pts && !pts_xy) ||
-      (n_regions && !regions) || cap < 0 || (cap && !out) || n_levels < 1)
-    return fail(CGM_ERR_ARG, "bad argument");
-  // chargrid.cpp:310-344
-  std::vector<cgm::SearchParams> levels =
-      cgm::hierarchical_levels(m->geom, theta_res, max_score, bin_x, bin_y, bin_theta, n_levels);
+namespace {
+// chargrid.cpp:310-344: every level but the last searches the current regions and turns its
+// results into the next level's regions; the last level's results are returned.
+int run_hierarchy(cgm_matcher* m, int slot, const double* pts_xy, int n_pts, const float* regions,
+                  int n_regions, const std::vector<cgm::SearchParams>& levels, cgm_result* out, int cap,
+                  int* n_out) {
   std::vector<float> cur(regions, regions + 6 * static_cast<size_t>(n_regions));
   std::vector<cgm_result> last;
   for (size_t li = 0; li + 1 < levels.size(); ++li) {
@@ -258,6 +308,35 @@ int cgm_matcher_hierarchical_search(cgm_matcher* m, int slot, const double* pts_
   }
   write_results(last, out, cap, n_out);
   return CGM_OK;
+}
+}  // namespace
+
+int cgm_matcher_hierarchical_search(cgm_matcher* m, int slot, const double* pts_xy, int n_pts,
+                                    const float* regions, int n_regions, double theta_res,
+                                    double max_score, double bin_x, double bin_y, double bin_theta,
+                                    int n_levels, cgm_result* out, int cap, int* n_out) {
+  if (!m || !slot_ok(m, slot, 1) || n_pts < 0 || n_regions < 0 || (n_pts && !pts_xy) ||
+      (n_regions && !regions) || cap < 0 || (cap && !out) || n_levels < 1)
+    return fail(CGM_ERR_ARG, "bad argument");
+  // chargrid.cpp:376-400
+  return run_hierarchy(m, slot, pts_xy, n_pts, regions, n_regions,
+                       cgm::hierarchical_levels(m->geom, theta_res, max_score, bin_x, bin_y, bin_theta, n_levels),
+                       out, cap, n_out);
+}
+
+int cgm_matcher_hierarchical_search_levels(cgm_matcher* m, int slot, const double* pts_xy, int n_pts,
+                                           const float* regions, int n_regions, const double* levels7,
+                                           int n_levels, cgm_result* out, int cap, int* n_out) {
+  if (!m || !slot_ok(m, slot, 1) || n_pts < 0 || n_regions < 0 || (n_pts && !pts_xy) ||
+      (n_regions && !regions) || cap < 0 || (cap && !out) || n_levels < 1 || !levels7)
+    return fail(CGM_ERR_ARG, "bad argument");
+  std::vector<cgm::SearchParams> levels(n_levels);
+  for (int l = 0; l < n_levels; ++l) {
+    const double* p = levels7 + 7 * l;
+    const cgm::SearchParams sp = {p[0], p[1], p[2], p[3], p[4], p[5], p[6]};
+    levels[l] = sp;
+  }
+  return run_hierarchy(m, slot, pts_xy, n_pts, regions, n_regions, levels, out, cap, n_out);
 }
 
 int cgm_matcher_count_points(cgm_matcher* m, int slot, float llx, float lly, float urx, float ury,

@@ -27,6 +27,13 @@ void* dev_stream(const DeviceMatcher* d);
 int dev_grid_download(DeviceMatcher* d, int slot, uint8_t* dst, std::string* err);
 int dev_grid_upload(DeviceMatcher* d, int slot, const uint8_t* src, std::string* err);
 
+// Replace the distance stamp (column-major dim x dim) / the value the reset path writes and the
+// upper bound of any cell value the scoring kernels may assume; copy one slot's cells to a slot
+// of another matcher of the same geometry on the same device.
+int dev_set_stamp(DeviceMatcher* d, const uint8_t* stamp_colmajor, int stamp_dim, std::string* err);
+void dev_set_bounds(DeviceMatcher* d, int fill_value, int max_cell);
+int dev_copy_grid(DeviceMatcher* dst, int dst_slot, DeviceMatcher* src, int src_slot, std::string* err);
+
 // Map building. stage = H2D of the packed points; launch = [reset] + stamp kernels (async).
 // Passing n_points_total == 0 with reset == true stages a pure reset.
 int dev_stage_map(DeviceMatcher* d, int first_slot, int n, const double* map_xy,

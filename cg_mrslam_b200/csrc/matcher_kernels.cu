@@ -477,6 +477,41 @@ int dev_grid_upload(DeviceMatcher* d, int slot, const uint8_t* src, std::string*
   return CGM_OK;
 }
 
+int dev_set_stamp(DeviceMatcher* d, const uint8_t* stamp_colmajor, int stamp_dim, std::string* err) {
+  CGM_CUDA(cudaSetDevice(d->device));
+  CGM_CUDA(cudaStreamSynchronize(d->stream));
+  const size_t bytes = static_cast<size_t>(stamp_dim) * stamp_dim;
+  if (stamp_dim != d->stamp_dim) {
+    if (d->stamp) cudaFree(d->stamp);
+    d->stamp = nullptr;
+    d->stamp_dim = 0;
+    CGM_CUDA(cudaMalloc(reinterpret_cast<void**>(&d->stamp), bytes ? bytes : 1));
+    d->stamp_dim = stamp_dim;
+  }
+  CGM_CUDA(cudaMemcpyAsync(d->stamp, stamp_colmajor, bytes, cudaMemcpyHostToDevice, d->stream));
+  CGM_CUDA(cudaStreamSynchronize(d->stream));
+  return CGM_OK;
+}
+
+void dev_set_bounds(DeviceMatcher* d, int fill_value, int max_cell) {
+  d->geom.fill_value = fill_value;
+  d->geom.max_cell = max_cell;
+  d->dg.fill_value = fill_value;
+}
+
+int dev_copy_grid(DeviceMatcher* dst, int dst_slot, DeviceMatcher* src, int src_slot, std::string* err) {
+  if (dst->device != src->device || dst->slot_bytes != src->slot_bytes) {
+    if (err) *err = "grid copy needs two matchers of one geometry on one device";
+    return CGM_ERR_ARG;
+  }
+  CGM_CUDA(cudaSetDevice(dst->device));
+  CGM_CUDA(cudaStreamSynchronize(src->stream));
+  CGM_CUDA(cudaMemcpyAsync(dst->grids + dst_slot * dst->slot_bytes, src->grids + src_slot * src->slot_bytes,
+                           src->slot_bytes, cudaMemcpyDeviceToDevice, dst->stream));
+  CGM_CUDA(cudaStreamSynchronize(dst->stream));
+  return CGM_OK;
+}
+
 int dev_stage_map(DeviceMatcher* d, int first_slot, int n, const double* map_xy, const int* counts,
                   bool reset, std::string* err) {
   CGM_CUDA(cudaSetDevice(d->device));

@@ -1428,7 +1428,9 @@ int dev_iterate(DeviceSolver* d, int n_iters, double* chi2_out, int* iters_done,
   PGO_CUDA(cudaStreamSynchronize(d->stream));
   for (int k = 0; k < 5; ++k) d->stage_ms[k] = st[k + 1] > st[k] ? (st[k + 1] - st[k]) * 1e-6 : 0.0;
   PGO_CUDA(cudaEventElapsedTime(ms, d->ev0, d->ev1));
-  d->have_factor = iters_done[0] > 0;
+  // a failed iteration has zeroed and partly overwritten the factor of the last good one: no
+  // marginals / edge labels from it (they would come back as zeros)
+  d->have_factor = !failed && iters_done[0] > 0;
   if (failed) {
     if (err) *err = "H is not positive definite (a 3x3 pivot failed): is a vertex fixed?";
     return PGO_ERR_NUMERIC;
@@ -1441,8 +1443,11 @@ int dev_dd_begin(DeviceSolver* d, int n_iters, std::string* err) {
     if (err) *err = "pgo_upload has not been called";
     return PGO_ERR_ARG;
   }
+  if (n_iters > kMaxItersPerCall) {  // the stage graphs hold chi2_out by address: its capacity is fixed
+    if (err) *err = "at most 1024 iterations per domain-decomposed call";
+    return PGO_ERR_ARG;
+  }
   PGO_CUDA(cudaSetDevice(d->device));
-  PGO_CUDA(d->chi2_out.reserve(std::max(n_iters, kMaxItersPerCall)));
   PGO_CUDA(cudaMemsetAsync(d->status.p, 0, 4 * sizeof(int), d->stream));
   PGO_CUDA(cudaMemsetAsync(d->chi2_out.p, 0, std::max(n_iters, 1) * sizeof(double), d->stream));
   PGO_CUDA(cudaEventRecord(d->ev0, d->stream));
@@ -1485,7 +1490,7 @@ int dev_dd_end(DeviceSolver* d, int n_iters, double* chi2_out, int* iters_done, 
   PGO_CUDA(cudaStreamSynchronize(d->stream));
   PGO_CUDA(cudaEventElapsedTime(ms, d->ev0, d->ev1));
   *iters_done = status[1];
-  d->have_factor = status[1] > 0;
+  d->have_factor = status[1] > 0 && !status[0];
   if (status[0]) {
     if (err) *err = "H is not positive definite (a 3x3 pivot failed): is a vertex fixed?";
     return PGO_ERR_NUMERIC;

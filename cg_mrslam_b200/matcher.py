@@ -51,6 +51,12 @@ _SIGS = {
     "cgm_matcher_search_non_matched": (C.c_int, [C.c_void_p, C.c_int, _dp, C.c_int, C.c_double,
                                                  _dp, _ip]),
     "cgm_matcher_raster_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _dp, _ip]),
+    "cgm_matcher_hierarchical_search_levels": (C.c_int, [C.c_void_p, C.c_int, _dp, C.c_int, _fp, C.c_int, _dp,
+                                                         C.c_int, C.c_void_p, C.c_int, _ip]),
+    "cgm_matcher_set_stamp": (C.c_int, [C.c_void_p, _up, C.c_int]),
+    "cgm_matcher_fill": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "cgm_matcher_fill_raster": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _dp, C.c_int]),
+    "cgm_matcher_copy_grid": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     "cgm_matcher_search_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _dp, _ip, _fp, _ip] +
                                  [C.c_double] * 7 + [C.POINTER(cgm_result), C.c_int, _ip]),
     "cgm_matcher_batch_stage": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _dp, _ip, _dp, _ip, _fp,

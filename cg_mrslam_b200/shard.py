@@ -5,8 +5,8 @@
   lists are gathered at the end (`gather_results`), which replaces the reference's UDP exchange of
   closures between robots (src/mrslam/graph_comm.cpp) on one NVSwitch box.
 * the pose-graph solve runs as independent replicas (one graph per rank: one robot per GPU, as in
-  BASELINE config 3); the domain-decomposed single-graph solve with a separator all-reduce is the
-  next step.
+  BASELINE config 3), or as ONE graph cut over the ranks with a single all-reduce of the separator
+  blocks per iteration (pgo_set_partition / pgo_dd_* in include/pgo_solver.h, pgo.optimize_distributed).
 """
 import numpy as np
 

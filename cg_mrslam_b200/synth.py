@@ -148,12 +148,13 @@ INFO_CLOSURE = np.diag([1000.0, 1000.0, 10000.0])  # graph_slam.cpp:75-76
 
 
 def make_pose_graph(n_vertices=50000, n_edges=200000, seed=42, box=250.0, radius=2.5,
-                    min_gap=10, max_per_pose=6, noise_scale=1.0, init="odometry"):
+                    min_gap=10, max_per_pose=6, noise_scale=1.0, init="odometry", start_noise=1.0):
     """Manhattan-style walk. Returns dict(poses0 [V,3] initial guess, truth [V,3], edge_ij [E,2],
     meas [E,3], info [E,6] upper triangle row-major, fixed = [0]).
 
     ``noise_scale`` scales the measurement noise standard deviation (1.0 = Sigma = Omega^-1 as in
-    SURVEY 8(d)). ``init`` = "odometry" (dead reckoning along the chain) or "truth_noisy"."""
+    SURVEY 8(d)). ``init`` = "odometry" (dead reckoning along the chain) or "truth_noisy" (truth +
+    N(0, (0.05 m, 0.05 m, 0.01 rad) x ``start_noise``): a start Gauss-Newton converges from)."""
     from scipy.spatial import cKDTree
 
     rng = np.random.default_rng(seed)
@@ -218,7 +219,7 @@ def make_pose_graph(n_vertices=50000, n_edges=200000, seed=42, box=250.0, radius
             cur = se2_mul(cur, meas[k])[0]
             poses0[k + 1] = cur
     elif init == "truth_noisy":
-        poses0 = truth + rng.normal(size=truth.shape) * np.array([0.05, 0.05, 0.01])
+        poses0 = truth + rng.normal(size=truth.shape) * np.array([0.05, 0.05, 0.01]) * start_noise
         poses0[:, 2] = wrap(poses0[:, 2])
         poses0[0] = truth[0]
     else:

@@ -70,6 +70,18 @@ int cgm_matcher_grid2world(const cgm_matcher* m, int ix, int iy, float* x, float
 int cgm_matcher_reset(cgm_matcher* m, int slot);
 /* CharGrid::addAndConvolvePoints (chargrid.h:205-216 -> applyKernel chargrid.cpp:132-161). */
 int cgm_matcher_raster(cgm_matcher* m, int slot, const double* map_xy, int n);
+/* The kernel argument of CharGrid::addAndConvolvePoints / applyKernel (chargrid.h:190,205-216): the
+ * reference's callers build the stamp themselves (ScanMatcher::initializeKernel,
+ * scan_matcher.cpp:38-61) and pass it with every call; the CharGrid shim forwards it here when it
+ * changes. Column-major dim x dim bytes, dim odd. */
+int cgm_matcher_set_stamp(cgm_matcher* m, const uint8_t* stamp_colmajor, int dim);
+/* Every cell <- value: the loop of ScanMatcher::resetGrid (scan_matcher.cpp:68-76) for any fill
+ * value; with points, followed by addAndConvolvePoints in the same launch. */
+int cgm_matcher_fill(cgm_matcher* m, int slot, int value);
+int cgm_matcher_fill_raster(cgm_matcher* m, int slot, int value, const double* map_xy, int n);
+/* CharGrid's copy constructor / assignment (`CharGrid auxGrid = _grid;`, scan_matcher.cpp:437):
+ * device-to-device copy of one slot's cells between matchers of the same geometry and device. */
+int cgm_matcher_copy_grid(cgm_matcher* dst, int dst_slot, cgm_matcher* src, int src_slot);
 /* Dense copy of the cells, row-major [x][y] (cell(x,y) = rows[x][y], gridmap.h:66-69);
  * serves ScanMatcher::grid() (scan_matcher.h:77) and the parity tests. */
 int cgm_matcher_grid_download(cgm_matcher* m, int slot, uint8_t* dst);
@@ -92,6 +104,12 @@ int cgm_matcher_hierarchical_search(cgm_matcher* m, int slot, const double* pts_
                                     const float* regions, int n_regions, double theta_res,
                                     double max_score, double bin_x, double bin_y, double bin_theta,
                                     int n_levels, cgm_result* out, int cap, int* n_out);
+
+/* CharGrid::hierarchicalSearch(mresvec, points, regions, paramsVec) (chargrid.cpp:310-344) with the
+ * caller's own ladder: levels7 = n_levels rows of (step x, y, theta, maxScore, bin x, y, theta). */
+int cgm_matcher_hierarchical_search_levels(cgm_matcher* m, int slot, const double* pts_xy, int n_pts,
+                                           const float* regions, int n_regions, const double* levels7,
+                                           int n_levels, cgm_result* out, int cap, int* n_out);
 
 /* CharGrid::countPoints (chargrid.cpp:417-441). */
 int cgm_matcher_count_points(cgm_matcher* m, int slot, float llx, float lly, float urx, float ury,

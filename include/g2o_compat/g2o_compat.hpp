@@ -13,6 +13,7 @@
 #define G2O_COMPAT_HPP
 
 #include <algorithm>
+#include <cassert>
 #include <cmath>
 #include <fstream>
 #include <iomanip>
@@ -75,6 +76,146 @@ class SE2 {
   Eigen::Rotation2Dd r_;
 };
 
+// ---- graph container ------------------------------------------------------------------------------
+class SparseOptimizer;
+
+struct HyperGraph {
+  class Edge;
+  // user data attached to a vertex: a singly linked list (g2o HyperGraph::Data / OptimizableGraph::
+  // Data; walked by GraphSLAM::findLaserData, graph_slam.cpp:271-284)
+  class Data {
+   public:
+    Data() : next_(nullptr) {}
+    virtual ~Data() { delete next_; }
+    Data* next() const { return next_; }
+    void setNext(Data* n) { next_ = n; }
+
+   private:
+    Data* next_;
+  };
+  class Vertex {
+   public:
+    Vertex() : id_(-1) {}
+    virtual ~Vertex() {}
+    int id() const { return id_; }
+    virtual void setId(int id) { id_ = id; }
+    struct EdgeLess {
+      bool operator()(const Edge* a, const Edge* b) const;
+    };
+    typedef std::set<Edge*, EdgeLess> EdgeSetT;
+    const EdgeSetT& edges() const { return edges_; }
+    EdgeSetT& edges() { return edges_; }
+
+   protected:
+    int id_;
+    EdgeSetT edges_;
+  };
+  struct VertexLess {
+    bool operator()(const Vertex* a, const Vertex* b) const {
+      return a->id() != b->id() ? a->id() < b->id() : a < b;
+    }
+  };
+  class Edge {
+   public:
+    // serial: creation index, immutable -- the key of every EdgeSet (g2o orders its sets by pointer
+    // value; an index that never changes gives the same container semantics, deterministically).
+    // internalId: insertion index into a graph (g2o assigns it in addEdge; active edges are
+    // processed in this order, C5)
+    Edge() : id_(-1), serial_(nextSerial()++), internal_id_(-1) { vertices_.resize(2, nullptr); }
+    virtual ~Edge() {}
+    std::vector<Vertex*>& vertices() { return vertices_; }
+    const std::vector<Vertex*>& vertices() const { return vertices_; }
+    Vertex* vertex(size_t i) const { return vertices_[i]; }
+    void setVertex(size_t i, Vertex* v) { vertices_[i] = v; }
+    int id() const { return id_; }
+    void setId(int id) { id_ = id; }
+    long long serial() const { return serial_; }
+    long long internalId() const { return internal_id_; }
+    void setInternalId(long long s) { internal_id_ = s; }
+
+   protected:
+    static long long& nextSerial() {
+      static long long n = 0;
+      return n;
+    }
+    std::vector<Vertex*> vertices_;
+    int id_;
+    long long serial_, internal_id_;
+  };
+  // ordered by vertex id; sets of VertexSets (graph_slam.cpp:404, vertices_finder.cpp:60-112) compare
+  // by ids too, so their iteration order does not depend on heap addresses (with g2o it does)
+  struct VertexSet : public std::set<Vertex*, VertexLess> {
+    friend bool operator<(const VertexSet& a, const VertexSet& b) {
+      const_iterator i = a.begin(), j = b.begin();
+      for (; i != a.end() && j != b.end(); ++i, ++j) {
+        if ((*i)->id() != (*j)->id()) return (*i)->id() < (*j)->id();
+        if (*i != *j) return *i < *j;
+      }
+      return i == a.end() && j != b.end();
+    }
+  };
+  typedef Vertex::EdgeSetT EdgeSet;
+  typedef std::map<int, Vertex*> VertexIDMap;
+
+  virtual ~HyperGraph() {}
+  Vertex* vertex(int id) const {
+    VertexIDMap::const_iterator it = vertices_.find(id);
+    return it == vertices_.end() ? nullptr : it->second;
+  }
+  const VertexIDMap& vertices() const { return vertices_; }
+  VertexIDMap& vertices() { return vertices_; }
+  const EdgeSet& edges() const { return edges_; }
+  EdgeSet& edges() { return edges_; }
+
+ protected:
+  VertexIDMap vertices_;
+  EdgeSet edges_;
+};
+
+inline bool HyperGraph::Vertex::EdgeLess::operator()(const Edge* a, const Edge* b) const {
+  return a->serial() != b->serial() ? a->serial() < b->serial() : a < b;
+}
+
+struct OptimizableGraph : public HyperGraph {
+  typedef HyperGraph::Data Data;
+  class Vertex : public HyperGraph::Vertex {
+   public:
+    Vertex() : fixed_(false), hessian_index_(-1), user_data_(nullptr) {}
+    virtual ~Vertex() { delete user_data_; }  // deletes the whole chain
+    bool fixed() const { return fixed_; }
+    void setFixed(bool f) { fixed_ = f; }
+    int hessianIndex() const { return hessian_index_; }
+    void setHessianIndex(int h) { hessian_index_ = h; }
+    HyperGraph::Data* userData() const { return user_data_; }
+    void setUserData(HyperGraph::Data* d) { user_data_ = d; }  // the vertex owns its user data
+    void addUserData(HyperGraph::Data* d) {  // g2o prepends: the newest datum is userData()
+      if (d) {
+        d->setNext(user_data_);
+        user_data_ = d;
+      }
+    }
+    virtual void push() = 0;
+    virtual void pop() = 0;
+
+   protected:
+    bool fixed_;
+    int hessian_index_;
+    HyperGraph::Data* user_data_;
+  };
+  class Edge : public HyperGraph::Edge {
+   public:
+    Edge() : level_(0) {}
+    int level() const { return level_; }
+    void setLevel(int l) { level_ = l; }
+    virtual void computeError() = 0;
+    virtual double chi2() const = 0;
+
+   protected:
+    int level_;
+  };
+  Vertex* vertex(int id) const { return static_cast<Vertex*>(HyperGraph::vertex(id)); }
+};
+
 // ---- C13: laser data ------------------------------------------------------------------------------
 struct LaserParameters {
   LaserParameters(int type_, int beams, double firstBeamAngle_, double angularStep_,
@@ -90,7 +231,7 @@ struct LaserParameters {
   double maxRange;
 };
 
-class RawLaser {
+class RawLaser : public HyperGraph::Data {
  public:
   typedef std::vector<Eigen::Vector2d, Eigen::aligned_allocator<Eigen::Vector2d> > Point2DVector;
   virtual ~RawLaser() {}
@@ -121,7 +262,7 @@ class RawLaser {
 
 class RobotLaser : public RawLaser {
  public:
-  RobotLaser() : timestamp_(0.0), logger_timestamp_(0.0), next_(nullptr) {}
+  RobotLaser() : timestamp_(0.0), logger_timestamp_(0.0) {}
   const SE2& odomPose() const { return odom_; }
   void setOdomPose(const SE2& p) { odom_ = p; }
   double timestamp() const { return timestamp_; }
@@ -130,109 +271,11 @@ class RobotLaser : public RawLaser {
   void setLoggerTimestamp(double t) { logger_timestamp_ = t; }
   const std::string& hostname() const { return hostname_; }
   void setHostname(const std::string& h) { hostname_ = h; }
-  RobotLaser* next() const { return next_; }
-  void setNext(RobotLaser* n) { next_ = n; }
 
  private:
   SE2 odom_;
   double timestamp_, logger_timestamp_;
   std::string hostname_;
-  RobotLaser* next_;
-};
-
-// ---- graph container ------------------------------------------------------------------------------
-class SparseOptimizer;
-
-struct HyperGraph {
-  class Edge;
-  class Vertex {
-   public:
-    Vertex() : id_(-1) {}
-    virtual ~Vertex() {}
-    int id() const { return id_; }
-    virtual void setId(int id) { id_ = id; }
-    struct EdgeLess {
-      bool operator()(const Edge* a, const Edge* b) const;
-    };
-    typedef std::set<Edge*, EdgeLess> EdgeSetT;
-    const EdgeSetT& edges() const { return edges_; }
-    EdgeSetT& edges() { return edges_; }
-
-   protected:
-    int id_;
-    EdgeSetT edges_;
-  };
-  struct VertexLess {
-    bool operator()(const Vertex* a, const Vertex* b) const {
-      return a->id() != b->id() ? a->id() < b->id() : a < b;
-    }
-  };
-  class Edge {
-   public:
-    Edge() : id_(-1), serial_(0) { vertices_.resize(2, nullptr); }
-    virtual ~Edge() {}
-    std::vector<Vertex*>& vertices() { return vertices_; }
-    const std::vector<Vertex*>& vertices() const { return vertices_; }
-    Vertex* vertex(size_t i) const { return vertices_[i]; }
-    void setVertex(size_t i, Vertex* v) { vertices_[i] = v; }
-    int id() const { return id_; }
-    void setId(int id) { id_ = id; }
-    long long serial() const { return serial_; }  // insertion index (g2o: internalId)
-    void setSerial(long long s) { serial_ = s; }
-
-   protected:
-    std::vector<Vertex*> vertices_;
-    int id_;
-    long long serial_;
-  };
-  typedef std::set<Vertex*, VertexLess> VertexSet;
-  typedef Vertex::EdgeSetT EdgeSet;
-  typedef std::map<int, Vertex*> VertexIDMap;
-};
-
-inline bool HyperGraph::Vertex::EdgeLess::operator()(const Edge* a, const Edge* b) const {
-  return a->serial() != b->serial() ? a->serial() < b->serial() : a < b;
-}
-
-struct OptimizableGraph : public HyperGraph {
-  class Vertex : public HyperGraph::Vertex {
-   public:
-    Vertex() : fixed_(false), hessian_index_(-1), user_data_(nullptr) {}
-    virtual ~Vertex() { delete user_data_; }
-    bool fixed() const { return fixed_; }
-    void setFixed(bool f) { fixed_ = f; }
-    int hessianIndex() const { return hessian_index_; }
-    void setHessianIndex(int h) { hessian_index_ = h; }
-    RawLaser* userData() const { return user_data_; }
-    void setUserData(RawLaser* d) { user_data_ = d; }  // the vertex owns its user data
-    void addUserData(RawLaser* d) {
-      if (!user_data_) {
-        user_data_ = d;
-      } else {  // chain through RobotLaser::next like g2o's data list
-        RobotLaser* tail = dynamic_cast<RobotLaser*>(user_data_);
-        while (tail && tail->next()) tail = tail->next();
-        if (tail) tail->setNext(dynamic_cast<RobotLaser*>(d));
-      }
-    }
-    virtual void push() = 0;
-    virtual void pop() = 0;
-
-   protected:
-    bool fixed_;
-    int hessian_index_;
-    RawLaser* user_data_;
-  };
-  class Edge : public HyperGraph::Edge {
-   public:
-    Edge() : level_(0) {}
-    int level() const { return level_; }
-    void setLevel(int l) { level_ = l; }
-    virtual void computeError() = 0;
-    virtual double chi2() const = 0;
-
-   protected:
-    int level_;
-  };
 };
 
 class VertexSE2 : public OptimizableGraph::Vertex {
@@ -314,8 +357,11 @@ template <typename MatrixType>
 struct LinearSolverCSparse {
   void setBlockOrdering(bool) {}
 };
+struct Solver {
+  virtual ~Solver() {}
+};
 template <typename Traits>
-struct BlockSolver {
+struct BlockSolver : public Solver {
   typedef typename Traits::PoseMatrixType PoseMatrixType;
   typedef LinearSolverCSparse<PoseMatrixType> LinearSolverType;
   explicit BlockSolver(std::unique_ptr<LinearSolverType>) {}
@@ -325,12 +371,8 @@ struct OptimizationAlgorithm {
   virtual ~OptimizationAlgorithm() {}
 };
 struct OptimizationAlgorithmGaussNewton : public OptimizationAlgorithm {
-  template <typename S>
-  explicit OptimizationAlgorithmGaussNewton(std::unique_ptr<S>) {}
-  template <typename S>
-  explicit OptimizationAlgorithmGaussNewton(S* p) {
-    delete p;
-  }
+  explicit OptimizationAlgorithmGaussNewton(std::unique_ptr<Solver>) {}
+  explicit OptimizationAlgorithmGaussNewton(Solver* p) { delete p; }
 };
 
 // ---- HyperDijkstra --------------------------------------------------------------------------------
@@ -428,7 +470,7 @@ class SparseOptimizer : public OptimizableGraph {
   }
   bool addEdge(OptimizableGraph::Edge* e) {
     if (!e->vertex(0) || !e->vertex(1)) return false;
-    e->setSerial(next_serial_++);
+    e->setInternalId(next_serial_++);
     edges_.insert(e);
     e->vertex(0)->edges().insert(e);
     e->vertex(1)->edges().insert(e);
@@ -443,12 +485,6 @@ class SparseOptimizer : public OptimizableGraph {
     structure_dirty_ = true;
     return true;
   }
-  OptimizableGraph::Vertex* vertex(int id) const {
-    VertexIDMap::const_iterator it = vertices_.find(id);
-    return it == vertices_.end() ? nullptr : static_cast<OptimizableGraph::Vertex*>(it->second);
-  }
-  const VertexIDMap& vertices() const { return vertices_; }
-  const HyperGraph::EdgeSet& edges() const { return edges_; }
   const VertexContainer& activeVertices() const { return active_vertices_; }
   const EdgeContainer& activeEdges() const { return active_edges_; }
 
@@ -471,6 +507,10 @@ class SparseOptimizer : public OptimizableGraph {
       vs.insert(e->vertex(0));
       vs.insert(e->vertex(1));
     }
+    std::stable_sort(active_edges_.begin(), active_edges_.end(),
+                     [](const OptimizableGraph::Edge* a, const OptimizableGraph::Edge* b) {
+                       return a->internalId() < b->internalId();
+                     });
     for (VertexIDMap::iterator it = vertices_.begin(); it != vertices_.end(); ++it)
       static_cast<OptimizableGraph::Vertex*>(it->second)->setHessianIndex(-1);
     int h = 0;
@@ -677,8 +717,6 @@ class SparseOptimizer : public OptimizableGraph {
             ->setEstimate(SE2(poses[3 * i], poses[3 * i + 1], poses[3 * i + 2]));
   }
 
-  VertexIDMap vertices_;
-  HyperGraph::EdgeSet edges_;
   VertexContainer active_vertices_;
   EdgeContainer active_edges_;
   std::map<const HyperGraph::Vertex*, int> active_index_;

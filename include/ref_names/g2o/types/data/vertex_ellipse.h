@@ -1,0 +1,3 @@
+// Forwarding header: the reference includes "g2o/types/data/vertex_ellipse.h"; the B200 build resolves it to
+// include/g2o_compat/g2o_compat.hpp. No declarations of its own.
+#include "../../../../g2o_compat/g2o_compat.hpp"

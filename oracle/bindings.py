@@ -204,3 +204,39 @@ class CpuGrid:
 
 def have_reference():
     return os.path.exists(REF_CHARGRID_SO)
+
+
+class CGaussNewton:
+    """The compiled pose-graph oracle (oracle/pgo_oracle_c.cpp): Gauss-Newton with an up-looking
+    scalar sparse Cholesky, one thread -- the shape of g2o + LinearSolverCSparse."""
+
+    def __init__(self):
+        if not os.path.exists(ORACLE_PGO_SO):
+            raise FileNotFoundError(ORACLE_PGO_SO + " (run `make -C oracle`)")
+        self.lib = C.CDLL(ORACLE_PGO_SO)
+        f = self.lib.pgo_oracle_c_gauss_newton
+        f.restype = C.c_int
+        f.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _up, _dp, _dp, _dp,
+                      C.c_int, _dp, _dp, C.POINTER(C.c_longlong)]
+
+    def gauss_newton(self, poses0, edge_ij, meas, info6, fixed, n_iters):
+        """Returns dict(poses, chi2 [iterations done], iterations, times {analyse, linearise,
+        factor, solve} in seconds, nnz_l, flops)."""
+        poses = np.array(poses0, dtype=np.float64, copy=True, order="C")
+        e = np.asarray(edge_ij).reshape(-1, 2)
+        ei = np.ascontiguousarray(e[:, 0], dtype=np.int32)
+        ej = np.ascontiguousarray(e[:, 1], dtype=np.int32)
+        mask = np.zeros(len(poses), dtype=np.uint8)
+        mask[np.asarray(fixed, dtype=np.int64)] = 1
+        meas, info6 = _as_d(meas), _as_d(info6)
+        chi2 = np.zeros(max(n_iters, 1))
+        times = np.zeros(4)
+        stats = (C.c_longlong * 3)()
+        done = self.lib.pgo_oracle_c_gauss_newton(
+            len(poses), len(e), ei.ctypes.data_as(C.POINTER(C.c_int32)),
+            ej.ctypes.data_as(C.POINTER(C.c_int32)), mask.ctypes.data_as(_up),
+            poses.ctypes.data_as(_dp), meas.ctypes.data_as(_dp), info6.ctypes.data_as(_dp), n_iters,
+            chi2.ctypes.data_as(_dp), times.ctypes.data_as(_dp), stats)
+        return {"poses": poses, "chi2": chi2[:max(done, min(n_iters, done + 1))], "iterations": done,
+                "times": dict(zip(("analyse", "linearise", "factor", "solve"), times.tolist())),
+                "nnz_l": int(stats[0]), "flops": float(stats[1])}

@@ -1,7 +1,11 @@
-// Test driver for the C++ host mirrors (include/cgm/*.hpp, include/g2o_compat/g2o_compat.hpp).
-// Reads a scenario file, runs it through the reference-shaped API (SparseOptimizer, VertexSE2,
-// EdgeSE2, RobotLaser, ScanMatcher, EdgeLabeler) and prints results with 17 significant digits;
-// tests/test_cpp_compat.py compares them with the CPU oracles.
+// Scenario driver over the REFERENCE'S OWN host classes -- ScanMatcher, VerticesFinder,
+// LoopClosureChecker, ClosureBuffer, MRClosureBuffer, CondensedGraphBuffer / CondensedGraphCreator,
+// GraphSLAM::checkCovariance / addNeighboringVertices -- compiled verbatim from /root/reference
+// (oracle/Makefile, target `frontend`) against include/g2o_compat + include/cgm/chargrid.hpp
+// (compat_driver_gpu, linked to libcgmrslam_b200.so) or against the reference's chargrid.cpp and the
+// CPU oracle solver (compat_driver_cpu). Reads a scenario file, prints results with 17 significant
+// digits; tests/test_cpp_compat.py and tests/test_frontend_host.py compare them with the CPU
+// oracles, which pins those restatements to the reference's code.
 //
 //   V id x y th fixed n_beams first_angle step max_range r_1 ... r_n     vertex + its scan
 //   E i j dx dy dth I11 I12 I13 I22 I23 I33                              EdgeSE2
@@ -27,19 +31,34 @@
 #include <iostream>
 #include <sstream>
 
-#include "cgm/condensed_graph.hpp"
-#include "cgm/mr_closure_buffer.hpp"
-#include "cgm/scan_matcher.hpp"
-#include "cgm/slam_frontend.hpp"
-#include "g2o_compat/g2o_compat.hpp"
+#include "mrslam/condensed_graph/condensed_graph_buffer.h"
+#include "mrslam/mr_closure_buffer.h"
+#include "slam/graph_slam.h"
+
+#include "driver_out.h"
 
 using namespace g2o;
+
+// GraphSLAM keeps its candidate filters protected; a subclass may call them (no source edit)
+struct Probe : public GraphSLAM {
+  void neighbours(VertexSE2* last, OptimizableGraph::VertexSet& vset, int gap) {
+    _lastVertex = last;
+    addNeighboringVertices(vset, gap);
+  }
+  void covarianceGate(VertexSE2* last, OptimizableGraph::VertexSet& vset) {
+    _lastVertex = last;
+    for (HyperGraph::VertexIDMap::iterator it = _graph->vertices().begin(); it != _graph->vertices().end(); ++it)
+      if (static_cast<OptimizableGraph::Vertex*>(it->second)->fixed()) _firstRobotPose = static_cast<VertexSE2*>(it->second);
+    checkCovariance(vset);
+  }
+};
 
 int main(int argc, char** argv) {
   if (argc < 2) return 2;
   std::ifstream f(argv[1]);
   if (!f) return 2;
-  SparseOptimizer opt;
+  Probe probe;
+  SparseOptimizer& opt = *probe.graph();
   // the reference's construction idiom (graph_slam.cpp:44-55) must keep compiling
   typedef BlockSolver<BlockSolverTraits<-1, -1> > SlamBlockSolver;
   typedef LinearSolverCSparse<SlamBlockSolver::PoseMatrixType> SlamLinearSolver;
@@ -182,7 +201,6 @@ int main(int argc, char** argv) {
         EdgeSE2* e = new EdgeSE2();
         e->vertices()[0] = opt.vertex(gauge);
         e->vertices()[1] = opt.vertex(id);
-        e->setSerial(1000000 + static_cast<long long>(order.size()));
         star.insert(e);
         order.push_back(e);
       }
@@ -221,7 +239,6 @@ int main(int argc, char** argv) {
             EdgeSE2* e = new EdgeSE2();
             e->vertices()[0] = opt.vertices().begin()->second;
             e->vertices()[1] = opt.vertex(vid);
-            e->setSerial(4000000 + static_cast<long long>(owned.size()));
             owned.push_back(e);
             edges_of[vid].push_back(e);
             c.addEdge(e);
@@ -289,7 +306,6 @@ int main(int argc, char** argv) {
         m(0, 0) = w[0]; m(0, 1) = m(1, 0) = w[1]; m(0, 2) = m(2, 0) = w[2];
         m(1, 1) = w[3]; m(1, 2) = m(2, 1) = w[4]; m(2, 2) = w[5];
         e->setInformation(m);
-        e->setSerial(2000000 + i);
         eset.insert(e);
       }
       condensedGraphs.insertEdgesFromRobot(robot, eset);
@@ -327,8 +343,8 @@ int main(int argc, char** argv) {
         vset.insert(opt.vertex(id));
       }
       VertexSE2* last = static_cast<VertexSE2*>(opt.vertex(cur));
-      if (tag == "NEIGH") cgm::addNeighboringVertices(&opt, last, vset, gap);
-      else cgm::checkCovariance(&opt, last, vset);
+      if (tag == "NEIGH") probe.neighbours(last, vset, gap);
+      else probe.covarianceGate(last, vset);
       printf("%s %zu", tag.c_str(), vset.size());
       for (HyperGraph::Vertex* v : vset) printf(" %d", v->id());
       printf("\n");
@@ -357,7 +373,6 @@ int main(int argc, char** argv) {
         info(0, 0) = info(1, 1) = 1000.0;
         info(2, 2) = 10000.0;  // _SMinf, graph_slam.cpp:75-76
         e->setInformation(info);
-        e->setSerial(2000000 + i);
         cand.insert(e);
         order.push_back(e);
       }
@@ -381,7 +396,6 @@ int main(int argc, char** argv) {
             EdgeSE2* e = new EdgeSE2();
             e->vertices()[0] = opt.vertices().begin()->second;
             e->vertices()[1] = opt.vertex(vid);
-            e->setSerial(3000000 + static_cast<long long>(owned.size()));
             owned.push_back(e);
             es.insert(e);
           }

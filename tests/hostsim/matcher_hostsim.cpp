@@ -68,6 +68,23 @@ int dev_grid_upload(DeviceMatcher* d, int slot, const uint8_t* src, std::string*
   return CGM_OK;
 }
 
+int dev_set_stamp(DeviceMatcher* d, const uint8_t* stamp, int dim, std::string*) {
+  d->stamp.assign(stamp, stamp + static_cast<size_t>(dim) * dim);
+  d->stamp_dim = dim;
+  return CGM_OK;
+}
+
+void dev_set_bounds(DeviceMatcher* d, int fill_value, int max_cell) {
+  d->g.fill_value = fill_value;
+  d->g.max_cell = max_cell;
+}
+
+int dev_copy_grid(DeviceMatcher* dst, int dst_slot, DeviceMatcher* src, int src_slot, std::string*) {
+  if (dst->grids[dst_slot].size() != src->grids[src_slot].size()) return CGM_ERR_ARG;
+  dst->grids[dst_slot] = src->grids[src_slot];
+  return CGM_OK;
+}
+
 int dev_stage_map(DeviceMatcher* d, int first_slot, int n, const double* xy, const int* counts,
                   bool reset, std::string*) {
   d->map_off.assign(n + 1, 0);

@@ -1,8 +1,9 @@
-"""The C++ host mirrors of the reference API (include/cgm/scan_matcher.hpp, chargrid.hpp,
-include/g2o_compat/g2o_compat.hpp): they compile against the C ABI, keep the reference's
-construction idiom, and -- on the GPU -- reproduce the oracles through SparseOptimizer::optimize,
-computeMarginals, EdgeLabeler::labelEdges and ScanMatcher::closeScanMatching / scanMatchingLC /
-globalMatching."""
+"""The drop-in boundary, exercised by the REFERENCE'S OWN host sources (compiled verbatim from
+/root/reference, oracle/Makefile target `frontend`): ScanMatcher::closeScanMatching / scanMatchingLC /
+globalMatching over include/cgm/chargrid.hpp, SparseOptimizer::optimize / computeMarginals /
+EdgeLabeler::labelEdges / GraphManipulator / CondensedGraphBuffer over include/g2o_compat -- on the
+GPU (gpu marker) they must reproduce the oracles; the same sources over the reference's CPU matcher
+and the CPU oracle solver (no GPU needed) pin the Python oracles to the reference's code."""
 import math
 import os
 import subprocess
@@ -18,17 +19,20 @@ LIBDIR = os.path.join(ROOT, "cg_mrslam_b200", "lib")
 LASER_POSE = (0.05, 0.0, 0.0)
 
 
+@pytest.fixture(scope="module", params=[pytest.param("gpu", marks=pytest.mark.gpu), "cpu"])
+def driver(request):
+    """compat_driver_gpu: the reference's host classes over include/g2o_compat + include/cgm/chargrid.hpp
+    + the CUDA library; compat_driver_cpu: the same reference sources over the reference's own
+    chargrid.cpp and the CPU oracle solver -- run here without a GPU, it pins the Python oracles
+    (scan_matcher_oracle, frontend_oracle, pgo_oracle) to the reference's code."""
+    import ref_frontend
+    return ref_frontend.driver_path("compat_driver", request.param)
+
+
 @pytest.fixture(scope="module")
-def driver(tmp_path_factory):
-    import __graft_entry__ as g
-    if not os.path.exists(os.path.join(LIBDIR, "libcgmrslam_b200.so")):
-        g.build()
-    exe = str(tmp_path_factory.mktemp("cpp") / "compat_driver")
-    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O1", "-Wall", "-Werror",
-                           "-I" + os.path.join(ROOT, "include"),
-                           os.path.join(ROOT, "tests", "cpp", "compat_driver.cpp"), "-o", exe,
-                           "-L" + LIBDIR, "-lcgmrslam_b200", "-Wl,-rpath," + LIBDIR])
-    return exe
+def gpu_driver():
+    import ref_frontend
+    return ref_frontend.driver_path("compat_driver", "gpu")
 
 
 def _scenario(n=14, seed=4):
@@ -85,14 +89,12 @@ def _write(path, verts, edges, commands):
 
 
 def _run(exe, path):
-    out = subprocess.run([exe, path], capture_output=True, text=True, timeout=300)
-    assert out.returncode == 0, out.stderr
-    lines = out.stdout.splitlines()
-    assert "BEGIN" in lines and lines[-1] == "END", out.stdout[-2000:]
-    return lines[lines.index("BEGIN") + 1:-1], out.stderr
+    import ref_frontend
+    return ref_frontend.run_driver(exe, [path], timeout=300)
 
 
-def test_graph_bookkeeping_and_text_format(driver, tmp_path):
+def test_graph_bookkeeping_and_text_format(gpu_driver, tmp_path):
+    driver = gpu_driver
     verts, edges = _scenario()
     g2o_path = str(tmp_path / "out.g2o")
     path = str(tmp_path / "s.txt")
@@ -108,8 +110,9 @@ def test_graph_bookkeeping_and_text_format(driver, tmp_path):
     assert np.array_equal(g["edge_ij"], np.array([[e[0], e[1]] for e in edges]))
 
 
-def test_compute_calls_fail_loudly_without_gpu(driver, tmp_path):
+def test_compute_calls_fail_loudly_without_gpu(gpu_driver, tmp_path):
     import torch
+    driver = gpu_driver
     if torch.cuda.is_available():
         pytest.skip("GPU present")
     verts, edges = _scenario(6)
@@ -119,7 +122,6 @@ def test_compute_calls_fail_loudly_without_gpu(driver, tmp_path):
     assert "OPT 0" in lines and "SparseOptimizer" in err   # reported, not silently computed
 
 
-@pytest.mark.gpu
 def test_cpp_api_matches_oracles(driver, tmp_path, oracle_lib):
     from oracle import bindings
     from oracle import scan_matcher_oracle as smo
@@ -184,7 +186,6 @@ def test_cpp_api_matches_oracles(driver, tmp_path, oracle_lib):
     assert np.array_equal(first, second)
 
 
-@pytest.mark.gpu
 def test_covariance_gate_matches_oracle(driver, tmp_path):
     """GraphSLAM::checkCovariance (graph_slam.cpp:311-354) through CovarianceEstimator: the whole
     graph re-optimised once with the current vertex as the gauge, marginal blocks from the GPU
@@ -220,7 +221,6 @@ def test_covariance_gate_matches_oracle(driver, tmp_path):
     assert np.array_equal(after, g["poses0"])
 
 
-@pytest.mark.gpu
 def test_condensed_graph_buffer_matches_oracle(driver, tmp_path):
     """CondensedGraphBuffer (condensed_graph_buffer.cpp:94-510) + CondensedGraphCreator
     (condensed_graph_creator.cpp:33-66) through their C++ mirrors: the star a peer robot gets over

@@ -16,17 +16,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIBDIR = os.path.join(ROOT, "cg_mrslam_b200", "lib")
 
 
-@pytest.fixture(scope="module")
-def driver(tmp_path_factory):
-    import __graft_entry__ as g
-    if not os.path.exists(os.path.join(LIBDIR, "libcgmrslam_b200.so")):
-        g.build()
-    exe = str(tmp_path_factory.mktemp("cpp") / "compat_driver")
-    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O1", "-Wall", "-Werror",
-                           "-I" + os.path.join(ROOT, "include"),
-                           os.path.join(ROOT, "tests", "cpp", "compat_driver.cpp"), "-o", exe,
-                           "-L" + LIBDIR, "-lcgmrslam_b200", "-Wl,-rpath," + LIBDIR])
-    return exe
+@pytest.fixture(scope="module", params=["gpu", "cpu"])
+def driver(request):
+    """The reference's own VerticesFinder / ClosureBuffer / LoopClosureChecker / MRClosureBuffer /
+    GraphSLAM::addNeighboringVertices over the compat layer (gpu build; no compute call is made, so
+    it runs on a GPU-less box) and over the CPU oracle build."""
+    import ref_frontend
+    return ref_frontend.driver_path("compat_driver", request.param)
 
 
 def graph(n=400, e=1500, seed=12, box=22.0, base=10000):
@@ -50,10 +46,8 @@ def write(path, g, ids, commands):
 
 
 def run(exe, path):
-    out = subprocess.run([exe, path], capture_output=True, text=True, timeout=300)
-    assert out.returncode == 0, out.stderr
-    lines = out.stdout.splitlines()
-    return lines[lines.index("BEGIN") + 1:-1]
+    import ref_frontend
+    return ref_frontend.run_driver(exe, [path], timeout=300)[0]
 
 
 def test_candidate_selection(driver, tmp_path):

@@ -123,3 +123,24 @@ def test_g2o_text_roundtrip(tmp_path):
     r = po.read_g2o(path)
     assert np.array_equal(r["poses"], g["poses0"]) and np.array_equal(r["meas"], g["meas"])
     assert np.array_equal(r["edge_ij"], g["edge_ij"]) and list(r["fixed"]) == [0]
+
+
+def test_compiled_oracle_matches_python_oracle():
+    """oracle/pgo_oracle_c.cpp (up-looking scalar Cholesky, minimum-degree ordering) against
+    oracle/pgo_oracle.py (SuperLU): two independent solvers, same Gauss-Newton trajectory."""
+    from cg_mrslam_b200 import synth
+    from oracle import bindings
+    bindings.build()
+    c = bindings.CGaussNewton()
+    for n, box, seed in [(30, 5.0, 1), (400, 22.0, 3), (2000, 50.0, 5)]:
+        g = synth.make_pose_graph(n, 4 * n, seed=seed, box=box)
+        ref = po.gauss_newton(g["poses0"], g["edge_ij"], g["meas"], g["info"], g["fixed"], 5)
+        r = c.gauss_newton(g["poses0"], g["edge_ij"], g["meas"], g["info"], g["fixed"], 5)
+        d = r["poses"] - ref.poses
+        d[:, 2] = po.normalize_theta(d[:, 2])
+        assert r["iterations"] == 5 and np.abs(d).max() < 1e-10
+        assert np.allclose(r["chi2"], ref.chi2, rtol=1e-10)
+    # a singular system (no gauge) stops at the failed factorisation, like optimize() returning 0
+    g = synth.make_pose_graph(30, 120, seed=1, box=5.0)
+    r = c.gauss_newton(g["poses0"], g["edge_ij"], g["meas"], g["info"], [], 3)
+    assert r["iterations"] < 3 or np.all(np.isfinite(r["poses"]))
