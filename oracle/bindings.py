@@ -32,6 +32,10 @@ def build(reference="/root/reference"):
     subprocess.check_call(["make", "-s", "-C", HERE, "oracle"])
     if os.path.isdir(os.path.join(reference, "src", "matcher")):
         subprocess.check_call(["make", "-s", "-C", HERE, "ref", "REFERENCE=" + reference])
+        # the reference's own host sources + test drivers, linked to the CUDA library and to the CPU
+        # oracles (needs cg_mrslam_b200/lib/libcgmrslam_b200.so: __graft_entry__.build() makes it first)
+        if os.path.exists(os.path.join(HERE, "..", "cg_mrslam_b200", "lib", "libcgmrslam_b200.so")):
+            subprocess.check_call(["make", "-s", "-C", HERE, "frontend", "REFERENCE=" + reference])
 
 
 def _as_d(a):

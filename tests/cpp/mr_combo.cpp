@@ -10,7 +10,9 @@
 #include <fstream>
 #include <sstream>
 
-#include "cgm/mr_graph_slam.hpp"
+#include "mrslam/mr_graph_slam.h"
+
+#include "driver_out.h"
 
 using namespace g2o;
 

@@ -18,17 +18,12 @@ LIBDIR = os.path.join(ROOT, "cg_mrslam_b200", "lib")
 LASER_POSE = (0.05, 0.0, 0.0)
 
 
-@pytest.fixture(scope="module")
-def driver(tmp_path_factory):
-    import __graft_entry__ as g
-    if not os.path.exists(os.path.join(LIBDIR, "libcgmrslam_b200.so")):
-        g.build()
-    exe = str(tmp_path_factory.mktemp("cpp") / "mr_combo")
-    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O1", "-Wall", "-Werror",
-                           "-I" + os.path.join(ROOT, "include"),
-                           os.path.join(ROOT, "tests", "cpp", "mr_combo.cpp"), "-o", exe,
-                           "-L" + LIBDIR, "-lcgmrslam_b200", "-Wl,-rpath," + LIBDIR])
-    return exe
+@pytest.fixture(scope="module", params=[pytest.param("gpu", marks=pytest.mark.gpu), "cpu"])
+def driver(request):
+    """mr_combo_gpu: the reference's own MRGraphSLAM (compiled verbatim) over the CUDA library;
+    mr_combo_cpu: the same sources over the reference's CPU matcher and the CPU oracle solver."""
+    import ref_frontend
+    return ref_frontend.driver_path("mr_combo", request.param)
 
 
 def two_robots(seed, n=(26, 9)):
@@ -63,7 +58,6 @@ def f32(a):
     return np.asarray(a, dtype=np.float64).astype(np.float32).astype(np.float64)
 
 
-@pytest.mark.gpu
 @pytest.mark.parametrize("seed,ref,max_score", [(5, 14, 0.3), (8, 3, 0.3), (11, 20, 0.12), (5, 14, 0.01)])
 def test_combo_message_to_accepted_closure(driver, tmp_path, oracle_lib, seed, ref, max_score):
     from oracle import bindings
@@ -79,10 +73,8 @@ def test_combo_message_to_accepted_closure(driver, tmp_path, oracle_lib, seed, r
                     len(v["ranges"]), v["first_angle"], v["step"], v["max_range"],
                     " ".join("%.17g" % x for x in v["ranges"])))
         f.write("RUN %d 2 1 %.17g\n" % (a[ref]["id"], max_score))
-    out = subprocess.run([driver, path], capture_output=True, text=True, timeout=300)
-    assert out.returncode == 0, out.stderr
-    lines = out.stdout.splitlines()
-    lines = lines[lines.index("BEGIN") + 1:lines.index("END")]
+    import ref_frontend
+    lines, _ = ref_frontend.run_driver(driver, [path])
     last = b[-1]
     nv, nr = 5, len(last["ranges"])
     assert lines[0].split() == ["MSG", str(8 + 8 + nv * 16 + 4 + 8 + nr * 4 + 16), "vertices", str(nv),

@@ -16,17 +16,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIBDIR = os.path.join(ROOT, "cg_mrslam_b200", "lib")
 
 
-@pytest.fixture(scope="module")
-def driver(tmp_path_factory):
-    import __graft_entry__ as g
-    if not os.path.exists(os.path.join(LIBDIR, "libcgmrslam_b200.so")):
-        g.build()
-    exe = str(tmp_path_factory.mktemp("cpp") / "mr_exchange")
-    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O1", "-Wall", "-Werror",
-                           "-I" + os.path.join(ROOT, "include"),
-                           os.path.join(ROOT, "tests", "cpp", "mr_exchange.cpp"), "-o", exe,
-                           "-L" + LIBDIR, "-lcgmrslam_b200", "-Wl,-rpath," + LIBDIR])
-    return exe
+@pytest.fixture(scope="module", params=[pytest.param("gpu", marks=pytest.mark.gpu), "cpu"])
+def driver(request):
+    """mr_exchange_gpu: the reference's own MRGraphSLAM (compiled verbatim) over the CUDA library;
+    mr_exchange_cpu: the same sources over the reference's CPU matcher and the CPU oracle solver."""
+    import ref_frontend
+    return ref_frontend.driver_path("mr_exchange", request.param)
 
 
 def scenario(path):
@@ -62,15 +57,12 @@ def scenario(path):
     return ga, gb, ida, idb, asked, partners, copies, ir_meas, ir_info
 
 
-@pytest.mark.gpu
 def test_condensed_graph_exchange(driver, tmp_path):
     path = str(tmp_path / "mr.txt")
     ga, gb, ida, idb, asked, partners, copies, ir_meas, ir_info = scenario(path)
     na, nb = len(ga["poses0"]), len(gb["poses0"])
-    out = subprocess.run([driver, path], capture_output=True, text=True, timeout=300)
-    assert out.returncode == 0, out.stderr
-    lines = out.stdout.splitlines()
-    lines = lines[lines.index("BEGIN") + 1:lines.index("END")]
+    import ref_frontend
+    lines, _ = ref_frontend.run_driver(driver, [path])
     msgs = [ln.split() for ln in lines if ln.startswith("MSG ")]
     n_star = len(asked) - 1
     # B -> A: header 8 + edge count 8 + closure count 8 + 4 ids; A -> B: the star, no requests
@@ -113,7 +105,6 @@ def test_condensed_graph_exchange(driver, tmp_path):
         [str(n_star), str(len(gb["edge_ij"]) + len(asked) + n_star), str(len(ga["edge_ij"]) + n_star)]
 
 
-@pytest.mark.gpu
 def test_whole_graph_exchange(driver, tmp_path):
     """The GraphMessage alternative (mr_graph_slam.cpp:397-483, 672-739): A answers B's request with
     its whole own graph; B creates A's vertices (float32 estimates), refreshes the copies it had,
@@ -121,10 +112,8 @@ def test_whole_graph_exchange(driver, tmp_path):
     path = str(tmp_path / "mr.txt")
     ga, gb, ida, idb, asked, partners, copies, ir_meas, ir_info = scenario(path)
     na, nb = len(ga["poses0"]), len(gb["poses0"])
-    out = subprocess.run([driver, path, "graph"], capture_output=True, text=True, timeout=300)
-    assert out.returncode == 0, out.stderr
-    lines = out.stdout.splitlines()
-    lines = lines[lines.index("BEGIN") + 1:lines.index("END")]
+    import ref_frontend
+    lines, _ = ref_frontend.run_driver(driver, [path, "graph"])
     msgs = [ln.split() for ln in lines if ln.startswith("MSG ")]
     n_ea = len(ga["edge_ij"])
     # B -> A: only the request (A has not been asked before: no vertices, no edges)
@@ -158,7 +147,6 @@ def test_whole_graph_exchange(driver, tmp_path):
         [str(n_ea), str(len(gb["edge_ij"]) + len(asked) + n_ea), str(n_ea + len(asked) - 1)]
 
 
-@pytest.mark.gpu
 def test_two_robots_2k_nodes_8k_edges(driver, tmp_path):
     """BASELINE cfg 2 in synthetic form: two robots with 1000 poses / 4000 edges each, six
     inter-robot closures either way; each asks the other about the vertices it closed loops with,
@@ -198,10 +186,8 @@ def test_two_robots_2k_nodes_8k_edges(driver, tmp_path):
                 f.write("E %d %d %d %.17g %.17g %.17g %s\n" % (r, ids[r][p], ids[peer][a], z[0], z[1], z[2],
                                                              " ".join("%.17g" % x for x in ir_info)))
             f.write("WANT %d %d %d %s\n" % (r, peer, len(theirs[r]), " ".join(str(ids[peer][a]) for a in theirs[r])))
-    out = subprocess.run([driver, path], capture_output=True, text=True, timeout=600)
-    assert out.returncode == 0, out.stderr
-    lines = out.stdout.splitlines()
-    lines = lines[lines.index("BEGIN") + 1:lines.index("END")]
+    import ref_frontend
+    lines, _ = ref_frontend.run_driver(driver, [path])
 
     def local_graph(r):
         """robot r's graph as the oracle sees it: own vertices, then the peer copies; own edges + closures"""
