@@ -48,6 +48,9 @@ def parse():
     ap.add_argument("--e2e-chunks", type=int, default=4,
                     help="handles / host threads the end-to-end step is pipelined over")
     ap.add_argument("--gn-batch", type=int, default=128, help="graph instances per GPU in the GN arm")
+    ap.add_argument("--no-bag", action="store_true", help="skip the real-data rows (bag replay)")
+    ap.add_argument("--bag-cpu-keyframes", type=int, default=500,
+                    help="keyframes of the bag the CPU arm of the real-data rows replays (bounded sample)")
     return ap.parse_args()
 
 
@@ -203,6 +206,10 @@ def reference_arm(args):
     if not args.no_gn:
         blk, _, _ = gn_cpu()
         line["gn"] = {"impl": "reference", "metric": "GN iters/sec (50k-node SE2 graph)", **blk}
+    if not args.no_bag:
+        rd = real_data(args, with_gpu=False)
+        if rd is not None:
+            line["real_data"] = rd
     print(json.dumps(line))
 
 
@@ -442,6 +449,64 @@ def gn_cpu(n_iters=PARITY_ITERS):
 
 
 # ------------------------------------------------------------------------------------------------
+# Real data (BASELINE cfgs 0-2): what the product actually calls, per keyframe
+# ------------------------------------------------------------------------------------------------
+def bag_rows(kind, n_keyframes, device=0):
+    """Replays robot_0 of the reference's 2robots-hospital bag through the REFERENCE'S OWN GraphSLAM
+    (src/slam + src/matcher/scan_matcher.cpp compiled verbatim, tests/cpp/ref_replay.cpp;
+    srslam.cpp:190-221): kind "gpu" = over include/cgm/chargrid.hpp + include/g2o_compat +
+    libcgmrslam_b200.so, kind "cpu" = over the reference's chargrid.cpp and the CPU oracle solver.
+    Returns per-keyframe latencies in ms, averaged over windows of the keyframe index."""
+    import tempfile
+    import replay_util
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_replay_" + kind)
+    fixture = os.path.join(ROOT, "tests", "golden", "bag_2robots_robot0_full.npz")
+    if not (os.path.exists(exe) and os.path.exists(fixture)):
+        return None
+    fx = np.load(fixture)
+    with tempfile.TemporaryDirectory() as d:
+        kf, res = os.path.join(d, "kf.txt"), os.path.join(d, "out.txt")
+        replay_util.write_keyframes(kf, fx, n_keyframes)
+        t0 = time.perf_counter()
+        subprocess.check_call([exe, kf, "-", "0", str(n_keyframes)], stdout=subprocess.DEVNULL,
+                              stderr=subprocess.DEVNULL, env=dict(os.environ, CGM_OUT=res, CGM_DEVICE=str(device)))
+        wall = time.perf_counter() - t0
+        frames, _, _ = replay_util.parse(open(res).read().splitlines())
+    ms = np.array([f["ms"] for f in frames[1:]])          # keyframe 0 only initialises
+    edges = np.cumsum([len(f["edges"]) for f in frames])[1:]
+    rows = []
+    for lo, hi in ((100, 200), (400, 500), (780, 880)):
+        if hi <= len(ms):
+            w = ms[lo:hi]
+            rows.append({"keyframes": [lo, hi], "graph_vertices": [lo + 1, hi], "graph_edges": int(edges[hi - 1]),
+                         "closeScanMatching_ms": float(w[:, 0].mean()),
+                         "findConstraints_ms": float(w[:, 1].mean()),
+                         "optimize5_ms": float(w[:, 2].mean()),
+                         "worst_keyframe_ms": float(w.sum(axis=1).max())})
+    return {"keyframes": len(frames), "wall_s": wall, "total_ms": {"closeScanMatching": float(ms[:, 0].sum()),
+            "findConstraints": float(ms[:, 1].sum()), "optimize5": float(ms[:, 2].sum())}, "rows": rows}
+
+
+def real_data(args, device=0, with_gpu=True):
+    out = {"what": "per-keyframe latency of the reference's own keyframe loop (srslam.cpp:190-221) on robot_0 of "
+                   "2robots-hospital.bag, 361-beam scans: closeScanMatching = addDataSM (24x24x65 candidates on "
+                   "the 1200^2 / 0.025 m grid, scan_matcher.cpp:148-151), findConstraints = optimize(1) + "
+                   "covariance gate (marginals) + loop-closure sweeps (10x30x65 x regions x 2, "
+                   "scan_matcher.cpp:230-254) + vote, optimize5 = initializeOptimization + optimize(5)",
+           "unit": "ms per keyframe (mean over the keyframe window)"}
+    if with_gpu:
+        out["gpu"] = bag_rows("gpu", 1 << 20, device)
+    out["cpu"] = bag_rows("cpu", args.bag_cpu_keyframes)
+    if out["cpu"] is not None:
+        out["cpu"]["what"] = ("the same reference sources over the reference's CPU matcher (chargrid.cpp, up to 4 "
+                              "OpenMP threads) and the compiled CPU solver oracle (not g2o); first %d keyframes"
+                              % args.bag_cpu_keyframes)
+    if out.get("gpu") is None and out["cpu"] is None:
+        return None
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
 def ours(args):
@@ -639,6 +704,10 @@ def ours(args):
                                 "chi2_gpu": [float(x) for x in par_chi2],
                                 "chi2_cpu": [float(x) for x in cpu_chi2]}
                 assert par_done == PARITY_ITERS and gn["parity_max_abs"] <= 1e-6, gn["parity_max_abs"]
+            if not args.no_bag:
+                rd = real_data(args, local)
+                if rd is not None:
+                    line["real_data"] = rd
         if gn is not None:
             gn.pop("_parity", None)
         if gn is not None:

@@ -36,6 +36,7 @@
 #include <vector>
 
 #include "../cgm_matcher.h"
+#include "device.hpp"
 #include "eigen_lite.hpp"
 
 typedef std::vector<Eigen::Vector2i, Eigen::aligned_allocator<Eigen::Vector2i> > Vector2iVector;
@@ -93,13 +94,6 @@ inline bool ok(int rc, const char* what) {
   if (rc == CGM_OK) return true;
   std::cerr << "cgm: " << what << " failed: " << cgm_last_error() << std::endl;
   return false;
-}
-
-// The CUDA device new CharGrid / SparseOptimizer objects are created on (one process per GPU
-// normally selects it with CUDA_VISIBLE_DEVICES; CGM_DEVICE overrides the default of 0).
-inline int& default_device() {
-  static int device = std::getenv("CGM_DEVICE") ? std::atoi(std::getenv("CGM_DEVICE")) : 0;
-  return device;
 }
 
 }  // namespace cgm

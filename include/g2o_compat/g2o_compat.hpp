@@ -27,6 +27,7 @@
 #include <string>
 #include <vector>
 
+#include "../cgm/device.hpp"
 #include "../cgm/eigen_lite.hpp"
 #include "../pgo_solver.h"
 
@@ -443,11 +444,18 @@ class SparseOptimizer : public OptimizableGraph {
   typedef std::vector<OptimizableGraph::Vertex*> VertexContainer;
   typedef std::vector<OptimizableGraph::Edge*> EdgeContainer;
 
-  explicit SparseOptimizer(int device = 0)
-      : solver_(nullptr), algorithm_(nullptr), verbose_(false), next_serial_(0), device_(device),
-        structure_dirty_(true) {}
+  explicit SparseOptimizer(int device = -1)
+      : solver_(nullptr), algorithm_(nullptr), verbose_(false), next_serial_(0),
+        device_(device >= 0 ? device : cgm::default_device()), structure_dirty_(true), use_clock_(0) {
+    for (int k = 0; k < kSolverSlots; ++k) {
+      slots_[k] = nullptr;
+      slot_key_[k] = 0;
+      slot_used_[k] = 0;
+    }
+  }
   ~SparseOptimizer() {
-    if (solver_) pgo_destroy(solver_);
+    for (int k = 0; k < kSolverSlots; ++k)
+      if (slots_[k]) pgo_destroy(slots_[k]);
     delete algorithm_;
     for (HyperGraph::EdgeSet::iterator it = edges_.begin(); it != edges_.end(); ++it) delete *it;
     for (VertexIDMap::iterator it = vertices_.begin(); it != vertices_.end(); ++it) delete it->second;
@@ -656,17 +664,12 @@ class SparseOptimizer : public OptimizableGraph {
       std::cerr << "SparseOptimizer: initializeOptimization has not been called" << std::endl;
       return false;
     }
-    if (!solver_ && pgo_create(&solver_, device_, nullptr) != PGO_OK) {
-      std::cerr << "SparseOptimizer: " << pgo_last_error() << std::endl;
-      solver_ = nullptr;
-      return false;
-    }
     const int nv = static_cast<int>(active_vertices_.size());
     const int ne = static_cast<int>(active_edges_.size());
     // fixed flags may change between calls (GraphManipulator::fixGauge): they are structure
     std::vector<uint8_t> fixed(nv);
     for (int i = 0; i < nv; ++i) fixed[i] = active_vertices_[i]->fixed() ? 1 : 0;
-    if (structure_dirty_ || fixed != last_fixed_) {
+    if (structure_dirty_ || fixed != last_fixed_ || !solver_) {
       active_index_.clear();
       for (int i = 0; i < nv; ++i) active_index_[active_vertices_[i]] = i;
       std::vector<int32_t> ei(ne), ej(ne);
@@ -674,6 +677,34 @@ class SparseOptimizer : public OptimizableGraph {
         ei[e] = active_index_[active_edges_[e]->vertex(0)];
         ej[e] = active_index_[active_edges_[e]->vertex(1)];
       }
+      // A keyframe alternates between two structures -- the graph with its own gauge
+      // (graph_slam.cpp:392-393,564-565) and the same graph with the newest vertex as the gauge
+      // (the covariance gate, graph_manipulator.cpp:116-145): one solver handle per structure, so
+      // that the second optimize() of a keyframe finds its analysis and its captured iteration
+      // graph still in place (pgo_set_graph recognises an unchanged structure).
+      uint64_t key = 1469598103934665603ull;
+      auto mix = [&key](uint64_t v) { key = (key ^ v) * 1099511628211ull; };
+      mix(static_cast<uint64_t>(nv));
+      mix(static_cast<uint64_t>(ne));
+      for (int i = 0; i < nv; ++i) mix(fixed[i]);
+      for (int e = 0; e < ne; ++e) mix((static_cast<uint64_t>(static_cast<uint32_t>(ei[e])) << 32) | static_cast<uint32_t>(ej[e]));
+      int slot = -1;
+      for (int k = 0; k < kSolverSlots; ++k)
+        if (slots_[k] && slot_key_[k] == key) slot = k;
+      if (slot < 0) {
+        slot = 0;
+        for (int k = 1; k < kSolverSlots; ++k)
+          if (slot_used_[k] < slot_used_[slot]) slot = k;  // least recently used (or still empty)
+      }
+      if (!slots_[slot] && pgo_create(&slots_[slot], device_, nullptr) != PGO_OK) {
+        std::cerr << "SparseOptimizer: " << pgo_last_error() << std::endl;
+        slots_[slot] = nullptr;
+        solver_ = nullptr;
+        return false;
+      }
+      solver_ = slots_[slot];
+      slot_key_[slot] = key;
+      slot_used_[slot] = ++use_clock_;
       if (pgo_set_graph(solver_, nv, ne, ei.data(), ej.data(), fixed.data()) != PGO_OK) {
         std::cerr << "SparseOptimizer: " << pgo_last_error() << std::endl;
         return false;
@@ -721,12 +752,17 @@ class SparseOptimizer : public OptimizableGraph {
   EdgeContainer active_edges_;
   std::map<const HyperGraph::Vertex*, int> active_index_;
   std::vector<uint8_t> last_fixed_;
-  pgo_solver* solver_;
+  static const int kSolverSlots = 2;
+  pgo_solver* slots_[kSolverSlots];
+  uint64_t slot_key_[kSolverSlots];
+  long long slot_used_[kSolverSlots];
+  pgo_solver* solver_;  // the slot of the current structure
   OptimizationAlgorithm* algorithm_;
   bool verbose_;
   long long next_serial_;
   int device_;
   bool structure_dirty_;
+  long long use_clock_;
 };
 
 // ---- C11: EdgeLabeler -----------------------------------------------------------------------------

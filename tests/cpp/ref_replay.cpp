@@ -10,11 +10,20 @@
 // every decision (which edges enter the graph, which closures are buffered / accepted: vertex
 // indices exact) and every estimate (1e-6).
 //
-// usage:  ref_replay keyframes.txt [graph.g2o [id_robot [n_keyframes]]]
+// The pipeline is chaotic at the float-ulp level (the matcher's window bounds are floats:
+// scan_matcher.cpp:147-150 turns a 1e-13 difference of an estimate into a 7e-9 difference of a
+// measurement now and then, and such differences eventually flip a discrete decision), so two
+// different solvers cannot be compared free-running over ~900 keyframes. They are compared in
+// LOCKSTEP instead: the GPU build dumps every vertex estimate after every keyframe (--dump), the
+// CPU build follows (--follow): at each keyframe it computes its own result from the same state,
+// reports how far it is from the GPU's (line "D k max|diff|") and then adopts the GPU's estimates.
+//
+// usage:  ref_replay keyframes.txt [graph.g2o [id_robot [n_keyframes [--dump|--follow states.bin]]]]
 // input:  n_beams first_angle step max_range laser_x laser_y laser_th min_inliers
 //         then one line per keyframe: odom_x odom_y odom_th r_1 ... r_n
 #include <algorithm>
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
@@ -74,6 +83,10 @@ int main(int argc, char** argv) {
   f >> nb >> first >> step >> maxr >> lx >> ly >> lth >> min_inliers;
   const int id_robot = argc > 3 ? std::atoi(argv[3]) : 0;
   const int limit = argc > 4 ? std::atoi(argv[4]) : 1 << 30;
+  FILE* dump = nullptr;
+  FILE* follow = nullptr;
+  if (argc > 6 && std::string(argv[5]) == "--dump") dump = std::fopen(argv[6], "wb");
+  if (argc > 6 && std::string(argv[5]) == "--follow") follow = std::fopen(argv[6], "rb");
   Probe gslam;
   gslam.setIdRobot(id_robot);  // vertex ids = id_robot * 10000 + k (graph_slam.cpp:92,157)
   gslam.setBaseId(10000);
@@ -109,9 +122,42 @@ int main(int argc, char** argv) {
       t_sm += t1 - t0;
       t_fc += t2 - t1;
       t_opt += t3 - t2;
+      printf("T %d %.4f %.4f %.4f\n", k, t1 - t0, t2 - t1, t3 - t2);  // ms: addDataSM, findConstraints, optimize(5)
       currEst = gslam.lastVertex()->estimate();  // srslam.cpp:214
     }
     odom_prev = odom;
+    if (dump) {  // every estimate after this keyframe
+      const int n = static_cast<int>(gslam.graph()->vertices().size());
+      std::fwrite(&n, sizeof n, 1, dump);
+      for (HyperGraph::VertexIDMap::const_iterator it = gslam.graph()->vertices().begin();
+           it != gslam.graph()->vertices().end(); ++it) {
+        const VertexSE2* v = static_cast<const VertexSE2*>(it->second);
+        const double rec[4] = {static_cast<double>(v->id()), v->estimate().translation().x(),
+                               v->estimate().translation().y(), v->estimate().rotation().angle()};
+        std::fwrite(rec, sizeof rec, 1, dump);
+      }
+    }
+    if (follow) {
+      int n = 0;
+      if (std::fread(&n, sizeof n, 1, follow) != 1 || n != static_cast<int>(gslam.graph()->vertices().size())) {
+        printf("D %d -1\n", k);  // the leader has a different vertex set: not comparable
+        return 4;
+      }
+      double worst = 0.0;
+      for (int i = 0; i < n; ++i) {
+        double rec[4];
+        if (std::fread(rec, sizeof rec, 1, follow) != 1) return 4;
+        VertexSE2* v = static_cast<VertexSE2*>(gslam.graph()->vertex(static_cast<int>(rec[0])));
+        if (!v) return 4;
+        const SE2 mine = v->estimate();
+        worst = std::max(worst, std::fabs(mine.translation().x() - rec[1]));
+        worst = std::max(worst, std::fabs(mine.translation().y() - rec[2]));
+        worst = std::max(worst, std::fabs(normalize_theta(mine.rotation().angle() - rec[3])));
+        v->setEstimate(SE2(rec[1], rec[2], rec[3]));
+      }
+      printf("D %d %.3e\n", k, worst);
+      currEst = gslam.lastVertex()->estimate();
+    }
     const SE2 est = gslam.lastVertex()->estimate();
     printf("K %d %d %.17g %.17g %.17g\n", k, gslam.lastVertex()->id(), est.translation().x(),
            est.translation().y(), est.rotation().angle());

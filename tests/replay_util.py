@@ -24,18 +24,27 @@ def parse(lines):
     """-> (frames: list of dict(est, edges [(from, to, xyz, w)], cands [(from, to, xyz)]), poses {id: xyz},
     times dict or None)."""
     frames, poses, times = [], {}, None
+    pending = None
+    pending_t = None
     for ln in lines:
         tok = ln.split()
         if not tok:
             continue
         if tok[0] == "K":
-            frames.append({"id": int(tok[2]), "est": np.array([float(x) for x in tok[3:6]]), "edges": [], "cands": []})
+            frames.append({"id": int(tok[2]), "est": np.array([float(x) for x in tok[3:6]]), "edges": [], "cands": [],
+                           "follow_diff": pending, "ms": pending_t})
+            pending = None
+            pending_t = None
         elif tok[0] == "E":
             frames[-1]["edges"].append((int(tok[1]), int(tok[2]), np.array([float(x) for x in tok[3:6]]), float(tok[6])))
         elif tok[0] == "C":
             frames[-1]["cands"].append((int(tok[1]), int(tok[2]), np.array([float(x) for x in tok[3:6]])))
         elif tok[0] == "P":
             poses[int(tok[1])] = np.array([float(x) for x in tok[2:5]])
+        elif tok[0] == "T":
+            pending_t = [float(x) for x in tok[2:5]]
+        elif tok[0] == "D":
+            pending = float(tok[2])      # printed before the K line of its keyframe
         elif tok[0] == "TIMES_MS":
             times = {tok[i]: float(tok[i + 1]) for i in range(1, len(tok) - 1, 2)}
     return frames, poses, times
