@@ -56,6 +56,11 @@ struct Params {
   const Incidence* inc;
   const int* ff_edges;
   int n_ff;
+  // warp-cooperative linearisation: incidence entries regrouped per warp (see gn_linearise)
+  const int4* winc;      // {edge, pos, p, role | count_chi2 << 1}
+  const int* wg_ptr;     // [n_wgroups + 1] entry ranges; a range of more than 32 entries is ONE vertex
+  const int* wg_info;    // bit 0: some vertex of the group has two entries with one pos (parallel edges)
+  int n_wgroups;
   double* poses;
   const double* meas;
   const double* info6;
@@ -279,68 +284,9 @@ __device__ double block_sum(double v, double* scratch) {
   return r;
 }
 
-// ---- phase 1: linearise ------------------------------------------------------------------------
-template <bool kTab>
-__device__ void phase_linearise(const Params& P) {
-  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
-  double chi = 0.0;
-  for (int p = tid; p < P.n; p += nthreads) {
-    double diag[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, b[3] = {0, 0, 0};
-    for (int t = P.inc_ptr[p]; t < P.inc_ptr[p + 1]; ++t) {
-      const Incidence inc = P.inc[t];
-      const int edge = inc.edge_role >> 1, role = inc.edge_role & 1;
-      EdgeLin L;
-      if (kTab) linearise_edge_tab(P, edge, &L);
-      else linearise_edge(P, edge, &L);
-      const double* jo = role ? L.jj : L.ji;  // this vertex
-      const double* jx = role ? L.ji : L.jj;  // the other one
-      double A[9];                            // Jo^T Omega
-#pragma unroll
-      for (int r = 0; r < 3; ++r)
-#pragma unroll
-        for (int c = 0; c < 3; ++c)
-          A[3 * r + c] = jo[r] * L.om[c] + jo[3 + r] * L.om[3 + c] + jo[6 + r] * L.om[6 + c];
-#pragma unroll
-      for (int r = 0; r < 3; ++r) {
-#pragma unroll
-        for (int c = 0; c < 3; ++c)
-          diag[3 * r + c] += A[3 * r] * jo[c] + A[3 * r + 1] * jo[3 + c] + A[3 * r + 2] * jo[6 + c];
-        b[r] -= A[3 * r] * L.e[0] + A[3 * r + 1] * L.e[1] + A[3 * r + 2] * L.e[2];
-      }
-      if (inc.pos >= 0) {
-        // block (row = other vertex, column = this vertex) += Jx^T Omega Jo = (A Jx)^T
-        double* dst = P.M + 9 * static_cast<size_t>(inc.pos);
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
-#pragma unroll
-          for (int c = 0; c < 3; ++c)
-            dst[3 * c + r] += A[3 * r] * jx[c] + A[3 * r + 1] * jx[3 + c] + A[3 * r + 2] * jx[6 + c];
-      }
-      // each edge's chi2 is counted by its i-side visit, or by the j-side one when i is fixed
-      if (role == 0 || P.vpos[P.edge_i[edge]] < 0) chi += edge_chi2(L);
-    }
-    double* d = P.M + 9 * static_cast<size_t>(P.col_ptr[p]);
-#pragma unroll
-    for (int i = 0; i < 9; ++i) d[i] = diag[i];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) P.rhs[3 * p + i] = b[i];
-  }
-  for (int t = tid; t < P.n_ff; t += nthreads) {
-    EdgeLin L;
-    if (kTab) linearise_edge_tab(P, P.ff_edges[t], &L);
-    else linearise_edge(P, P.ff_edges[t], &L);
-    chi += edge_chi2(L);
-  }
-  // one partial per WARP, in a fixed order: no CTA barrier, a warp retires as soon as its own
-  // vertices are done (degrees differ by several times)
-  for (int o = 16; o; o >>= 1) chi += __shfl_down_sync(0xffffffffu, chi, o);
-  if ((threadIdx.x & 31) == 0) P.chi2_partial[blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)] = chi;
-
-}
-
+// ---- phase 1: linearise (gn_linearise below) -----------------------------------------------------
 const int kThreads = 256;
-// linearise: one vertex per thread, degrees differ by several times: small CTAs keep the wait for
-// the heaviest vertex of a CTA (its chi2 reduction is a barrier) short
+// linearise: one warp per group of vertices (<= 32 incidences), 4 warps per CTA
 const int kLinThreads = 128;
 
 // ---- supernodal single-GPU iteration (pgo_supernodal.h) ------------------------------------------
@@ -360,6 +306,7 @@ struct WarpGroup {
 };
 
 const int kCtaThreads = 256;   // CTA tasks
+const int kDiagThreads = 128;  // diagonal tasks: a chain of short steps over <= 136 block pairs
 const int kUpdateThreads = 128;  // outer-product tiles: 4 warps, two 8-row strips each
 const int kWarpsPerCta = 4;    // warp tasks: 4 per CTA
 
@@ -367,12 +314,62 @@ __device__ __forceinline__ bool sn_failed(const SNView& V) {
   return *reinterpret_cast<volatile int*>(V.status) != 0;
 }
 
-// fa: panel factorisation, one CTA per (panel, row chunk)
-__global__ void __launch_bounds__(kCtaThreads) sn_k_factor(SNView V, const Task* tasks) {
+__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b);
+
+// fd: diagonal part of a big panel (block L D L^T + the inverse R of its unit triangular factor),
+// one CTA per panel
+__global__ void __launch_bounds__(kDiagThreads) sn_k_diag(SNView V, const Task* tasks) {
   extern __shared__ double sm[];
   V = sn_at_instance(V, blockIdx.y);
   if (sn_failed(V)) return;
-  sn_task_factor(CtaGroup(), V, tasks[blockIdx.x], sm);
+  sn_task_diag(CtaGroup(), V, tasks[blockIdx.x], sm);
+}
+
+// The row tasks' GEMM  raw <- raw R  on the fp64 tensor cores (mma.sync.m8n8k4.f64): every warp
+// owns strips of 8 scalar rows; it reads a strip's A fragments (all k) into registers, multiplies
+// with the B fragments of R^T (staged [n][k] with a leading dimension = 4 mod 16: conflict-free) one
+// 8-column tile at a time, skipping the k steps below the diagonal (R is upper triangular), and
+// writes the tile back in place -- no other warp touches those rows.
+struct RowsMulDmma {
+  template <class G>
+  __device__ __forceinline__ void operator()(const G&, double* raw, int S, int nrows, const double* Rt, int ldr,
+                                             int w) const {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int fr = lane >> 2, fk = lane & 3;
+    const int n3 = 3 * w, k4 = (n3 + 3) >> 2, n_tiles = (n3 + 7) >> 3, n_rows = 3 * nrows;
+    for (int strip = warp; 8 * strip < n_rows; strip += nw) {
+      const int row = 8 * strip + fr;
+      double a[12];
+#pragma unroll
+      for (int ks = 0; ks < 12; ++ks) {
+        const int k = 4 * ks + fk;
+        a[ks] = k < n3 ? raw[(k / 3) * S + 3 * row + (k % 3)] : 0.0;
+      }
+      __syncwarp();
+      for (int j = 0; j < n_tiles; ++j) {
+        double c0 = 0.0, c1 = 0.0;
+        const double* bp = Rt + (8 * j + fr) * ldr + fk;
+        const int ks_end = min(k4, 2 * j + 2);
+#pragma unroll
+        for (int ks = 0; ks < 12; ++ks)
+          if (ks < ks_end) dmma884(c0, c1, a[ks], bp[4 * ks]);
+        if (row < n_rows) {
+          const int n = 8 * j + 2 * fk;
+          if (n < n3) raw[(n / 3) * S + 3 * row + (n % 3)] = c0;
+          if (n + 1 < n3) raw[((n + 1) / 3) * S + 3 * row + ((n + 1) % 3)] = c1;
+        }
+      }
+    }
+    __syncthreads();
+  }
+};
+
+// fa: rows below a big panel, one CTA per (panel, row chunk)
+__global__ void __launch_bounds__(kCtaThreads) sn_k_rows(SNView V, const Task* tasks) {
+  extern __shared__ double sm[];
+  V = sn_at_instance(V, blockIdx.y);
+  if (sn_failed(V)) return;
+  sn_task_rows(CtaGroup(), V, tasks[blockIdx.x], sm, RowsMulDmma());
 }
 // fb: outer-product tiles, one CTA per tile, on the fp64 tensor cores.
 //   C[3 ti x 3 tj] = A[3 ti x 3 w] * B[3 w x 3 tj],  A = the scaled blocks Y(a,t) = M(a,t) Dinv_t of
@@ -419,14 +416,6 @@ __device__ __forceinline__ void update_tile(const SNView& V, const Task& T, doub
   const int lx = tid & 31, wy = tid >> 5, ny = nthr >> 5;
   const int lane = lx, warp = wy, fr = lane >> 2, fk = lane & 3;
   const int mt = (3 * ni + 7) / 8;
-  if (i0 == 0 && j0 == 0 && q_last == T.id && last.scratch >= 0) {  // move a scratch-published diagonal part into place
-    const int w = last.w, len = w + m;
-    const double* src = V.scratch + 9 * static_cast<size_t>(last.scratch);
-    for (int idx = tid; idx < w * w * 9; idx += nthr) {
-      const int i = idx / (w * 9), t = (idx / 9) % w, k = idx % 9;
-      if (i >= t) V.M[9 * static_cast<size_t>(sn_colpos(last.base, len, t) + (i - t)) + k] = __ldcg(src + idx);
-    }
-  }
   // scatter positions of the tile's block pairs: the column's two look-ups once per lane, then one
   // independent look-up per row (all staging loops are two-dimensional: no integer division)
   if (lx < tj) {
@@ -473,7 +462,7 @@ __device__ __forceinline__ void update_tile(const SNView& V, const Task& T, doub
         const bool is_a = gidx < nga;
         const int blk = 8 * (is_a ? gidx : gidx - nga) + al_l;
         if (blk >= (is_a ? ni : nj)) continue;
-        const double* base = (is_a ? V.Y + 9 * static_cast<size_t>(i0) : V.M + 9 * static_cast<size_t>(j0)) + 9 * blk;
+        const double* base = V.M + 9 * static_cast<size_t>(is_a ? i0 : j0) + 9 * blk;
         double* drow = (is_a ? As : Bt) + 3 * blk * ldk;
         for (int t = t_l; t < w; t += 4) {
           const size_t col = static_cast<size_t>(sn_colpos(pd.base, len, t) + (w - t) + off);
@@ -487,6 +476,25 @@ __device__ __forceinline__ void update_tile(const SNView& V, const Task& T, doub
       }
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+    // A = Y = M Dinv: scale the staged A blocks by the panel's Dinv_t (block (al, t) of As; lanes run
+    // over al so that a warp shares t and the nine Dinv loads are broadcasts)
+    for (int idx = tid; idx < ti * w; idx += nthr) {
+      const int al = idx % ti, t = idx / ti;
+      if (al >= ni) continue;
+      const double* dv = V.Dinv + 9 * static_cast<size_t>(pd.c0 + t);
+      double* blk = As + 3 * al * ldk + 3 * t;
+      double dd[9];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) dd[k] = __ldcg(dv + k);
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        const double m0 = blk[r * ldk], m1 = blk[r * ldk + 1], m2 = blk[r * ldk + 2];
+        blk[r * ldk] = m0 * dd[0] + m1 * dd[3] + m2 * dd[6];
+        blk[r * ldk + 1] = m0 * dd[1] + m1 * dd[4] + m2 * dd[7];
+        blk[r * ldk + 2] = m0 * dd[2] + m1 * dd[5] + m2 * dd[8];
+      }
+    }
     __syncthreads();
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -579,11 +587,136 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) sn_k_fwd_rows(SNView V, con
   sn_forward_rows(WarpGroup(), V, tasks[i].id, tasks[i].r0, tasks[i].r1, nullptr);
 }
 
-// linearise + chi2 (phase 1) as plain kernels
+// linearise + assemble (phase 1): g2o's EdgeSE2::linearizeOplus + constructQuadraticForm + buildSystem
+//  as ONE warp-cooperative kernel. Every incidence (edge, end) is one lane: the lane
+// evaluates the edge (error, both Jacobians: sines / cosines come from the gn_trig table, edge data
+// are 72-byte gathers) and forms its contribution to the Hessian row of its own end -- the diagonal
+// block, the right-hand side, and the off-diagonal block this end owns. Lanes are laid out so that
+// the incidences of a vertex are consecutive (host: dev_set_structure), and the contributions are
+// summed per vertex with a segmented warp-shuffle reduction (5 shuffle steps, fixed order: bitwise
+// reproducible); only the head lane of a vertex writes H_pp and b_p. Off-diagonal blocks have one
+// contributing lane each and are written directly -- except parallel edges (two constraints between
+// one pair of vertices), whose lanes are adjacent and go through the same reduction keyed by the
+// block position. No atomics. A vertex of degree > 32 is a group of its own, reduced round by round.
+__device__ __forceinline__ double shfl_down_d(double v, int off) { return __shfl_down_sync(0xffffffffu, v, off); }
+
 __global__ void __launch_bounds__(kLinThreads) gn_linearise(Params P) {
   P = params_at(P, blockIdx.y);
   if (*reinterpret_cast<volatile int*>(P.status) != 0) return;
-  phase_linearise<true>(P);
+  const int lane = threadIdx.x & 31, g = blockIdx.x * (kLinThreads / 32) + (threadIdx.x >> 5);
+  double chi = 0.0;
+  if (g < P.n_wgroups) {
+    const int e0 = P.wg_ptr[g], e1 = P.wg_ptr[g + 1];
+    const bool dup = P.wg_info[g] & 1, big = e1 - e0 > 32;
+    double carry[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // lane 0 of a big vertex: h00 h10 h11 h20 h21 h22 b0 b1 b2
+    int p_big = -1;
+    for (int base = e0; base < e1; base += 32) {
+      const int idx = base + lane;
+      const bool act = idx < e1;
+      int4 en = make_int4(0, -1, -2 - lane, 0);
+      if (act) en = P.winc[idx];
+      double v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, off[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+      if (act) {
+        EdgeLin L;
+        linearise_edge_tab(P, en.x, &L);
+        const bool role = en.w & 1;
+        const double* jo = role ? L.jj : L.ji;  // this vertex
+        const double* jx = role ? L.ji : L.jj;  // the other one
+        double A[9];                            // Jo^T Omega
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+            A[3 * r + c] = jo[r] * L.om[c] + jo[3 + r] * L.om[3 + c] + jo[6 + r] * L.om[6 + c];
+        int k = 0;
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+          for (int c = 0; c <= r; ++c)  // lower triangle of Jo^T Omega Jo
+            v[k++] = A[3 * r] * jo[c] + A[3 * r + 1] * jo[3 + c] + A[3 * r + 2] * jo[6 + c];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) v[6 + r] = -(A[3 * r] * L.e[0] + A[3 * r + 1] * L.e[1] + A[3 * r + 2] * L.e[2]);
+        if (en.y >= 0)  // block (row = other vertex, column = this vertex) = Jx^T Omega Jo = (A Jx)^T
+#pragma unroll
+          for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+              off[3 * c + r] = A[3 * r] * jx[c] + A[3 * r + 1] * jx[3 + c] + A[3 * r + 2] * jx[6 + c];
+        if (en.w & 2) chi += edge_chi2(L);
+      }
+      // per-vertex sums: segmented reduction over the lanes with the same p
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int pk = __shfl_down_sync(0xffffffffu, en.z, o);
+        const bool take = lane + o < 32 && pk == en.z;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+          const double other = shfl_down_d(v[i], o);
+          if (take) v[i] += other;
+        }
+      }
+      if (dup) {  // parallel edges: the same with the block position as the key
+        int key = en.y >= 0 ? en.y : -2 - lane;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int pk = __shfl_down_sync(0xffffffffu, key, o);
+          const bool take = lane + o < 32 && pk == key;
+#pragma unroll
+          for (int i = 0; i < 9; ++i) {
+            const double other = shfl_down_d(off[i], o);
+            if (take) off[i] += other;
+          }
+        }
+        const int prev = __shfl_up_sync(0xffffffffu, key, 1);
+        if (lane > 0 && prev == key) en.y = -1;  // not the head of its run: nothing to write
+      }
+      if (act && en.y >= 0) {
+        double* dst = P.M + 9 * static_cast<size_t>(en.y);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) dst[i] = off[i];
+      }
+      const int prev_p = __shfl_up_sync(0xffffffffu, en.z, 1);
+      const bool head = act && (lane == 0 || prev_p != en.z);
+      if (big) {
+        if (lane == 0) {
+          p_big = en.z;
+#pragma unroll
+          for (int i = 0; i < 9; ++i) carry[i] += v[i];
+        }
+      } else if (head) {
+        double* d = P.M + 9 * static_cast<size_t>(P.col_ptr[en.z]);
+        d[0] = v[0];
+        d[1] = d[3] = v[1];
+        d[4] = v[2];
+        d[2] = d[6] = v[3];
+        d[5] = d[7] = v[4];
+        d[8] = v[5];
+        P.rhs[3 * en.z] = v[6];
+        P.rhs[3 * en.z + 1] = v[7];
+        P.rhs[3 * en.z + 2] = v[8];
+      }
+    }
+    if (big && lane == 0) {
+      double* d = P.M + 9 * static_cast<size_t>(P.col_ptr[p_big]);
+      d[0] = carry[0];
+      d[1] = d[3] = carry[1];
+      d[4] = carry[2];
+      d[2] = d[6] = carry[3];
+      d[5] = d[7] = carry[4];
+      d[8] = carry[5];
+      P.rhs[3 * p_big] = carry[6];
+      P.rhs[3 * p_big + 1] = carry[7];
+      P.rhs[3 * p_big + 2] = carry[8];
+    }
+    // edges between two fixed vertices only add to chi2: dealt to the first groups, one per lane
+    for (int t = g * 32 + lane; t < P.n_ff; t += P.n_wgroups * 32) {
+      EdgeLin L;
+      linearise_edge_tab(P, P.ff_edges[t], &L);
+      chi += edge_chi2(L);
+    }
+  }
+  for (int o = 16; o; o >>= 1) chi += __shfl_down_sync(0xffffffffu, chi, o);
+  if (lane == 0) P.chi2_partial[blockIdx.x * (kLinThreads / 32) + (threadIdx.x >> 5)] = chi;
 }
 // sin / cos of every pose angle and every measurement angle of this iteration (see linearise_edge_tab)
 __global__ void gn_trig(Params P) {
@@ -607,17 +740,19 @@ __global__ void gn_chi2(Params P, int n_partials) {
   const double s = block_sum(v, scratch);
   if (threadIdx.x == 0) P.chi2_out[P.status[1]] = s;  // status[1] = iterations done so far
 }
-// VertexSE2::oplusImpl (C3); the last kernel of an iteration
+// VertexSE2::oplusImpl (C3); the last kernel of an iteration. One thread per pose scalar: the
+// estimates are read and written coalesced, the step x is gathered through vpos (L2-resident).
 __global__ void gn_update(Params P) {
   P = params_at(P, blockIdx.y);
   if (*reinterpret_cast<volatile int*>(P.status) != 0) return;
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p < P.n) {
-    const int v = P.perm_vertex[p];
-    double* q = P.poses + 3 * static_cast<size_t>(v);
-    q[0] += P.x[3 * p];
-    q[1] += P.x[3 * p + 1];
-    q[2] = normalize_theta(q[2] + P.x[3 * p + 2]);
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < 3 * P.n_vertices) {
+    const int v = t / 3, k = t - 3 * v;
+    const int p = P.vpos[v];
+    if (p >= 0) {
+      const double q = P.poses[t] + P.x[3 * static_cast<size_t>(p) + k];
+      P.poses[t] = k == 2 ? normalize_theta(q) : q;
+    }
   }
 }
 __global__ void gn_count_iteration(Params P) {  // one thread per instance
@@ -787,11 +922,13 @@ struct DeviceSolver {
   uint64_t launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaStream_t aux = nullptr, aux2 = nullptr, aux3 = nullptr;  // further branches while capturing the iteration graph
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr, ev_join3 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_fork2 = nullptr, ev_join = nullptr, ev_join2 = nullptr, ev_join3 = nullptr;
   Params P;
   bool have_structure = false, have_values = false, have_factor = false;
   Buf<int> edge_i, edge_j, vpos, inc_ptr, ff_edges, col_ptr, row_idx, perm_vertex, status, scratch_i;
   Buf<Incidence> inc;
+  Buf<int4> winc;
+  Buf<int> wg_ptr, wg_info;
   Buf<unsigned long long> stamps;
   double stage_ms[5] = {0, 0, 0, 0, 0};
   Buf<double> poses, meas, info6, M, Dinv, rhs, u, x, chi2_partial, chi2_out, many_rhs, scratch_d, trig;
@@ -801,7 +938,7 @@ struct DeviceSolver {
   // separator panels [1] (domain decomposition)
   struct TaskSet {
     Supernodal::Lists L;   // host copy: level pointers and launch geometry
-    Buf<Task> ff, fa, fb, ss, sa, sf, sb;
+    Buf<Task> ff, fd, fa, fb, ss, sa, sf, sb;
   } sets[2];
   // [0]: the whole iteration (single GPU) or the local stage; [1]: the shared stage
   cudaGraph_t graph[2] = {nullptr, nullptr};
@@ -813,7 +950,6 @@ struct DeviceSolver {
   Buf<PanelDesc> pn_desc;
   Buf<SuperDesc> sn_desc;
   Buf<double> diag_scratch;
-  Buf<double> Y;
   Buf<double> many_u, many_x;  // substitution vectors of the marginals (u / x never move)
   // domain decomposition
   DDParams D;
@@ -846,7 +982,8 @@ int dev_create(DeviceSolver** out, int device, void* stream, std::string* err) {
     const int cta_bytes = static_cast<int>(sizeof(double) * kCtaSmemDoubles);
     const int warp_bytes = static_cast<int>(sizeof(double) * (std::max(kWarpSmemDoubles, kWarpSubstDoubles) + 1) *
                                             kWarpsPerCta);
-    const void* cta_kernels[] = {reinterpret_cast<const void*>(sn_k_factor), reinterpret_cast<const void*>(sn_k_update),
+    const void* cta_kernels[] = {reinterpret_cast<const void*>(sn_k_diag), reinterpret_cast<const void*>(sn_k_rows),
+                                 reinterpret_cast<const void*>(sn_k_update),
                                  reinterpret_cast<const void*>(sn_k_bwd_tri), reinterpret_cast<const void*>(sn_k_fwd_tri)};
     for (size_t i = 0; i < sizeof(cta_kernels) / sizeof(cta_kernels[0]) && e == cudaSuccess; ++i)
       e = cudaFuncSetAttribute(cta_kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, cta_bytes);
@@ -869,6 +1006,7 @@ int dev_create(DeviceSolver** out, int device, void* stream, std::string* err) {
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d->aux2, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d->aux3, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->ev_fork, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->ev_fork2, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->ev_join, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->ev_join2, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->ev_join3, cudaEventDisableTiming);
@@ -901,12 +1039,11 @@ void dev_destroy(DeviceSolver* d) {
   d->sn_desc.release();
   for (size_t i = 0; i < sizeof(sb) / sizeof(sb[0]); ++i) sb[i]->release();
   for (int k = 0; k < 2; ++k) {
-    Buf<Task>* tb[] = {&d->sets[k].ff, &d->sets[k].fa, &d->sets[k].fb, &d->sets[k].ss,
+    Buf<Task>* tb[] = {&d->sets[k].ff, &d->sets[k].fd, &d->sets[k].fa, &d->sets[k].fb, &d->sets[k].ss,
                        &d->sets[k].sa, &d->sets[k].sf, &d->sets[k].sb};
     for (size_t i = 0; i < sizeof(tb) / sizeof(tb[0]); ++i) tb[i]->release();
   }
   d->diag_scratch.release();
-  d->Y.release();
   d->many_u.release();
   d->many_x.release();
   for (int k = 0; k < 2; ++k) {
@@ -916,10 +1053,14 @@ void dev_destroy(DeviceSolver* d) {
     d->graph[k] = nullptr;
   }
   d->inc.release();
+  d->winc.release();
+  d->wg_ptr.release();
+  d->wg_info.release();
   d->stamps.release();
   d->owner.release();
   d->pose_x.release();
   if (d->ev_fork) cudaEventDestroy(d->ev_fork);
+  if (d->ev_fork2) cudaEventDestroy(d->ev_fork2);
   if (d->ev_join) cudaEventDestroy(d->ev_join);
   if (d->ev_join2) cudaEventDestroy(d->ev_join2);
   if (d->ev_join3) cudaEventDestroy(d->ev_join3);
@@ -946,6 +1087,50 @@ int dev_set_structure(DeviceSolver* d, const Symbolic& S, const GraphTables& G, 
   PGO_CUDA(d->inc_ptr.upload(G.inc_ptr, s));
   PGO_CUDA(d->inc.upload(G.inc, s));
   PGO_CUDA(d->ff_edges.upload(G.ff_edges, s));
+  // warp groups of the linearisation: whole vertices, <= 32 incidences per group (a vertex of higher
+  // degree is a group of its own); inside a vertex the entries are ordered by the off-diagonal block
+  // they own, so that parallel edges sit next to each other
+  std::vector<int4> winc;
+  std::vector<int> wg_ptr(1, 0), wg_info;
+  {
+    winc.reserve(G.inc.size());
+    int in_group = 0, flags = 0;
+    auto close_group = [&]() {
+      if (static_cast<int>(winc.size()) > wg_ptr.back()) {
+        wg_ptr.push_back(static_cast<int>(winc.size()));
+        wg_info.push_back(flags);
+      }
+      in_group = 0;
+      flags = 0;
+    };
+    std::vector<int4> mine;
+    for (int p = 0; p < S.n; ++p) {
+      const int deg = G.inc_ptr[p + 1] - G.inc_ptr[p];
+      if (deg == 0) continue;
+      mine.clear();
+      for (int t = G.inc_ptr[p]; t < G.inc_ptr[p + 1]; ++t) {
+        const int edge = G.inc[t].edge_role >> 1, role = G.inc[t].edge_role & 1;
+        const int chi = role == 0 || G.vpos[G.edge_i[edge]] < 0 ? 1 : 0;  // every edge's chi2 once
+        mine.push_back(make_int4(edge, G.inc[t].pos, p, role | (chi << 1)));
+      }
+      std::stable_sort(mine.begin(), mine.end(), [](const int4& a, const int4& b) { return a.y < b.y; });
+      int dup = 0;
+      for (size_t k = 1; k < mine.size(); ++k) dup |= mine[k].y >= 0 && mine[k].y == mine[k - 1].y;
+      if (deg > 32 || in_group + deg > 32) close_group();
+      winc.insert(winc.end(), mine.begin(), mine.end());
+      in_group += deg;
+      flags |= dup;
+      if (deg > 32) close_group();
+    }
+    close_group();
+    if (wg_info.empty()) {  // no incidences at all: one empty group (it still sums the chi2 of fixed-fixed edges)
+      wg_ptr.push_back(0);
+      wg_info.push_back(0);
+    }
+  }
+  PGO_CUDA(d->winc.upload(winc, s));
+  PGO_CUDA(d->wg_ptr.upload(wg_ptr, s));
+  PGO_CUDA(d->wg_info.upload(wg_info, s));
   PGO_CUDA(d->col_ptr.upload(S.col_ptr, s));
   PGO_CUDA(d->row_idx.upload(S.row_idx, s));
   const Supernodal& N = S.sn;
@@ -959,6 +1144,7 @@ int dev_set_structure(DeviceSolver* d, const Symbolic& S, const GraphTables& G, 
     DeviceSolver::TaskSet& ts = d->sets[k];
     ts.L = N.lists(S.world == 1 ? (k == 0 ? Supernodal::kAllOwners : -3) : (k == 0 ? G.rank : -1));
     PGO_CUDA(ts.ff.upload(ts.L.ff, s));
+    PGO_CUDA(ts.fd.upload(ts.L.fd, s));
     PGO_CUDA(ts.fa.upload(ts.L.fa, s));
     PGO_CUDA(ts.fb.upload(ts.L.fb, s));
     PGO_CUDA(ts.ss.upload(ts.L.ss, s));
@@ -980,7 +1166,6 @@ int dev_set_structure(DeviceSolver* d, const Symbolic& S, const GraphTables& G, 
   // per-instance stride of the factor storage: a multiple of 32 doubles
   const size_t m_stride = (9 * static_cast<size_t>(S.nnzb) + 3 * n_shared + 8 + 31) / 32 * 32;
   PGO_CUDA(d->M.reserve(B * m_stride));
-  PGO_CUDA(d->Y.reserve(B * m_stride));
   PGO_CUDA(d->owner.upload(S.owner, s));
   PGO_CUDA(d->pose_x.reserve(3 * static_cast<size_t>(G.n_vertices)));
   PGO_CUDA(d->Dinv.reserve(B * 9 * static_cast<size_t>(S.n)));
@@ -999,6 +1184,10 @@ int dev_set_structure(DeviceSolver* d, const Symbolic& S, const GraphTables& G, 
   P.inc = d->inc.p;
   P.ff_edges = d->ff_edges.p;
   P.n_ff = static_cast<int>(G.ff_edges.size());
+  P.winc = d->winc.p;
+  P.wg_ptr = d->wg_ptr.p;
+  P.wg_info = d->wg_info.p;
+  P.n_wgroups = static_cast<int>(wg_info.size());
   P.poses = d->poses.p;
   P.meas = d->meas.p;
   P.info6 = d->info6.p;
@@ -1023,7 +1212,6 @@ int dev_set_structure(DeviceSolver* d, const Symbolic& S, const GraphTables& G, 
   V.tbl_off = d->tbl_off.p;
   V.tbl = d->tbl.p;
   V.M = d->M.p;
-  V.Y = d->Y.p;
   V.Dinv = d->Dinv.p;
   V.z = d->rhs.p;
   V.u = d->u.p;
@@ -1035,7 +1223,7 @@ int dev_set_structure(DeviceSolver* d, const Symbolic& S, const GraphTables& G, 
   V.s_vec = 3LL * S.n;
   V.s_scratch = static_cast<long long>(scratch_stride);
   V.s_status = 4;
-  d->lin_blocks = std::max(1, std::min(4 * d->sm_count, (S.n + kLinThreads - 1) / kLinThreads));
+  d->lin_blocks = (P.n_wgroups + kLinThreads / 32 - 1) / (kLinThreads / 32);  // one warp per group
   PGO_CUDA(d->chi2_out.reserve(B * kMaxItersPerCall));
   PGO_CUDA(d->chi2_partial.reserve(std::max(B * d->lin_blocks * (kLinThreads / 32), static_cast<size_t>(d->grid))));
   PGO_CUDA(d->status.reserve(4 * B));
@@ -1178,20 +1366,26 @@ static int enqueue_factor(DeviceSolver* d, const DeviceSolver::TaskSet& ts, int*
                                                                       stride);
       ++*nodes;
     }
-    // wide panels on the main branch, narrow ones (less shared memory: more CTAs per SM) beside them
+    // big panels: the diagonal parts first (they leave R for the row tasks)
+    const int n_fd = L.fd_ptr[l + 1] - L.fd_ptr[l];
+    if (n_fd) {
+      sn_k_diag<<<dim3(n_fd, B), kDiagThreads, sizeof(double) * L.fd_smem[l], st>>>(V, ts.fd.p + L.fd_ptr[l]);
+      ++*nodes;
+    }
+    // rows of wide panels on the main branch, of narrow ones (less shared memory: more CTAs per SM) beside them
     const int n_fal = L.fa_large[l], n_fas = n_fa - n_fal;
     cudaStream_t s_fas = st;
-    if (n_fas && n_fal) {
-      if (s_small == st && s_large == st) PGO_CUDA(cudaEventRecord(d->ev_fork, st));
-      PGO_CUDA(cudaStreamWaitEvent(d->aux3, d->ev_fork, 0));
+    if (n_fas && n_fal) {  // forks AFTER the diagonal tasks
+      PGO_CUDA(cudaEventRecord(d->ev_fork2, st));
+      PGO_CUDA(cudaStreamWaitEvent(d->aux3, d->ev_fork2, 0));
       s_fas = d->aux3;
     }
     if (n_fal) {
-      sn_k_factor<<<dim3(n_fal, B), kCtaThreads, sizeof(double) * L.fa_smem[l], st>>>(V, ts.fa.p + L.fa_ptr[l]);
+      sn_k_rows<<<dim3(n_fal, B), kCtaThreads, sizeof(double) * L.fa_smem[l], st>>>(V, ts.fa.p + L.fa_ptr[l]);
       ++*nodes;
     }
     if (n_fas) {
-      sn_k_factor<<<dim3(n_fas, B), kCtaThreads / 2, sizeof(double) * L.fa_smem_small[l], s_fas>>>(
+      sn_k_rows<<<dim3(n_fas, B), kCtaThreads / 2, sizeof(double) * L.fa_smem_small[l], s_fas>>>(
           V, ts.fa.p + L.fa_ptr[l] + n_fal);
       ++*nodes;
     }
@@ -1315,6 +1509,7 @@ static int enqueue_stage(DeviceSolver* d, int stage, std::string* err) {
     // the exchange tail behind it) and the backward accumulators
     PGO_CUDA(cudaMemsetAsync(P.M, 0, sizeof(double) * static_cast<size_t>(P.s_M) * B, st));
     PGO_CUDA(cudaMemsetAsync(P.x, 0, sizeof(double) * static_cast<size_t>(P.s_vec) * B, st));
+    if (!dd) PGO_CUDA(cudaMemsetAsync(P.rhs, 0, sizeof(double) * static_cast<size_t>(P.s_vec) * B, st));
     if (dd) gn_dd_linearise<<<d->lin_blocks, kThreads, 0, st>>>(P, d->D);
     else {
       gn_trig<<<dim3((P.n_vertices + P.n_edges + 255) / 256, B), 256, 0, st>>>(P);
@@ -1348,7 +1543,7 @@ static int enqueue_stage(DeviceSolver* d, int stage, std::string* err) {
     if (rc != PGO_OK) return rc;
     gn_stamp<<<1, 1, 0, st>>>(d->stamps.p, 4);
     if (dd) gn_dd_update<<<std::max(1, (P.n + 255) / 256), 256, 0, st>>>(P, d->D);
-    else gn_update<<<dim3(std::max(1, (P.n + 255) / 256), B), 256, 0, st>>>(P);
+    else gn_update<<<dim3(std::max(1, (3 * P.n_vertices + 255) / 256), B), 256, 0, st>>>(P);
     gn_count_iteration<<<1, B, 0, st>>>(P);
     gn_stamp<<<1, 1, 0, st>>>(d->stamps.p, 5);
     nodes += 6;
