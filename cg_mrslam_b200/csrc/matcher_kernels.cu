@@ -1,9 +1,9 @@
 // CUDA back-end of the scan matcher (sm_100a). Implements matcher_device.h.
 //
 // Kernels
-//   raster_tiles        resetGrid (scan_matcher.cpp:68-76) + addAndConvolvePoints/applyKernel
-//                       (chargrid.h:205-216, chargrid.cpp:132-161): one CTA per 32x128-cell tile,
-//                       min-stamping in shared memory, coalesced byte rows out.
+//   raster_bands        resetGrid (scan_matcher.cpp:68-76) + addAndConvolvePoints/applyKernel
+//                       (chargrid.h:205-216, chargrid.cpp:132-161): one CTA per band of whole grid
+//                       rows, min-stamping in shared memory, the band out as one bulk async copy.
 //   score_global        greedySearch inner loops (chargrid.cpp:239-287) straight from the
 //                       L2/L1-resident grid; any stride, any point extent. Reference kernel.
 //   score_tiled         the same arithmetic for stride-1 windows with the touched part of the
@@ -102,25 +102,41 @@ __device__ __forceinline__ void report(uint64_t* bins, const RegionDesc& reg, co
 // --------------------------------------------------------------------------------------------
 // raster
 // --------------------------------------------------------------------------------------------
-const int kTileR = 32, kTileC = 128, kRasterThreads = 256, kRasterBatch = 1024;
+const int kRasterThreads = 256, kRasterBatch = 1024;
 
+// One CTA per band of `band_rows` whole grid rows of one slot. The band lives in shared memory as
+// ints (min-stamping uses shared atomicMin), the slot's points are culled against the band's rows
+// ONCE (a 32 x 128 tile per CTA meant every point was tested by 132 CTAs; a band makes that 30),
+// and the finished band -- band_rows * pitch consecutive bytes of the slot -- leaves as ONE bulk
+// asynchronous copy (cp.async.bulk shared -> global through the TMA unit) from a byte staging
+// area. Shared memory: ints[band_rows][pitch] | bytes[band_rows][pitch].
 __global__ void __launch_bounds__(kRasterThreads)
-raster_tiles(uint8_t* grids, size_t slot_bytes, DevGeom g, int first_slot, const double* pts,
-             const int* pts_off, const uint8_t* stamp, int dim, int reset) {
-  __shared__ int tile[kTileR][kTileC];
+raster_bands(uint8_t* grids, size_t slot_bytes, DevGeom g, int first_slot, const double* pts,
+             const int* pts_off, const uint8_t* stamp, int dim, int reset, int band_rows) {
+  extern __shared__ __align__(128) uint8_t raster_smem[];
   __shared__ int2 list[kRasterBatch];
   __shared__ int n_list;
-  const int tiles_c = (g.cols + kTileC - 1) / kTileC;
-  const int r0 = (blockIdx.x / tiles_c) * kTileR, c0 = (blockIdx.x % tiles_c) * kTileC;
+  int* tile = reinterpret_cast<int*>(raster_smem);
+  const int pitch = g.pitch;
+  uint8_t* out = raster_smem + static_cast<size_t>(band_rows) * pitch * sizeof(int);
+  const int r0 = blockIdx.x * band_rows, nr = min(band_rows, g.rows - r0);
   const int slot = first_slot + blockIdx.y;
   uint8_t* grid = grids + static_cast<size_t>(slot) * slot_bytes;
   const int center = (dim - 1) / 2;
+  const int cells = nr * pitch;
 
-  for (int t = threadIdx.x; t < kTileR * kTileC; t += kRasterThreads) {
-    const int r = r0 + t / kTileC, c = c0 + t % kTileC;
-    int v = static_cast<uint8_t>(g.fill_value);
-    if (!reset && r < g.rows && c < g.cols) v = grid[static_cast<size_t>(r) * g.pitch + c];
-    tile[t / kTileC][t % kTileC] = v;
+  if (reset) {
+    const int v = static_cast<uint8_t>(g.fill_value);
+    for (int t = threadIdx.x; t < cells; t += kRasterThreads) tile[t] = v;
+  } else {  // stamp on top of what the slot holds: 4 cells per 32-bit load (pitch is a multiple of 16)
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(grid + static_cast<size_t>(r0) * pitch);
+    for (int t = threadIdx.x; t < cells / 4; t += kRasterThreads) {
+      const uint32_t w = src[t];
+      tile[4 * t] = w & 0xFF;
+      tile[4 * t + 1] = (w >> 8) & 0xFF;
+      tile[4 * t + 2] = (w >> 16) & 0xFF;
+      tile[4 * t + 3] = w >> 24;
+    }
   }
   const int p_begin = pts_off[blockIdx.y], p_end = pts_off[blockIdx.y + 1];
   for (int base = p_begin; base < p_end; base += kRasterBatch) {
@@ -133,9 +149,7 @@ raster_tiles(uint8_t* grids, size_t slot_bytes, DevGeom g, int first_slot, const
       const float gy = __fmul_rn(__fsub_rn(fy, g.lly), g.inv_res);
       if (!(fabsf(gx) < 1e9f) || !(fabsf(gy) < 1e9f)) continue;  // far outside: stamps nothing
       const int ix = __float2int_rn(gx), iy = __float2int_rn(gy);
-      if (ix + center < r0 || ix - center >= r0 + kTileR || iy + center < c0 ||
-          iy - center >= c0 + kTileC)
-        continue;
+      if (ix + center < r0 || ix - center >= r0 + nr || iy + center < 0 || iy - center >= g.cols) continue;
       list[atomicAdd(&n_list, 1)] = make_int2(ix, iy);
     }
     __syncthreads();
@@ -144,17 +158,31 @@ raster_tiles(uint8_t* grids, size_t slot_bytes, DevGeom g, int first_slot, const
       const int p = t / (dim * dim), cell = t % (dim * dim);
       const int i = cell / dim, j = cell % dim;
       const int r = list[p].x + i - center, c = list[p].y + j - center;  // chargrid.cpp:145-151
-      if (r < r0 || r >= r0 + kTileR || c < c0 || c >= c0 + kTileC) continue;
-      atomicMin(&tile[r - r0][c - c0], static_cast<int>(stamp[j * dim + i]));  // ker[j*kRows+i]
+      if (r < r0 || r >= r0 + nr || c < 0 || c >= g.cols) continue;
+      atomicMin(&tile[(r - r0) * pitch + c], static_cast<int>(stamp[j * dim + i]));  // ker[j*kRows+i]
     }
     __syncthreads();
   }
   __syncthreads();
-  for (int t = threadIdx.x; t < kTileR * kTileC; t += kRasterThreads) {
-    const int r = r0 + t / kTileC, c = c0 + t % kTileC;
-    if (r < g.rows && c < g.pitch)
-      grid[static_cast<size_t>(r) * g.pitch + c] =
-          c < g.cols ? static_cast<uint8_t>(tile[t / kTileC][t % kTileC]) : 0;
+  // bytes, 4 cells per thread and store; the pad columns cols .. pitch hold 0
+  for (int t = threadIdx.x; t < cells / 4; t += kRasterThreads) {
+    const int c = (4 * t) % pitch;
+    uint32_t w = 0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b)
+      if (c + b < g.cols) w |= static_cast<uint32_t>(tile[4 * t + b] & 0xFF) << (8 * b);
+    reinterpret_cast<uint32_t*>(out)[t] = w;
+  }
+  // make the generic-proxy writes visible to the async proxy, then one thread hands the band to TMA
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned src = static_cast<unsigned>(__cvta_generic_to_shared(out));
+    uint8_t* dst = grid + static_cast<size_t>(r0) * pitch;
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(cells)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // the band is in global memory when the CTA retires
   }
 }
 
@@ -330,6 +358,7 @@ struct DeviceMatcher {
   int stamp_dim = 0;
   int sm_count = 148;
   int smem_optin = 0;
+  size_t raster_smem_set = 0;
   // map stage
   DevBuf<double> map_pts;
   DevBuf<int> map_off;
@@ -551,13 +580,22 @@ int dev_launch_map(DeviceMatcher* d, std::string* err) {
   }
   CGM_CUDA(cudaSetDevice(d->device));
   if (d->map_n == 0) return CGM_OK;
-  const int tiles = ((d->geom.rows + kTileR - 1) / kTileR) * ((d->geom.cols + kTileC - 1) / kTileC);
+  // rows per band: as many as keep ints + bytes of a band within ~100 kB (two CTAs per SM)
+  int band_rows = std::min(32, std::max(1, static_cast<int>(100 * 1024 / (5 * static_cast<size_t>(d->geom.pitch)))));
+  if (band_rows > 8) band_rows &= ~7;
+  const int tiles = (d->geom.rows + band_rows - 1) / band_rows;
+  const size_t raster_smem_bytes = 5 * static_cast<size_t>(band_rows) * d->geom.pitch;
+  if (raster_smem_bytes > 48 * 1024 && raster_smem_bytes != d->raster_smem_set) {
+    CGM_CUDA(cudaFuncSetAttribute(raster_bands, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(raster_smem_bytes)));
+    d->raster_smem_set = raster_smem_bytes;
+  }
   CGM_CUDA(cudaEventRecord(d->ev[0], d->stream));
   for (int s0 = 0; s0 < d->map_n; s0 += 65535) {
     const int ns = std::min(65535, d->map_n - s0);
-    raster_tiles<<<dim3(tiles, ns), kRasterThreads, 0, d->stream>>>(
+    raster_bands<<<dim3(tiles, ns), kRasterThreads, raster_smem_bytes, d->stream>>>(
         d->grids, d->slot_bytes, d->dg, d->map_first + s0, d->map_pts.p, d->map_off.p + s0,
-        d->stamp, d->stamp_dim, d->map_reset ? 1 : 0);
+        d->stamp, d->stamp_dim, d->map_reset ? 1 : 0, band_rows);
     g_launches++;
   }
   CGM_CUDA(cudaGetLastError());

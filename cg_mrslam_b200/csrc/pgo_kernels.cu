@@ -306,7 +306,6 @@ struct WarpGroup {
 };
 
 const int kCtaThreads = 256;   // CTA tasks
-const int kDiagThreads = 128;  // diagonal tasks: a chain of short steps over <= 136 block pairs
 const int kUpdateThreads = 128;  // outer-product tiles: 4 warps, two 8-row strips each
 const int kWarpsPerCta = 4;    // warp tasks: 4 per CTA
 
@@ -314,62 +313,12 @@ __device__ __forceinline__ bool sn_failed(const SNView& V) {
   return *reinterpret_cast<volatile int*>(V.status) != 0;
 }
 
-__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b);
-
-// fd: diagonal part of a big panel (block L D L^T + the inverse R of its unit triangular factor),
-// one CTA per panel
-__global__ void __launch_bounds__(kDiagThreads) sn_k_diag(SNView V, const Task* tasks) {
+// fa: panel factorisation, one CTA per (panel, row chunk)
+__global__ void __launch_bounds__(kCtaThreads) sn_k_factor(SNView V, const Task* tasks) {
   extern __shared__ double sm[];
   V = sn_at_instance(V, blockIdx.y);
   if (sn_failed(V)) return;
-  sn_task_diag(CtaGroup(), V, tasks[blockIdx.x], sm);
-}
-
-// The row tasks' GEMM  raw <- raw R  on the fp64 tensor cores (mma.sync.m8n8k4.f64): every warp
-// owns strips of 8 scalar rows; it reads a strip's A fragments (all k) into registers, multiplies
-// with the B fragments of R^T (staged [n][k] with a leading dimension = 4 mod 16: conflict-free) one
-// 8-column tile at a time, skipping the k steps below the diagonal (R is upper triangular), and
-// writes the tile back in place -- no other warp touches those rows.
-struct RowsMulDmma {
-  template <class G>
-  __device__ __forceinline__ void operator()(const G&, double* raw, int S, int nrows, const double* Rt, int ldr,
-                                             int w) const {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    const int fr = lane >> 2, fk = lane & 3;
-    const int n3 = 3 * w, k4 = (n3 + 3) >> 2, n_tiles = (n3 + 7) >> 3, n_rows = 3 * nrows;
-    for (int strip = warp; 8 * strip < n_rows; strip += nw) {
-      const int row = 8 * strip + fr;
-      double a[12];
-#pragma unroll
-      for (int ks = 0; ks < 12; ++ks) {
-        const int k = 4 * ks + fk;
-        a[ks] = k < n3 ? raw[(k / 3) * S + 3 * row + (k % 3)] : 0.0;
-      }
-      __syncwarp();
-      for (int j = 0; j < n_tiles; ++j) {
-        double c0 = 0.0, c1 = 0.0;
-        const double* bp = Rt + (8 * j + fr) * ldr + fk;
-        const int ks_end = min(k4, 2 * j + 2);
-#pragma unroll
-        for (int ks = 0; ks < 12; ++ks)
-          if (ks < ks_end) dmma884(c0, c1, a[ks], bp[4 * ks]);
-        if (row < n_rows) {
-          const int n = 8 * j + 2 * fk;
-          if (n < n3) raw[(n / 3) * S + 3 * row + (n % 3)] = c0;
-          if (n + 1 < n3) raw[((n + 1) / 3) * S + 3 * row + ((n + 1) % 3)] = c1;
-        }
-      }
-    }
-    __syncthreads();
-  }
-};
-
-// fa: rows below a big panel, one CTA per (panel, row chunk)
-__global__ void __launch_bounds__(kCtaThreads) sn_k_rows(SNView V, const Task* tasks) {
-  extern __shared__ double sm[];
-  V = sn_at_instance(V, blockIdx.y);
-  if (sn_failed(V)) return;
-  sn_task_rows(CtaGroup(), V, tasks[blockIdx.x], sm, RowsMulDmma());
+  sn_task_factor(CtaGroup(), V, tasks[blockIdx.x], sm);
 }
 // fb: outer-product tiles, one CTA per tile, on the fp64 tensor cores.
 //   C[3 ti x 3 tj] = A[3 ti x 3 w] * B[3 w x 3 tj],  A = the scaled blocks Y(a,t) = M(a,t) Dinv_t of
@@ -416,6 +365,14 @@ __device__ __forceinline__ void update_tile(const SNView& V, const Task& T, doub
   const int lx = tid & 31, wy = tid >> 5, ny = nthr >> 5;
   const int lane = lx, warp = wy, fr = lane >> 2, fk = lane & 3;
   const int mt = (3 * ni + 7) / 8;
+  if (i0 == 0 && j0 == 0 && q_last == T.id && last.scratch >= 0) {  // move a scratch-published diagonal part into place
+    const int w = last.w, len = w + m;
+    const double* src = V.scratch + 9 * static_cast<size_t>(last.scratch);
+    for (int idx = tid; idx < w * w * 9; idx += nthr) {
+      const int i = idx / (w * 9), t = (idx / 9) % w, k = idx % 9;
+      if (i >= t) V.M[9 * static_cast<size_t>(sn_colpos(last.base, len, t) + (i - t)) + k] = __ldcg(src + idx);
+    }
+  }
   // scatter positions of the tile's block pairs: the column's two look-ups once per lane, then one
   // independent look-up per row (all staging loops are two-dimensional: no integer division)
   if (lx < tj) {
@@ -462,7 +419,7 @@ __device__ __forceinline__ void update_tile(const SNView& V, const Task& T, doub
         const bool is_a = gidx < nga;
         const int blk = 8 * (is_a ? gidx : gidx - nga) + al_l;
         if (blk >= (is_a ? ni : nj)) continue;
-        const double* base = V.M + 9 * static_cast<size_t>(is_a ? i0 : j0) + 9 * blk;
+        const double* base = (is_a ? V.Y + 9 * static_cast<size_t>(i0) : V.M + 9 * static_cast<size_t>(j0)) + 9 * blk;
         double* drow = (is_a ? As : Bt) + 3 * blk * ldk;
         for (int t = t_l; t < w; t += 4) {
           const size_t col = static_cast<size_t>(sn_colpos(pd.base, len, t) + (w - t) + off);
@@ -476,25 +433,6 @@ __device__ __forceinline__ void update_tile(const SNView& V, const Task& T, doub
       }
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
-    __syncthreads();
-    // A = Y = M Dinv: scale the staged A blocks by the panel's Dinv_t (block (al, t) of As; lanes run
-    // over al so that a warp shares t and the nine Dinv loads are broadcasts)
-    for (int idx = tid; idx < ti * w; idx += nthr) {
-      const int al = idx % ti, t = idx / ti;
-      if (al >= ni) continue;
-      const double* dv = V.Dinv + 9 * static_cast<size_t>(pd.c0 + t);
-      double* blk = As + 3 * al * ldk + 3 * t;
-      double dd[9];
-#pragma unroll
-      for (int k = 0; k < 9; ++k) dd[k] = __ldcg(dv + k);
-#pragma unroll
-      for (int r = 0; r < 3; ++r) {
-        const double m0 = blk[r * ldk], m1 = blk[r * ldk + 1], m2 = blk[r * ldk + 2];
-        blk[r * ldk] = m0 * dd[0] + m1 * dd[3] + m2 * dd[6];
-        blk[r * ldk + 1] = m0 * dd[1] + m1 * dd[4] + m2 * dd[7];
-        blk[r * ldk + 2] = m0 * dd[2] + m1 * dd[5] + m2 * dd[8];
-      }
-    }
     __syncthreads();
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -922,7 +860,7 @@ struct DeviceSolver {
   uint64_t launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaStream_t aux = nullptr, aux2 = nullptr, aux3 = nullptr;  // further branches while capturing the iteration graph
-  cudaEvent_t ev_fork = nullptr, ev_fork2 = nullptr, ev_join = nullptr, ev_join2 = nullptr, ev_join3 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_join2 = nullptr, ev_join3 = nullptr;
   Params P;
   bool have_structure = false, have_values = false, have_factor = false;
   Buf<int> edge_i, edge_j, vpos, inc_ptr, ff_edges, col_ptr, row_idx, perm_vertex, status, scratch_i;
@@ -938,7 +876,7 @@ struct DeviceSolver {
   // separator panels [1] (domain decomposition)
   struct TaskSet {
     Supernodal::Lists L;   // host copy: level pointers and launch geometry
-    Buf<Task> ff, fd, fa, fb, ss, sa, sf, sb;
+    Buf<Task> ff, fa, fb, ss, sa, sf, sb;
   } sets[2];
   // [0]: the whole iteration (single GPU) or the local stage; [1]: the shared stage
   cudaGraph_t graph[2] = {nullptr, nullptr};
@@ -950,6 +888,7 @@ struct DeviceSolver {
   Buf<PanelDesc> pn_desc;
   Buf<SuperDesc> sn_desc;
   Buf<double> diag_scratch;
+  Buf<double> Y;
   Buf<double> many_u, many_x;  // substitution vectors of the marginals (u / x never move)
   // domain decomposition
   DDParams D;
@@ -982,8 +921,7 @@ int dev_create(DeviceSolver** out, int device, void* stream, std::string* err) {
     const int cta_bytes = static_cast<int>(sizeof(double) * kCtaSmemDoubles);
     const int warp_bytes = static_cast<int>(sizeof(double) * (std::max(kWarpSmemDoubles, kWarpSubstDoubles) + 1) *
                                             kWarpsPerCta);
-    const void* cta_kernels[] = {reinterpret_cast<const void*>(sn_k_diag), reinterpret_cast<const void*>(sn_k_rows),
-                                 reinterpret_cast<const void*>(sn_k_update),
+    const void* cta_kernels[] = {reinterpret_cast<const void*>(sn_k_factor), reinterpret_cast<const void*>(sn_k_update),
                                  reinterpret_cast<const void*>(sn_k_bwd_tri), reinterpret_cast<const void*>(sn_k_fwd_tri)};
     for (size_t i = 0; i < sizeof(cta_kernels) / sizeof(cta_kernels[0]) && e == cudaSuccess; ++i)
       e = cudaFuncSetAttribute(cta_kernels[i], cudaFuncAttributeMaxDynamicSharedMemorySize, cta_bytes);
@@ -1006,7 +944,6 @@ int dev_create(DeviceSolver** out, int device, void* stream, std::string* err) {
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d->aux2, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d->aux3, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->ev_fork, cudaEventDisableTiming);
-  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->ev_fork2, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->ev_join, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->ev_join2, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->ev_join3, cudaEventDisableTiming);
@@ -1039,11 +976,12 @@ void dev_destroy(DeviceSolver* d) {
   d->sn_desc.release();
   for (size_t i = 0; i < sizeof(sb) / sizeof(sb[0]); ++i) sb[i]->release();
   for (int k = 0; k < 2; ++k) {
-    Buf<Task>* tb[] = {&d->sets[k].ff, &d->sets[k].fd, &d->sets[k].fa, &d->sets[k].fb, &d->sets[k].ss,
+    Buf<Task>* tb[] = {&d->sets[k].ff, &d->sets[k].fa, &d->sets[k].fb, &d->sets[k].ss,
                        &d->sets[k].sa, &d->sets[k].sf, &d->sets[k].sb};
     for (size_t i = 0; i < sizeof(tb) / sizeof(tb[0]); ++i) tb[i]->release();
   }
   d->diag_scratch.release();
+  d->Y.release();
   d->many_u.release();
   d->many_x.release();
   for (int k = 0; k < 2; ++k) {
@@ -1060,7 +998,6 @@ void dev_destroy(DeviceSolver* d) {
   d->owner.release();
   d->pose_x.release();
   if (d->ev_fork) cudaEventDestroy(d->ev_fork);
-  if (d->ev_fork2) cudaEventDestroy(d->ev_fork2);
   if (d->ev_join) cudaEventDestroy(d->ev_join);
   if (d->ev_join2) cudaEventDestroy(d->ev_join2);
   if (d->ev_join3) cudaEventDestroy(d->ev_join3);
@@ -1144,7 +1081,6 @@ int dev_set_structure(DeviceSolver* d, const Symbolic& S, const GraphTables& G, 
     DeviceSolver::TaskSet& ts = d->sets[k];
     ts.L = N.lists(S.world == 1 ? (k == 0 ? Supernodal::kAllOwners : -3) : (k == 0 ? G.rank : -1));
     PGO_CUDA(ts.ff.upload(ts.L.ff, s));
-    PGO_CUDA(ts.fd.upload(ts.L.fd, s));
     PGO_CUDA(ts.fa.upload(ts.L.fa, s));
     PGO_CUDA(ts.fb.upload(ts.L.fb, s));
     PGO_CUDA(ts.ss.upload(ts.L.ss, s));
@@ -1166,6 +1102,7 @@ int dev_set_structure(DeviceSolver* d, const Symbolic& S, const GraphTables& G, 
   // per-instance stride of the factor storage: a multiple of 32 doubles
   const size_t m_stride = (9 * static_cast<size_t>(S.nnzb) + 3 * n_shared + 8 + 31) / 32 * 32;
   PGO_CUDA(d->M.reserve(B * m_stride));
+  PGO_CUDA(d->Y.reserve(B * m_stride));
   PGO_CUDA(d->owner.upload(S.owner, s));
   PGO_CUDA(d->pose_x.reserve(3 * static_cast<size_t>(G.n_vertices)));
   PGO_CUDA(d->Dinv.reserve(B * 9 * static_cast<size_t>(S.n)));
@@ -1212,6 +1149,7 @@ int dev_set_structure(DeviceSolver* d, const Symbolic& S, const GraphTables& G, 
   V.tbl_off = d->tbl_off.p;
   V.tbl = d->tbl.p;
   V.M = d->M.p;
+  V.Y = d->Y.p;
   V.Dinv = d->Dinv.p;
   V.z = d->rhs.p;
   V.u = d->u.p;
@@ -1366,26 +1304,20 @@ static int enqueue_factor(DeviceSolver* d, const DeviceSolver::TaskSet& ts, int*
                                                                       stride);
       ++*nodes;
     }
-    // big panels: the diagonal parts first (they leave R for the row tasks)
-    const int n_fd = L.fd_ptr[l + 1] - L.fd_ptr[l];
-    if (n_fd) {
-      sn_k_diag<<<dim3(n_fd, B), kDiagThreads, sizeof(double) * L.fd_smem[l], st>>>(V, ts.fd.p + L.fd_ptr[l]);
-      ++*nodes;
-    }
-    // rows of wide panels on the main branch, of narrow ones (less shared memory: more CTAs per SM) beside them
+    // wide panels on the main branch, narrow ones (less shared memory: more CTAs per SM) beside them
     const int n_fal = L.fa_large[l], n_fas = n_fa - n_fal;
     cudaStream_t s_fas = st;
-    if (n_fas && n_fal) {  // forks AFTER the diagonal tasks
-      PGO_CUDA(cudaEventRecord(d->ev_fork2, st));
-      PGO_CUDA(cudaStreamWaitEvent(d->aux3, d->ev_fork2, 0));
+    if (n_fas && n_fal) {
+      if (s_small == st && s_large == st) PGO_CUDA(cudaEventRecord(d->ev_fork, st));
+      PGO_CUDA(cudaStreamWaitEvent(d->aux3, d->ev_fork, 0));
       s_fas = d->aux3;
     }
     if (n_fal) {
-      sn_k_rows<<<dim3(n_fal, B), kCtaThreads, sizeof(double) * L.fa_smem[l], st>>>(V, ts.fa.p + L.fa_ptr[l]);
+      sn_k_factor<<<dim3(n_fal, B), kCtaThreads, sizeof(double) * L.fa_smem[l], st>>>(V, ts.fa.p + L.fa_ptr[l]);
       ++*nodes;
     }
     if (n_fas) {
-      sn_k_rows<<<dim3(n_fas, B), kCtaThreads / 2, sizeof(double) * L.fa_smem_small[l], s_fas>>>(
+      sn_k_factor<<<dim3(n_fas, B), kCtaThreads / 2, sizeof(double) * L.fa_smem_small[l], s_fas>>>(
           V, ts.fa.p + L.fa_ptr[l] + n_fal);
       ++*nodes;
     }

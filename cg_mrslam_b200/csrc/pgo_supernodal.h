@@ -44,6 +44,8 @@ struct SNView {
   const int* tbl;
   // numeric
   double* M;        // [nnzb][9]
+  double* Y;        // [nnzb][9] Y(a,t) = M(a,t) Dinv_t for the rows below big panels (the scaled
+                    // operand of the outer products, written by the panel factorisation)
   double* Dinv;     // [n][9]
   double* z;        // [n][3] right-hand side, overwritten by the forward substitution
   double* u;        // [n][3]
@@ -58,6 +60,7 @@ struct SNView {
 // The view of instance b of a batch (blockIdx.y on the device).
 PGO_HD SNView sn_at_instance(SNView V, int b) {
   V.M += b * V.s_M;
+  V.Y += b * V.s_M;
   V.Dinv += b * V.s_Dinv;
   V.z += b * V.s_vec;
   V.u += b * V.s_vec;
@@ -67,13 +70,14 @@ PGO_HD SNView sn_at_instance(SNView V, int b) {
   return V;
 }
 
-PGO_HD constexpr int sn_max3(int a, int b, int c) { return a > b ? (a > c ? a : c) : (b > c ? b : c); }
 // doubles of shared memory a group needs for any task of its kind
 static const int kPairDoubles = (kPanelWidth * (kPanelWidth + 1) / 2 + 1) / 2;  // int table
-static const int kFactorSmemDoubles = sn_max3(sn_rows_doubles(kPanelWidth, kRowChunk), sn_diag_doubles(kPanelWidth),
-                                              0);  // row task / diagonal task
+static const int kFactorSmemDoubles = kPanelWidth * kPanelWidth * 9 + kPanelWidth * 9 + kPairDoubles +
+                                      3 * kPanelWidth +
+                                      3 * kPanelWidth * (3 * kRowChunk + 1);  // factor task
 static const int kTriSmemDoubles = 6 * kMaxSuperWidth + kPanelWidth * kPanelWidth * 9 + kPanelWidth * 9 +
                                    3 * 256;  // a wide supernode's vectors (substitution)
+PGO_HD constexpr int sn_max3(int a, int b, int c) { return a > b ? (a > c ? a : c) : (b > c ? b : c); }
 static const int kCtaSmemDoubles = sn_max3(kFactorSmemDoubles, kTileSmemDoubles, kTriSmemDoubles);
 static const int kSmallPairDoubles = (kSmallWidth * (kSmallWidth + 1) / 2 + 1) / 2;
 static const int kWarpSmemDoubles = sn_fused_doubles(kSmallWidth, kSmallRows);  // fused
@@ -271,6 +275,23 @@ PGO_HD void sn_store_rows(const G& g, const SNView& V, const PanelDesc& pd, int 
   }
 }
 
+// Y(a,t) = M(a,t) Dinv_t for the staged rows: the scaled operand of the panel's outer products.
+template <class G>
+PGO_HD void sn_store_scaled_rows(const G& g, const SNView& V, const PanelDesc& pd, int r0, int nrows,
+                                 int ldx, const double* xs, const double* Di) {
+  for (int t = 0; t < pd.w; ++t) {
+    double* dst = V.Y + 9 * static_cast<size_t>(sn_colpos(pd.base, pd.w + pd.m, t) + (pd.w - t) + r0);
+    const double* d = Di + 9 * t;
+    for (int a = g.rank(); a < nrows; a += g.size()) {
+      for (int r = 0; r < 3; ++r) {
+        const double m0 = xs[(3 * t) * ldx + 3 * a + r], m1 = xs[(3 * t + 1) * ldx + 3 * a + r],
+                     m2 = xs[(3 * t + 2) * ldx + 3 * a + r];
+        for (int c = 0; c < 3; ++c) dst[9 * a + 3 * r + c] = m0 * d[c] + m1 * d[3 + c] + m2 * d[6 + c];
+      }
+    }
+  }
+}
+
 // M(a,t) -= sum_{s<t} M(a,s) G(s,t), one scalar row per rank.
 template <class G>
 PGO_HD void sn_solve_rows(const G& g, int w, const double* Dg, double* xs, int ldx, int n_scalar) {
@@ -348,124 +369,30 @@ PGO_HD void sn_forward_fused(const G& g, const SNView& V, const PanelDesc& pd, i
 }
 
 // ---- factorisation tasks ---------------------------------------------------------------------------
-// A big panel is factorised in two steps per level:
-//   fd (sn_task_diag, one task per panel): block L D L^T of the w x w diagonal part, and
-//      R = (I + G)^-1, the inverse of the panel's unit upper triangular factor (G(s,t) = Dinv_s
-//      M(t,s)^T, s < t), obtained by running the row solve on the rows of the identity. The final
-//      diagonal blocks go to M, Dinv to Dinv, R^T to the scratch area.
-//   fa (sn_task_rows, one task per chunk of rows below the panel): the triangular solve of the rows
-//      M(a,:) (I + G) = M0(a,:) becomes the product M(a,:) = M0(a,:) R -- a GEMM with a 3w x 3w
-//      matrix (on the device: fp64 tensor cores) instead of a chain of 16 dependent block steps per
-//      scalar row. The right-hand side rides along as one more row (z R), which performs the
-//      forward substitution of the panel's columns; then z_{r_a} -= sum_t M(a,t) u_t for the rows
-//      below. (The scaled operand Y = M Dinv of the outer products is not stored: the update tasks
-//      scale their A operand after staging it -- a third less factor traffic, half the storage.)
-// The staged rows keep the layout of global memory (column t: 9 nrows consecutive doubles, block a
-// at 9 a, entry (r, c) at 3 r + c), so loads and stores are plain coalesced copies; scalar row
-// rho = 3 a + r, scalar column k = 3 t + c sits at raw[t S + 3 rho + c].
+// fa: factor the diagonal part (every row-chunk task of a panel repeats it: w <= 16, cheap) and
+// finish the rows [r0, r1) below it. The r0 == 0 task publishes the diagonal part and Dinv.
 template <class G>
-PGO_HD void sn_task_diag(const G& g, const SNView& V, const Task& T, double* sm) {
+PGO_HD void sn_task_factor(const G& g, const SNView& V, const Task& T, double* sm) {
   const PanelDesc pd = V.pn[T.id];
-  const int w = pd.w, n3 = 3 * w, ldx = n3 + 1;
+  const int w = pd.w, nrows = T.r1 - T.r0, ldx = 3 * nrows + 1;
   double* Dg = sm;
   double* Di = Dg + w * w * 9;
   int* pairs = reinterpret_cast<int*>(Di + w * 9);
-  double* xs = Di + w * 9 + kPairDoubles;
+  double* us = Di + w * 9 + kPairDoubles;
+  double* xs = us + 3 * w;
+  sn_load_rows_async(g, V, pd, T.r0, nrows, ldx, xs);  // in flight during the diagonal factorisation
   sn_load_diag(g, V, pd.base, w + pd.m, w, Dg);
-  for (int idx = g.rank(); idx < n3 * ldx; idx += g.size()) xs[idx] = 0.0;
+  sn_load_rhs(g, V, pd, nrows, ldx, xs);
   g.sync();
-  for (int k = g.rank(); k < n3; k += g.size()) xs[k * ldx + k] = 1.0;
-  sn_factor_diag(g, V, w, Dg, Di, pairs);  // ends with a sync
-  sn_solve_rows(g, w, Dg, xs, ldx, n3);    // xs[col * ldx + row] = R[row][col]
-  g.sync();
-  sn_store_diag(g, V, pd, Dg, Di, -1);
-  double* dst = V.scratch + 9 * static_cast<size_t>(pd.scratch);  // R^T, dense 3w x 3w
-  for (int idx = g.rank(); idx < n3 * n3; idx += g.size()) {
-    const int n = idx / n3, k = idx - n * n3;
-    dst[idx] = xs[n * ldx + k];
-  }
-  g.sync();
-}
-
-// raw <- raw R for the 3 nrows scalar rows of the staged chunk, one row per rank (the plain
-// statement; the device kernel multiplies on the tensor cores, pgo_kernels.cu: rows_mul_dmma)
-struct SnRowsMulPlain {
-  template <class G>
-  PGO_HD void operator()(const G& g, double* raw, int S, int nrows, const double* Rt, int ldr, int w) const {
-    const int n3 = 3 * w;
-    for (int row = g.rank(); row < 3 * nrows; row += g.size()) {
-      double out[3 * kPanelWidth];
-      for (int n = 0; n < n3; ++n) {
-        double acc = 0.0;
-        for (int k = 0; k <= n; ++k) acc += raw[(k / 3) * S + 3 * row + k % 3] * Rt[n * ldr + k];  // R upper triangular
-        out[n] = acc;
-      }
-      for (int n = 0; n < n3; ++n) raw[(n / 3) * S + 3 * row + n % 3] = out[n];
-    }
-  }
-};
-
-template <class G, class Mul>
-PGO_HD void sn_task_rows(const G& g, const SNView& V, const Task& T, double* sm, const Mul& mul) {
-  const PanelDesc pd = V.pn[T.id];
-  const int w = pd.w, nrows = T.r1 - T.r0, n3 = 3 * w, n8 = sn_round8(n3), ldr = sn_tile_ld(w), S = 9 * nrows;
-  const int len = w + pd.m;
-  double* raw = sm;
-  double* Rt = raw + w * S + 24;
-  double* Di = Rt + n8 * ldr;
-  double* z0 = Di + 9 * w;
-  double* z1 = z0 + n3;
-  double* us = z1 + n8;
-  for (int t = 0; t < w; ++t) {  // in flight while R^T, Dinv and z are fetched
-    const double* src = V.M + 9 * static_cast<size_t>(sn_colpos(pd.base, len, t) + (w - t) + T.r0);
-    double* dst = raw + t * S;
-    for (int q = g.rank(); q < S; q += g.size()) sn_copy_async(dst + q, src + q);
-  }
-  for (int q = g.rank(); q < 24; q += g.size()) raw[w * S + q] = 0.0;
-  {
-    const double* src = V.scratch + 9 * static_cast<size_t>(pd.scratch);
-    for (int idx = g.rank(); idx < n8 * ldr; idx += g.size()) {
-      const int n = idx / ldr, k = idx - n * ldr;
-      Rt[idx] = n < n3 && k < n3 ? sn_ld(src + n * n3 + k) : 0.0;
-    }
-  }
-  sn_load_dinv(g, V, pd.c0, w, Di);
-  for (int idx = g.rank(); idx < n3; idx += g.size()) z0[idx] = sn_ld(V.z + 3 * static_cast<size_t>(pd.c0) + idx);
+  sn_factor_diag(g, V, w, Dg, Di, pairs);
   sn_copy_wait();
   g.sync();
-  mul(g, raw, S, nrows, Rt, ldr, w);
-  for (int n = g.rank(); n < n3; n += g.size()) {  // the right-hand side: z R
-    double acc = 0.0;
-    for (int k = 0; k <= n; ++k) acc += z0[k] * Rt[n * ldr + k];
-    z1[n] = acc;
-  }
+  sn_solve_rows(g, w, Dg, xs, ldx, 3 * nrows + 1);
   g.sync();
-  for (int idx = g.rank(); idx < n3; idx += g.size()) {  // u_t = Dinv_t z_t
-    const int t = idx / 3, k = idx - 3 * t;
-    const double* d = Di + 9 * t + 3 * k;
-    const double v = d[0] * z1[3 * t] + d[1] * z1[3 * t + 1] + d[2] * z1[3 * t + 2];
-    us[idx] = v;
-    if (T.r0 == 0) V.u[3 * static_cast<size_t>(pd.c0) + idx] = v;
-  }
-  g.sync();
-  for (int t = 1; t < w; ++t) {  // column 0 is never modified inside the panel
-    double* dst = V.M + 9 * static_cast<size_t>(sn_colpos(pd.base, len, t) + (w - t) + T.r0);
-    const double* src = raw + t * S;
-    for (int q = g.rank(); q < S; q += g.size()) dst[q] = src[q];
-  }
-  const int* rows = V.row_idx + pd.base + w + T.r0;
-  for (int a = g.rank(); a < nrows; a += g.size()) {  // z_{r_a} -= sum_t M(a,t) u_t
-    double acc[3] = {0.0, 0.0, 0.0};
-    for (int t = 0; t < w; ++t) {
-      const double* b = raw + t * S + 9 * a;
-      const double* uu = us + 3 * t;
-      acc[0] += b[0] * uu[0] + b[1] * uu[1] + b[2] * uu[2];
-      acc[1] += b[3] * uu[0] + b[4] * uu[1] + b[5] * uu[2];
-      acc[2] += b[6] * uu[0] + b[7] * uu[1] + b[8] * uu[2];
-    }
-    const int r = rows[a];
-    for (int k = 0; k < 3; ++k) sn_add(V.z + 3 * static_cast<size_t>(r) + k, -acc[k]);
-  }
+  sn_store_rows(g, V, pd, T.r0, nrows, ldx, xs);
+  sn_store_scaled_rows(g, V, pd, T.r0, nrows, ldx, xs, Di);
+  if (T.r0 == 0) sn_store_diag(g, V, pd, Dg, Di, pd.scratch);
+  sn_forward_fused(g, V, pd, T.r0, nrows, ldx, xs, Di, us, T.r0 == 0);
   g.sync();
 }
 
@@ -475,13 +402,14 @@ PGO_HD int sn_target(const SNView& V, int meta, int a, int b) {
 
 // fb: one tile of an outer product
 //   M(r_a, r_b) -= sum over the columns t of the panels [T.id - np + 1, T.id] of Y(a,t) M(b,t)^T,
-//   Y(a,t) = M(a,t) Dinv_t (formed on the fly),  a >= b rows of the LAST panel's below list.
+//   Y(a,t) = M(a,t) Dinv_t,  a >= b rows of the LAST panel's below list.
 // np = 1 and the "inside" flag: the update a panel owes the later columns of its own supernode
 // (needed by the next panel); np = all panels of a supernode: the update the supernode owes its
 // ancestors, applied once with the whole supernode as the inner dimension instead of once per
 // panel (fewer, longer products and a fraction of the atomics).
-// T.r0 = first row a, T.r1 = first column b, T.aux = ti | tj << 8 | np << 16 | inside << 28.
-// This is the plain statement of the task, used by the host check; the device runs the same
+// T.r0 = first row a, T.r1 = first column b, T.aux = ti | tj << 8 | np << 16 | inside << 28. The
+// (0,0) tile also moves a scratch-published diagonal part into place (nothing reads it in this
+// phase). This is the plain statement of the task, used by the host check; the device runs the same
 // task as a tensor-core GEMM (sn_k_update in pgo_kernels.cu).
 template <class G>
 PGO_HD void sn_task_update(const G& g, const SNView& V, const Task& T, double* sm) {
@@ -493,6 +421,14 @@ PGO_HD void sn_task_update(const G& g, const SNView& V, const Task& T, double* s
   const int m = last.m, i0 = T.r0, j0 = T.r1;
   const int jlim = inside ? V.sn[last.sn].W - last.sn_off - last.w : m;
   const int ni = m - i0 < ti ? m - i0 : ti, nj = jlim - j0 < tj ? jlim - j0 : tj;
+  if (i0 == 0 && j0 == 0 && q_last == T.id && last.scratch >= 0) {
+    const int w = last.w, len = w + m;
+    const double* src = V.scratch + 9 * static_cast<size_t>(last.scratch);
+    for (int idx = g.rank(); idx < w * w * 9; idx += g.size()) {
+      const int i = idx / (w * 9), t = (idx / 9) % w, k = idx % 9;
+      if (i >= t) V.M[9 * static_cast<size_t>(sn_colpos(last.base, len, t) + (i - t)) + k] = sn_ld(src + idx);
+    }
+  }
   for (int item = g.rank(); item < ni * nj; item += g.size()) {
     const int a = i0 + item / nj, b = j0 + item % nj;
     if (a < b) continue;
@@ -501,12 +437,9 @@ PGO_HD void sn_task_update(const G& g, const SNView& V, const Task& T, double* s
       const PanelDesc pd = V.pn[q];
       const int w = pd.w, len = w + pd.m, off = pd.m - m;
       for (int t = 0; t < w; ++t) {
-        double mb[9], ma[9], d[9], y[9];
-        sn_ld9(V.M + 9 * static_cast<size_t>(sn_colpos(pd.base, len, t) + (w - t) + off + a), ma);
+        double mb[9], y[9];
+        sn_ld9(V.Y + 9 * static_cast<size_t>(sn_colpos(pd.base, len, t) + (w - t) + off + a), y);
         sn_ld9(V.M + 9 * static_cast<size_t>(sn_colpos(pd.base, len, t) + (w - t) + off + b), mb);
-        sn_ld9(V.Dinv + 9 * static_cast<size_t>(pd.c0 + t), d);
-        for (int r = 0; r < 3; ++r)
-          for (int c = 0; c < 3; ++c) y[3 * r + c] = ma[3 * r] * d[c] + ma[3 * r + 1] * d[3 + c] + ma[3 * r + 2] * d[6 + c];
         for (int r = 0; r < 3; ++r)
           for (int c = 0; c < 3; ++c)
             acc[3 * r + c] += y[3 * r] * mb[3 * c] + y[3 * r + 1] * mb[3 * c + 1] + y[3 * r + 2] * mb[3 * c + 2];

@@ -539,7 +539,7 @@ bool build_supernodal(Symbolic& S, std::string* err) {
   std::vector<int> plevel(N.n_panels, 0);
   N.pn_meta.assign(N.n_panels + 1, 0);
   N.pn_scratch.assign(N.n_panels, -1);
-  std::vector<std::pair<int, Task> > ff, fd, fa, fb;
+  std::vector<std::pair<int, Task> > ff, fa, fb;
   for (int K = 0; K < N.n_panels; ++K) {
     const int c0 = N.pn_first[K], w = N.pn_first[K + 1] - c0;
     const int base = cp[c0] + w, m = cp[c0 + 1] - base;  // below rows: ri[base .. base + m)
@@ -581,16 +581,15 @@ bool build_supernodal(Symbolic& S, std::string* err) {
       const Task t = {K, 0, m, 0};
       ff.push_back(std::make_pair(plevel[K], t));
     } else {
-      // one diagonal task (factor the w x w part, invert its unit triangular factor), then one
-      // row task per chunk of rows below (a GEMM with that inverse)
-      const Task td = {K, 0, 0, 0};
-      fd.push_back(std::make_pair(plevel[K], td));
-      for (int r0 = 0; r0 == 0 || r0 < m; r0 += kRowChunk) {
+      int chunks = 0;
+      for (int r0 = 0; r0 == 0 || r0 < m; r0 += kRowChunk, ++chunks) {
         const Task t = {K, r0, std::min(m, r0 + kRowChunk), 0};
         fa.push_back(std::make_pair(plevel[K], t));
       }
-      N.pn_scratch[K] = static_cast<int>(N.scratch_blocks);   // (3 w)^2 doubles = w^2 blocks
-      N.scratch_blocks += static_cast<int64_t>(w) * w;
+      if (chunks > 1) {
+        N.pn_scratch[K] = static_cast<int>(N.scratch_blocks);
+        N.scratch_blocks += static_cast<int64_t>(w) * w;
+      }
       // Outer products. Inside a supernode every panel updates the supernode's later columns
       // (the next panel needs them); the update of the ANCESTORS (rows x rows below the
       // supernode) is applied once per supernode, by its last panel's level, with all the
@@ -629,7 +628,6 @@ bool build_supernodal(Symbolic& S, std::string* err) {
   }
   N.pn_meta[N.n_panels] = static_cast<int>(N.colbase.size());
   bucket_tasks(ff, N.n_plevels, &N.ff_ptr, &N.ff);
-  bucket_tasks(fd, N.n_plevels, &N.fd_ptr, &N.fd);
   bucket_tasks(fa, N.n_plevels, &N.fa_ptr, &N.fa);
   bucket_tasks(fb, N.n_plevels, &N.fb_ptr, &N.fb);
 
@@ -690,14 +688,13 @@ Supernodal::Lists Supernodal::lists(int owner) const {
     }
   };
   filter(ff_ptr, ff, pn_owner, n_plevels, &L.ff_ptr, &L.ff);
-  filter(fd_ptr, fd, pn_owner, n_plevels, &L.fd_ptr, &L.fd);
   filter(fa_ptr, fa, pn_owner, n_plevels, &L.fa_ptr, &L.fa);
   filter(fb_ptr, fb, pn_owner, n_plevels, &L.fb_ptr, &L.fb);
   filter(ss_ptr, ss, sn_owner, n_slevels, &L.ss_ptr, &L.ss);
   filter(sa_ptr, sa, sn_owner, n_slevels, &L.sa_ptr, &L.sa);
   filter(sf_ptr, sf, pn_owner, n_slevels, &L.sf_ptr, &L.sf);
   filter(sb_ptr, sb, pn_owner, n_slevels, &L.sb_ptr, &L.sb);
-  L.fd_smem.assign(n_plevels, 0);
+  const int pair_doubles = (kPanelWidth * (kPanelWidth + 1) / 2 + 1) / 2;
   L.fa_smem.assign(n_plevels, 0);
   L.fa_smem_small.assign(n_plevels, 0);
   L.fa_large.assign(n_plevels, 0);
@@ -718,9 +715,10 @@ Supernodal::Lists Supernodal::lists(int owner) const {
         L.ff_smem_small[l] = std::max(L.ff_smem_small[l], need);
       }
     }
-    for (int i = L.fd_ptr[l]; i < L.fd_ptr[l + 1]; ++i)
-      L.fd_smem[l] = std::max(L.fd_smem[l], sn_diag_doubles(pn[L.fd[i].id].w));
-    auto factor_need = [&](const Task& t) { return sn_rows_doubles(pn[t.id].w, t.r1 - t.r0); };
+    auto factor_need = [&](const Task& t) {
+      const int w = pn[t.id].w;
+      return w * w * 9 + w * 9 + pair_doubles + 3 * w + 3 * w * (3 * (t.r1 - t.r0) + 1);
+    };
     std::stable_partition(L.fa.begin() + L.fa_ptr[l], L.fa.begin() + L.fa_ptr[l + 1],
                           [&](const Task& t) { return factor_need(t) > kFactorSmallDoubles; });
     for (int i = L.fa_ptr[l]; i < L.fa_ptr[l + 1]; ++i) {

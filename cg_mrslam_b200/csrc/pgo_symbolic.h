@@ -39,7 +39,7 @@ static const int kSubstWarpWidth = 4;   // substitutions: supernodes this narrow
 static const int kSubstSmallDoubles = 320;  // ... launched apart from the narrow ones above this need
 static const int kSmallRows = 32;    // ... if the panel also has at most this many rows below it
 static const int kFusedSmallDoubles = 704;  // 5.5 kB per warp: 8+ CTAs of 4 warps per SM
-static const int kFactorSmallDoubles = 5400;  // 43 kB: row tasks below this need run 4+ per SM
+static const int kFactorSmallDoubles = 5400;  // 43 kB: a panel of <= 8 columns with a full row chunk
 static const int kRowChunk = 64;     // rows below a panel per CTA task of the panel factorisation
 // outer-product tile of one CTA task (tensor-core GEMM, pgo_kernels.cu): ti x tj blocks with
 // ti a multiple of 8 and tj in {8, 16, 24, 32}; operands staged as [3 ti][ld] and [3 tj][ld]
@@ -58,17 +58,6 @@ PGO_HOST_DEVICE inline constexpr int sn_fused_doubles(int w, int m) {
   return w * w * 9 + w * 9 + (kSmallWidth * (kSmallWidth + 1) / 2 + 1) / 2 + 3 * w + 3 * w * (3 * m + 1);
 }
 PGO_HOST_DEVICE inline constexpr int sn_subst_doubles(int W) { return 6 * W + 9 * W * W + 9 * W + 96; }
-// diagonal task (sn_task_diag): Dg[w*w*9] Di[w*9] pair table, xs[3w][3w+1] (the identity rows that
-// become the inverse of the panel's unit triangular factor)
-PGO_HOST_DEVICE inline constexpr int sn_diag_doubles(int w) {
-  return w * w * 9 + w * 9 + (kPanelWidth * (kPanelWidth + 1) / 2 + 1) / 2 + 3 * w * (3 * w + 1);
-}
-// row task (sn_task_rows): raw[w][9 nrows] (+ 24 so that a partial last 8-row strip stays inside),
-// Rt[round8(3w)][sn_tile_ld(w)], Di[9w], z0[3w], z1[round8(3w)], us[3w]
-PGO_HOST_DEVICE inline constexpr int sn_round8(int x) { return (x + 7) & ~7; }
-PGO_HOST_DEVICE inline constexpr int sn_rows_doubles(int w, int nrows) {
-  return 9 * w * nrows + 24 + sn_round8(3 * w) * sn_tile_ld(w) + 9 * w + 3 * w + sn_round8(3 * w) + 3 * w;
-}
 static const int kMaxSuperWidth = 1008;   // at most 63 panels per supernode
 static const int kUpdateGroup = 4;        // panels per tile task of an ancestors' update
 
@@ -86,8 +75,7 @@ struct PanelDesc {
   int c0, w, m;   // first column, width, rows below the panel (later chain columns included)
   int base;       // col_ptr[c0]
   int meta;       // offset of the panel's rows in colbase / tbl_off
-  int scratch;    // block offset of the panel's inverse triangular factor ((3w)^2 doubles) in the
-                  // scratch area, or -1 (small panels: fused tasks)
+  int scratch;    // block offset in the diagonal scratch area, or -1
   int sn_off;     // offset of c0 inside its supernode
   int sn;         // supernode
 };
@@ -112,15 +100,14 @@ struct Supernodal {
   // colbase[pn_meta[K] + b] + tbl[tbl_off[pn_meta[K] + b] + a].
   std::vector<int> pn_meta;    // n_panels + 1
   std::vector<int> colbase, tbl_off, tbl;
-  // big panels: where the diagonal task leaves R^T, R = (I + G)^-1 the inverse of the panel's unit
-  // upper triangular factor, for the row tasks of the same level: offset in blocks or -1
+  // panels whose factorisation is split over several CTA tasks write their diagonal part to a
+  // scratch area first (the other tasks still read the unfactored blocks): offset in blocks or -1
   std::vector<int> pn_scratch;
   int64_t scratch_blocks = 0;
   // factorisation tasks by panel level: fused (factor + update) warp tasks for small panels,
-  // CTA tasks for the rest (fd: the panel's diagonal part; fa: a chunk of the rows below it;
-  // fb: one tile of the outer product)
-  std::vector<int> ff_ptr, fd_ptr, fa_ptr, fb_ptr;  // n_plevels + 1
-  std::vector<Task> ff, fd, fa, fb;
+  // CTA tasks for the rest (fa: factor a row chunk; fb: one tile of the outer product)
+  std::vector<int> ff_ptr, fa_ptr, fb_ptr;  // n_plevels + 1
+  std::vector<Task> ff, fa, fb;
   // substitution tasks by supernode level: ss = whole small supernode (warp), sa = triangular part
   // of a wide supernode (CTA), sb = backward gather over the rows below a wide supernode's panel
   // (warp, chunks of 64 rows), sf = forward scatter over the same rows (chunks of 32; only for
@@ -133,9 +120,9 @@ struct Supernodal {
   // (kAllOwners: everything, the single-GPU case), by level, with per-level shared-memory needs
   struct Lists {
     int n_plevels = 0, n_slevels = 0;
-    std::vector<int> ff_ptr, fd_ptr, fa_ptr, fb_ptr, ss_ptr, sa_ptr, sf_ptr, sb_ptr;
-    std::vector<Task> ff, fd, fa, fb, ss, sa, sf, sb;
-    std::vector<int> fd_smem, fa_smem, fb_smem;  // doubles of shared memory of the largest task per level
+    std::vector<int> ff_ptr, fa_ptr, fb_ptr, ss_ptr, sa_ptr, sf_ptr, sb_ptr;
+    std::vector<Task> ff, fa, fb, ss, sa, sf, sb;
+    std::vector<int> fa_smem, fb_smem;  // doubles of shared memory of the largest task per level
     // factor tasks: per level the ones needing more than kFactorSmallDoubles come first
     // (fa_large[l] of them, fa_smem[l]); the rest (narrow panels) are launched apart with
     // fa_smem_small[l], so that four of them fit an SM instead of two

@@ -56,7 +56,9 @@ extern "C" int pgo_hostsim_solve(int n, int n_blocks, const int32_t* brow, const
   V.colbase = N.colbase.data();
   V.tbl_off = N.tbl_off.data();
   V.tbl = N.tbl.data();
+  std::vector<double> Y(M.size(), 0.0);
   V.M = M.data();
+  V.Y = Y.data();
   V.Dinv = Dinv.data();
   V.z = z.data();
   V.u = u.data();
@@ -68,8 +70,7 @@ extern "C" int pgo_hostsim_solve(int n, int n_blocks, const int32_t* brow, const
   std::vector<double> sm(kCtaSmemDoubles);
   const SeqGroup g;
   for (int l = 0; l < N.n_plevels; ++l) {
-    for (int i = N.fd_ptr[l]; i < N.fd_ptr[l + 1]; ++i) sn_task_diag(g, V, N.fd[i], sm.data());
-    for (int i = N.fa_ptr[l]; i < N.fa_ptr[l + 1]; ++i) sn_task_rows(g, V, N.fa[i], sm.data(), SnRowsMulPlain());
+    for (int i = N.fa_ptr[l]; i < N.fa_ptr[l + 1]; ++i) sn_task_factor(g, V, N.fa[i], sm.data());
     for (int i = N.ff_ptr[l]; i < N.ff_ptr[l + 1]; ++i) sn_task_fused(g, V, N.ff[i], sm.data());
     for (int i = N.fb_ptr[l]; i < N.fb_ptr[l + 1]; ++i) sn_task_update(g, V, N.fb[i], sm.data());
   }

@@ -8,8 +8,8 @@ for expr in "$@"; do
   sed -i "$expr" "$f"
   echo "== variant: $expr"
   make -s -C cg_mrslam_b200/csrc 2>&1 | grep -i "error" | head -5
-  for b in 1 64; do
-    python tools/pgo_profile_run.py 6 $b 2>&1 | grep -o "ms per instance-iteration [0-9.]*" | sed "s/^/batch $b: /"
+  for b in 1 128; do
+    python tools/pgo_profile_run.py 4 $b 2>&1 | grep -o "ms per instance-iteration [0-9.]*" | sed "s/^/batch $b: /"
   done
 done
 cp /tmp/variant_backup "$f"
