@@ -45,6 +45,9 @@ def parse():
     ap.add_argument("--cpu-pairs", type=int, default=0, help="pairs in the CPU sample (0 = auto)")
     ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 global, 2 tiled")
     ap.add_argument("--no-gn", action="store_true")
+    ap.add_argument("--workload", default="both", choices=["both", "gn"],
+                    help="gn: the GN metric alone as the top-level line (both arms), so that a driver "
+                         "can form value(ours) / value(reference) for it")
     ap.add_argument("--e2e-chunks", type=int, default=4,
                     help="handles / host threads the end-to-end step is pipelined over")
     ap.add_argument("--gn-batch", type=int, default=128, help="graph instances per GPU in the GN arm")
@@ -124,6 +127,15 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def ncu_traffic(key):
+    """DRAM traffic and on-chip figures of a kernel from the committed ncu captures
+    (profiles/ncu_traffic.json names the capture and the kernel revision); {} if absent."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(key, {})
+    except Exception:
+        return {}
+
+
 def peaks():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))), "measured"
@@ -177,9 +189,24 @@ WORKLOAD = ("cfg5 scan matcher: %d pairs per GPU per step, 1081-beam scans, one 
             "1.01M-candidate window per pair, LC grid 700x700 res 0.1, raster + score + compact")
 
 
+def gn_reference_line(args):
+    blk, _, _ = gn_cpu()
+    return {"impl": "reference", "metric": "GN iters/sec (50k-node SE2 graph)", "value": blk["value"],
+            "unit": "iters/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 / blk["value"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "cfg4 synthetic Manhattan graph, %d vertices / %d edges, seed 42" % (GN_V, GN_E)},
+            "cpu_baseline": blk,
+            "e2e": {"value": blk["value"], "unit": "iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+
+
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
+        return
+    if args.workload == "gn":
+        print(json.dumps(gn_reference_line(args)))
         return
     cores = os.cpu_count() or 1
     n_threads = min(cores, 64)
@@ -345,8 +372,8 @@ def gn_ours(args, local, world, barrier):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                      "frac": achieved / pk["hbm_gbs"],
                      # DRAM bytes per instance-iteration summed over the kernels of one iteration
-                     # (ncu dram__bytes_read + write, 16 instances): profiles/r01_gn_dram_traffic_batch16.txt
-                     "traffic": 957.6e6, "peak_kind": pk_kind,
+                     "traffic": ncu_traffic("gn_iteration").get("dram_bytes_per_instance_iteration"),
+                     "traffic_source": ncu_traffic("gn_iteration").get("source"), "peak_kind": pk_kind,
                      "kernel": "iteration graph (sn_k_factor / sn_k_update / sn_k_bwd_* + linearise)",
                      "algorithmic_bytes": nbytes,
                      "fp64": {"flops_per_iteration": st.get("factor_flops", 0.0),
@@ -530,6 +557,27 @@ def ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    if args.workload == "gn":
+        gn = gn_ours(args, local, world, barrier)
+        if rank == 0:
+            par = gn.pop("_parity")
+            line = {"metric": gn["metric"], "value": gn["value"], "unit": gn["unit"], "n_gpus": world,
+                    "steps": args.steps, "warmup": args.warmup, "ms_per_step": gn["ms_per_iter"] * gn["config"]["batch"],
+                    "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                    "data": "synthetic", "config": gn["config"], "roofline": gn["roofline"], "e2e": gn["e2e"],
+                    "gpu_launches": gn["gpu_launches"], "single_graph": gn["single_graph"]}
+            if world == 1:
+                blk, cpu_poses, _ = gn_cpu()
+                line["cpu_baseline"] = blk
+                d = par[2] - cpu_poses
+                d[:, 2] = (d[:, 2] + math.pi) % (2.0 * math.pi) - math.pi
+                line["parity_max_abs"] = float(np.abs(d).max())
+            if "dd" in gn:
+                line["dd"] = gn["dd"]
+            print(json.dumps(line))
+        if world > 1:
+            dist.destroy_process_group()
+        return
     n = args.pairs
     maps, curs = make_pairs(n, rank)
     map_counts = np.array([len(p) for p in maps], dtype=np.int32)
@@ -574,6 +622,28 @@ def ours(args):
     kms.append(m.kernel_ms())  # last step's per-kernel split (events on the same stream)
     res, n_out = m.batch_collect(cap=4)
     found = int((n_out > 0).sum())
+
+    # ---- strong scaling of the same job: BASELINE cfg 5 is 10 k pairs IN TOTAL, so at N GPUs each
+    # rank takes n / N of them (device-resident, same kernels; launch and planning overheads do
+    # not shrink with the share, which is what this line shows) ------------------------------------
+    strong_ms = None
+    if world > 1:
+        ns = max(1, n // world)
+        m.batch_stage(cur_np[:int(np.sum(cur_counts[:ns]))], cur_counts[:ns], regions[:ns], reg_counts[:ns], step,
+                      MAX_SCORE, BINS, map_pts=map_np[:int(np.sum(map_counts[:ns]))], map_counts=map_counts[:ns])
+        for _ in range(args.warmup):
+            m.batch_launch()
+        m.batch_collect(cap=4)
+        barrier()
+        with torch.cuda.stream(stream):
+            ev0.record(stream)
+            for _ in range(args.steps):
+                m.batch_launch()
+            ev1.record(stream)
+        barrier()
+        strong_ms = ev0.elapsed_time(ev1)
+        strong_cand = m.batch_stats()["candidates"]
+        m.batch_collect(cap=4)
 
     # ---- end-to-end arm: host buffers in, host results out, every step -------------------------
     # The step's pairs are cut into K chunks, one cgm_matcher handle + stream + host thread each
@@ -635,7 +705,7 @@ def ours(args):
     gn = None if args.no_gn else gn_ours(args, local, world, barrier)
 
     cand = stats["candidates"]
-    t = torch.tensor([dev_ms, e2e_sec * 1e3], dtype=torch.float64, device="cuda")
+    t = torch.tensor([dev_ms, e2e_sec * 1e3, strong_ms or 0.0], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms_max, e2e_ms_max = float(t[0]), float(t[1])
@@ -646,6 +716,7 @@ def ours(args):
         pk, pk_kind = peaks()
         alg_bytes = stats["cell_reads"] + 4 * cand
         score_ms = kms[-1]["score"]
+        tr = ncu_traffic("score_tiled")
         achieved = alg_bytes / (score_ms * 1e-3) / 1e9 if score_ms > 0 else 0.0
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -661,12 +732,14 @@ def ours(args):
             "roofline": {
                 "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                 "frac": achieved / pk["hbm_gbs"],
-                # ncu dram__bytes_read + write of a 300-pair launch of the same kernel
-                # (profiles/r01_ncu_score_tiled_s3.txt: 34.39 MB + 0.05 MB), scaled per pair
-                "traffic": (34.391040e6 + 54.016e3) / 300.0 * n if args.kernel != 1 else None,
-                "on_chip": {"alu_pipe_pct": 64.0, "shared_wavefronts_pct": 55.7, "issue_active_pct": 59.8,
-                            "source": "profiles/r01_ncu_score_tiled_s3.txt (the limiter is the "
-                                      "shared-memory gather + integer pipe, not HBM)"},
+                # ncu dram__bytes_read + write of the same kernel, per pair (profiles/ncu_traffic.json)
+                "traffic": (tr.get("dram_bytes_per_pair") * n
+                            if args.kernel != 1 and tr.get("dram_bytes_per_pair") else None),
+                "on_chip": {"alu_pipe_pct": tr.get("alu_pipe_pct"),
+                            "shared_wavefronts_pct": tr.get("shared_wavefronts_pct"),
+                            "issue_active_pct": tr.get("issue_active_pct"),
+                            "source": tr.get("source"),
+                            "note": "the limiter is the shared-memory gather + integer pipe, not HBM"},
                 "peak_kind": pk_kind,
                 "kernel": "score_tiled" if args.kernel != 1 else "score_global",
                 "kernel_ms": score_ms, "algorithmic_bytes": alg_bytes,
@@ -681,6 +754,12 @@ def ours(args):
             "gpu_launches": int(launches2 - launches1),
             "clocks": clocks,
         }
+        if world > 1:
+            line["strong_scaling"] = {
+                "what": "the same job with %d pairs IN TOTAL (BASELINE cfg 5), %d per GPU, device-resident" %
+                        (n // world * world, n // world),
+                "value": strong_cand * world * args.steps / (float(t[2]) * 1e-3), "unit": UNIT,
+                "ms_per_step": float(t[2]) / args.steps}
         # CPU baseline on a bounded sample, rank 0 at N=1 only
         if world == 1:
             cores = os.cpu_count() or 1
