@@ -8,7 +8,9 @@ odometry moved more than 0.25 m or turned more than pi/4 since the last one. The
 the latest odometry / scan at 10 Hz of wall-clock time; offline the rule is evaluated at every
 odometry message and paired with the most recent scan (appendix A: a replay must fix a sampling
 rule; parity is CPU oracle vs GPU on the identical replay). The fixture holds float64 odometry
-poses (x, y, yaw), float32 ranges as stored in the bag, and the scan geometry.
+poses (x, y, yaw), float32 ranges as stored in the bag, the scan geometry, and per keyframe the bag
+time (s) and the robot's latest ground-truth pose (the multi-robot replay needs both: message
+cadence and the simulated communication range, graph_comm.cpp:66-68,152).
 The bags are under /root/reference/bagfiles/*.tar.gz (extract first). Test-data tooling only."""
 import math
 import struct
@@ -84,12 +86,16 @@ def parse_odom(b):
 def main():
     path, robot, count, out = sys.argv[1], sys.argv[2], int(sys.argv[3]), sys.argv[4]
     odom_topic, scan_topic = "/%s/odom" % robot, "/%s/base_scan" % robot
+    gt_topic = "/%s/base_pose_ground_truth" % robot
     last_scan = None
     geom = None
-    key_odom, key_ranges = [], []
+    key_odom, key_ranges, key_time, key_gt = [], [], [], []
     last = None
+    last_gt = (float("nan"),) * 3
     for topic, t, payload in messages(path):
-        if topic == scan_topic:
+        if topic == gt_topic:
+            last_gt = parse_odom(payload)     # nav_msgs/Odometry as well
+        elif topic == scan_topic:
             amin, ainc, rmax, ranges = parse_scan(payload)
             geom = (amin, ainc, rmax)
             last_scan = ranges
@@ -105,9 +111,12 @@ def main():
                 last = (x, y, yaw)
                 key_odom.append(last)
                 key_ranges.append(last_scan)
+                key_time.append(t * 1e-9)
+                key_gt.append(last_gt)
                 if len(key_odom) >= count:
                     break
     np.savez_compressed(out, odom=np.array(key_odom), ranges=np.array(key_ranges, dtype=np.float32),
+                        time=np.array(key_time), gt=np.array(key_gt),
                         first_angle=np.float64(geom[0]), angular_step=np.float64(geom[1]),
                         max_range=np.float64(geom[2]), robot=robot, source=path.split("/")[-1])
     print("keyframes", len(key_odom), "beams", key_ranges[0].shape, "geom", geom, "->", out)
