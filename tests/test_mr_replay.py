@@ -53,7 +53,8 @@ def cpu_run(tmp_path_factory):
 def _same_graph(a, b, r, tol):
     ea, eb = a["edges%d" % r], b["edges%d" % r]
     assert ea.shape == eb.shape, (r, ea.shape, eb.shape)
-    key = lambda e: np.lexsort((np.round(e[:, 4], 3), np.round(e[:, 3], 3), np.round(e[:, 2], 3), e[:, 1], e[:, 0]))
+    key = lambda e: np.lexsort((np.round(e[:, 4], 3), np.round(e[:, 3], 3), np.round(e[:, 2], 3), e[:, 6], e[:, 1],
+                                e[:, 0]))
     ea, eb = ea[key(ea)], eb[key(eb)]
     assert np.array_equal(ea[:, [0, 1, 6]], eb[:, [0, 1, 6]]), r          # vertex indices, levels: exact
     d = ea[:, 2:5] - eb[:, 2:5]
