@@ -1,6 +1,8 @@
 // extern "C" surface of the pose-graph solver (include/pgo_solver.h): argument checking, active
 // set / hessian-index bookkeeping, structure analysis (pgo_symbolic.cpp),
 // spanning-tree initial guess (C10) and marshalling into the device back-end (pgo_device.h).
+#include <dlfcn.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -36,6 +38,39 @@ struct Pose {
   double x, y, th;
 };
 
+// NCCL, bound at run time (libnccl.so.2: the copy already in the process -- a host program's, or
+// PyTorch's -- else the system one), so that the library has no link-time dependency on it. Only
+// the domain-decomposed solve (pgo_dd_*) needs it.
+struct NcclApi {
+  typedef struct { char internal[128]; } UniqueId;  // ncclUniqueId (nccl.h:37-38)
+  int (*get_unique_id)(UniqueId*) = nullptr;
+  int (*comm_init_rank)(void**, int, UniqueId, int) = nullptr;
+  int (*all_reduce)(const void*, void*, size_t, int, int, void*, void*) = nullptr;
+  int (*comm_destroy)(void*) = nullptr;
+  const char* (*get_error_string)(int) = nullptr;
+  bool ok = false;
+};
+const int kNcclDouble = 8, kNcclSum = 0;  // ncclFloat64, ncclSum (nccl.h:260,286)
+
+NcclApi& nccl() {
+  static NcclApi api;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (h) {
+      api.get_unique_id = reinterpret_cast<int (*)(NcclApi::UniqueId*)>(dlsym(h, "ncclGetUniqueId"));
+      api.comm_init_rank = reinterpret_cast<int (*)(void**, int, NcclApi::UniqueId, int)>(dlsym(h, "ncclCommInitRank"));
+      api.all_reduce =
+          reinterpret_cast<int (*)(const void*, void*, size_t, int, int, void*, void*)>(dlsym(h, "ncclAllReduce"));
+      api.comm_destroy = reinterpret_cast<int (*)(void*)>(dlsym(h, "ncclCommDestroy"));
+      api.get_error_string = reinterpret_cast<const char* (*)(int)>(dlsym(h, "ncclGetErrorString"));
+      api.ok = api.get_unique_id && api.comm_init_rank && api.all_reduce && api.comm_destroy;
+    }
+  }
+  return api;
+}
+
 Pose se2_inv(const Pose& a) {  // C1
   Pose r;
   r.th = normalize_theta(-a.th);
@@ -68,6 +103,8 @@ struct pgo_solver {
   bool have_graph = false, have_values = false;
   double last_ms = 0.0;
   int rank = 0, world = 1;
+  void* nccl_comm = nullptr;   // ncclComm_t of the domain decomposition (pgo_dd_set_comm / pgo_dd_comm_init)
+  bool own_comm = false;
   int analysed_rank = -1, analysed_world = -1, analysed_batch = -1;  // what the stored analysis was made for
   long long structure_hits = 0;  // pgo_set_graph calls answered from the stored analysis
 };
@@ -93,6 +130,7 @@ int pgo_create(pgo_solver** out, int device, void* stream) {
 
 void pgo_destroy(pgo_solver* s) {
   if (!s) return;
+  if (s->nccl_comm && s->own_comm && nccl().ok) nccl().comm_destroy(s->nccl_comm);
   pgo::dev_destroy(s->dev);
   delete s;
 }
@@ -423,6 +461,70 @@ int pgo_dd_pose_commit(pgo_solver* s) {
   std::string err;
   const int rc = pgo::dev_dd_pose_commit(s->dev, &err);
   return rc ? fail(rc, err) : PGO_OK;
+}
+
+int pgo_dd_unique_id(void* out128) {
+  if (!out128) return fail(PGO_ERR_ARG, "null argument");
+  if (!nccl().ok) return fail(PGO_ERR_CUDA, "libnccl.so.2 could not be loaded");
+  const int rc = nccl().get_unique_id(static_cast<NcclApi::UniqueId*>(out128));
+  return rc ? fail(PGO_ERR_CUDA, std::string("ncclGetUniqueId: ") + nccl().get_error_string(rc)) : PGO_OK;
+}
+
+int pgo_dd_comm_init(pgo_solver* s, const void* unique_id128, int rank, int world) {
+  if (!s || !unique_id128 || world < 1 || rank < 0 || rank >= world) return fail(PGO_ERR_ARG, "bad argument");
+  if (!nccl().ok) return fail(PGO_ERR_CUDA, "libnccl.so.2 could not be loaded");
+  if (s->nccl_comm && s->own_comm) nccl().comm_destroy(s->nccl_comm);
+  s->nccl_comm = nullptr;
+  NcclApi::UniqueId id;
+  std::memcpy(&id, unique_id128, sizeof id);
+  const int rc = nccl().comm_init_rank(&s->nccl_comm, world, id, rank);
+  if (rc) return fail(PGO_ERR_CUDA, std::string("ncclCommInitRank: ") + nccl().get_error_string(rc));
+  s->own_comm = true;
+  return pgo_set_partition(s, rank, world);
+}
+
+int pgo_dd_set_comm(pgo_solver* s, void* nccl_comm, int rank, int world) {
+  if (!s || !nccl_comm) return fail(PGO_ERR_ARG, "bad argument");
+  if (!nccl().ok) return fail(PGO_ERR_CUDA, "libnccl.so.2 could not be loaded");
+  if (s->nccl_comm && s->own_comm) nccl().comm_destroy(s->nccl_comm);
+  s->nccl_comm = nccl_comm;
+  s->own_comm = false;
+  return pgo_set_partition(s, rank, world);
+}
+
+int pgo_dd_iterate(pgo_solver* s, int n_iters, double* chi2_out, int* iters_done) {
+  if (!s || !s->have_values || n_iters < 0) return fail(PGO_ERR_ARG, "bad argument (pgo_upload first)");
+  if (!s->nccl_comm) return fail(PGO_ERR_ARG, "no communicator (pgo_dd_comm_init / pgo_dd_set_comm first)");
+  std::string err;
+  void* stream = pgo::dev_stream(s->dev);
+  int rc = pgo::dev_dd_begin(s->dev, n_iters, &err);
+  if (rc) return fail(rc, err);
+  void* ptr = nullptr;
+  long long n = 0;
+  for (int it = 0; it < n_iters; ++it) {
+    rc = pgo::dev_dd_local(s->dev, &err);
+    if (rc) return fail(rc, err);
+    pgo::dev_dd_exchange(s->dev, &ptr, &n);
+    int nrc = nccl().all_reduce(ptr, ptr, static_cast<size_t>(n), kNcclDouble, kNcclSum, s->nccl_comm, stream);
+    if (nrc) return fail(PGO_ERR_CUDA, std::string("ncclAllReduce: ") + nccl().get_error_string(nrc));
+    rc = pgo::dev_dd_shared(s->dev, &err);
+    if (rc) return fail(rc, err);
+  }
+  int done = 0;
+  float ms = 0.f;
+  const int rc_end = pgo::dev_dd_end(s->dev, n_iters, chi2_out, &done, &ms, &err);
+  s->last_ms = ms;
+  if (iters_done) *iters_done = done;
+  if (rc_end && rc_end != PGO_ERR_NUMERIC) return fail(rc_end, err);
+  // every rank ends with every estimate: owners contribute theirs, the rest zeros
+  std::string err2;
+  rc = pgo::dev_dd_pose_exchange(s->dev, &ptr, &n, &err2);
+  if (rc) return fail(rc, err2);
+  const int nrc = nccl().all_reduce(ptr, ptr, static_cast<size_t>(n), kNcclDouble, kNcclSum, s->nccl_comm, stream);
+  if (nrc) return fail(PGO_ERR_CUDA, std::string("ncclAllReduce: ") + nccl().get_error_string(nrc));
+  rc = pgo::dev_dd_pose_commit(s->dev, &err2);
+  if (rc) return fail(rc, err2);
+  return rc_end ? fail(rc_end, err) : PGO_OK;
 }
 
 int pgo_analyse_partition(int n_vertices, int n_edges, const int32_t* edge_i, const int32_t* edge_j,

@@ -54,6 +54,10 @@ _SIGS = {
     "pgo_dd_end": (C.c_int, [C.c_void_p, C.c_int, _dp, C.POINTER(C.c_int)]),
     "pgo_dd_pose_exchange": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_int64)]),
     "pgo_dd_pose_commit": (C.c_int, [C.c_void_p]),
+    "pgo_dd_unique_id": (C.c_int, [C.c_void_p]),
+    "pgo_dd_comm_init": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "pgo_dd_set_comm": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "pgo_dd_iterate": (C.c_int, [C.c_void_p, C.c_int, _dp, C.POINTER(C.c_int)]),
     "pgo_analyse_partition": (C.c_int, [C.c_int, C.c_int, _ip, _ip, _bp, C.c_int, _ip,
                                         C.POINTER(C.c_int64)]),
     "pgo_get_stats": (C.c_int, [C.c_void_p, C.POINTER(pgo_stats)]),
@@ -118,6 +122,25 @@ class Solver:
     def set_partition(self, rank, world):
         """Domain decomposition: this solver is rank `rank` of `world` (before set_graph)."""
         self._check(self.lib.pgo_set_partition(self.h, rank, world))
+
+    def comm_init(self, rank, world, broadcast_bytes):
+        """Domain decomposition with the all-reduce inside the library: creates the solver's NCCL
+        communicator. ``broadcast_bytes(b)`` must return rank 0's bytes on every rank (e.g. through
+        torch.distributed); call before set_graph."""
+        uid = C.create_string_buffer(128)
+        if rank == 0:
+            self._check(self.lib.pgo_dd_unique_id(uid))
+        data = broadcast_bytes(uid.raw)
+        self._check(self.lib.pgo_dd_comm_init(self.h, C.c_char_p(data), rank, world))
+
+    def optimize_dd(self, n_iters):
+        """optimize(n) of ONE graph cut over the ranks, the whole loop in C (pgo_dd_iterate)."""
+        chi2 = np.zeros(max(n_iters, 1))
+        done = C.c_int()
+        rc = self.lib.pgo_dd_iterate(self.h, n_iters, _p(chi2, _dp), C.byref(done))
+        if rc and rc != PGO_ERR_NUMERIC:
+            self._check(rc)
+        return done.value, chi2[:n_iters]
 
     def set_graph(self, n_vertices, edge_ij, fixed):
         """initializeOptimization: structure of the active graph. ``fixed`` = vertex indices."""

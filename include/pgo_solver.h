@@ -140,6 +140,17 @@ int pgo_dd_pose_commit(pgo_solver* s);
 /* Host-only (no device needed): the partition the analysis would choose. vertex_owner[v] = rank,
  * -1 = shared separator, -2 = fixed. stats[0] = shared vertices, stats[1] = factor blocks in shared
  * columns, stats[2 + r] = block updates sourced by rank r, stats[2 + world] = by the separators. */
+/* The same loop inside the library, with NCCL (pgo_set_partition(handle, vertex_rank,
+ * ncclComm_t)): pgo_dd_set_comm adopts the host program's ncclComm_t, pgo_dd_comm_init creates one
+ * from a 128-byte ncclUniqueId (pgo_dd_unique_id on rank 0, broadcast by the caller); both imply
+ * pgo_set_partition(rank, world) and must precede pgo_set_graph. pgo_dd_iterate = n x (local stage,
+ * ncclAllReduce of the separator blocks on the solver's stream, shared stage) + the final exchange
+ * of the estimates. libnccl.so.2 is bound at run time (dlopen), not at link time. */
+int pgo_dd_unique_id(void* out128);
+int pgo_dd_comm_init(pgo_solver* s, const void* unique_id128, int rank, int world);
+int pgo_dd_set_comm(pgo_solver* s, void* nccl_comm, int rank, int world);
+int pgo_dd_iterate(pgo_solver* s, int n_iters, double* chi2_out, int* iters_done);
+
 int pgo_analyse_partition(int n_vertices, int n_edges, const int32_t* edge_i, const int32_t* edge_j,
                           const uint8_t* fixed, int world, int32_t* vertex_owner, int64_t* stats);
 

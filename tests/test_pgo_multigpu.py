@@ -36,9 +36,23 @@ d = s.poses() - ref.poses
 d[:, 2] = po.normalize_theta(d[:, 2])
 assert done == 4 and np.abs(d).max() < 1e-6, (done, np.abs(d).max())
 assert np.allclose(chi2, ref.chi2, rtol=1e-9)
+# the same with the loop and the all-reduce INSIDE the library (pgo_dd_iterate, NCCL bound by dlopen)
+def bcast(b):
+    t = torch.tensor(list(b), dtype=torch.uint8, device="cuda")
+    dist.broadcast(t, 0)
+    return bytes(t.cpu().numpy().tobytes())
+s2 = pgo.Solver(device=local)
+s2.comm_init(rank, world, bcast)
+s2.set_graph(3000, g["edge_ij"], g["fixed"])
+s2.upload(g["poses0"], g["meas"], g["info"])
+done2, chi2b = s2.optimize_dd(4)
+d2 = s2.poses() - ref.poses
+d2[:, 2] = po.normalize_theta(d2[:, 2])
+assert done2 == 4 and np.abs(d2).max() < 1e-6, (done2, np.abs(d2).max())
+assert np.allclose(chi2b, ref.chi2, rtol=1e-9)
 dist.barrier()
 if rank == 0:
-    print("DD_OK", world, float(np.abs(d).max()))
+    print("DD_OK", world, float(np.abs(d).max()), float(np.abs(d2).max()))
 dist.destroy_process_group()
 '''
 
