@@ -53,14 +53,15 @@ def cpu_run(tmp_path_factory):
 def _same_graph(a, b, r, tol):
     ea, eb = a["edges%d" % r], b["edges%d" % r]
     assert ea.shape == eb.shape, (r, ea.shape, eb.shape)
-    key = lambda e: np.lexsort((np.round(e[:, 4], 3), np.round(e[:, 3], 3), np.round(e[:, 2], 3), e[:, 6], e[:, 1],
-                                e[:, 0]))
+    # by (from, to, level, information, measurement): parallel edges of one kind may swap between two
+    # runs only if their measurements are equal to within the differences we are measuring anyway
+    key = lambda e: np.lexsort((e[:, 4], e[:, 3], e[:, 2], e[:, 5], e[:, 6], e[:, 1], e[:, 0]))
     ea, eb = ea[key(ea)], eb[key(eb)]
     assert np.array_equal(ea[:, [0, 1, 6]], eb[:, [0, 1, 6]]), r          # vertex indices, levels: exact
     d = ea[:, 2:5] - eb[:, 2:5]
     d[:, 2] = (d[:, 2] + np.pi) % (2 * np.pi) - np.pi
     worst = float(np.abs(d).max()) if len(d) else 0.0
-    assert np.allclose(ea[:, 5], eb[:, 5], rtol=tol), r                    # information(0,0)
+    assert np.allclose(ea[:, 5], eb[:, 5], rtol=max(tol, 1e-6)), r         # information(0,0)
     va, vb = a["vertices%d" % r], b["vertices%d" % r]
     assert np.array_equal(va[:, 0], vb[:, 0]), r
     dv = va[:, 1:] - vb[:, 1:]
