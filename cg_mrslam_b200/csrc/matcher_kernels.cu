@@ -17,6 +17,8 @@
 // come from the host (ThetaDesc); integer sums are exact in any order.
 #include <cuda_runtime.h>
 
+#include <mutex>
+
 #include <algorithm>
 #include <atomic>
 #include <cstdio>
@@ -358,7 +360,6 @@ struct DeviceMatcher {
   int stamp_dim = 0;
   int sm_count = 148;
   int smem_optin = 0;
-  size_t raster_smem_set = 0;
   // map stage
   DevBuf<double> map_pts;
   DevBuf<int> map_off;
@@ -585,10 +586,18 @@ int dev_launch_map(DeviceMatcher* d, std::string* err) {
   if (band_rows > 8) band_rows &= ~7;
   const int tiles = (d->geom.rows + band_rows - 1) / band_rows;
   const size_t raster_smem_bytes = 5 * static_cast<size_t>(band_rows) * d->geom.pitch;
-  if (raster_smem_bytes > 48 * 1024 && raster_smem_bytes != d->raster_smem_set) {
-    CGM_CUDA(cudaFuncSetAttribute(raster_bands, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(raster_smem_bytes)));
-    d->raster_smem_set = raster_smem_bytes;
+  {
+    // the opt-in limit is a property of the FUNCTION (per device), shared by every matcher of the
+    // process: raise it monotonically
+    static std::mutex mu;
+    static size_t limit[64] = {0};
+    std::lock_guard<std::mutex> lock(mu);
+    size_t& cur = limit[d->device & 63];
+    if (raster_smem_bytes > 48 * 1024 && raster_smem_bytes > cur) {
+      CGM_CUDA(cudaFuncSetAttribute(raster_bands, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    static_cast<int>(raster_smem_bytes)));
+      cur = raster_smem_bytes;
+    }
   }
   CGM_CUDA(cudaEventRecord(d->ev[0], d->stream));
   for (int s0 = 0; s0 < d->map_n; s0 += 65535) {

@@ -184,3 +184,44 @@ def test_full_size_properties():
         m.close()
     assert all(cases.same(a, b) for a, b in zip(out["global"], out["tiled"]))
     assert sum(len(r) for r in out["tiled"]) > 0
+
+
+def test_two_geometries_in_one_process(oracle_lib):
+    """GraphSLAM holds a close matcher (1200^2, 0.025 m) and a loop-closure matcher (700^2, 0.1 m) and
+    uses them alternately (graph_slam.cpp:59-62,244,444): the rasteriser's shared-memory opt-in is a
+    property of the kernel, not of the matcher (regression: the second geometry used to lower it
+    under the first one's need). Also: a caller-supplied stamp, fill + raster in one launch, and a
+    device-to-device grid copy (CharGrid's value semantics)."""
+    pair = cases.scan_pair(11, 361, math.pi)
+    ms = {name: matcher.Matcher(cfg["ll"], cfg["ur"], cfg["res"], cfg["kernel_range"])
+          for name, cfg in (("close", cases.CLOSE), ("lc", cases.LC))}
+    for rep in range(3):
+        for name, cfg in (("close", cases.CLOSE), ("lc", cases.LC), ("close", cases.CLOSE)):
+            m = ms[name]
+            m.raster_batch([pair["map_pts"]])
+            g = oracle_lib.grid(cfg["ll"], cfg["ur"], cfg["res"])
+            k2 = int(cfg["kernel_range"] * 128)
+            g.fill(k2)
+            g.raster(pair["map_pts"], oracle_lib.make_stamp(cfg["res"], cfg["kernel_range"]))
+            assert np.array_equal(m.download(), g.download()), (rep, name)
+    # set_stamp + fill_raster + copy_grid through the C ABI
+    import ctypes as C
+    m = ms["lc"]
+    stamp = oracle_lib.make_stamp(0.1, 0.3)                      # a different kernel than the matcher's own
+    sb = np.ascontiguousarray(stamp, dtype=np.uint8).ravel()
+    assert m.lib.cgm_matcher_set_stamp(m.h, sb.ctypes.data_as(C.POINTER(C.c_ubyte)), stamp.shape[0]) == 0
+    pts = np.ascontiguousarray(pair["map_pts"], dtype=np.float64)
+    assert m.lib.cgm_matcher_fill_raster(m.h, 0, 38, pts.ctypes.data_as(C.POINTER(C.c_double)), len(pts)) == 0
+    g = oracle_lib.grid(cases.LC["ll"], cases.LC["ur"], cases.LC["res"])
+    g.fill(38)
+    g.raster(pair["map_pts"], stamp)
+    assert np.array_equal(m.download(), g.download())
+    other = matcher.Matcher(cases.LC["ll"], cases.LC["ur"], cases.LC["res"], cases.LC["kernel_range"])
+    assert other.lib.cgm_matcher_copy_grid(other.h, 0, m.h, 0) == 0
+    assert np.array_equal(other.download(), g.download())
+    sub = matcher.subsample(pair["cur_pts"], 0.1)
+    regions, th = cases.lc_regions([(0.0, 0.0, 0.0)])
+    assert cases.same(other.greedy_search_res(sub, regions, th, 0.3, cases.BINS),
+                      g.greedy_search_res(sub, regions, th, 0.3, cases.BINS))
+    for x in list(ms.values()) + [other]:
+        x.close()
