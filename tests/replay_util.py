@@ -60,11 +60,19 @@ def angle_diff(a, b):
     return (a - b + np.pi) % (2 * np.pi) - np.pi
 
 
-def compare(got, want, n, tol):
+def compare(got, want, n, tol, allow_tie=False):
     """Frames [0, n) of two parsed replays: identical vertex indices everywhere, estimates and
-    measurements within tol. Returns (kinds dict, worst difference)."""
+    measurements within tol. Returns (kinds dict, worst difference).
+
+    allow_tie: the one kind of decision that two solvers agreeing to 1e-13 cannot be asked to share.
+    When the robot turns in place, consecutive keyframes coincide; VerticesFinder::findClosestVertex
+    (vertices_finder.cpp:95-112) then picks among vertices whose distances differ at rounding level,
+    and graph_slam.cpp:417 drops the match if the pick happens to be the previous keyframe. If the two
+    runs differ by exactly such an edge (its endpoints less than 5 cm apart), the comparison stops
+    there (stats["tie_at"] = keyframe): from then on the graphs differ."""
     worst = 0.0
-    stats = {"edges": 0, "closures": 0, "cands": 0}
+    stats = {"edges": 0, "closures": 0, "cands": 0, "tie_at": None}
+    where = {}
 
     def d3(a, b):
         d = a - b
@@ -74,6 +82,14 @@ def compare(got, want, n, tol):
     for k in range(n):
         g, w = got[k], want[k]
         assert g["id"] == w["id"], (k, g["id"], w["id"])
+        where[g["id"]] = g["est"][:2]
+        ge, we = [(e[0], e[1]) for e in g["edges"]], [(e[0], e[1]) for e in w["edges"]]
+        if allow_tie and ge != we:
+            odd = set(ge) ^ set(we)
+            assert odd and all(a in where and b in where and np.hypot(*(where[a] - where[b])) < 0.05 for a, b in odd), \
+                (k, g["edges"], w["edges"])
+            stats["tie_at"] = k
+            return stats, worst
         assert [(e[0], e[1]) for e in g["edges"]] == [(e[0], e[1]) for e in w["edges"]], (k, g["edges"], w["edges"])
         assert [(e[0], e[1]) for e in g["cands"]] == [(e[0], e[1]) for e in w["cands"]], (k, g["cands"], w["cands"])
         worst = max(worst, d3(g["est"], w["est"]))
