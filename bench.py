@@ -403,26 +403,24 @@ def gn_domain_decomposed(args, g, local, world, barrier, poses0, meas, info, chi
     import torch.distributed as dist
     from cg_mrslam_b200 import pgo
     rank = dist.get_rank()
-    stream = torch.cuda.Stream()
-    s = pgo.Solver(device=local, stream=stream.cuda_stream)
-    s.set_partition(rank, world)
+    s = pgo.Solver(device=local)
+
+    def bcast(b):
+        t = torch.tensor(list(b), dtype=torch.uint8, device="cuda")
+        dist.broadcast(t, 0)
+        return bytes(t.cpu().numpy().tobytes())
+
+    # the solver's own NCCL communicator: the loop (local stage, ncclAllReduce of the separator
+    # blocks, shared stage) runs inside the C ABI (pgo_dd_iterate), no Python between the stages
+    s.comm_init(rank, world, bcast)
     s.set_graph(len(g["poses0"]), g["edge_ij"], g["fixed"])
-
-    def all_reduce(ts):
-        with torch.cuda.stream(stream):
-            dist.all_reduce(ts[0])
-
-    ptr_n = None
     res = {}
     for phase, iters in (("warmup", args.warmup), ("timed", args.steps)):
         s.upload(poses0, meas, info)
         barrier()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record(stream)
-        done, chi2 = pgo.optimize_distributed([s], iters, all_reduce)
-        ev1.record(stream)
+        done, chi2 = s.optimize_dd(iters)
         barrier()
-        res[phase] = (done, chi2, ev0.elapsed_time(ev1))
+        res[phase] = (done, chi2, s.stats()["last_iterate_ms"])
     done, chi2, ms = res["timed"]
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
