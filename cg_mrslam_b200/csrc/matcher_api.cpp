@@ -102,6 +102,10 @@ int cgm_matcher_create(cgm_matcher** out, int device, void* stream, int n_slots,
   m->n_slots = n_slots;
   m->kernel_range = kernel_range;
   m->stamp = cgm::make_stamp(resolution, kernel_range, kscale, &m->stamp_dim);
+  if (m->stamp_dim > 63) {  // the rasteriser tabulates the stamp's cells in shared memory
+    delete m;
+    return fail(CGM_ERR_CAPACITY, "distance stamp wider than 63 cells (kernel_range / resolution > 31)");
+  }
   // Cells only ever hold the fill value or a stamp value; the kernels size their packed
   // accumulators from this bound (a raw grid upload raises it to 255).
   for (size_t i = 0; i < m->stamp.size(); ++i)
@@ -178,8 +182,8 @@ int cgm_matcher_raster(cgm_matcher* m, int slot, const double* map_xy, int n) {
 }
 
 int cgm_matcher_set_stamp(cgm_matcher* m, const uint8_t* stamp_colmajor, int dim) {
-  if (!m || !stamp_colmajor || dim <= 0 || dim % 2 == 0 || dim > 255)
-    return fail(CGM_ERR_ARG, "bad stamp (odd dimension 1..255 expected)");
+  if (!m || !stamp_colmajor || dim <= 0 || dim % 2 == 0 || dim > 63)
+    return fail(CGM_ERR_ARG, "bad stamp (odd dimension 1..63 expected)");
   std::string err;
   const int rc = cgm::dev_set_stamp(m->dev, stamp_colmajor, dim, &err);
   if (rc) return fail(rc, err);

@@ -105,6 +105,7 @@ __device__ __forceinline__ void report(uint64_t* bins, const RegionDesc& reg, co
 // raster
 // --------------------------------------------------------------------------------------------
 const int kRasterThreads = 256, kRasterBatch = 1024;
+const int kStampCells = 4096;  // a stamp of up to 63 x 63 cells (cgm_matcher_set_stamp checks)
 
 // One CTA per band of `band_rows` whole grid rows of one slot. The band lives in shared memory as
 // ints (min-stamping uses shared atomicMin), the slot's points are culled against the band's rows
@@ -118,6 +119,7 @@ raster_bands(uint8_t* grids, size_t slot_bytes, DevGeom g, int first_slot, const
   extern __shared__ __align__(128) uint8_t raster_smem[];
   __shared__ int2 list[kRasterBatch];
   __shared__ int n_list;
+  __shared__ uchar4 cell_of[kStampCells];  // stamp cell -> (i, j, value): no divisions in the stamping loop
   int* tile = reinterpret_cast<int*>(raster_smem);
   const int pitch = g.pitch;
   uint8_t* out = raster_smem + static_cast<size_t>(band_rows) * pitch * sizeof(int);
@@ -126,6 +128,11 @@ raster_bands(uint8_t* grids, size_t slot_bytes, DevGeom g, int first_slot, const
   uint8_t* grid = grids + static_cast<size_t>(slot) * slot_bytes;
   const int center = (dim - 1) / 2;
   const int cells = nr * pitch;
+  const int dim2 = dim * dim;
+  for (int t = threadIdx.x; t < dim2; t += kRasterThreads) {
+    const int i = t / dim, j = t - i * dim;
+    cell_of[t] = make_uchar4(static_cast<unsigned char>(i), static_cast<unsigned char>(j), stamp[j * dim + i], 0);  // ker[j*kRows+i]
+  }
 
   if (reset) {
     const int v = static_cast<uint8_t>(g.fill_value);
@@ -155,13 +162,15 @@ raster_bands(uint8_t* grids, size_t slot_bytes, DevGeom g, int first_slot, const
       list[atomicAdd(&n_list, 1)] = make_int2(ix, iy);
     }
     __syncthreads();
-    const int work = n_list * dim * dim;
-    for (int t = threadIdx.x; t < work; t += kRasterThreads) {
-      const int p = t / (dim * dim), cell = t % (dim * dim);
-      const int i = cell / dim, j = cell % dim;
-      const int r = list[p].x + i - center, c = list[p].y + j - center;  // chargrid.cpp:145-151
-      if (r < r0 || r >= r0 + nr || c < 0 || c >= g.cols) continue;
-      atomicMin(&tile[(r - r0) * pitch + c], static_cast<int>(stamp[j * dim + i]));  // ker[j*kRows+i]
+    // one warp per point, the lanes over the stamp's cells (chargrid.cpp:145-151)
+    for (int p = threadIdx.x >> 5; p < n_list; p += kRasterThreads >> 5) {
+      const int2 ip = list[p];
+      for (int cell = threadIdx.x & 31; cell < dim2; cell += 32) {
+        const uchar4 cv = cell_of[cell];
+        const int r = ip.x + cv.x - center, c = ip.y + cv.y - center;
+        if (r < r0 || r >= r0 + nr || c < 0 || c >= g.cols) continue;
+        atomicMin(&tile[(r - r0) * pitch + c], static_cast<int>(cv.z));
+      }
     }
     __syncthreads();
   }
@@ -169,10 +178,12 @@ raster_bands(uint8_t* grids, size_t slot_bytes, DevGeom g, int first_slot, const
   // bytes, 4 cells per thread and store; the pad columns cols .. pitch hold 0
   for (int t = threadIdx.x; t < cells / 4; t += kRasterThreads) {
     const int c = (4 * t) % pitch;
+    const int4 v = reinterpret_cast<const int4*>(tile)[t];  // one 16-byte load: no bank conflicts
     uint32_t w = 0;
-#pragma unroll
-    for (int b = 0; b < 4; ++b)
-      if (c + b < g.cols) w |= static_cast<uint32_t>(tile[4 * t + b] & 0xFF) << (8 * b);
+    if (c < g.cols) w |= static_cast<uint32_t>(v.x & 0xFF);
+    if (c + 1 < g.cols) w |= static_cast<uint32_t>(v.y & 0xFF) << 8;
+    if (c + 2 < g.cols) w |= static_cast<uint32_t>(v.z & 0xFF) << 16;
+    if (c + 3 < g.cols) w |= static_cast<uint32_t>(v.w & 0xFF) << 24;
     reinterpret_cast<uint32_t*>(out)[t] = w;
   }
   // make the generic-proxy writes visible to the async proxy, then one thread hands the band to TMA

@@ -58,6 +58,7 @@ struct Params {
   int n_ff;
   // warp-cooperative linearisation: incidence entries regrouped per warp (see gn_linearise)
   const int4* winc;      // {edge, pos, p, role | count_chi2 << 1}
+  const int2* winc_ends; // {edge_i, edge_j} of the entry's edge
   const int* wg_ptr;     // [n_wgroups + 1] entry ranges; a range of more than 32 entries is ONE vertex
   const int* wg_info;    // bit 0: some vertex of the group has two entries with one pos (parallel edges)
   int n_wgroups;
@@ -214,8 +215,7 @@ __device__ void linearise_edge(const Params& P, int edge, EdgeLin* L) {
 // The same with the sines / cosines taken from P.trig (gn_trig runs first): an iteration evaluates
 // every edge from both of its ends, and each evaluation needs the rotations of theta_i, -theta_i,
 // theta_z and -theta_z; with the table an iteration costs V + E sincos instead of ~10 E.
-__device__ void linearise_edge_tab(const Params& P, int edge, EdgeLin* L) {
-  const int vi = P.edge_i[edge], vj = P.edge_j[edge];
+__device__ void linearise_edge_tab(const Params& P, int edge, int vi, int vj, EdgeLin* L) {
   const SE2d xi = load_pose(P.poses, vi);
   const SE2d xj = load_pose(P.poses, vj);
   const double si = P.trig[2 * vi], ci = P.trig[2 * vi + 1];
@@ -406,30 +406,24 @@ __device__ __forceinline__ void update_tile(const SNView& V, const Task& T, doub
         if (row < 3 * ti) As[row * ldk + c] = 0.0;
         else Bt[(row - 3 * ti) * ldk + c] = 0.0;
       }
-    // A = Y rows (scaled by the panel factorisation), B transposed = M rows: plain copies of 3x3
-    // blocks into row-major [3 block + row][3 t + column], as asynchronous 8-byte global->shared
-    // copies so that every block of the chunk is in flight at once. A warp instruction covers 8
-    // consecutive blocks of 4 consecutive columns, a half-warp 4 x 4: with ldk = 4 (mod 16) the
-    // block stride is 12 and the column stride 3 (mod 16 doubles), so the 16 writes of a half-warp
-    // fall on 16 different banks, and each column's blocks are one contiguous run in global memory.
-    {
-      const int al_l = (lx & 3) | ((lx >> 4) << 2), t_l = (lx >> 2) & 3;
-      const int nga = (ni + 7) >> 3, ngb = (nj + 7) >> 3;
-      for (int gidx = wy; gidx < nga + ngb; gidx += ny) {
-        const bool is_a = gidx < nga;
-        const int blk = 8 * (is_a ? gidx : gidx - nga) + al_l;
-        if (blk >= (is_a ? ni : nj)) continue;
-        const double* base = (is_a ? V.Y + 9 * static_cast<size_t>(i0) : V.M + 9 * static_cast<size_t>(j0)) + 9 * blk;
-        double* drow = (is_a ? As : Bt) + 3 * blk * ldk;
-        for (int t = t_l; t < w; t += 4) {
-          const size_t col = static_cast<size_t>(sn_colpos(pd.base, len, t) + (w - t) + off);
-          const double* src = base + 9 * col;
-          double* dst = drow + 3 * t;
-#pragma unroll
-          for (int r = 0; r < 3; ++r)
-#pragma unroll
-            for (int j = 0; j < 3; ++j) cp_async8(dst + r * ldk + j, src + 3 * r + j);
-        }
+    // A = Y rows (scaled by the panel factorisation), B transposed = M rows, copied into row-major
+    // [3 block + row][3 t + column] with asynchronous 8-byte global->shared copies so that the whole
+    // chunk is in flight at once. One warp per (operand, column): the tile's blocks of a column are
+    // ONE contiguous run of 9 n doubles in global memory, and the lanes walk it double by double, so
+    // a warp instruction reads 256 consecutive bytes = 8 full sectors (the first version had the
+    // lanes on different blocks: 32 sectors per instruction, a quarter of each used, and the L1
+    // data path 81 % busy -- profiles/r02_ncu_sn_k_update_b128.txt). Double q of the run is row
+    // q / 3, column q % 3 of the operand: destination (q / 3) ldk + 3 t + q % 3.
+    for (int c = wy; c < 2 * w; c += ny) {
+      const bool is_a = c < w;
+      const int t = is_a ? c : c - w;
+      const int n9 = 9 * (is_a ? ni : nj);
+      const size_t col = static_cast<size_t>(sn_colpos(pd.base, len, t) + (w - t) + off);
+      const double* src = (is_a ? V.Y + 9 * static_cast<size_t>(i0) : V.M + 9 * static_cast<size_t>(j0)) + 9 * col;
+      double* dst = (is_a ? As : Bt) + 3 * t;
+      for (int q = lx; q < n9; q += 32) {
+        const int row = q / 3;
+        cp_async8(dst + row * ldk + (q - 3 * row), src + q);
       }
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
@@ -556,7 +550,8 @@ __global__ void __launch_bounds__(kLinThreads) gn_linearise(Params P) {
       double v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, off[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
       if (act) {
         EdgeLin L;
-        linearise_edge_tab(P, en.x, &L);
+        const int2 ends = P.winc_ends[idx];  // the edge's two vertices: no dependent look-up through edge_i / edge_j
+        linearise_edge_tab(P, en.x, ends.x, ends.y, &L);
         const bool role = en.w & 1;
         const double* jo = role ? L.jj : L.ji;  // this vertex
         const double* jx = role ? L.ji : L.jj;  // the other one
@@ -649,7 +644,8 @@ __global__ void __launch_bounds__(kLinThreads) gn_linearise(Params P) {
     // edges between two fixed vertices only add to chi2: dealt to the first groups, one per lane
     for (int t = g * 32 + lane; t < P.n_ff; t += P.n_wgroups * 32) {
       EdgeLin L;
-      linearise_edge_tab(P, P.ff_edges[t], &L);
+      const int e = P.ff_edges[t];
+      linearise_edge_tab(P, e, P.edge_i[e], P.edge_j[e], &L);
       chi += edge_chi2(L);
     }
   }
@@ -866,6 +862,7 @@ struct DeviceSolver {
   Buf<int> edge_i, edge_j, vpos, inc_ptr, ff_edges, col_ptr, row_idx, perm_vertex, status, scratch_i;
   Buf<Incidence> inc;
   Buf<int4> winc;
+  Buf<int2> winc_ends;
   Buf<int> wg_ptr, wg_info;
   Buf<unsigned long long> stamps;
   double stage_ms[5] = {0, 0, 0, 0, 0};
@@ -992,6 +989,7 @@ void dev_destroy(DeviceSolver* d) {
   }
   d->inc.release();
   d->winc.release();
+  d->winc_ends.release();
   d->wg_ptr.release();
   d->wg_info.release();
   d->stamps.release();
@@ -1066,6 +1064,11 @@ int dev_set_structure(DeviceSolver* d, const Symbolic& S, const GraphTables& G, 
     }
   }
   PGO_CUDA(d->winc.upload(winc, s));
+  {
+    std::vector<int2> ends(winc.size());
+    for (size_t k = 0; k < winc.size(); ++k) ends[k] = make_int2(G.edge_i[winc[k].x], G.edge_j[winc[k].x]);
+    PGO_CUDA(d->winc_ends.upload(ends, s));
+  }
   PGO_CUDA(d->wg_ptr.upload(wg_ptr, s));
   PGO_CUDA(d->wg_info.upload(wg_info, s));
   PGO_CUDA(d->col_ptr.upload(S.col_ptr, s));
@@ -1122,6 +1125,7 @@ int dev_set_structure(DeviceSolver* d, const Symbolic& S, const GraphTables& G, 
   P.ff_edges = d->ff_edges.p;
   P.n_ff = static_cast<int>(G.ff_edges.size());
   P.winc = d->winc.p;
+  P.winc_ends = d->winc_ends.p;
   P.wg_ptr = d->wg_ptr.p;
   P.wg_info = d->wg_info.p;
   P.n_wgroups = static_cast<int>(wg_info.size());

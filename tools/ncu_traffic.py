@@ -15,7 +15,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-OUT = os.path.join(ROOT, "profiles")
+OUT = os.environ.get("CGM_PROFILE_OUT", os.path.join(ROOT, "profiles"))
 METRICS = "dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum"
 
 MATCHER = r'''
