@@ -428,16 +428,27 @@ __device__ __forceinline__ void update_tile(const SNView& V, const Task& T, doub
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int mi = warp + ny * h;
-      if (mi < mt) {
-        const double* ap = As + (8 * mi + fr) * ldk + fk;
-        const double* bp = Bt + fr * ldk + fk;
+    // a warp's two 8-row strips share every B fragment: 2 + NT shared-memory loads per k step for
+    // 2 NT DMMAs (the loop is bound by shared-memory bandwidth: ncu, 0.74 wavefronts / clock / SM)
+    {
+      const double* bp = Bt + fr * ldk + fk;
+      const double* ap0 = As + (8 * warp + fr) * ldk + fk;
+      const double* ap1 = As + (8 * (warp + ny) + fr) * ldk + fk;
+      if (warp + ny < mt) {
         for (int k0 = 0; k0 < k4; k0 += 4) {
-          const double a = ap[k0];
+          const double a0 = ap0[k0], a1 = ap1[k0];
 #pragma unroll
-          for (int n = 0; n < NT; ++n) dmma884(acc[h][n][0], acc[h][n][1], a, bp[8 * n * ldk + k0]);
+          for (int n = 0; n < NT; ++n) {
+            const double b = bp[8 * n * ldk + k0];
+            dmma884(acc[0][n][0], acc[0][n][1], a0, b);
+            dmma884(acc[1][n][0], acc[1][n][1], a1, b);
+          }
+        }
+      } else if (warp < mt) {
+        for (int k0 = 0; k0 < k4; k0 += 4) {
+          const double a0 = ap0[k0];
+#pragma unroll
+          for (int n = 0; n < NT; ++n) dmma884(acc[0][n][0], acc[0][n][1], a0, bp[8 * n * ldk + k0]);
         }
       }
     }
