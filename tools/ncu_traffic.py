@@ -41,8 +41,7 @@ def run_ncu(tag, cmd, skip_launches=0):
     rows = list(csv.DictReader(ln for ln in open(path) if not ln.startswith("==")))
     agg = collections.OrderedDict()
     for r in rows:
-        m = re.search(r"(sn_k_\w+|gn_\w+|score_\w+|raster_\w+|compact_\w+|\w+)\(", r["Kernel Name"] + "(")
-        name = m.group(1) if m else r["Kernel Name"][:40]
+        name = re.sub(r"<.*$", "", re.sub(r"^.*::", "", r["Kernel Name"].split("(")[0])).replace("void ", "").strip()
         v = float(r["Metric Value"].replace(",", ""))
         unit = r["Metric Unit"].lower()
         scale = {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9, "ns": 1e-3, "nsecond": 1e-3, "us": 1, "usecond": 1,
