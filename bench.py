@@ -52,7 +52,7 @@ def parse():
                     help="handles / host threads the end-to-end step is pipelined over")
     ap.add_argument("--gn-batch", type=int, default=128, help="graph instances per GPU in the GN arm")
     ap.add_argument("--no-bag", action="store_true", help="skip the real-data rows (bag replay)")
-    ap.add_argument("--bag-cpu-keyframes", type=int, default=500,
+    ap.add_argument("--bag-cpu-keyframes", type=int, default=502,
                     help="keyframes of the bag the CPU arm of the real-data rows replays (bounded sample)")
     return ap.parse_args()
 
