@@ -26,3 +26,22 @@ s.upload(poses + rng.normal(size=poses.shape) * 0.01, rel, info)
 done, chi2, out = s.optimize(3)
 print("dense done", done, chi2[-1])
 s.close()
+# scan matcher: band rasteriser (bulk shared->global stores), tiled and global scorers, hierarchy
+from cg_mrslam_b200 import matcher
+rng = np.random.default_rng(1)
+for ll, ur, kr in (((-15.0, -15.0), (15.0, 15.0), 0.2), ((-35.0, -35.0), (35.0, 35.0), 0.5)):
+    res = 0.025 if kr < 0.3 else 0.1
+    m = matcher.Matcher(ll, ur, res, kr, n_slots=3)
+    pts = np.column_stack([rng.uniform(ll[0] * 1.05, ur[0] * 1.05, 700), rng.uniform(ll[1] * 1.05, ur[1] * 1.05, 700)])
+    m.reset(0); m.raster(pts, 0)
+    m.raster_batch([pts[:300], pts[300:], pts[:0]], 0)
+    cells = m.download(0)
+    scan = pts[:181] * 0.3
+    reg = np.array([[-0.3, -0.3, -0.2, 0.3, 0.3, 0.2], [1.0, 1.0, 0.0, 1.4, 1.4, 0.1]], dtype=np.float32)
+    r1 = m.greedy_search_res(scan, reg, 0.025, 200.0, (0.5, 0.5, 0.5), slot=0)
+    r2 = m.greedy_search(scan, reg, (res, res, 0.025), 200.0, (0.5, 0.5, 0.5), slot=1)
+    r3 = m.hierarchical_search(scan, reg, 0.025, 200.0, (0.5, 0.5, 0.5), 3, slot=1)
+    outs = m.search_batch([scan, scan * 0.5, scan[:7]], [reg, reg[:1], reg], (res, res, 0.025), 200.0, (0.5, 0.5, 0.5))
+    print("matcher", m.rows, m.cols, int(cells.min()), len(r1), len(r2), len(r3), [len(o) for o in outs],
+          m.count_points(ll, ur, 0), len(m.search_non_matched(scan, 50.0, 0)))
+    m.close()
