@@ -496,7 +496,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) sn_k_bwd_rows(SNView V, con
   if (i >= n || sn_failed(V)) return;
   sn_backward_rows(WarpGroup(), V, tasks[i].id, tasks[i].r0, tasks[i].r1);
 }
-__global__ void __launch_bounds__(32 * kWarpsPerCta) sn_k_bwd_small(SNView V, const Task* tasks, int n, int stride) {
+__global__ void __launch_bounds__(32 * kWarpsPerCta, 8) sn_k_bwd_small(SNView V, const Task* tasks, int n, int stride) {
   extern __shared__ double sm[];
   const int i = blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
   V = sn_at_instance(V, blockIdx.y);
@@ -543,7 +543,7 @@ __global__ void __launch_bounds__(32 * kWarpsPerCta) sn_k_fwd_rows(SNView V, con
 // block position. No atomics. A vertex of degree > 32 is a group of its own, reduced round by round.
 __device__ __forceinline__ double shfl_down_d(double v, int off) { return __shfl_down_sync(0xffffffffu, v, off); }
 
-__global__ void __launch_bounds__(kLinThreads) gn_linearise(Params P) {
+__global__ void __launch_bounds__(kLinThreads, 5) gn_linearise(Params P) {
   P = params_at(P, blockIdx.y);
   if (*reinterpret_cast<volatile int*>(P.status) != 0) return;
   const int lane = threadIdx.x & 31, g = blockIdx.x * (kLinThreads / 32) + (threadIdx.x >> 5);
