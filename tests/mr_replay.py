@@ -37,7 +37,7 @@ _ip = C.POINTER(C.c_int)
 
 
 def fixture(bag, robot):
-    return np.load(os.path.join(ROOT, "tests", "golden", "bag_%s_robot%d.npz" % (bag, robot)))
+    return np.load(os.path.join(ROOT, "tests", "golden", "bag_%s_robot%d_full.npz" % (bag, robot)))
 
 
 class RobotLib:
@@ -226,8 +226,10 @@ def main():
         dist = (rank, world, all_gather_bytes)
     follow = dump = None
     if args.follow:
-        z = np.load(args.follow, allow_pickle=True)
-        follow = {r: list(z["r%d" % r]) for r in range(args.robots)}
+        # one file with every robot's states, or (a leader that ran one robot per rank) one per rank
+        zs = [np.load(args.follow, allow_pickle=True)] if os.path.exists(args.follow) else \
+            [np.load(args.follow.replace(".npz", ".rank%d.npz" % r), allow_pickle=True) for r in range(args.robots)]
+        follow = {r: list(next(z for z in zs if "r%d" % r in z.files)["r%d" % r]) for r in range(args.robots)}
         for r in follow:                                   # index by keyframe number (keyframe 0 = initial)
             follow[r] = [None] + follow[r]
     if args.dump:
@@ -243,7 +245,7 @@ def main():
             for i, x in enumerate(lst):
                 a[i] = x
             arrs["r%d" % r] = a
-        np.savez_compressed(args.dump, **arrs)
+        np.savez_compressed(args.dump if dist is None else args.dump.replace(".npz", ".rank%d.npz" % dist[0]), **arrs)
     if dist is not None:
         import torch.distributed as td
         td.barrier()

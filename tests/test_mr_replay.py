@@ -1,5 +1,5 @@
 """BASELINE cfg 3 as a parity case: the first 200 keyframes of all FOUR robots of the reference's
-4robots-hospital bag (tests/golden/bag_4robots_robot*.npz), replayed through the REFERENCE'S OWN
+4robots-hospital bag (tests/golden/bag_4robots_robot*_full.npz: 532-599 keyframes per robot), replayed through the REFERENCE'S OWN
 MRGraphSLAM with the message cadence and the simulated communication range of the reference
 (tests/mr_replay.py restates src/cg_mrslam.cpp:206-259 + src/mrslam/graph_comm.cpp:66-68,126-154 as a
 deterministic schedule). Robots 0-1, 0-2, 0-3 and 2-3 meet within that span: ComboMessages are
