@@ -229,7 +229,7 @@ def main():
         # one file with every robot's states, or (a leader that ran one robot per rank) one per rank
         zs = [np.load(args.follow, allow_pickle=True)] if os.path.exists(args.follow) else \
             [np.load(args.follow.replace(".npz", ".rank%d.npz" % r), allow_pickle=True) for r in range(args.robots)]
-        follow = {r: list(next(z for z in zs if "r%d" % r in z.files)["r%d" % r]) for r in range(args.robots)}
+        follow = {r: list(zs[r if len(zs) > 1 else 0]["r%d" % r]) for r in range(args.robots)}
         for r in follow:                                   # index by keyframe number (keyframe 0 = initial)
             follow[r] = [None] + follow[r]
     if args.dump:
