@@ -344,7 +344,10 @@ int pgo_initial_guess(pgo_solver* s) {
   std::string err;
   int rc = pgo::dev_get_poses(s->dev, 0, poses.data(), &err);
   if (rc) return fail(rc, err);
-  // adjacency in ascending edge index (C10 tie rule: hop count, then edge index)
+  // C10 with a tie rule that does not depend on the order in which the caller lists the edges (g2o's
+  // depends on pointer values): breadth-first by levels from the fixed vertices; the vertices of a
+  // level are expanded in ascending index, the edges of a vertex in ascending (other end, direction,
+  // measurement); the first edge to reach a vertex sets it.
   std::vector<int> ptr(nv + 1, 0);
   for (int e = 0; e < ne; ++e) {
     ++ptr[s->edge_i[e] + 1];
@@ -356,29 +359,46 @@ int pgo_initial_guess(pgo_solver* s) {
     adj[cur[s->edge_i[e]]++] = 2 * e;      // forward: this vertex is Xi
     adj[cur[s->edge_j[e]]++] = 2 * e + 1;  // backward: this vertex is Xj
   }
+  const double* meas = s->meas.data();
+  const int32_t* ei = s->edge_i.data();
+  const int32_t* ej = s->edge_j.data();
+  auto before = [meas, ei, ej](int a, int b) {
+    const int ea = a >> 1, eb = b >> 1;
+    const int wa = (a & 1) ? ei[ea] : ej[ea], wb = (b & 1) ? ei[eb] : ej[eb];
+    if (wa != wb) return wa < wb;
+    if ((a & 1) != (b & 1)) return (a & 1) < (b & 1);
+    for (int k = 0; k < 3; ++k)
+      if (meas[3 * ea + k] != meas[3 * eb + k]) return meas[3 * ea + k] < meas[3 * eb + k];
+    return false;
+  };
+  for (int v = 0; v < nv; ++v) std::stable_sort(adj.begin() + ptr[v], adj.begin() + ptr[v + 1], before);
   std::vector<char> seen(nv, 0);
-  std::deque<int> q;
+  std::vector<int> level, next;
   for (int v = 0; v < nv; ++v)
     if (s->fixed[v]) {
       seen[v] = 1;
-      q.push_back(v);
+      level.push_back(v);
     }
-  while (!q.empty()) {
-    const int v = q.front();
-    q.pop_front();
-    const Pose xv = {poses[3 * v], poses[3 * v + 1], poses[3 * v + 2]};
-    for (int t = ptr[v]; t < ptr[v + 1]; ++t) {
-      const int e = adj[t] >> 1, forward = !(adj[t] & 1);
-      const int w = forward ? s->edge_j[e] : s->edge_i[e];
-      if (seen[w]) continue;
-      const Pose z = {s->meas[3 * e], s->meas[3 * e + 1], s->meas[3 * e + 2]};
-      const Pose xw = forward ? se2_mul(xv, z) : se2_mul(xv, se2_inv(z));  // EdgeSE2::initialEstimate
-      poses[3 * w] = xw.x;
-      poses[3 * w + 1] = xw.y;
-      poses[3 * w + 2] = xw.th;
-      seen[w] = 1;
-      q.push_back(w);
+  while (!level.empty()) {
+    next.clear();
+    for (size_t q = 0; q < level.size(); ++q) {
+      const int v = level[q];
+      const Pose xv = {poses[3 * v], poses[3 * v + 1], poses[3 * v + 2]};
+      for (int t = ptr[v]; t < ptr[v + 1]; ++t) {
+        const int e = adj[t] >> 1, forward = !(adj[t] & 1);
+        const int w = forward ? s->edge_j[e] : s->edge_i[e];
+        if (seen[w]) continue;
+        const Pose z = {s->meas[3 * e], s->meas[3 * e + 1], s->meas[3 * e + 2]};
+        const Pose xw = forward ? se2_mul(xv, z) : se2_mul(xv, se2_inv(z));  // EdgeSE2::initialEstimate
+        poses[3 * w] = xw.x;
+        poses[3 * w + 1] = xw.y;
+        poses[3 * w + 2] = xw.th;
+        seen[w] = 1;
+        next.push_back(w);
+      }
     }
+    std::sort(next.begin(), next.end());
+    level.swap(next);
   }
   rc = pgo::dev_set_poses(s->dev, 0, poses.data(), &err);
   return rc ? fail(rc, err) : PGO_OK;

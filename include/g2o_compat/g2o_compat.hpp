@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <cassert>
 #include <cmath>
+#include <cstdio>
 #include <fstream>
 #include <iomanip>
 #include <iostream>
@@ -32,6 +33,114 @@
 #include "../pgo_solver.h"
 
 namespace g2o {
+
+// ---- call trace (test instrumentation, off unless a driver opens it) ------------------------------
+// The reference's front-end takes discrete decisions from solver outputs (closest vertex, covariance
+// gate, closure votes); two correct solvers that agree to 1e-13 can still break an exact tie
+// differently, after which two free runs are two different SLAM sessions. To compare a whole bag the
+// tests run two builds of the same sources in LOCKSTEP at the granularity of the solver calls: the
+// leader (this header over the CUDA library) records the result of every optimize /
+// computeInitialGuess / computeMarginals / labelEdges; the follower (the same header over the CPU
+// oracle solver) computes its own result from the same inputs, the trace notes the difference, and
+// the follower carries on with the leader's numbers. Records are keyed by vertex id, so that
+// pointer-ordered containers on either side do not matter.
+namespace trace {
+enum Kind { kOptimize = 1, kInitialGuess = 2, kMarginals = 3, kStarMeas = 4, kStarInfo = 5, kKinds = 6 };
+struct Stream {
+  FILE* f = nullptr;
+  int mode = 0;                   // 0 off, 1 record, 2 follow
+  long long calls[kKinds] = {0, 0, 0, 0, 0, 0};
+  double worst[kKinds] = {0, 0, 0, 0, 0, 0};   // poses, measurements: absolute (angles wrapped);
+                                               // covariance / information blocks: relative to the block's largest entry
+  long long parted_at = -1;       // index of the first call whose keys differed (the runs have parted)
+  long long n_calls = 0;
+};
+inline Stream* streams() {
+  static Stream s[16];
+  return s;
+}
+inline int& current() {
+  static int c = 0;
+  return c;
+}
+inline bool open(int stream, const char* path, bool follow) {
+  Stream& t = streams()[stream & 15];
+  if (t.f) std::fclose(t.f);
+  t = Stream();
+  t.f = std::fopen(path, follow ? "rb" : "wb");
+  t.mode = t.f ? (follow ? 2 : 1) : 0;
+  return t.f != nullptr;
+}
+inline void select(int stream) { current() = stream & 15; }
+inline void close(int stream) {
+  Stream& t = streams()[stream & 15];
+  if (t.f) std::fclose(t.f);
+  t.f = nullptr;
+  t.mode = 0;
+}
+inline const Stream& stats(int stream) { return streams()[stream & 15]; }
+
+// One solver result: `keys.size()` rows of `width` doubles. angle_col: column holding an angle (or
+// -1); relative: compare relative to the row's largest magnitude.
+inline void exchange(int kind, const std::vector<long long>& keys, int width, std::vector<double>& values,
+                     int angle_col, bool relative) {
+  Stream& t = streams()[current()];
+  if (!t.mode) return;
+  const long long n = static_cast<long long>(keys.size());
+  ++t.n_calls;
+  if (t.mode == 1) {
+    const long long head[3] = {kind, n, width};
+    std::fwrite(head, sizeof head, 1, t.f);
+    if (n) {
+      std::fwrite(keys.data(), sizeof(long long), n, t.f);
+      std::fwrite(values.data(), sizeof(double), n * width, t.f);
+    }
+    ++t.calls[kind];
+    return;
+  }
+  long long head[3] = {0, 0, 0};
+  std::vector<long long> lk;
+  std::vector<double> lv;
+  bool ok = std::fread(head, sizeof head, 1, t.f) == 1 && head[0] == kind && head[1] == n && head[2] == width;
+  if (ok && n) {
+    lk.resize(n);
+    lv.resize(n * width);
+    ok = std::fread(lk.data(), sizeof(long long), n, t.f) == static_cast<size_t>(n) &&
+         std::fread(lv.data(), sizeof(double), n * width, t.f) == static_cast<size_t>(n * width);
+  }
+  std::map<long long, long long> row_of;
+  if (ok) {
+    for (long long i = 0; i < n; ++i) row_of[lk[i]] = i;
+    std::set<long long> own(keys.begin(), keys.end());
+    for (long long i = 0; i < n && ok; ++i) ok = row_of.count(keys[i]) != 0;
+    ok = ok && own.size() == row_of.size();   // the same set of keys on both sides
+  }
+  if (!ok) {  // not the call the leader made here: the runs have parted, stop following
+    t.parted_at = t.n_calls - 1;
+    t.mode = 0;
+    return;
+  }
+  const double two_pi = 6.283185307179586476925286766559;
+  for (long long i = 0; i < n; ++i) {
+    const double* theirs = lv.data() + row_of[keys[i]] * width;
+    double* mine = values.data() + i * width;
+    double scale = 1.0;
+    if (relative) {
+      scale = 0.0;
+      for (int c = 0; c < width; ++c) scale = std::max(scale, std::fabs(theirs[c]));
+      if (!(scale > 0.0)) scale = 1.0;
+    }
+    for (int c = 0; c < width; ++c) {
+      double d = mine[c] - theirs[c];
+      if (c == angle_col) d -= two_pi * std::floor(d / two_pi + 0.5);
+      d = std::fabs(d) / scale;
+      if (!(d <= t.worst[kind])) t.worst[kind] = d;   // also catches NaN
+      mine[c] = theirs[c];
+    }
+  }
+  ++t.calls[kind];
+}
+}  // namespace trace
 
 // ---- C2: normalize_theta ------------------------------------------------------------------------
 inline double normalize_theta(double theta) {
@@ -515,10 +624,13 @@ class SparseOptimizer : public OptimizableGraph {
       vs.insert(e->vertex(0));
       vs.insert(e->vertex(1));
     }
-    std::stable_sort(active_edges_.begin(), active_edges_.end(),
-                     [](const OptimizableGraph::Edge* a, const OptimizableGraph::Edge* b) {
-                       return a->internalId() < b->internalId();
-                     });
+    // A canonical order -- by end points, then measurement, then insertion -- instead of g2o's order of
+    // insertion: LoopClosureChecker hands accepted closures over in heap-address order
+    // (closure_checker.h:38), so the order of insertion differs from process to process, and with it
+    // would the summation order of the solver and the spanning tree of computeInitialGuess (which
+    // breaks hop-count ties by position in this list). With this order two processes holding the
+    // same graph compute the same numbers.
+    std::stable_sort(active_edges_.begin(), active_edges_.end(), canonical_before);
     for (VertexIDMap::iterator it = vertices_.begin(); it != vertices_.end(); ++it)
       static_cast<OptimizableGraph::Vertex*>(it->second)->setHessianIndex(-1);
     int h = 0;
@@ -531,6 +643,23 @@ class SparseOptimizer : public OptimizableGraph {
     return !active_vertices_.empty();
   }
 
+  static bool canonical_before(const OptimizableGraph::Edge* a, const OptimizableGraph::Edge* b) {
+    const int a0 = a->vertex(0)->id(), a1 = a->vertex(1)->id(), b0 = b->vertex(0)->id(), b1 = b->vertex(1)->id();
+    if (a0 != b0) return a0 < b0;
+    if (a1 != b1) return a1 < b1;
+    const EdgeSE2* ea = dynamic_cast<const EdgeSE2*>(a);
+    const EdgeSE2* eb = dynamic_cast<const EdgeSE2*>(b);
+    if (ea && eb) {
+      const double ka[3] = {ea->measurement().translation().x(), ea->measurement().translation().y(),
+                            ea->measurement().rotation().angle()};
+      const double kb[3] = {eb->measurement().translation().x(), eb->measurement().translation().y(),
+                            eb->measurement().rotation().angle()};
+      for (int k = 0; k < 3; ++k)
+        if (ka[k] != kb[k]) return ka[k] < kb[k];
+    }
+    return a->internalId() < b->internalId();
+  }
+
   // C7: returns the iterations done (0 on solver failure)
   int optimize(int iterations) {
     if (!upload()) return 0;
@@ -538,7 +667,10 @@ class SparseOptimizer : public OptimizableGraph {
     std::vector<double> poses(3 * active_vertices_.size());
     const int rc = pgo_iterate(solver_, iterations, poses.data(), nullptr, &done);
     if (rc != PGO_OK) std::cerr << "optimize: " << pgo_last_error() << std::endl;
-    if (done > 0) download(poses);
+    if (done > 0) {
+      trace_poses(trace::kOptimize, poses);
+      download(poses);
+    }
     if (verbose_) std::cerr << "optimize: " << done << " iterations" << std::endl;
     return rc == PGO_OK ? done : 0;
   }
@@ -550,7 +682,10 @@ class SparseOptimizer : public OptimizableGraph {
       return;
     }
     std::vector<double> poses(3 * active_vertices_.size());
-    if (pgo_get_poses(solver_, poses.data()) == PGO_OK) download(poses);
+    if (pgo_get_poses(solver_, poses.data()) == PGO_OK) {
+      trace_poses(trace::kInitialGuess, poses);
+      download(poses);
+    }
   }
 
   // C9: blockIndices are HESSIAN indices (as in graph_manipulator.cpp:134-142)
@@ -573,6 +708,12 @@ class SparseOptimizer : public OptimizableGraph {
     if (pgo_marginals(solver_, static_cast<int>(r.size()), r.data(), c.data(), cov.data()) != PGO_OK) {
       std::cerr << "computeMarginals: " << pgo_last_error() << std::endl;
       return false;
+    }
+    if (trace::streams()[trace::current()].mode) {
+      std::vector<long long> keys(blockIndices.size());
+      for (size_t k = 0; k < blockIndices.size(); ++k)
+        keys[k] = (static_cast<long long>(active_vertices_[r[k]]->id()) << 32) | static_cast<unsigned>(active_vertices_[c[k]]->id());
+      trace::exchange(trace::kMarginals, keys, 9, cov, -1, true);
     }
     for (size_t k = 0; k < blockIndices.size(); ++k) {
       Eigen::MatrixXd* b = spinv.block(blockIndices[k].first, blockIndices[k].second, true);
@@ -741,6 +882,12 @@ class SparseOptimizer : public OptimizableGraph {
     }
     return true;
   }
+  void trace_poses(int kind, std::vector<double>& poses) {
+    if (!trace::streams()[trace::current()].mode) return;
+    std::vector<long long> keys(active_vertices_.size());
+    for (size_t i = 0; i < active_vertices_.size(); ++i) keys[i] = active_vertices_[i]->id();
+    trace::exchange(kind, keys, 3, poses, 2, false);
+  }
   void download(const std::vector<double>& poses) {
     for (size_t i = 0; i < active_vertices_.size(); ++i)
       if (!active_vertices_[i]->fixed())
@@ -795,6 +942,12 @@ class EdgeLabeler {
                              meas.data(), info.data()) != PGO_OK) {
       std::cerr << "labelEdges: " << pgo_last_error() << std::endl;
       return -1;
+    }
+    if (trace::streams()[trace::current()].mode) {
+      std::vector<long long> keys(es.size());
+      for (size_t k = 0; k < es.size(); ++k) keys[k] = es[k]->vertex(1)->id();
+      trace::exchange(trace::kStarMeas, keys, 3, meas, 2, false);
+      trace::exchange(trace::kStarInfo, keys, 9, info, -1, true);
     }
     for (size_t k = 0; k < es.size(); ++k) {
       es[k]->setMeasurement(SE2(meas[3 * k], meas[3 * k + 1], meas[3 * k + 2]));

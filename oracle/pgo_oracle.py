@@ -238,29 +238,33 @@ def marginals(res, hidx, block_pairs):
 def initial_guess(poses0, edge_ij, meas, fixed):
     """computeInitialGuess (C10): breadth-first from the fixed vertices over the active edges
     (uniform cost), each newly reached vertex set by EdgeSE2::initialEstimate from its parent
-    (Xj = Xi*Z or Xi = Xj*Z^-1). Ties: fewer hops first, then smaller edge index."""
+    (Xj = Xi*Z or Xi = Xj*Z^-1). g2o breaks ties by pointer order; here the rule does not depend on
+    the order of the edge list: the vertices of a level are expanded in ascending index, the edges of
+    a vertex in ascending (other end, direction, measurement), the first edge to reach a vertex sets
+    it."""
     poses = np.array(poses0, dtype=np.float64, copy=True)
+    meas = np.asarray(meas, dtype=np.float64)
     n = len(poses)
     adj = [[] for _ in range(n)]
     for e, (i, j) in enumerate(np.asarray(edge_ij)):
-        adj[int(i)].append((e, int(j), True))
-        adj[int(j)].append((e, int(i), False))
+        adj[int(i)].append((int(j), 0, float(meas[e][0]), float(meas[e][1]), float(meas[e][2]), e))
+        adj[int(j)].append((int(i), 1, float(meas[e][0]), float(meas[e][1]), float(meas[e][2]), e))
     seen = np.zeros(n, dtype=bool)
-    q = deque()
-    for f in sorted(int(v) for v in fixed):
-        seen[f] = True
-        q.append(f)
-    while q:
-        v = q.popleft()
-        for e, w, forward in adj[v]:  # ascending edge index
-            if seen[w]:
-                continue
-            if forward:   # v is Xi, w is Xj
-                poses[w] = se2_mul(poses[v], meas[e])[0]
-            else:         # v is Xj, w is Xi
-                poses[w] = se2_mul(poses[v], se2_inv(meas[e]))[0]
-            seen[w] = True
-            q.append(w)
+    level = sorted(int(v) for v in fixed)
+    seen[level] = True
+    while level:
+        nxt = []
+        for v in level:
+            for w, backward, _, _, _, e in sorted(adj[v], key=lambda t: t[:5]):
+                if seen[w]:
+                    continue
+                if not backward:   # v is Xi, w is Xj
+                    poses[w] = se2_mul(poses[v], meas[e])[0]
+                else:              # v is Xj, w is Xi
+                    poses[w] = se2_mul(poses[v], se2_inv(meas[e]))[0]
+                seen[w] = True
+                nxt.append(w)
+        level = sorted(nxt)
     return poses
 
 

@@ -585,7 +585,9 @@ int pgo_marginals(pgo_solver* s, int n_blocks, const int32_t* vr, const int32_t*
   return PGO_OK;
 }
 
-// C10: spanning tree from the fixed vertices, uniform edge cost, ties by (hops, edge index)
+// C10: spanning tree from the fixed vertices, uniform edge cost. Ties independent of the order of the
+// edge list: levels of a breadth-first search, a level's vertices in ascending index, a vertex's
+// edges in ascending (other end, direction, measurement); the first edge to reach a vertex sets it.
 int pgo_initial_guess(pgo_solver* s) {
   if (!s || !s->have_values) return fail(PGO_ERR_ARG, "pgo_upload first");
   const Graph& g = s->g;
@@ -594,29 +596,45 @@ int pgo_initial_guess(pgo_solver* s) {
     adj[g.ei[e]].push_back(2 * e);      // this vertex is Xi
     adj[g.ej[e]].push_back(2 * e + 1);  // this vertex is Xj
   }
+  const std::vector<double>& meas = s->meas;
+  auto before = [&g, &meas](int a, int b) {
+    const int ea = a >> 1, eb = b >> 1;
+    const int wa = (a & 1) ? g.ei[ea] : g.ej[ea], wb = (b & 1) ? g.ei[eb] : g.ej[eb];
+    if (wa != wb) return wa < wb;
+    if ((a & 1) != (b & 1)) return (a & 1) < (b & 1);
+    for (int k = 0; k < 3; ++k)
+      if (meas[3 * ea + k] != meas[3 * eb + k]) return meas[3 * ea + k] < meas[3 * eb + k];
+    return false;
+  };
+  for (int v = 0; v < g.nv; ++v) std::stable_sort(adj[v].begin(), adj[v].end(), before);
   std::vector<char> seen(g.nv, 0);
-  std::vector<int> queue;
+  std::vector<int> level, next;
   for (int v = 0; v < g.nv; ++v)
     if (g.fixed[v]) {
       seen[v] = 1;
-      queue.push_back(v);
+      level.push_back(v);
     }
-  for (size_t head = 0; head < queue.size(); ++head) {
-    const int v = queue[head];
-    const SE2 xv = {s->poses[3 * v], s->poses[3 * v + 1], s->poses[3 * v + 2]};
-    for (size_t t = 0; t < adj[v].size(); ++t) {
-      const int e = adj[v][t] >> 1;
-      const bool forward = !(adj[v][t] & 1);
-      const int w = forward ? g.ej[e] : g.ei[e];
-      if (seen[w]) continue;
-      const SE2 z = {s->meas[3 * e], s->meas[3 * e + 1], s->meas[3 * e + 2]};
-      const SE2 xw = forward ? mul(xv, z) : mul(xv, inv(z));  // EdgeSE2::initialEstimate (C4)
-      s->poses[3 * w] = xw.x;
-      s->poses[3 * w + 1] = xw.y;
-      s->poses[3 * w + 2] = xw.th;
-      seen[w] = 1;
-      queue.push_back(w);
+  while (!level.empty()) {
+    next.clear();
+    for (size_t q = 0; q < level.size(); ++q) {
+      const int v = level[q];
+      const SE2 xv = {s->poses[3 * v], s->poses[3 * v + 1], s->poses[3 * v + 2]};
+      for (size_t t = 0; t < adj[v].size(); ++t) {
+        const int e = adj[v][t] >> 1;
+        const bool forward = !(adj[v][t] & 1);
+        const int w = forward ? g.ej[e] : g.ei[e];
+        if (seen[w]) continue;
+        const SE2 z = {s->meas[3 * e], s->meas[3 * e + 1], s->meas[3 * e + 2]};
+        const SE2 xw = forward ? mul(xv, z) : mul(xv, inv(z));  // EdgeSE2::initialEstimate (C4)
+        s->poses[3 * w] = xw.x;
+        s->poses[3 * w + 1] = xw.y;
+        s->poses[3 * w + 2] = xw.th;
+        seen[w] = 1;
+        next.push_back(w);
+      }
     }
+    std::sort(next.begin(), next.end());
+    level.swap(next);
   }
   return PGO_OK;
 }

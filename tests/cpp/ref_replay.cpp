@@ -14,9 +14,11 @@
 // scan_matcher.cpp:147-150 turns a 1e-13 difference of an estimate into a 7e-9 difference of a
 // measurement now and then, and such differences eventually flip a discrete decision), so two
 // different solvers cannot be compared free-running over ~900 keyframes. They are compared in
-// LOCKSTEP instead: the GPU build dumps every vertex estimate after every keyframe (--dump), the
-// CPU build follows (--follow): at each keyframe it computes its own result from the same state,
-// reports how far it is from the GPU's (line "D k max|diff|") and then adopts the GPU's estimates.
+// LOCKSTEP instead, at the granularity of the solver calls (g2o::trace in g2o_compat.hpp): the GPU
+// build records the result of every optimize / computeMarginals / ... (--dump), the CPU build
+// follows (--follow): it computes every call from the same inputs, the trace notes how far its
+// result is from the GPU's, and it carries on with the GPU's numbers (line "D k worst-so-far"; the
+// totals per kind of call are on the TRACE line).
 //
 // usage:  ref_replay keyframes.txt [graph.g2o [id_robot [n_keyframes [--dump|--follow states.bin]]]]
 // input:  n_beams first_angle step max_range laser_x laser_y laser_th min_inliers
@@ -83,10 +85,13 @@ int main(int argc, char** argv) {
   f >> nb >> first >> step >> maxr >> lx >> ly >> lth >> min_inliers;
   const int id_robot = argc > 3 ? std::atoi(argv[3]) : 0;
   const int limit = argc > 4 ? std::atoi(argv[4]) : 1 << 30;
-  FILE* dump = nullptr;
-  FILE* follow = nullptr;
-  if (argc > 6 && std::string(argv[5]) == "--dump") dump = std::fopen(argv[6], "wb");
-  if (argc > 6 && std::string(argv[5]) == "--follow") follow = std::fopen(argv[6], "rb");
+  // lockstep at the granularity of the solver calls (include/g2o_compat/g2o_compat.hpp, namespace trace)
+  bool follow = false;
+  if (argc > 6 && std::string(argv[5]) == "--dump" && !g2o::trace::open(0, argv[6], false)) return 2;
+  if (argc > 6 && std::string(argv[5]) == "--follow") {
+    if (!g2o::trace::open(0, argv[6], true)) return 2;
+    follow = true;
+  }
   Probe gslam;
   gslam.setIdRobot(id_robot);  // vertex ids = id_robot * 10000 + k (graph_slam.cpp:92,157)
   gslam.setBaseId(10000);
@@ -126,37 +131,17 @@ int main(int argc, char** argv) {
       currEst = gslam.lastVertex()->estimate();  // srslam.cpp:214
     }
     odom_prev = odom;
-    if (dump) {  // every estimate after this keyframe
-      const int n = static_cast<int>(gslam.graph()->vertices().size());
-      std::fwrite(&n, sizeof n, 1, dump);
-      for (HyperGraph::VertexIDMap::const_iterator it = gslam.graph()->vertices().begin();
-           it != gslam.graph()->vertices().end(); ++it) {
-        const VertexSE2* v = static_cast<const VertexSE2*>(it->second);
-        const double rec[4] = {static_cast<double>(v->id()), v->estimate().translation().x(),
-                               v->estimate().translation().y(), v->estimate().rotation().angle()};
-        std::fwrite(rec, sizeof rec, 1, dump);
-      }
-    }
     if (follow) {
-      int n = 0;
-      if (std::fread(&n, sizeof n, 1, follow) != 1 || n != static_cast<int>(gslam.graph()->vertices().size())) {
-        printf("D %d -1\n", k);  // the leader has a different vertex set: not comparable
+      const g2o::trace::Stream& t = g2o::trace::stats(0);
+      if (t.parted_at >= 0) {
+        printf("D %d -1\n", k);  // the leader made a different solver call here: the runs have parted
         return 4;
       }
+      // the follower's own results against the leader's, every solver call so far: estimates and
+      // star measurements (absolute), covariance / information blocks (relative)
       double worst = 0.0;
-      for (int i = 0; i < n; ++i) {
-        double rec[4];
-        if (std::fread(rec, sizeof rec, 1, follow) != 1) return 4;
-        VertexSE2* v = static_cast<VertexSE2*>(gslam.graph()->vertex(static_cast<int>(rec[0])));
-        if (!v) return 4;
-        const SE2 mine = v->estimate();
-        worst = std::max(worst, std::fabs(mine.translation().x() - rec[1]));
-        worst = std::max(worst, std::fabs(mine.translation().y() - rec[2]));
-        worst = std::max(worst, std::fabs(normalize_theta(mine.rotation().angle() - rec[3])));
-        v->setEstimate(SE2(rec[1], rec[2], rec[3]));
-      }
+      for (int q = 1; q < g2o::trace::kKinds; ++q) worst = std::max(worst, t.worst[q]);
       printf("D %d %.3e\n", k, worst);
-      currEst = gslam.lastVertex()->estimate();
     }
     const SE2 est = gslam.lastVertex()->estimate();
     printf("K %d %d %.17g %.17g %.17g\n", k, gslam.lastVertex()->id(), est.translation().x(),
@@ -186,6 +171,13 @@ int main(int argc, char** argv) {
            v->estimate().translation().y(), v->estimate().rotation().angle());
   }
   printf("EDGES %zu\n", gslam.graph()->edges().size());
+  {
+    const g2o::trace::Stream& t = g2o::trace::stats(0);
+    printf("TRACE optimize %lld %.3e initial_guess %lld %.3e marginals %lld %.3e star_meas %lld %.3e star_info %lld %.3e\n",
+           t.calls[1], t.worst[1], t.calls[2], t.worst[2], t.calls[3], t.worst[3], t.calls[4], t.worst[4], t.calls[5],
+           t.worst[5]);
+    g2o::trace::close(0);
+  }
   printf("TIMES_MS addDataSM %.3f findConstraints %.3f optimize %.3f keyframes %d\n", t_sm, t_fc, t_opt, k);
   if (argc > 2 && std::string(argv[2]) != "-") printf("SAVE %d\n", gslam.saveGraph(argv[2]) ? 1 : 0);
   printf("END\n");

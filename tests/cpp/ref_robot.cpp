@@ -65,6 +65,7 @@ void robot_destroy(void* h) { delete static_cast<Robot*>(h); }
 // one keyframe: cg_mrslam.cpp:209-226
 void robot_keyframe(void* h, double ox, double oy, double oth, const double* ranges) {
   Robot* r = static_cast<Robot*>(h);
+  g2o::trace::select(r->idRobot());
   const SE2 odom(ox, oy, oth);
   r->currEst *= r->odom_prev.inverse() * odom;
   r->odom_prev = odom;
@@ -83,6 +84,7 @@ int robot_last_vertex(void* h) { return static_cast<Robot*>(h)->lastVertex()->id
 // [int32 peer][int32 size][bytes]; returns the bytes used (0 = nothing to send), -1 if buf is short.
 int robot_outgoing(void* h, const int* peers, int n_peers, char* buf, int cap) {
   Robot* r = static_cast<Robot*>(h);
+  g2o::trace::select(r->idRobot());
   int used = 0;
   static char scratch[MAX_LENGTH_MSG];
   auto append = [&](int peer, RobotMessage* m) -> bool {
@@ -117,6 +119,7 @@ int robot_outgoing(void* h, const int* peers, int n_peers, char* buf, int cap) {
 // GraphComm::receiveFromThrd + processQueueThrd for one datagram (graph_comm.cpp:178-211)
 int robot_deliver(void* h, const char* data, int n) {
   Robot* r = static_cast<Robot*>(h);
+  g2o::trace::select(r->idRobot());
   RobotMessage* msg = r->createMsgfromCharArray(data, n);
   if (!msg) return -1;
   StampedRobotMessage vmsg;
@@ -163,23 +166,22 @@ int robot_edges(void* h, double* out, int cap_rows) {
   return n;
 }
 
-// lockstep: adopt the leader's estimates (same vertex set expected); returns max |difference| before
-// adopting, or -1 when the vertex sets differ
-double robot_follow(void* h, const double* rows, int n) {
-  Robot* r = static_cast<Robot*>(h);
-  if (n != static_cast<int>(r->graph()->vertices().size())) return -1.0;
-  double worst = 0.0;
-  for (int k = 0; k < n; ++k) {
-    VertexSE2* v = static_cast<VertexSE2*>(r->graph()->vertex(static_cast<int>(rows[4 * k])));
-    if (!v) return -1.0;
-    const SE2 mine = v->estimate();
-    worst = std::max(worst, std::fabs(mine.translation().x() - rows[4 * k + 1]));
-    worst = std::max(worst, std::fabs(mine.translation().y() - rows[4 * k + 2]));
-    worst = std::max(worst, std::fabs(normalize_theta(mine.rotation().angle() - rows[4 * k + 3])));
-    v->setEstimate(SE2(rows[4 * k + 1], rows[4 * k + 2], rows[4 * k + 3]));
-  }
-  r->currEst = r->lastVertex()->estimate();
-  return worst;
+// lockstep at the granularity of the solver calls (g2o::trace, include/g2o_compat/g2o_compat.hpp):
+// one trace file per robot; the leader records, the follower computes every call itself, notes the
+// difference and carries on with the leader's result
+int robot_trace_open(void* h, const char* path, int follow) {
+  return g2o::trace::open(static_cast<Robot*>(h)->idRobot(), path, follow != 0) ? 0 : -1;
 }
+// out[0] = index of the call at which the runs parted (-1: they have not), then per kind of call
+// (optimize, initial guess, marginals, star measurements, star information): count, worst difference
+void robot_trace_stats(void* h, double* out) {
+  const g2o::trace::Stream& t = g2o::trace::stats(static_cast<Robot*>(h)->idRobot());
+  out[0] = static_cast<double>(t.parted_at);
+  for (int k = 1; k < g2o::trace::kKinds; ++k) {
+    out[2 * k - 1] = static_cast<double>(t.calls[k]);
+    out[2 * k] = t.worst[k];
+  }
+}
+void robot_trace_close(void* h) { g2o::trace::close(static_cast<Robot*>(h)->idRobot()); }
 
 }  // extern "C"

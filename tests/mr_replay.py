@@ -18,8 +18,9 @@ GPU box, gloo in the CPU tests) in place of the reference's UDP sockets.
     python tests/mr_replay.py --kind cpu --bag 4robots --robots 4 --keyframes 120 --out /tmp/a.npz
     torchrun --nproc-per-node 4 tests/mr_replay.py --kind gpu --dist ...      # one robot per GPU
 
-Lockstep (see tests/cpp/ref_replay.cpp for why): --dump writes every robot's estimates after each
-of its keyframes, --follow makes this run adopt them (and records how far its own were).
+Lockstep (see tests/cpp/ref_replay.cpp for why) at the granularity of the solver calls: --dump STEM
+records every robot's solver results (STEM.r<robot>.bin, g2o::trace in g2o_compat.hpp), --follow STEM
+makes this run compute every call itself, note the difference and carry on with the recorded result.
 Test / bench tooling; nothing in the package imports it."""
 import argparse
 import ctypes as C
@@ -61,8 +62,10 @@ class RobotLib:
         lib.robot_vertices.argtypes = [C.c_void_p, _dp, C.c_int]
         lib.robot_edges.restype = C.c_int
         lib.robot_edges.argtypes = [C.c_void_p, _dp, C.c_int]
-        lib.robot_follow.restype = C.c_double
-        lib.robot_follow.argtypes = [C.c_void_p, _dp, C.c_int]
+        lib.robot_trace_open.restype = C.c_int
+        lib.robot_trace_open.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+        lib.robot_trace_stats.argtypes = [C.c_void_p, _dp]
+        lib.robot_trace_close.argtypes = [C.c_void_p]
 
 
 class Robot:
@@ -107,9 +110,16 @@ class Robot:
     def deliver(self, data):
         assert self.rl.lib.robot_deliver(self.h, data, len(data)) == 0
 
-    def follow(self, rows):
-        rows = np.ascontiguousarray(rows)
-        return self.rl.lib.robot_follow(self.h, rows.ctypes.data_as(_dp), len(rows))
+    def trace_open(self, stem, follow):
+        path = "%s.r%d.bin" % (stem, self.id)
+        assert self.rl.lib.robot_trace_open(self.h, path.encode(), 1 if follow else 0) == 0, path
+
+    def trace_stats(self):
+        """(parted_at or -1, {kind: (calls, worst difference)})"""
+        out = np.zeros(11)
+        self.rl.lib.robot_trace_stats(self.h, out.ctypes.data_as(_dp))
+        kinds = ("optimize", "initial_guess", "marginals", "star_meas", "star_info")
+        return int(out[0]), {k: (int(out[2 * i + 1]), float(out[2 * i + 2])) for i, k in enumerate(kinds)}
 
 
 def split_datagrams(blob):
@@ -125,11 +135,14 @@ def split_datagrams(blob):
 def run(kind, bag, n_robots, n_keyframes, min_inliers=7, mr=(0.15, 5, 10), dist=None, dump=None, follow=None,
         log=None):
     """Returns a dict of per-robot records. dist = (rank, world, all_gather_bytes) for one robot per
-    rank; dump / follow = dict robot -> list of vertex arrays per keyframe (lockstep)."""
+    rank; dump / follow = file stem of the per-robot solver-call traces (lockstep)."""
     rl = RobotLib(kind)
     fxs = [fixture(bag, r) for r in range(n_robots)]
     mine = range(n_robots) if dist is None else [dist[0]]
     robots = {r: Robot(rl, r, fxs[r], min_inliers, mr) for r in mine}
+    for rb in robots.values():
+        if dump or follow:
+            rb.trace_open(dump or follow, follow is not None)
     n_kf = [min(n_keyframes, len(fx["odom"])) for fx in fxs]
     t0 = min(fx["time"][0] for fx in fxs)
     t1 = max(fx["time"][n - 1] for fx, n in zip(fxs, n_kf))
@@ -145,12 +158,10 @@ def run(kind, bag, n_robots, n_keyframes, min_inliers=7, mr=(0.15, 5, 10), dist=
                 if r in robots:
                     rb = robots[r]
                     rb.keyframe()
-                    if follow is not None:
-                        d = rb.follow(follow[r][done[r]])
-                        assert d >= 0.0, ("vertex sets differ", r, done[r])
-                        rec[r]["follow_diff"].append(d)
-                    if dump is not None:
-                        dump[r].append(rb.vertices())
+                    if follow is not None:                # worst difference of any solver call so far
+                        parted, kinds = rb.trace_stats()
+                        assert parted < 0, ("the follower's solver calls part from the leader's", r, done[r], parted)
+                        rec[r]["follow_diff"].append(max(w for _, w in kinds.values()))
                     v = rb.vertices()
                     rec[r]["est"].append(v[v[:, 0] == rl.lib.robot_last_vertex(rb.h)][0, 1:])
                     rec[r]["n_edges"].append(len(rb.edges()))
@@ -179,6 +190,10 @@ def run(kind, bag, n_robots, n_keyframes, min_inliers=7, mr=(0.15, 5, 10), dist=
         result["n_edges%d" % r] = np.array(rec[r]["n_edges"])
         result["vertices%d" % r] = robots[r].vertices()
         result["edges%d" % r] = robots[r].edges()
+        if dump or follow:
+            parted, kinds = robots[r].trace_stats()
+            result["trace%d" % r] = np.array([[c, w] for c, w in kinds.values()])   # rows: optimize, initial guess,
+            rl.lib.robot_trace_close(robots[r].h)                                    # marginals, star meas, star info
     return result
 
 
@@ -224,28 +239,10 @@ def main():
             return [bytes(p[:int(s)].cpu().numpy().tobytes()) for p, s in zip(parts, sizes)]
 
         dist = (rank, world, all_gather_bytes)
-    follow = dump = None
-    if args.follow:
-        # one file with every robot's states, or (a leader that ran one robot per rank) one per rank
-        zs = [np.load(args.follow, allow_pickle=True)] if os.path.exists(args.follow) else \
-            [np.load(args.follow.replace(".npz", ".rank%d.npz" % r), allow_pickle=True) for r in range(args.robots)]
-        follow = {r: list(zs[r if len(zs) > 1 else 0]["r%d" % r]) for r in range(args.robots)}
-        for r in follow:                                   # index by keyframe number (keyframe 0 = initial)
-            follow[r] = [None] + follow[r]
-    if args.dump:
-        dump = {r: [] for r in range(args.robots)}
     res = run(args.kind, args.bag, args.robots, args.keyframes, mr=(0.15, args.min_inliers_mr, 10), dist=dist,
-              dump=dump, follow=follow)
+              dump=args.dump, follow=args.follow)
     out = args.out if dist is None else args.out.replace(".npz", ".rank%d.npz" % dist[0])
     np.savez_compressed(out, **res)
-    if args.dump:
-        arrs = {}
-        for r, lst in dump.items():
-            a = np.empty(len(lst), dtype=object)
-            for i, x in enumerate(lst):
-                a[i] = x
-            arrs["r%d" % r] = a
-        np.savez_compressed(args.dump if dist is None else args.dump.replace(".npz", ".rank%d.npz" % dist[0]), **arrs)
     if dist is not None:
         import torch.distributed as td
         td.barrier()

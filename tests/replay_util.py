@@ -46,7 +46,9 @@ def parse(lines):
         elif tok[0] == "D":
             pending = float(tok[2])      # printed before the K line of its keyframe
         elif tok[0] == "TIMES_MS":
-            times = {tok[i]: float(tok[i + 1]) for i in range(1, len(tok) - 1, 2)}
+            times = dict(times or {}, **{tok[i]: float(tok[i + 1]) for i in range(1, len(tok) - 1, 2)})
+        elif tok[0] == "TRACE":      # per kind of solver call: how many, worst difference follower vs leader
+            times = dict(times or {}, trace={tok[i]: (int(tok[i + 1]), float(tok[i + 2])) for i in range(1, len(tok) - 2, 3)})
     return frames, poses, times
 
 

@@ -46,14 +46,38 @@ def test_cpu_replay_reproduces_golden(robot, tmp_path):
         assert stats["cands"] > 0
 
 
+def test_call_trace_mechanism(tmp_path):
+    """The lockstep instrument itself, without a GPU: the CPU build leading the CPU build follows
+    with zero difference through every solver call; a follower fed DIFFERENT scans makes the same
+    sequence of calls on different numbers, and the trace reports the difference."""
+    exe = ref_frontend.driver_path("ref_replay", "cpu")
+    fx = np.load(FIXTURE % 0)
+    path, other, states = str(tmp_path / "kf.txt"), str(tmp_path / "other.txt"), str(tmp_path / "trace.bin")
+    replay_util.write_keyframes(path, fx, 60)
+    ref_frontend.run_driver(exe, [path, "-", 0, 60, "--dump", states], timeout=600)
+    lines, _ = ref_frontend.run_driver(exe, [path, "-", 0, 60, "--follow", states], timeout=600)
+    frames, _, times = replay_util.parse(lines)
+    assert max(f["follow_diff"] for f in frames[1:]) == 0.0
+    assert times["trace"]["optimize"] == (3 * 59, 0.0) and times["trace"]["marginals"][0] == 59
+    fy = np.load(FIXTURE % 1)                            # another robot's scans against robot 0's trace
+    replay_util.write_keyframes(other, fy, 60)
+    lines, _ = ref_frontend.run_driver(exe, [other, "-", 0, 60, "--follow", states], timeout=600)
+    frames, _, times = replay_util.parse(lines)
+    assert max(f["follow_diff"] for f in frames[1:]) > 1e-3   # reported, not hidden
+    assert times["trace"]["optimize"][1] > 1e-3
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("robot", [0, 1])
 def test_gpu_replay_matches_reference_pipeline(robot, tmp_path):
-    """The whole bag in LOCKSTEP (see tests/cpp/ref_replay.cpp): ~885 keyframes per robot, default
-    quorum (7 inliers). The GPU build leads and dumps every estimate after every keyframe; the CPU
-    build (reference matcher + CPU oracle solver) follows on the same state. Every decision of
-    every keyframe must be identical (vertex indices of new graph edges and of buffered closure
-    candidates), measurements and the follower's own estimates within 1e-6 of the leader's."""
+    """The whole bag in LOCKSTEP at the granularity of the solver calls (tests/cpp/ref_replay.cpp,
+    g2o::trace in include/g2o_compat/g2o_compat.hpp): ~885 keyframes per robot, default quorum
+    (7 inliers). The GPU build leads and records the result of every optimize / computeInitialGuess /
+    computeMarginals; the CPU build (reference matcher + CPU oracle solver) computes every one of
+    these calls from the same inputs and carries on with the leader's numbers. Every decision of every
+    keyframe must be identical (vertex indices of new graph edges and of buffered closure
+    candidates, to the end of the bag), measurements identical, and every solver result of the
+    follower within 1e-6 of the leader's (estimates absolute, covariance blocks relative)."""
     g2o_path = str(tmp_path / ("robot-%d.g2o" % robot))
     states = str(tmp_path / "states.bin")
     fx = np.load(FIXTURE % robot)
@@ -67,15 +91,20 @@ def test_gpu_replay_matches_reference_pipeline(robot, tmp_path):
                                        [path, "-", robot, n, "--follow", states], timeout=3000)
     want, want_poses, cpu_times = replay_util.parse(lines)
     assert len(frames) == len(want) == n > 800
-    stats, worst = replay_util.compare(frames, want, n, TOL, allow_tie=True)
-    upto = stats["tie_at"] if stats["tie_at"] is not None else n
-    assert upto >= 300, stats                           # (a coincident-keyframe tie: see replay_util.compare)
-    follow = max(f["follow_diff"] for f in want[1:upto])
-    assert 0.0 <= follow < TOL, follow                  # solver parity at every keyframe, same inputs
+    stats, worst = replay_util.compare(frames, want, n, TOL)
+    follow = max(f["follow_diff"] for f in want[1:])
+    assert 0.0 <= follow < TOL, follow                  # -1 = the runs parted
+    trace = cpu_times["trace"]
+    assert trace["optimize"][0] >= 3 * (n - 1) and trace["marginals"][0] > 500, trace
+    assert all(w < TOL for _, w in trace.values()), trace
     assert sorted(poses) == sorted(want_poses)
+    for v in poses:                                     # the final graphs: the same estimates
+        d = poses[v] - want_poses[v]
+        assert abs(d[0]) < TOL and abs(d[1]) < TOL and abs(replay_util.angle_diff(poses[v][2], want_poses[v][2])) < TOL
     assert stats["closures"] > 0 and stats["cands"] > 50, stats
     print("replay robot", robot, n, "keyframes:", stats, "max |measurement diff| = %.2e," % worst,
-          "max |estimate diff| per keyframe = %.2e" % follow, "GPU ms", times, "CPU ms", cpu_times)
+          "solver calls (count, worst difference):", trace, "GPU ms", {k: v for k, v in times.items() if k != "trace"},
+          "CPU ms", {k: v for k, v in cpu_times.items() if k != "trace"})
     if robot == 0:
         condensed_graph_on_replayed_graph(g2o_path, poses)
 

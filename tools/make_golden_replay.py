@@ -1,6 +1,6 @@
 """Golden outputs of the bag replays: the reference's own GraphSLAM (compiled verbatim) over the
 reference's CPU matcher and the CPU oracle solver (oracle/_ref/ref_replay_cpu, built by
-`make -C oracle frontend`), run HERE on the keyframe fixtures tests/golden/bag_*_full.npz.
+`make -C oracle frontend`), run HERE on the keyframe fixtures tests/golden/bag_2robots_*_full.npz.
 
     python tools/make_golden_replay.py            # all fixtures (minutes per robot)
 
@@ -23,7 +23,7 @@ import replay_util  # noqa: E402
 
 def main():
     exe = os.path.join(ROOT, "oracle", "_ref", "ref_replay_cpu")
-    for fx_path in sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "bag_*_full.npz"))):
+    for fx_path in sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "bag_2robots_*_full.npz"))):
         name = os.path.basename(fx_path)[len("bag_"):-len("_full.npz")]
         robot = int(name.rsplit("robot", 1)[1])
         fx = np.load(fx_path)
@@ -33,7 +33,7 @@ def main():
             res = os.path.join(d, "out.txt")
             subprocess.check_call([exe, kf, "-", str(robot)], env=dict(os.environ, CGM_OUT=res),
                                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-            lines = [ln for ln in open(res).read().splitlines() if not ln.startswith(("TIMES_MS", "T "))]
+            lines = [ln for ln in open(res).read().splitlines() if not ln.startswith(("TIMES_MS", "T ", "TRACE"))]
         out = os.path.join(ROOT, "tests", "golden", "replay_%s_cpu.txt.gz" % name)
         with gzip.open(out, "wt") as f:
             f.write("\n".join(lines) + "\n")
