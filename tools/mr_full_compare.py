@@ -1,5 +1,5 @@
 """Evidence run for BASELINE cfg 3 at full length (every keyframe of the 4-robot bag, the reference's
-default inter-robot quorum): compares a GPU leader's output (single process, or one robot per rank /
+default inter-robot quorum; lockstep at the granularity of the solver calls, g2o::trace): compares a GPU leader's output (single process, or one robot per rank /
 GPU) with the CPU follower's (tests/mr_replay.py --follow), with the checks of
 tests/test_mr_replay.py::test_four_robots_gpu_lockstep.
 
@@ -90,5 +90,12 @@ for r in range(4):
           % (r, span, len(a["vertices%d" % r]), len(e), inter, int((e[:, 6] > 0).sum()), worst, fd))
     assert same_traffic and worst < TOL and fd < TOL
     worst_all = max(worst_all, worst, fd)
+kinds = ("optimize", "computeInitialGuess", "computeMarginals", "labelEdges measurement", "labelEdges information")
+if "trace0" in b.files:
+    print("solver calls of the follower against the leader's, per kind (count, worst difference; estimates and measurements"
+          " absolute, covariance / information blocks relative to the block's largest entry):")
+    for i, k in enumerate(kinds):
+        print("   %-24s %6d calls, worst %.2e" % (k, sum(int(b["trace%d" % r][i, 0]) for r in range(4)),
+                                                  max(float(b["trace%d" % r][i, 1]) for r in range(4))))
 print("datagrams %d (identical in both runs), sizes %d..%d bytes; worst difference %.2e (tolerance 1e-6)"
       % (len(b["msgs"]), int(b["msgs"][:, 3].min()), int(b["msgs"][:, 3].max()), worst_all))
