@@ -43,7 +43,7 @@ def fixture(bag, robot):
 
 class RobotLib:
     def __init__(self, kind):
-        path = os.path.join(ROOT, "oracle", "_ref", "libref_robot_%s.so" % kind)
+        path = os.environ.get("CGM_ROBOT_LIB") or os.path.join(ROOT, "oracle", "_ref", "libref_robot_%s.so" % kind)
         if not os.path.exists(path):
             raise FileNotFoundError(path + " (make -C oracle frontend; needs /root/reference)")
         self.lib = lib = C.CDLL(path)
