@@ -834,10 +834,14 @@ struct Buf {
   size_t cap = 0;
   cudaError_t reserve(size_t n) {
     if (n <= cap && p) return cudaSuccess;
+    // a buffer that grows again (the keyframe loop adds a vertex per keyframe: every structure array is
+    // one element short every time) gets half as much again, up to 64 MB of slack: cudaFree
+    // synchronises the device and the pair costs ~0.1 ms per buffer, ~30 buffers per pgo_set_graph
+    size_t want = n ? n : 1;
+    if (p && cap) want = std::max(want, std::min(cap + cap / 2, cap + (size_t(64) << 20) / sizeof(T)));
     if (p) cudaFree(p);
     p = nullptr;
     cap = 0;
-    const size_t want = n ? n : 1;
     cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&p), want * sizeof(T));
     if (e == cudaSuccess) cap = want;
     return e;
@@ -1693,8 +1697,15 @@ int dev_marginals(DeviceSolver* d, int n, const int* col_p, const int* row_p, do
   std::vector<int> rhs_of(n);
   for (int k = 0; k < n; ++k)
     rhs_of[k] = static_cast<int>(std::lower_bound(cols.begin(), cols.end(), col_p[k]) - cols.begin());
-  const int batch_cols = 16;  // 48 right-hand sides per cooperative launch
   const size_t stride = 3 * static_cast<size_t>(d->P.n);
+  // Columns per pass (3 right-hand sides each, solved as batch instances of the substitution kernels).
+  // On the graphs of the keyframe loop (a few hundred poses) a pass is bound by its ~50 dependent
+  // launches, not by its work, and the covariance gate asks for a block per candidate vertex
+  // (graph_manipulator.cpp:134-142): as many columns per pass as three vector sets of 256 MB allow,
+  // at most 64 (measured on the 884-keyframe replay, ms per request: 9.1 with 16 columns per pass, 4.5
+  // with 64, 5.8 with 128, 10.5 with 256).
+  const size_t cap_cols = std::max<size_t>(16, (256u << 20) / (3 * stride * sizeof(double) + 1));
+  const int batch_cols = static_cast<int>(std::min<size_t>(std::min<size_t>(64, cap_cols), std::max<size_t>(cols.size(), 1)));
   PGO_CUDA(d->many_rhs.reserve(3 * batch_cols * stride));
   // the marginals' substitution vectors are separate: the iteration graph holds u / x by address
   PGO_CUDA(d->many_u.reserve(3 * batch_cols * stride));

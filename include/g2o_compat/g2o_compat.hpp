@@ -14,6 +14,7 @@
 
 #include <algorithm>
 #include <cassert>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <fstream>
@@ -79,6 +80,22 @@ inline void close(int stream) {
   t.mode = 0;
 }
 inline const Stream& stats(int stream) { return streams()[stream & 15]; }
+// wall-clock milliseconds spent in the solver library, by entry point (always on: two clock reads per
+// call): [0] pgo_set_graph, [1] pgo_upload, [2] pgo_iterate, [3] pgo_marginals, [4] pgo_initial_guess
+// (+ pose read-back), [5] pgo_label_star_edges; [6 + k]: the number of calls of entry k
+inline double* wall_ms() {
+  static double t[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  return t;
+}
+struct Clock {
+  int k;
+  std::chrono::steady_clock::time_point t0;
+  explicit Clock(int kind) : k(kind), t0(std::chrono::steady_clock::now()) {}
+  ~Clock() {
+    wall_ms()[k] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    wall_ms()[6 + k] += 1.0;
+  }
+};
 
 // One solver result: `keys.size()` rows of `width` doubles. angle_col: column holding an angle (or
 // -1); relative: compare relative to the row's largest magnitude.
@@ -665,7 +682,11 @@ class SparseOptimizer : public OptimizableGraph {
     if (!upload()) return 0;
     int done = 0;
     std::vector<double> poses(3 * active_vertices_.size());
-    const int rc = pgo_iterate(solver_, iterations, poses.data(), nullptr, &done);
+    int rc;
+    {
+      trace::Clock clk(2);
+      rc = pgo_iterate(solver_, iterations, poses.data(), nullptr, &done);
+    }
     if (rc != PGO_OK) std::cerr << "optimize: " << pgo_last_error() << std::endl;
     if (done > 0) {
       trace_poses(trace::kOptimize, poses);
@@ -677,6 +698,7 @@ class SparseOptimizer : public OptimizableGraph {
 
   void computeInitialGuess() {  // C10
     if (!upload()) return;
+    trace::Clock clk(4);
     if (pgo_initial_guess(solver_) != PGO_OK) {
       std::cerr << "computeInitialGuess: " << pgo_last_error() << std::endl;
       return;
@@ -705,7 +727,12 @@ class SparseOptimizer : public OptimizableGraph {
       c.push_back(by_hidx[hc]);
     }
     std::vector<double> cov(9 * blockIndices.size());
-    if (pgo_marginals(solver_, static_cast<int>(r.size()), r.data(), c.data(), cov.data()) != PGO_OK) {
+    int rc_m;
+    {
+      trace::Clock clk(3);
+      rc_m = pgo_marginals(solver_, static_cast<int>(r.size()), r.data(), c.data(), cov.data());
+    }
+    if (rc_m != PGO_OK) {
       std::cerr << "computeMarginals: " << pgo_last_error() << std::endl;
       return false;
     }
@@ -846,7 +873,12 @@ class SparseOptimizer : public OptimizableGraph {
       solver_ = slots_[slot];
       slot_key_[slot] = key;
       slot_used_[slot] = ++use_clock_;
-      if (pgo_set_graph(solver_, nv, ne, ei.data(), ej.data(), fixed.data()) != PGO_OK) {
+      int rc_g;
+      {
+        trace::Clock clk(0);
+        rc_g = pgo_set_graph(solver_, nv, ne, ei.data(), ej.data(), fixed.data());
+      }
+      if (rc_g != PGO_OK) {
         std::cerr << "SparseOptimizer: " << pgo_last_error() << std::endl;
         return false;
       }
@@ -876,7 +908,12 @@ class SparseOptimizer : public OptimizableGraph {
       info[6 * e + 4] = w(1, 2);
       info[6 * e + 5] = w(2, 2);
     }
-    if (pgo_upload(solver_, poses.data(), meas.data(), info.data()) != PGO_OK) {
+    int rc_u;
+    {
+      trace::Clock clk(1);
+      rc_u = pgo_upload(solver_, poses.data(), meas.data(), info.data());
+    }
+    if (rc_u != PGO_OK) {
       std::cerr << "SparseOptimizer: " << pgo_last_error() << std::endl;
       return false;
     }
@@ -938,8 +975,13 @@ class EdgeLabeler {
       vs.push_back(vb);
     }
     std::vector<double> meas(3 * es.size()), info(9 * es.size());
-    if (pgo_label_star_edges(opt_->solver(), gauge, static_cast<int>(es.size()), vs.data(),
-                             meas.data(), info.data()) != PGO_OK) {
+    int rc_l;
+    {
+      trace::Clock clk(5);
+      rc_l = pgo_label_star_edges(opt_->solver(), gauge, static_cast<int>(es.size()), vs.data(), meas.data(),
+                                  info.data());
+    }
+    if (rc_l != PGO_OK) {
       std::cerr << "labelEdges: " << pgo_last_error() << std::endl;
       return -1;
     }

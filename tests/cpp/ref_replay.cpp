@@ -178,6 +178,11 @@ int main(int argc, char** argv) {
            t.worst[5]);
     g2o::trace::close(0);
   }
+  {
+    const double* w = g2o::trace::wall_ms();
+    printf("SOLVER_MS set_graph %.3f %.0f upload %.3f %.0f iterate %.3f %.0f marginals %.3f %.0f initial_guess %.3f %.0f\n", w[0],
+           w[6], w[1], w[7], w[2], w[8], w[3], w[9], w[4], w[10]);
+  }
   printf("TIMES_MS addDataSM %.3f findConstraints %.3f optimize %.3f keyframes %d\n", t_sm, t_fc, t_opt, k);
   if (argc > 2 && std::string(argv[2]) != "-") printf("SAVE %d\n", gslam.saveGraph(argv[2]) ? 1 : 0);
   printf("END\n");

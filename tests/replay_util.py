@@ -47,6 +47,8 @@ def parse(lines):
             pending = float(tok[2])      # printed before the K line of its keyframe
         elif tok[0] == "TIMES_MS":
             times = dict(times or {}, **{tok[i]: float(tok[i + 1]) for i in range(1, len(tok) - 1, 2)})
+        elif tok[0] == "SOLVER_MS":  # wall clock inside the solver library by entry point: (ms, calls)
+            times = dict(times or {}, solver_ms={tok[i]: (float(tok[i + 1]), int(float(tok[i + 2]))) for i in range(1, len(tok) - 2, 3)})
         elif tok[0] == "TRACE":      # per kind of solver call: how many, worst difference follower vs leader
             times = dict(times or {}, trace={tok[i]: (int(tok[i + 1]), float(tok[i + 2])) for i in range(1, len(tok) - 2, 3)})
     return frames, poses, times

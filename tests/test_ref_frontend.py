@@ -104,7 +104,7 @@ def test_gpu_replay_matches_reference_pipeline(robot, tmp_path):
     assert stats["closures"] > 0 and stats["cands"] > 50, stats
     print("replay robot", robot, n, "keyframes:", stats, "max |measurement diff| = %.2e," % worst,
           "solver calls (count, worst difference):", trace, "GPU ms", {k: v for k, v in times.items() if k != "trace"},
-          "CPU ms", {k: v for k, v in cpu_times.items() if k != "trace"})
+          "CPU ms", {k: v for k, v in cpu_times.items() if k != "trace"})   # solver_ms: (ms, calls) inside the solver library
     if robot == 0:
         condensed_graph_on_replayed_graph(g2o_path, poses)
 

@@ -33,7 +33,7 @@ def main():
             res = os.path.join(d, "out.txt")
             subprocess.check_call([exe, kf, "-", str(robot)], env=dict(os.environ, CGM_OUT=res),
                                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-            lines = [ln for ln in open(res).read().splitlines() if not ln.startswith(("TIMES_MS", "T ", "TRACE"))]
+            lines = [ln for ln in open(res).read().splitlines() if not ln.startswith(("TIMES_MS", "T ", "TRACE", "SOLVER_MS"))]
         out = os.path.join(ROOT, "tests", "golden", "replay_%s_cpu.txt.gz" % name)
         with gzip.open(out, "wt") as f:
             f.write("\n".join(lines) + "\n")
