@@ -251,8 +251,16 @@ class Dissector {
         u = v;
       }
     }
-    const int w = bfs_dist(u, id, d4_[2]);
-    bfs_dist(w, id, d4_[3]);
+    // Graphs of the keyframe loop (hundreds of poses, re-analysed whenever a vertex is added) take the
+    // quick route: one axis only (x = d_p - d_q, d_p, d_q as sweeps). The second axis and its three
+    // sweeps cost as much again and buy nothing measurable on graphs this small.
+    const bool quick = g_.n <= kQuickOrderingVertices;
+    if (quick) {
+      for (int i = 0; i < n; ++i) d4_[2][s[i]] = d4_[3][s[i]] = 0;
+    } else {
+      const int w = bfs_dist(u, id, d4_[2]);
+      bfs_dist(w, id, d4_[3]);
+    }
 
     int lo = std::max(1, static_cast<int>(bal * n)), hi = std::min(n - 1, n - lo);
     // sort keys packed into one word: primary key, secondary key, position in s (all three are
@@ -286,6 +294,7 @@ class Dissector {
     for (int attempt = 0; attempt < 3 && best_k < 0;
          ++attempt, lo = attempt == 1 ? std::max(1, lo / 2) : 1, hi = n - lo)
       for (int cand = 0; cand < 6; ++cand) {
+        if (quick && cand >= 1 && cand <= 3) continue;   // y == 0: these repeat sweep 0
         sweep(cand);
         for (int i = 0; i < n; ++i) pos_[keyed[i]] = i;
         std::fill(diff_a.begin(), diff_a.end(), 0);

@@ -58,6 +58,7 @@ PGO_HOST_DEVICE inline constexpr int sn_fused_doubles(int w, int m) {
   return w * w * 9 + w * 9 + (kSmallWidth * (kSmallWidth + 1) / 2 + 1) / 2 + 3 * w + 3 * w * (3 * m + 1);
 }
 PGO_HOST_DEVICE inline constexpr int sn_subst_doubles(int W) { return 6 * W + 9 * W * W + 9 * W + 96; }
+static const int kQuickOrderingVertices = 4096;  // at most this many free vertices: cheaper dissection cuts
 static const int kMaxSuperWidth = 1008;   // at most 63 panels per supernode
 static const int kUpdateGroup = 4;        // panels per tile task of an ancestors' update
 
